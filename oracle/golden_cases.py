@@ -1,0 +1,36 @@
+"""Definitions shared by oracle/make_golden.py (writer) and the tests (readers): which model presets,
+seeds and synthetic images the committed golden fixtures were produced with.  TEST INFRASTRUCTURE."""
+import torch
+
+from rba_b200 import config as rcfg
+
+CASES = {
+    # name: preset, encoder levels, decoder layers, weight seed / perturbation, image seed and sizes
+    "tiny_1dl": dict(preset="tiny", levels=1, dec_layers=1, seed=11, perturb=0.02, img_seed=1, sizes=[(70, 100)]),
+    "tiny_3lvl": dict(preset="tiny", levels=3, dec_layers=3, seed=12, perturb=0.02, img_seed=2, sizes=[(64, 96), (64, 96)]),
+    "swin_b_1dl": dict(preset="swin_b_1dl", levels=1, dec_layers=1, seed=13, perturb=0.02, img_seed=3, sizes=[(96, 160)]),
+}
+
+
+def case_model_config(case):
+    if case["preset"] == "tiny":
+        return rcfg.tiny_test(levels=case["levels"], dec_layers=case["dec_layers"])
+    if case["preset"] == "swin_b_1dl":
+        return rcfg.swin_b_1dl()
+    if case["preset"] == "swin_l_1dl":
+        return rcfg.swin_l_1dl()
+    raise KeyError(case["preset"])
+
+
+def case_images(case):
+    g = torch.Generator().manual_seed(case["img_seed"])
+    return [torch.randint(0, 256, (3, h, w), dtype=torch.uint8, generator=g) for h, w in case["sizes"]]
+
+
+def state_checksum(sd):
+    """Guards against RNG drift between the container that wrote the fixture and the one reading it."""
+    s = 0.0
+    for k, v in sd.items():
+        if v.is_floating_point():
+            s += float(v.double().abs().sum())
+    return s

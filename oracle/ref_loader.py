@@ -14,6 +14,7 @@ back to its own pure-PyTorch statement `ms_deform_attn_core_pytorch`
 (mask2former/modeling/pixel_decoder/ops/modules/ms_deform_attn.py:116-121).
 """
 import importlib
+import importlib.util
 import os
 import sys
 import types
@@ -64,6 +65,14 @@ def _install():
         importlib.import_module(mod)
 
 
+def _merge(dst, src):
+    for k, v in src.items():
+        if isinstance(v, dict) and isinstance(dst.get(k), dict):
+            _merge(dst[k], v)
+        else:
+            dst[k] = v
+
+
 def load_cfg(name_or_path="swin_b_1dl", overrides=None):
     """Dumped ckpt YAMLs are plain YAML; returns a shim CfgNode."""
     _install()
@@ -72,8 +81,15 @@ def load_cfg(name_or_path="swin_b_1dl", overrides=None):
     path = name_or_path
     if not os.path.isfile(path):
         path = os.path.join(REF_ROOT, "ckpts", name_or_path, "config.yaml")
+    # defaults exactly as train_net.setup builds them (train_net.py:356-362): the reference's own
+    # add_maskformer2_config over a skeleton of the detectron2 nodes it touches, then the YAML on top.
+    spec = importlib.util.spec_from_file_location("_ref_m2f_config", os.path.join(REF_ROOT, "mask2former", "config.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    cfg = CfgNode({"INPUT": {"CROP": {}}, "SOLVER": {}, "MODEL": {"SEM_SEG_HEAD": {}}, "DATASETS": {}, "TEST": {}})
+    mod.add_maskformer2_config(cfg)
     with open(path) as f:
-        cfg = CfgNode(yaml.safe_load(f))
+        _merge(cfg, CfgNode(yaml.safe_load(f)))
     for dotted, v in (overrides or {}).items():
         node = cfg
         keys = dotted.split(".")

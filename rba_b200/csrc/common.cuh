@@ -1,0 +1,132 @@
+// Shared device/host helpers for the rba_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+
+#include "../../include/rba_b200.h"
+
+namespace rba {
+
+// ---- error plumbing (thread-local message, int status through the C ABI) ----
+std::string& last_error_ref();
+int fail(int code, const char* fmt, ...);
+extern std::atomic<int64_t> g_launches;
+
+#define RBA_CHECK(cond, ...)                                  \
+  do {                                                        \
+    if (!(cond)) return ::rba::fail(RBA_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+#define RBA_CUDA(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      return ::rba::fail(RBA_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+// Call right after a kernel launch: counts it and surfaces launch-configuration errors.
+#define RBA_LAUNCHED()                                                                                  \
+  do {                                                                                                  \
+    ::rba::g_launches.fetch_add(1, std::memory_order_relaxed);                                          \
+    cudaError_t _e = cudaGetLastError();                                                                \
+    if (_e != cudaSuccess)                                                                              \
+      return ::rba::fail(RBA_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- bf16 split planes ----
+// x ~= hi + lo with hi = bf16_rn(x), lo = bf16_rn(x - hi): |x - hi - lo| <= 2^-18 |x|.
+__device__ __forceinline__ void split2(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+__device__ __forceinline__ float bf16_bits_to_float(uint16_t b) { return __uint_as_float(((uint32_t)b) << 16); }
+__device__ __forceinline__ float bf16lo(uint32_t packed) { return __uint_as_float(packed << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t packed) { return __uint_as_float(packed & 0xffff0000u); }
+
+// Stores 4 consecutive values as split planes (8-byte stores, idx must be a multiple of 4).
+__device__ __forceinline__ void store_split4(uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int64_t idx,
+                                             float a, float b, float c, float d) {
+  __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+  split2(a, h0, l0);
+  split2(b, h1, l1);
+  split2(c, h2, l2);
+  split2(d, h3, l3);
+  uint2 H, L;
+  H.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+  H.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+  L.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  L.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+  *reinterpret_cast<uint2*>(hi + idx) = H;
+  *reinterpret_cast<uint2*>(lo + idx) = L;
+}
+__device__ __forceinline__ void store_split1(uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int64_t idx, float a) {
+  __nv_bfloat16 h, l;
+  split2(a, h, l);
+  hi[idx] = __bfloat16_as_ushort(h);
+  lo[idx] = __bfloat16_as_ushort(l);
+}
+
+// ---- warp reductions ----
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- activations ----
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+template <int ACT>
+__device__ __forceinline__ float apply_act(float x) {
+  if (ACT == RBA_ACT_RELU) return fmaxf(x, 0.0f);
+  if (ACT == RBA_ACT_GELU) return gelu_erf(x);
+  return x;
+}
+__device__ __forceinline__ float apply_act_rt(float x, int act) {
+  if (act == RBA_ACT_RELU) return fmaxf(x, 0.0f);
+  if (act == RBA_ACT_GELU) return gelu_erf(x);
+  return x;
+}
+
+// ---- Swin window geometry (swin.py:250-271, 277-287) ----
+// Windowed row r = ((b*nWh + wh)*nWw + ww)*ws*ws + i*ws + j lives at (wh*ws+i, ww*ws+j) of the SHIFTED padded
+// frame; shifted = roll(x, -shift) so its source in the padded frame is ((hs+shift)%Hp, (wsft+shift)%Wp).
+// Returns the token index b*H*W + h*W + w, or -1 when the source lies in the bottom/right padding.
+struct SwinGeom {
+  int H, W, ws, shift, nWh, nWw, Hp, Wp;
+};
+__host__ __device__ inline SwinGeom make_swin_geom(int H, int W, int ws, int shift) {
+  SwinGeom g;
+  g.H = H; g.W = W; g.ws = ws; g.shift = shift;
+  g.nWh = (H + ws - 1) / ws; g.nWw = (W + ws - 1) / ws;
+  g.Hp = g.nWh * ws; g.Wp = g.nWw * ws;
+  return g;
+}
+__host__ __device__ inline int64_t swin_row_to_token(const SwinGeom& g, int64_t r) {
+  const int n = g.ws * g.ws;
+  int64_t win = r / n;
+  int t = (int)(r - win * n);
+  int i = t / g.ws, j = t - i * g.ws;
+  int ww = (int)(win % g.nWw);
+  int64_t tmp = win / g.nWw;
+  int wh = (int)(tmp % g.nWh);
+  int64_t b = tmp / g.nWh;
+  int h = wh * g.ws + i + g.shift; if (h >= g.Hp) h -= g.Hp;
+  int w = ww * g.ws + j + g.shift; if (w >= g.Wp) w -= g.Wp;
+  if (h >= g.H || w >= g.W) return -1;
+  return (b * g.H + h) * g.W + w;
+}
+
+}  // namespace rba

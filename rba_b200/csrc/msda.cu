@@ -1,0 +1,180 @@
+// Multi-scale deformable attention, forward sampling step.
+//
+// Drop-in for the reference FFI `MultiScaleDeformableAttention.ms_deform_attn_forward`
+// (ops/src/vision.cpp:18-21 -> ops/src/cuda/ms_deform_attn_cuda.cu:25-84 -> kernel
+// ops/src/cuda/ms_deform_im2col_cuda.cuh:242-304).  Semantics (== grid_sample bilinear / zeros /
+// align_corners=False, ops/functions/ms_deform_attn_func.py:52-72):
+//   out[b,q,m,:] = sum_{l,p} w[b,q,m,l,p] * bilinear(value_l[b,:,m,:], (x*W_l - 0.5, y*H_l - 0.5))
+// with taps outside the map contributing zero and samples outside (-1,H)x(-1,W) skipped.
+//
+// Layout / mapping: value is (B,S,M,D) with D contiguous, so one thread per output element with d fastest
+// makes every tap a D*4-byte coalesced gather (128 B for D=32) and the location/weight loads warp-uniform
+// broadcasts.  The op is gather/latency bound (16 taps x 128 B per (q,head) at 1 level x 4 points): the grid is
+// sized to cover all B*Lq*M*D elements at 256 threads/CTA, no shared memory, no reuse to exploit.
+#include "common.cuh"
+
+namespace rba {
+
+constexpr int MSDA_MAX_LEVELS = 8;
+struct MsdaLevels {
+  int H[MSDA_MAX_LEVELS], W[MSDA_MAX_LEVELS], start[MSDA_MAX_LEVELS];
+};
+
+__global__ void __launch_bounds__(256)
+msda_forward_kernel(const float* __restrict__ value, MsdaLevels lv, const float* __restrict__ loc,
+                    const float* __restrict__ attw, int64_t total, int S, int M, int D, int Lq, int L, int P,
+                    float* __restrict__ out) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int d = (int)(idx % D);
+  int64_t t = idx / D;
+  const int m = (int)(t % M);
+  t /= M;                                   // t = b*Lq + q
+  const int64_t b = t / Lq;
+  const float* vb = value + (b * S) * (int64_t)M * D + (int64_t)m * D + d;
+  const int64_t vstride = (int64_t)M * D;   // between spatial positions
+  const float* lp = loc + (t * M + m) * (int64_t)L * P * 2;
+  const float* wp = attw + (t * M + m) * (int64_t)L * P;
+  float acc = 0.f;
+  for (int l = 0; l < L; ++l) {
+    const int H = lv.H[l], W = lv.W[l];
+    const float* vl = vb + (int64_t)lv.start[l] * vstride;
+    for (int p = 0; p < P; ++p) {
+      const float x = lp[(l * P + p) * 2 + 0];
+      const float y = lp[(l * P + p) * 2 + 1];
+      const float wgt = wp[l * P + p];
+      const float h_im = y * H - 0.5f;
+      const float w_im = x * W - 0.5f;
+      if (h_im > -1.f && w_im > -1.f && h_im < H && w_im < W) {
+        const int h0 = (int)floorf(h_im), w0 = (int)floorf(w_im);
+        const float lh = h_im - h0, lw = w_im - w0;
+        const float hh = 1.f - lh, hw = 1.f - lw;
+        const int h1 = h0 + 1, w1 = w0 + 1;
+        float v00 = 0.f, v01 = 0.f, v10 = 0.f, v11 = 0.f;
+        if (h0 >= 0 && w0 >= 0) v00 = __ldg(vl + ((int64_t)h0 * W + w0) * vstride);
+        if (h0 >= 0 && w1 <= W - 1) v01 = __ldg(vl + ((int64_t)h0 * W + w1) * vstride);
+        if (h1 <= H - 1 && w0 >= 0) v10 = __ldg(vl + ((int64_t)h1 * W + w0) * vstride);
+        if (h1 <= H - 1 && w1 <= W - 1) v11 = __ldg(vl + ((int64_t)h1 * W + w1) * vstride);
+        const float s = hh * hw * v00 + hh * lw * v01 + lh * hw * v10 + lh * lw * v11;
+        acc = fmaf(wgt, s, acc);
+      }
+    }
+  }
+  out[idx] = acc;
+}
+
+// Engine variant (ops/modules/ms_deform_attn.py:102-109 fused in): takes the raw output of the merged
+// sampling_offsets | attention_weights Linear, `oa` [B*Lq, M*L*P*3] = offsets (M,L,P,2) then logits (M,L,P),
+// applies softmax over L*P, builds sampling locations from the encoder reference points of
+// msdeformattn.py:150-162 (valid_ratios == 1: ref = ((j+0.5)/W_q, (i+0.5)/H_q) of the query's own level),
+// samples, and writes the result as split planes for the output_proj GEMM.
+template <int MAXLP>
+__global__ void __launch_bounds__(256)
+msda_fused_kernel(const float* __restrict__ value, MsdaLevels lv, const float* __restrict__ oa, int64_t total, int S,
+                  int M, int D, int L, int P, uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int d = (int)(idx % D);
+  int64_t t = idx / D;
+  const int m = (int)(t % M);
+  t /= M;                                   // b*S + q  (Lq == S for encoder self-attention)
+  const int64_t b = t / S;
+  const int q = (int)(t - b * S);
+  int lq = 0;
+  for (int l = 1; l < L; ++l)
+    if (q >= lv.start[l]) lq = l;
+  const int qi = (q - lv.start[lq]) / lv.W[lq], qj = (q - lv.start[lq]) % lv.W[lq];
+  const float ref_x = (qj + 0.5f) / (float)lv.W[lq], ref_y = (qi + 0.5f) / (float)lv.H[lq];
+  const int LP = L * P;
+  const float* row = oa + t * (int64_t)(M * LP * 3);
+  const float* offp = row + (int64_t)m * LP * 2;
+  const float* lgp = row + (int64_t)M * LP * 2 + (int64_t)m * LP;
+  float e[MAXLP];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < MAXLP; ++i)
+    if (i < LP) { e[i] = lgp[i]; mx = fmaxf(mx, e[i]); }
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXLP; ++i)
+    if (i < LP) { e[i] = expf(e[i] - mx); sum += e[i]; }
+  const float inv = 1.f / sum;
+  const float* vb = value + (b * S) * (int64_t)M * D + (int64_t)m * D + d;
+  const int64_t vstride = (int64_t)M * D;
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXLP; ++i) {
+    if (i < LP) {
+      const int l = i / P;
+      const int H = lv.H[l], W = lv.W[l];
+      const float* vl = vb + (int64_t)lv.start[l] * vstride;
+      const float x = ref_x + offp[2 * i] / (float)W;
+      const float y = ref_y + offp[2 * i + 1] / (float)H;
+      const float h_im = y * H - 0.5f;
+      const float w_im = x * W - 0.5f;
+      if (h_im > -1.f && w_im > -1.f && h_im < H && w_im < W) {
+        const int h0 = (int)floorf(h_im), w0 = (int)floorf(w_im);
+        const float lh = h_im - h0, lw = w_im - w0;
+        const float hh = 1.f - lh, hw = 1.f - lw;
+        const int h1 = h0 + 1, w1 = w0 + 1;
+        float v00 = 0.f, v01 = 0.f, v10 = 0.f, v11 = 0.f;
+        if (h0 >= 0 && w0 >= 0) v00 = __ldg(vl + ((int64_t)h0 * W + w0) * vstride);
+        if (h0 >= 0 && w1 <= W - 1) v01 = __ldg(vl + ((int64_t)h0 * W + w1) * vstride);
+        if (h1 <= H - 1 && w0 >= 0) v10 = __ldg(vl + ((int64_t)h1 * W + w0) * vstride);
+        if (h1 <= H - 1 && w1 <= W - 1) v11 = __ldg(vl + ((int64_t)h1 * W + w1) * vstride);
+        const float s = hh * hw * v00 + hh * lw * v01 + lh * hw * v10 + lh * lw * v11;
+        acc = fmaf(e[i] * inv, s, acc);
+      }
+    }
+  }
+  store_split1(out_hi, out_lo, idx, acc);
+}
+
+int msda_fused(const float* value, const int* Hs, const int* Ws, const float* oa, int B, int S, int M, int D, int L,
+               int P, uint16_t* out_hi, uint16_t* out_lo, cudaStream_t st) {
+  RBA_CHECK(L <= MSDA_MAX_LEVELS && L * P <= 16, "msda_fused: L=%d P=%d unsupported", L, P);
+  MsdaLevels lv;
+  int start = 0;
+  for (int l = 0; l < L; ++l) { lv.H[l] = Hs[l]; lv.W[l] = Ws[l]; lv.start[l] = start; start += Hs[l] * Ws[l]; }
+  RBA_CHECK(start == S, "msda_fused: level sizes do not sum to S");
+  const int64_t total = (int64_t)B * S * M * D;
+  msda_fused_kernel<16><<<(unsigned)cdiv(total, 256), 256, 0, st>>>(value, lv, oa, total, S, M, D, L, P, out_hi, out_lo);
+  RBA_LAUNCHED();
+  return RBA_OK;
+}
+
+}  // namespace rba
+
+extern "C" int rba_msda_forward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                const float* sampling_loc, const float* attn_weight, int B, int S, int M, int D, int Lq,
+                                int L, int P, int im2col_step, float* out, void* stream) {
+  using namespace rba;
+  RBA_CHECK(value && spatial_shapes && level_start_index && sampling_loc && attn_weight && out,
+            "rba_msda_forward: null pointer");
+  RBA_CHECK(B >= 0 && S > 0 && M > 0 && D > 0 && Lq > 0 && L > 0 && P > 0, "rba_msda_forward: bad shape");
+  RBA_CHECK(L <= MSDA_MAX_LEVELS, "rba_msda_forward: L=%d > %d levels", L, MSDA_MAX_LEVELS);
+  if (B == 0) return RBA_OK;
+  // same precondition as the reference host function (ms_deform_attn_cuda.cu:55-57)
+  RBA_CHECK(im2col_step > 0, "rba_msda_forward: im2col_step must be positive");
+  const int step = B < im2col_step ? B : im2col_step;
+  RBA_CHECK(B % step == 0, "batch(%d) must divide im2col_step(%d)", B, step);
+  // spatial_shapes / level_start_index are HOST int64 arrays here (the Python shim passes .cpu() copies;
+  // they are L*3 integers and shape metadata, not data).
+  MsdaLevels lv;
+  int64_t total_s = 0;
+  for (int l = 0; l < L; ++l) {
+    lv.H[l] = (int)spatial_shapes[2 * l];
+    lv.W[l] = (int)spatial_shapes[2 * l + 1];
+    lv.start[l] = (int)level_start_index[l];
+    RBA_CHECK(lv.H[l] > 0 && lv.W[l] > 0, "rba_msda_forward: empty level %d", l);
+    RBA_CHECK(lv.start[l] >= 0 && (int64_t)lv.start[l] + (int64_t)lv.H[l] * lv.W[l] <= S,
+              "rba_msda_forward: level %d exceeds value length", l);
+    total_s += (int64_t)lv.H[l] * lv.W[l];
+  }
+  RBA_CHECK(total_s == S, "rba_msda_forward: sum(H*W)=%lld != S=%d", (long long)total_s, S);
+  const int64_t total = (int64_t)B * Lq * M * D;
+  msda_forward_kernel<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      value, lv, sampling_loc, attn_weight, total, S, M, D, Lq, L, P, out);
+  RBA_LAUNCHED();
+  return RBA_OK;
+}

@@ -1,0 +1,458 @@
+// Normalisation-family kernels: LayerNorm with Swin row gathers, GroupNorm fused with the FPN
+// elementwise tail, patch embedding, fp32 -> split-plane conversion.  All HBM-bound streaming kernels:
+// one pass over the input (row cached in registers), 16-byte vector accesses, one warp per row.
+#include "common.cuh"
+
+namespace rba {
+
+// ------------------------------------------------------------------------------------------------
+// fp32 -> bf16 split planes
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+split_kernel(const float* __restrict__ x, int64_t rows, int cols, int64_t ld, uint16_t* __restrict__ hi,
+             uint16_t* __restrict__ lo, int64_t ldp) {
+  const int c4 = cols >> 2;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = rows * c4;
+  for (; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / c4;
+    int c = (int)(i - r * c4) * 4;
+    float4 v = *reinterpret_cast<const float4*>(x + r * ld + c);
+    store_split4(hi, lo, r * ldp + c, v.x, v.y, v.z, v.w);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm (swin.py:247, :293 norm2, :334 PatchMerging.norm, :673 out norms; decoder LayerNorms)
+// ------------------------------------------------------------------------------------------------
+// mode 0: rows 1:1.  mode 1: Swin window gather (pad + roll(-shift) + window_partition, swin.py:250-271),
+// padded rows are written as exact zeros (F.pad happens AFTER norm1, swin.py:247-254).
+// mode 2: PatchMerging 2x2 gather in the order x0,x1,x2,x3 = (0,0),(1,0),(0,1),(1,1) (swin.py:327-331), LN over 4C.
+template <int MAXV>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, int mode,
+                 int64_t out_rows, int H, int W, int C, SwinGeom geom, float eps, float* __restrict__ y,
+                 uint16_t* __restrict__ y_hi, uint16_t* __restrict__ y_lo) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= out_rows) return;
+  const int CO = (mode == 2) ? 4 * C : C;       // normalised width
+  const int nv = CO >> 2;                        // float4s per row
+  const float* base;
+  bool valid = true;
+  if (mode == 0) {
+    base = x + r * C;
+  } else if (mode == 1) {
+    int64_t t = swin_row_to_token(geom, r);
+    valid = t >= 0;
+    base = x + (valid ? t : 0) * C;
+  } else {
+    const int W2 = W >> 1, H2 = H >> 1;
+    int j = (int)(r % W2);
+    int64_t tmp = r / W2;
+    int i = (int)(tmp % H2);
+    int64_t b = tmp / H2;
+    base = x + ((b * H + 2 * i) * W + 2 * j) * (int64_t)C;   // segment s -> (dh, dw) = (s & 1, s >> 1)
+  }
+  if (!valid) {
+    for (int v = lane; v < nv; v += 32) {
+      if (y) *reinterpret_cast<float4*>(y + r * CO + 4 * v) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (y_hi) {
+        *reinterpret_cast<uint2*>(y_hi + r * CO + 4 * v) = make_uint2(0u, 0u);
+        *reinterpret_cast<uint2*>(y_lo + r * CO + 4 * v) = make_uint2(0u, 0u);
+      }
+    }
+    return;
+  }
+  float4 cache[MAXV];
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    int v = lane + 32 * k;
+    if (v < nv) {
+      int e = 4 * v;
+      const float* p = base + e;
+      if (mode == 2) {
+        const int seg = e / C;
+        p = base + ((int64_t)(seg & 1) * W + (seg >> 1)) * C + (e - seg * C);
+      }
+      cache[k] = *reinterpret_cast<const float4*>(p);
+      sum += (cache[k].x + cache[k].y) + (cache[k].z + cache[k].w);
+    }
+  }
+  const float mean = warp_sum(sum) / (float)CO;
+  float sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    int v = lane + 32 * k;
+    if (v < nv) {
+      float a = cache[k].x - mean, b = cache[k].y - mean, c = cache[k].z - mean, d = cache[k].w - mean;
+      sq += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)CO + eps);
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    int v = lane + 32 * k;
+    if (v < nv) {
+      int e = 4 * v;
+      float4 g = *reinterpret_cast<const float4*>(gamma + e);
+      float4 bt = *reinterpret_cast<const float4*>(beta + e);
+      float4 o;
+      o.x = (cache[k].x - mean) * rstd * g.x + bt.x;
+      o.y = (cache[k].y - mean) * rstd * g.y + bt.y;
+      o.z = (cache[k].z - mean) * rstd * g.z + bt.z;
+      o.w = (cache[k].w - mean) * rstd * g.w + bt.w;
+      if (y) *reinterpret_cast<float4*>(y + r * CO + e) = o;
+      if (y_hi) store_split4(y_hi, y_lo, r * CO + e, o.x, o.y, o.z, o.w);
+    }
+  }
+}
+
+int layernorm(const float* x, const float* gamma, const float* beta, int mode, int B, int H, int W, int C, int ws,
+              int shift, float eps, float* y, uint16_t* y_hi, uint16_t* y_lo, cudaStream_t st) {
+  RBA_CHECK(x && gamma && beta && (y || y_hi), "layernorm: null pointer");
+  RBA_CHECK((y_hi == nullptr) == (y_lo == nullptr), "layernorm: planes must come in pairs");
+  RBA_CHECK(C % 4 == 0 && C > 0, "layernorm: C=%d must be a multiple of 4", C);
+  int64_t rows;
+  SwinGeom g = make_swin_geom(H, W, ws > 0 ? ws : 1, shift);
+  if (mode == 0) rows = (int64_t)B * H * W;
+  else if (mode == 1) {
+    RBA_CHECK(ws > 0 && shift >= 0 && shift < ws, "layernorm: bad window %d shift %d", ws, shift);
+    rows = (int64_t)B * g.nWh * g.nWw * ws * ws;
+  } else if (mode == 2) {
+    RBA_CHECK(H % 2 == 0 && W % 2 == 0, "layernorm: PatchMerging gather needs even H,W (got %d,%d)", H, W);
+    rows = (int64_t)B * (H / 2) * (W / 2);
+  } else return fail(RBA_ERR_INVALID, "layernorm: bad mode %d", mode);
+  if (rows == 0) return RBA_OK;
+  const int CO = mode == 2 ? 4 * C : C;
+  const int nv = CO / 4;
+  const int warps = 8;
+  dim3 grid((unsigned)cdiv(rows, warps));
+#define RBA_LN(MV) layernorm_kernel<MV><<<grid, warps * 32, 0, st>>>(x, gamma, beta, mode, rows, H, W, C, g, eps, y, y_hi, y_lo)
+  if (nv <= 32) RBA_LN(1);
+  else if (nv <= 64) RBA_LN(2);
+  else if (nv <= 128) RBA_LN(4);
+  else if (nv <= 256) RBA_LN(8);
+  else if (nv <= 512) RBA_LN(16);
+  else if (nv <= 1024) RBA_LN(32);
+  else return fail(RBA_ERR_INVALID, "layernorm: width %d too large", CO);
+#undef RBA_LN
+  RBA_LAUNCHED();
+  return RBA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm(32, C) on token-major (B, HW, C) tensors (msdeformattn.py:227,234 input_proj; :275-290 FPN norms)
+// ------------------------------------------------------------------------------------------------
+// Pass 1: per (b, chunk) partial sums of x and x^2 per group, accumulated in double (deterministic:
+// fixed chunking, fixed summation order).  Pass 2 (fused apply): finalises mean/rstd from the partials,
+// then y = GN(x) [+ bilinear_up(prev)] [relu], msdeformattn.py:356-360.
+constexpr int GN_ROWS_PER_CHUNK = 256;
+
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(const float* __restrict__ x, int64_t x_bs, int HW, int C, int groups, int nchunks,
+                double* __restrict__ part) {
+  // grid: (nchunks, B); block: 256 threads. thread -> channel-quad cq = tid % (C/4), row lane rl = tid / (C/4)
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int cq_n = C >> 2;
+  const int rows_par = 256 / cq_n;               // rows processed in parallel (C=256 -> 4)
+  const int cq = threadIdx.x % cq_n, rl = threadIdx.x / cq_n;
+  const int r0 = chunk * GN_ROWS_PER_CHUNK;
+  const int r1 = min(r0 + GN_ROWS_PER_CHUNK, HW);
+  const int cpg = C / groups;                    // channels per group (8)
+  float s = 0.f, q = 0.f;
+  if (rl < rows_par) {
+    const float* xb = x + (int64_t)b * x_bs + 4 * cq;
+    for (int r = r0 + rl; r < r1; r += rows_par) {
+      float4 v = *reinterpret_cast<const float4*>(xb + (int64_t)r * C);
+      s += (v.x + v.y) + (v.z + v.w);
+      q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    }
+  }
+  __shared__ float ss[256], sq[256];
+  ss[threadIdx.x] = s;
+  sq[threadIdx.x] = q;
+  __syncthreads();
+  // one thread per group sums its quads over all row lanes, in a fixed order
+  if (threadIdx.x < groups) {
+    const int g = threadIdx.x;
+    const int q0 = g * cpg / 4, qn = cpg / 4;    // quads of this group (cpg multiple of 4)
+    double ds = 0.0, dq = 0.0;
+    for (int rr = 0; rr < rows_par; ++rr)
+      for (int k = 0; k < qn; ++k) {
+        ds += (double)ss[rr * cq_n + q0 + k];
+        dq += (double)sq[rr * cq_n + q0 + k];
+      }
+    double* p = part + (((int64_t)b * nchunks + chunk) * groups + g) * 2;
+    p[0] = ds;
+    p[1] = dq;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gn_finalize_kernel(const double* __restrict__ part, int nchunks, int groups, int64_t count, float eps,
+                   float* __restrict__ mean_rstd) {
+  // grid: B; block: groups threads
+  const int b = blockIdx.x, g = threadIdx.x;
+  if (g >= groups) return;
+  double s = 0.0, q = 0.0;
+  for (int c = 0; c < nchunks; ++c) {
+    const double* p = part + (((int64_t)b * nchunks + c) * groups + g) * 2;
+    s += p[0];
+    q += p[1];
+  }
+  double mean = s / (double)count;
+  double var = q / (double)count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  mean_rstd[((int64_t)b * groups + g) * 2 + 0] = (float)mean;
+  mean_rstd[((int64_t)b * groups + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// PyTorch bilinear source index (align_corners=False, no antialias) for arbitrary sizes.
+__device__ __forceinline__ void bilin_coeff(int o, int in, int out, int& i0, int& i1, float& l1) {
+  float scale = (float)in / (float)out;
+  float src = ((float)o + 0.5f) * scale - 0.5f;
+  if (src < 0.f) src = 0.f;
+  i0 = (int)src;
+  if (i0 > in - 1) i0 = in - 1;
+  i1 = min(i0 + 1, in - 1);
+  l1 = src - (float)i0;
+}
+
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const float* __restrict__ x, int64_t x_bs, const float* __restrict__ gamma,
+                const float* __restrict__ beta, const float* __restrict__ mean_rstd, int B, int H, int W, int C,
+                int groups, const float* __restrict__ prev, int64_t prev_bs, int hp, int wp, int relu,
+                float* __restrict__ y, uint16_t* __restrict__ y_hi, uint16_t* __restrict__ y_lo, int64_t y_bs) {
+  const int cq_n = C >> 2;
+  const int64_t total = (int64_t)B * H * W * cq_n;
+  const int cpg = C / groups;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cq = (int)(i % cq_n);
+    int64_t pix = i / cq_n;
+    const int xw = (int)(pix % W);
+    int64_t t = pix / W;
+    const int yh = (int)(t % H);
+    const int b = (int)(t / H);
+    const int c = 4 * cq;
+    const int g = c / cpg;
+    const float mean = mean_rstd[((int64_t)b * groups + g) * 2], rstd = mean_rstd[((int64_t)b * groups + g) * 2 + 1];
+    const int64_t inb = (int64_t)(yh * W + xw) * C + c;          // offset inside the image
+    float4 v = *reinterpret_cast<const float4*>(x + (int64_t)b * x_bs + inb);
+    float4 gm = *reinterpret_cast<const float4*>(gamma + c);
+    float4 bt = *reinterpret_cast<const float4*>(beta + c);
+    float4 o;
+    o.x = (v.x - mean) * rstd * gm.x + bt.x;
+    o.y = (v.y - mean) * rstd * gm.y + bt.y;
+    o.z = (v.z - mean) * rstd * gm.z + bt.z;
+    o.w = (v.w - mean) * rstd * gm.w + bt.w;
+    if (prev) {
+      int y0, y1, x0, x1; float ly, lx;
+      bilin_coeff(yh, hp, H, y0, y1, ly);
+      bilin_coeff(xw, wp, W, x0, x1, lx);
+      const float* pb = prev + (int64_t)b * prev_bs + c;
+      float4 p00 = *reinterpret_cast<const float4*>(pb + ((int64_t)y0 * wp + x0) * C);
+      float4 p01 = *reinterpret_cast<const float4*>(pb + ((int64_t)y0 * wp + x1) * C);
+      float4 p10 = *reinterpret_cast<const float4*>(pb + ((int64_t)y1 * wp + x0) * C);
+      float4 p11 = *reinterpret_cast<const float4*>(pb + ((int64_t)y1 * wp + x1) * C);
+      const float hy = 1.f - ly, hx = 1.f - lx;
+      o.x += hy * (hx * p00.x + lx * p01.x) + ly * (hx * p10.x + lx * p11.x);
+      o.y += hy * (hx * p00.y + lx * p01.y) + ly * (hx * p10.y + lx * p11.y);
+      o.z += hy * (hx * p00.z + lx * p01.z) + ly * (hx * p10.z + lx * p11.z);
+      o.w += hy * (hx * p00.w + lx * p01.w) + ly * (hx * p10.w + lx * p11.w);
+    }
+    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    if (y) *reinterpret_cast<float4*>(y + (int64_t)b * y_bs + inb) = o;
+    if (y_hi) store_split4(y_hi, y_lo, (int64_t)b * y_bs + inb, o.x, o.y, o.z, o.w);
+  }
+}
+
+int64_t groupnorm_ws_doubles(int B, int H, int W, int C, int groups) {
+  int64_t nchunks = cdiv((int64_t)H * W, GN_ROWS_PER_CHUNK);
+  return (int64_t)B * nchunks * groups * 2 + (int64_t)B * groups;  // partials + (mean,rstd) floats (2 floats = 1 double)
+}
+
+// x_bs / prev_bs / y_bs: elements between consecutive images (>= H*W*C), so a level can live inside a
+// concatenated multi-level buffer.
+int groupnorm(const float* x, int64_t x_bs, const float* gamma, const float* beta, int B, int H, int W, int C, int groups,
+              float eps, const float* prev, int64_t prev_bs, int hp, int wp, int relu, float* y, uint16_t* y_hi,
+              uint16_t* y_lo, int64_t y_bs, double* ws, cudaStream_t st) {
+  RBA_CHECK(x && gamma && beta && ws && (y || y_hi), "groupnorm: null pointer");
+  RBA_CHECK(C % groups == 0 && (C / groups) % 4 == 0, "groupnorm: C/groups=%d must be a multiple of 4", C / groups);
+  RBA_CHECK(C <= 1024 && (256 % (C / 4)) == 0 && groups <= 256, "groupnorm: C=%d unsupported", C);
+  if (B == 0) return RBA_OK;
+  const int HW = H * W;
+  const int nchunks = (int)cdiv(HW, GN_ROWS_PER_CHUNK);
+  double* part = ws;
+  float* mean_rstd = reinterpret_cast<float*>(ws + (int64_t)B * nchunks * groups * 2);
+  gn_stats_kernel<<<dim3(nchunks, B), 256, 0, st>>>(x, x_bs, HW, C, groups, nchunks, part);
+  RBA_LAUNCHED();
+  gn_finalize_kernel<<<B, 256, 0, st>>>(part, nchunks, groups, (int64_t)HW * (C / groups), eps, mean_rstd);
+  RBA_LAUNCHED();
+  const int64_t total = (int64_t)B * HW * (C / 4);
+  int blocks = (int)std::min<int64_t>(cdiv(total, 256), 148 * 16);
+  gn_apply_kernel<<<blocks, 256, 0, st>>>(x, x_bs, gamma, beta, mean_rstd, B, H, W, C, groups, prev, prev_bs, hp, wp, relu, y,
+                                         y_hi, y_lo, y_bs);
+  RBA_LAUNCHED();
+  return RBA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Patch embedding: normalise + zero pad + 4x4/4 conv + LayerNorm (maskformer_model.py:255-257, swin.py:479-495)
+// ------------------------------------------------------------------------------------------------
+// One warp per token; the 48 (=3*4*4) normalised inputs are loaded by lanes 0..47->(2 rounds), broadcast through
+// shared memory; each lane produces C/32 output channels; conv weights [C][48] are read through L1 (24 KB for C=128).
+template <typename T>
+__global__ void __launch_bounds__(256)
+patch_embed_kernel(const T* __restrict__ img, int B, int H, int W, int Hp, int Wp, float m0, float m1, float m2, float s0,
+                   float s1, float s2, const float* __restrict__ cw, const float* __restrict__ cb,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, int C, float* __restrict__ tokens) {
+  __shared__ float sIn[8][48];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Th = Hp >> 2, Tw = Wp >> 2;
+  const int64_t ntok = (int64_t)B * Th * Tw;
+  const int64_t tok = (int64_t)blockIdx.x * 8 + warp;
+  if (tok >= ntok) return;
+  const int tx = (int)(tok % Tw);
+  int64_t t = tok / Tw;
+  const int ty = (int)(t % Th);
+  const int b = (int)(t / Th);
+  for (int e = lane; e < 48; e += 32) {
+    int ch = e >> 4, ky = (e >> 2) & 3, kx = e & 3;
+    int yy = ty * 4 + ky, xx = tx * 4 + kx;
+    float v = 0.f;                                  // ImageList pads the NORMALISED image with 0
+    if (yy < H && xx < W) {
+      float raw = (float)img[(((int64_t)b * 3 + ch) * H + yy) * W + xx];
+      float mean = ch == 0 ? m0 : (ch == 1 ? m1 : m2);
+      float sd = ch == 0 ? s0 : (ch == 1 ? s1 : s2);
+      v = (raw - mean) / sd;
+    }
+    sIn[warp][e] = v;
+  }
+  __syncwarp();
+  constexpr int MAXC = 8;                           // C <= 256
+  float o[MAXC];
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXC; ++k) {
+    int c = lane + 32 * k;
+    o[k] = 0.f;
+    if (c < C) {
+      float acc = cb[c];
+      const float* wr = cw + (int64_t)c * 48;
+#pragma unroll
+      for (int e = 0; e < 48; ++e) acc = fmaf(wr[e], sIn[warp][e], acc);
+      o[k] = acc;
+      sum += acc;
+    }
+  }
+  const float mean = warp_sum(sum) / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXC; ++k) {
+    int c = lane + 32 * k;
+    if (c < C) { float d = o[k] - mean; sq += d * d; }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)C + 1e-5f);
+#pragma unroll
+  for (int k = 0; k < MAXC; ++k) {
+    int c = lane + 32 * k;
+    if (c < C) tokens[tok * C + c] = (o[k] - mean) * rstd * gamma[c] + beta[c];
+  }
+}
+
+int patch_embed(const void* images, int img_dtype, int B, int H, int W, int Hp, int Wp, const float* mean,
+                const float* stdv, const float* conv_w, const float* conv_b, const float* gamma, const float* beta, int C,
+                float* tokens, cudaStream_t st) {
+  RBA_CHECK(images && conv_w && conv_b && gamma && beta && tokens, "patch_embed: null pointer");
+  RBA_CHECK(Hp % 4 == 0 && Wp % 4 == 0 && Hp >= H && Wp >= W, "patch_embed: bad padded size");
+  RBA_CHECK(C <= 256, "patch_embed: C=%d > 256", C);
+  const int64_t ntok = (int64_t)B * (Hp / 4) * (Wp / 4);
+  if (ntok == 0) return RBA_OK;
+  dim3 grid((unsigned)cdiv(ntok, 8));
+  if (img_dtype == RBA_IMG_U8)
+    patch_embed_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)images, B, H, W, Hp, Wp, mean[0], mean[1], mean[2],
+                                                      stdv[0], stdv[1], stdv[2], conv_w, conv_b, gamma, beta, C, tokens);
+  else if (img_dtype == RBA_IMG_F32)
+    patch_embed_kernel<float><<<grid, 256, 0, st>>>((const float*)images, B, H, W, Hp, Wp, mean[0], mean[1], mean[2],
+                                                    stdv[0], stdv[1], stdv[2], conv_w, conv_b, gamma, beta, C, tokens);
+  else return fail(RBA_ERR_INVALID, "patch_embed: bad image dtype %d", img_dtype);
+  RBA_LAUNCHED();
+  return RBA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Elementwise: y[r,:] = (a ? a[r,:] : 0) + (b ? b[r % period,:] : 0)  -> fp32 and/or split planes
+// (with_pos_embed / level_embed adds / query broadcast: msdeformattn.py:84,123; mask2former_transformer_decoder.py:415,422-423)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ew_add_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t rows, int cols, int64_t period,
+              float* __restrict__ y, uint16_t* __restrict__ y_hi, uint16_t* __restrict__ y_lo) {
+  const int c4 = cols >> 2;
+  const int64_t total = rows * c4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / c4;
+    const int c = (int)(i - r * c4) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a) v = *reinterpret_cast<const float4*>(a + r * cols + c);
+    if (b) {
+      float4 w = *reinterpret_cast<const float4*>(b + (r % period) * cols + c);
+      v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+    }
+    if (y) *reinterpret_cast<float4*>(y + r * cols + c) = v;
+    if (y_hi) store_split4(y_hi, y_lo, r * cols + c, v.x, v.y, v.z, v.w);
+  }
+}
+
+int ew_add(const float* a, const float* b, int64_t rows, int cols, int64_t period, float* y, uint16_t* y_hi,
+           uint16_t* y_lo, cudaStream_t st) {
+  RBA_CHECK((a || b) && (y || y_hi), "ew_add: null pointer");
+  RBA_CHECK(cols % 4 == 0 && period > 0, "ew_add: cols must be a multiple of 4");
+  if (rows == 0) return RBA_OK;
+  const int64_t total = rows * (cols / 4);
+  int blocks = (int)std::min<int64_t>(cdiv(total, 256), 148 * 16);
+  ew_add_kernel<<<blocks, 256, 0, st>>>(a, b, rows, cols, period, y, y_hi, y_lo);
+  RBA_LAUNCHED();
+  return RBA_OK;
+}
+
+}  // namespace rba
+
+// ---- C ABI ----
+extern "C" int rba_k_split(const float* x, int64_t rows, int cols, int64_t ld, uint16_t* hi, uint16_t* lo, int64_t ldp,
+                           void* stream) {
+  using namespace rba;
+  RBA_CHECK(x && hi && lo, "rba_k_split: null pointer");
+  RBA_CHECK(cols % 4 == 0 && ld % 4 == 0 && ldp % 4 == 0, "rba_k_split: cols/ld/ldp must be multiples of 4");
+  if (rows == 0 || cols == 0) return RBA_OK;
+  int64_t total = rows * (cols / 4);
+  int blocks = (int)std::min<int64_t>(cdiv(total, 256), 148 * 16);
+  split_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ld, hi, lo, ldp);
+  RBA_LAUNCHED();
+  return RBA_OK;
+}
+
+extern "C" int rba_k_layernorm(const float* x, const float* gamma, const float* beta, int mode, int B, int H, int W, int C,
+                               int ws, int shift, float eps, float* y, uint16_t* y_hi, uint16_t* y_lo, void* stream) {
+  return rba::layernorm(x, gamma, beta, mode, B, H, W, C, ws, shift, eps, y, y_hi, y_lo, (cudaStream_t)stream);
+}
+
+extern "C" int64_t rba_k_groupnorm_ws(int B, int H, int W, int C, int groups) {
+  return rba::groupnorm_ws_doubles(B, H, W, C, groups);
+}
+
+extern "C" int rba_k_groupnorm(const float* x, const float* gamma, const float* beta, int B, int H, int W, int C, int groups,
+                               float eps, const float* prev, int hp, int wp, int relu, float* y, uint16_t* y_hi,
+                               uint16_t* y_lo, double* workspace, void* stream) {
+  const int64_t bs = (int64_t)H * W * C;
+  return rba::groupnorm(x, bs, gamma, beta, B, H, W, C, groups, eps, prev, (int64_t)hp * wp * C, hp, wp, relu, y, y_hi,
+                        y_lo, bs, workspace, (cudaStream_t)stream);
+}
+
+extern "C" int rba_k_patch_embed(const void* images, int img_dtype, int B, int H, int W, int Hp, int Wp, const float* mean,
+                                 const float* stdv, const float* conv_w, const float* conv_b, const float* gamma,
+                                 const float* beta, int C, float* tokens, void* stream) {
+  return rba::patch_embed(images, img_dtype, B, H, W, Hp, Wp, mean, stdv, conv_w, conv_b, gamma, beta, C, tokens,
+                          (cudaStream_t)stream);
+}

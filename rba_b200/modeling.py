@@ -1,0 +1,156 @@
+"""Host-side mirror of the reference's plugin interface for the hot path.
+
+`MaskFormer` here is what `META_ARCH_REGISTRY.get("MaskFormer")` resolves to when rba_b200 is plugged in
+(INTEGRATION.md): same constructor contract (`MaskFormer(cfg)` / `from_config`), same `state_dict` keys as the
+reference model (mask2former/maskformer_model.py:23-24), same call contract
+`model([{"image": CHW tensor, ...}]) -> [{"sem_seg": (K,H,W) tensor}]` (maskformer_model.py:227-356), same
+error behaviour for the things it does not do (training, panoptic/instance inference raise).  All arithmetic
+runs in librba_b200.so; torch only carries buffers."""
+from collections import OrderedDict
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from . import weights
+from ._lib import RbaError
+from .config import ModelConfig, model_config_from_cfg
+from .engine import Engine
+
+
+class MaskFormer(nn.Module):
+    """B200-native drop-in for the reference meta-architecture (eval / semantic branch)."""
+
+    def __init__(self, cfg, seed=0):
+        super().__init__()
+        self.mc = cfg.validate() if isinstance(cfg, ModelConfig) else model_config_from_cfg(cfg)
+        self.num_queries = self.mc.num_queries
+        self.size_divisibility = self.mc.size_divisibility
+        self.semantic_on, self.panoptic_on, self.instance_on = True, False, False
+        self.sem_seg_postprocess_before_inference = False
+        # host master copy of the reference-layout state_dict (what DetectionCheckpointer reads and writes)
+        self._sd = weights.init_state_dict(self.mc, seed=seed)
+        self._device = torch.device("cpu")
+        self._engine = None
+        self.training = False
+
+    @classmethod
+    def from_config(cls, cfg):
+        return {"cfg": cfg}
+
+    # ---- nn.Module surface used by the reference's callers (evaluate_ood.py:108-124) ----
+    @property
+    def device(self):
+        return self._device
+
+    def state_dict(self, *args, destination=None, prefix="", keep_vars=False):
+        out = destination if destination is not None else OrderedDict()
+        for k, v in self._sd.items():
+            out[prefix + k] = v
+        return out
+
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        sd = OrderedDict(state_dict)
+        # legacy key upgrades of the reference (mask_former_head.py:31-53, mask2former_transformer_decoder.py:237-258)
+        for k in list(sd.keys()):
+            nk = k
+            if k.startswith("sem_seg_head.") and not k.startswith("sem_seg_head.predictor") \
+                    and not k.startswith("sem_seg_head.pixel_decoder."):
+                nk = k.replace("sem_seg_head.", "sem_seg_head.pixel_decoder.", 1)
+            nk = nk.replace("static_query", "query_feat")
+            if nk != k:
+                sd[nk] = sd.pop(k)
+        missing = [k for k in self._sd if k not in sd]
+        unexpected = [k for k in sd if k not in self._sd]
+        errors = []
+        for k, v in sd.items():
+            if k in self._sd:
+                if tuple(v.shape) != tuple(self._sd[k].shape):
+                    errors.append(f"size mismatch for {k}: {tuple(v.shape)} vs {tuple(self._sd[k].shape)}")
+                else:
+                    self._sd[k] = v.detach().to("cpu", self._sd[k].dtype).contiguous().clone()
+        if errors or (strict and (missing or unexpected)):
+            raise RuntimeError("Error(s) in loading state_dict for MaskFormer: " + "; ".join(
+                errors + ([f"missing {missing}"] if strict and missing else []) + ([f"unexpected {unexpected}"] if strict and unexpected else [])))
+        self._engine = None  # weights changed: rebuild lazily
+        return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
+
+    def to(self, device=None, *args, **kwargs):
+        if device is not None:
+            device = torch.device(device)
+            if device.type == "cuda" and device.index is None:
+                device = torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
+            if device != self._device:
+                self._device = device
+                self._engine = None
+        return self
+
+    def cuda(self, device=None):
+        return self.to(torch.device("cuda", device if device is not None else 0))
+
+    def eval(self):
+        self.training = False
+        return self
+
+    def train(self, mode=True):
+        if mode:
+            raise RbaError("rba_b200.MaskFormer is inference-only (training is out of scope of the hot path)")
+        return self.eval()
+
+    # ---- engine ----
+    def engine(self):
+        if self._engine is None:
+            if self._device.type != "cuda":
+                raise RbaError("rba_b200.MaskFormer runs on CUDA only: call .to('cuda') (there is no CPU fallback)")
+            self._engine = Engine(self.mc, self._device).load_state_dict(self._sd)
+        return self._engine
+
+    def _batch(self, batched_inputs):
+        ims = [x["image"] for x in batched_inputs]
+        shapes = {tuple(im.shape) for im in ims}
+        if len(shapes) != 1:
+            raise RbaError("rba_b200.MaskFormer: images of one batch must share one size "
+                           f"(got {sorted(shapes)}); call per image like evaluate_ood.py does")
+        dt = {im.dtype for im in ims}
+        tgt = torch.uint8 if dt == {torch.uint8} else torch.float32
+        ims = [im.to(self._device, tgt, non_blocking=True) for im in ims]
+        return torch.stack(ims).contiguous()
+
+    @torch.no_grad()
+    def forward(self, batched_inputs, include_void=False, return_separately=False, return_aux=False,
+                return_ood_pred=False, **kwargs):
+        """maskformer_model.py:227-356, eval + SEMANTIC_ON branch."""
+        if include_void or return_aux or return_ood_pred or kwargs.get("return_panoptic_ood"):
+            raise RbaError("include_void / return_aux / return_ood_pred / panoptic outputs are not built (SURVEY §8f-3)")
+        images = self._batch(batched_inputs)
+        B, _, H, W = images.shape
+        out = self.engine().forward(images, rba=False, sem_seg=True, logits=return_separately, masks=return_separately)
+        results = []
+        for b, inp in enumerate(batched_inputs):
+            r = out["sem_seg"][b]
+            h, w = inp.get("height", H), inp.get("width", W)
+            if (h, w) != (H, W):  # sem_seg_postprocess resize (detectron2): bilinear, align_corners=False
+                r = F.interpolate(r[None], size=(h, w), mode="bilinear", align_corners=False)[0]
+            results.append({"sem_seg": r})
+        if return_separately:
+            Hp, Wp = self.engine().padded_hw(H, W)
+            up = F.interpolate(out["pred_masks"][-1:], size=(Hp, Wp), mode="bilinear", align_corners=False)[0]
+            return results, out["pred_logits"][-1], up
+        return results
+
+    @torch.no_grad()
+    def rba(self, batched_inputs):
+        """Fused path: evaluate_ood.get_RbA (evaluate_ood.py:143-150) without materialising sem_seg.
+        Returns a (B,H,W) tensor of anomaly scores."""
+        images = self._batch(batched_inputs)
+        return self.engine().forward(images, rba=True)["rba"]
+
+
+def build_model(cfg):
+    """detectron2.modeling.build_model equivalent for this meta-arch: construct + move to cfg.MODEL.DEVICE."""
+    name = cfg["MODEL"]["META_ARCHITECTURE"] if isinstance(cfg, dict) else cfg.MODEL.META_ARCHITECTURE
+    if name != "MaskFormer":
+        raise KeyError(f"No object named '{name}' found in 'META_ARCH' registry!")
+    m = MaskFormer(cfg)
+    dev = cfg["MODEL"]["DEVICE"] if isinstance(cfg, dict) else cfg.MODEL.DEVICE
+    return m.to(torch.device(dev))

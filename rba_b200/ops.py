@@ -1,0 +1,223 @@
+"""Thin torch-tensor wrappers over the C ABI.  torch supplies device memory and the current stream only;
+all compute happens in librba_b200.so.  Every function raises RbaError on failure — nothing falls back."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import RBA_ACT_GELU, RBA_ACT_NONE, RBA_ACT_RELU, RBA_GEMM_FFMA, RBA_GEMM_TC, RbaError, RbaGemmArgs  # noqa: F401
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _chk_cuda(*ts):
+    for t in ts:
+        if t is not None:
+            if not t.is_cuda:
+                raise RbaError("rba_b200 ops need CUDA tensors (no CPU path)")
+            if not t.is_contiguous():
+                raise RbaError("rba_b200 ops need contiguous tensors")
+
+
+def split_planes(x):
+    """fp32 [rows, cols] -> (hi, lo) bf16 planes (as torch.bfloat16 tensors)."""
+    _chk_cuda(x)
+    assert x.dtype == torch.float32 and x.dim() == 2
+    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.lib().rba_k_split(_p(x), x.shape[0], x.shape[1], x.shape[1], _p(hi), _p(lo), x.shape[1], _stream()))
+    return hi, lo
+
+
+def planes_to_float(hi, lo):
+    return hi.float() + lo.float()
+
+
+def score_fused(pred_masks, pred_logits, out_hw, want_sem_seg=False):
+    """maskformer_model.py:294-299,381-386 + evaluate_ood.py:148-150 fused.
+    pred_masks (B,Q,h,w), pred_logits (B,Q,K+1) -> rba (B,H,W) [, sem_seg (B,K,H,W)]."""
+    _chk_cuda(pred_masks, pred_logits)
+    B, Q, h, w = pred_masks.shape
+    K = pred_logits.shape[-1] - 1
+    H, W = out_hw
+    rba = torch.empty((B, H, W), dtype=torch.float32, device=pred_masks.device)
+    sem = torch.empty((B, K, H, W), dtype=torch.float32, device=pred_masks.device) if want_sem_seg else None
+    _lib.check(_lib.lib().rba_score_fused(_p(pred_masks), _p(pred_logits), B, Q, K, h, w, H, W, _p(rba), _p(sem), _stream()))
+    return (rba, sem) if want_sem_seg else rba
+
+
+def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_locations, attention_weights, im2col_step):
+    """Same signature and result as the reference pybind op (ops/src/vision.cpp:18-21)."""
+    _chk_cuda(value, sampling_locations, attention_weights)
+    if value.dtype != torch.float32:
+        raise RbaError("ms_deform_attn_forward: only float32 is built (the pixel decoder forces fp32, msdeformattn.py:323,329)")
+    B, S, M, D = value.shape
+    _, Lq, _, L, P, _ = sampling_locations.shape
+    ss = spatial_shapes.detach().to("cpu", torch.int64).contiguous()
+    ls = level_start_index.detach().to("cpu", torch.int64).contiguous()
+    out = torch.empty((B, Lq, M * D), dtype=torch.float32, device=value.device)
+    _lib.check(_lib.lib().rba_msda_forward(
+        _p(value), ctypes.cast(ss.data_ptr(), ctypes.POINTER(ctypes.c_int64)),
+        ctypes.cast(ls.data_ptr(), ctypes.POINTER(ctypes.c_int64)), _p(sampling_locations), _p(attention_weights),
+        B, S, M, D, Lq, L, P, int(im2col_step), _p(out), _stream()))
+    return out
+
+
+def ms_deform_attn_backward(*args, **kwargs):
+    raise RbaError("ms_deform_attn_backward: training is out of scope of the inference hot path (SURVEY §2 row 8)")
+
+
+def gemm(a, w, bias=None, act=RBA_ACT_NONE, residual=None, out_planes=False, out_f32=True, bias_per_row=False,
+         swin=None, backend=RBA_GEMM_FFMA, out=None):
+    """C = act(A W^T + bias) (+ residual).  a: (hi, lo) planes [M,K] or [batch,M,K]; w: planes [N,K] or [batch,N,K].
+    swin = (B, H, W, ws, shift) scatters windowed rows to token rows (output has B*H*W rows)."""
+    a_hi, a_lo = a
+    w_hi, w_lo = w
+    _chk_cuda(a_hi, a_lo, w_hi, w_lo, bias, residual, out)
+    batched = a_hi.dim() == 3
+    batch = a_hi.shape[0] if batched else 1
+    M, K = a_hi.shape[-2:]
+    N = w_hi.shape[-2]
+    dev = a_hi.device
+    rows_out = M
+    if swin is not None:
+        rows_out = swin[0] * swin[1] * swin[2]
+    shape = (batch, rows_out, N) if batched else (rows_out, N)
+    c = out
+    if c is None and out_f32:
+        c = residual.clone() if (swin is not None and residual is not None) else torch.empty(shape, dtype=torch.float32, device=dev)
+    c_hi = c_lo = None
+    if out_planes:
+        c_hi = torch.zeros(shape, dtype=torch.bfloat16, device=dev)
+        c_lo = torch.zeros(shape, dtype=torch.bfloat16, device=dev)
+    g = RbaGemmArgs()
+    g.a_hi, g.a_lo, g.lda = a_hi.data_ptr(), a_lo.data_ptr(), K
+    g.w_hi, g.w_lo, g.ldw = w_hi.data_ptr(), w_lo.data_ptr(), K
+    g.M, g.N, g.K, g.batch = M, N, K, batch
+    g.a_bstride = M * K if batched else 0
+    g.w_bstride = N * K if (batched and w_hi.dim() == 3) else 0
+    if bias is not None:
+        g.bias = bias.data_ptr()
+        g.bias_per_row = 1 if bias_per_row else 0
+        g.bias_bstride = bias.shape[-1] if (batched and bias.dim() == 2) else 0
+    g.act = act
+    if residual is not None:
+        g.residual = residual.data_ptr()
+    if c is not None:
+        g.c, g.ldc, g.c_bstride = c.data_ptr(), N, rows_out * N
+    if c_hi is not None:
+        g.c_hi, g.c_lo, g.ldcp, g.cp_bstride = c_hi.data_ptr(), c_lo.data_ptr(), N, rows_out * N
+    if swin is not None:
+        g.swin_map, g.sw_H, g.sw_W, g.sw_ws, g.sw_shift = 1, swin[1], swin[2], swin[3], swin[4]
+    g.backend = backend
+    _lib.check(_lib.lib().rba_k_gemm(ctypes.byref(g), _stream()))
+    if out_planes and c is not None:
+        return c, (c_hi, c_lo)
+    return (c_hi, c_lo) if out_planes else c
+
+
+def conv3x3(x, w, backend=RBA_GEMM_FFMA):
+    """x: planes (B,H,W,Cin) NHWC; w: planes [Cout, 9*Cin] (k = (ky*3+kx)*Cin + ci) -> fp32 (B,H,W,Cout)."""
+    x_hi, x_lo = x
+    w_hi, w_lo = w
+    _chk_cuda(x_hi, x_lo, w_hi, w_lo)
+    B, H, W, Cin = x_hi.shape
+    Cout = w_hi.shape[0]
+    y = torch.empty((B, H, W, Cout), dtype=torch.float32, device=x_hi.device)
+    _lib.check(_lib.lib().rba_k_conv3x3(_p(x_hi), _p(x_lo), _p(w_hi), _p(w_lo), B, H, W, Cin, Cout, _p(y), backend, _stream()))
+    return y
+
+
+def layernorm(x, gamma, beta, mode=0, B=1, H=1, W=None, ws=0, shift=0, eps=1e-5, want_f32=True, want_planes=False):
+    """x fp32 [B*H*W, C].  mode 0 plain / 1 Swin window gather / 2 PatchMerging gather (see rba_b200.h)."""
+    _chk_cuda(x, gamma, beta)
+    C = x.shape[-1]
+    if W is None:
+        W = x.numel() // C
+    if mode == 0:
+        rows, CO = B * H * W, C
+    elif mode == 1:
+        nWh, nWw = -(-H // ws), -(-W // ws)
+        rows, CO = B * nWh * nWw * ws * ws, C
+    else:
+        rows, CO = B * (H // 2) * (W // 2), 4 * C
+    y = torch.empty((rows, CO), dtype=torch.float32, device=x.device) if want_f32 else None
+    hi = lo = None
+    if want_planes:
+        hi = torch.empty((rows, CO), dtype=torch.bfloat16, device=x.device)
+        lo = torch.empty((rows, CO), dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.lib().rba_k_layernorm(_p(x), _p(gamma), _p(beta), mode, B, H, W, C, ws, shift, eps, _p(y), _p(hi), _p(lo), _stream()))
+    if want_f32 and want_planes:
+        return y, (hi, lo)
+    return y if want_f32 else (hi, lo)
+
+
+def window_attn(qkv, bias_table, B, H, W, C, heads, ws, shift):
+    _chk_cuda(qkv, bias_table)
+    rows = qkv.shape[0]
+    hi = torch.empty((rows, C), dtype=torch.bfloat16, device=qkv.device)
+    lo = torch.empty((rows, C), dtype=torch.bfloat16, device=qkv.device)
+    _lib.check(_lib.lib().rba_k_window_attn(_p(qkv), _p(bias_table), B, H, W, C, heads, ws, shift, _p(hi), _p(lo), _stream()))
+    return hi, lo
+
+
+def mha(q, k, v, mask, heads):
+    """q (B,Lq,E), k/v (B,Lk,E) fp32 projected; mask (B,Lq,Lk) uint8 (1 = blocked) or None -> planes (B*Lq, E)."""
+    _chk_cuda(q, k, v, mask)
+    B, Lq, E = q.shape
+    Lk = k.shape[1]
+    hi = torch.empty((B * Lq, E), dtype=torch.bfloat16, device=q.device)
+    lo = torch.empty((B * Lq, E), dtype=torch.bfloat16, device=q.device)
+    _lib.check(_lib.lib().rba_k_mha(_p(q), _p(k), _p(v), _p(mask), B, Lq, Lk, E, heads, _p(hi), _p(lo), _stream()))
+    return hi, lo
+
+
+def groupnorm(x, gamma, beta, groups=32, eps=1e-5, prev=None, relu=False, want_f32=True, want_planes=False):
+    """x fp32 (B,H,W,C) NHWC; y = GN(x) [+ bilinear_up(prev (B,hp,wp,C))] [relu]."""
+    _chk_cuda(x, gamma, beta, prev)
+    B, H, W, C = x.shape
+    hp, wp = (prev.shape[1], prev.shape[2]) if prev is not None else (0, 0)
+    n = int(_lib.lib().rba_k_groupnorm_ws(B, H, W, C, groups))
+    ws = torch.empty(n, dtype=torch.float64, device=x.device)
+    y = torch.empty_like(x) if want_f32 else None
+    hi = lo = None
+    if want_planes:
+        hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+        lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.lib().rba_k_groupnorm(_p(x), _p(gamma), _p(beta), B, H, W, C, groups, eps, _p(prev), hp, wp, int(relu),
+                                         _p(y), _p(hi), _p(lo), _p(ws), _stream()))
+    if want_f32 and want_planes:
+        return y, (hi, lo)
+    return y if want_f32 else (hi, lo)
+
+
+def patch_embed(images, Hp, Wp, mean, std, conv_w, conv_b, gamma, beta):
+    """images (B,3,H,W) uint8 or float32 -> tokens (B, (Hp/4)*(Wp/4), C)."""
+    _chk_cuda(images, conv_w, conv_b, gamma, beta)
+    B, _, H, W = images.shape
+    C = conv_w.shape[0]
+    dt = _lib.RBA_IMG_U8 if images.dtype == torch.uint8 else _lib.RBA_IMG_F32
+    if images.dtype not in (torch.uint8, torch.float32):
+        raise RbaError("patch_embed: images must be uint8 or float32")
+    tok = torch.empty((B, (Hp // 4) * (Wp // 4), C), dtype=torch.float32, device=images.device)
+    m = (ctypes.c_float * 3)(*mean)
+    s = (ctypes.c_float * 3)(*std)
+    _lib.check(_lib.lib().rba_k_patch_embed(_p(images), dt, B, H, W, Hp, Wp, m, s, _p(conv_w), _p(conv_b), _p(gamma), _p(beta),
+                                           C, _p(tok), _stream()))
+    return tok
+
+
+def attn_mask(masks, target_hw):
+    """masks (B,Q,h,w) fp32 -> (B,Q,th*tw) uint8, 1 = blocked (mask2former_transformer_decoder.py:483-486,:433)."""
+    _chk_cuda(masks)
+    B, Q, h, w = masks.shape
+    th, tw = target_hw
+    out = torch.empty((B, Q, th * tw), dtype=torch.uint8, device=masks.device)
+    _lib.check(_lib.lib().rba_k_attn_mask(_p(masks), B, Q, h, w, th, tw, _p(out), _stream()))
+    return out

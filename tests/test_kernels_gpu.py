@@ -1,0 +1,304 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (rba_b200.ops -> librba_b200.so), against the oracle /
+plain fp32-or-better PyTorch CPU statements of the same reference op.  Tolerances are written per test;
+the end-to-end bar is 1e-3 (north star), kernels are held to round-off."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import rba_oracle as O
+from conftest import load_golden
+from rba_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def planes(x, dev):
+    """CPU fp32 -> (hi, lo) bf16 planes on the device + the exact fp32 value they represent."""
+    hi = x.bfloat16()
+    lo = (x - hi.float()).bfloat16()
+    return (hi.to(dev).contiguous(), lo.to(dev).contiguous()), hi.float() + lo.float()
+
+
+def unplanes(p):
+    return (p[0].float() + p[1].float()).cpu()
+
+
+def rel_err(a, b):
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+def test_split_planes(dev):
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(37, 64, generator=g) * torch.logspace(-6, 4, 64)
+    hi, lo = ops.split_planes(x.to(dev))
+    back = unplanes((hi, lo))
+    assert ((back - x).abs() <= x.abs() * 2.0 ** -16 + 1e-30).all()
+    assert torch.equal(hi.cpu(), x.bfloat16())
+
+
+@pytest.mark.parametrize("C", [32, 128, 192, 1024])
+def test_layernorm_plain(dev, C):
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(77, C, generator=g) * 3 + 1
+    gm, bt = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    ref = F.layer_norm(x, (C,), gm, bt)
+    y, p = ops.layernorm(x.to(dev), gm.to(dev), bt.to(dev), mode=0, B=1, H=1, W=77, want_planes=True)
+    assert (y.cpu() - ref).abs().max() < 2e-5
+    assert (unplanes(p) - ref).abs().max() < 2e-4
+
+
+@pytest.mark.parametrize("H,W,shift", [(24, 36, 0), (30, 41, 6), (7, 50, 6), (12, 12, 0)])
+def test_layernorm_window_gather(dev, H, W, shift):
+    """swin.py:247-271: norm1, pad, roll(-shift), window_partition."""
+    B, C, ws = 2, 64, 12
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(B, H * W, C, generator=g)
+    gm, bt = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    xn = F.layer_norm(x, (C,), gm, bt).view(B, H, W, C)
+    xn = F.pad(xn, (0, 0, 0, (ws - W % ws) % ws, 0, (ws - H % ws) % ws))
+    if shift:
+        xn = torch.roll(xn, shifts=(-shift, -shift), dims=(1, 2))
+    ref = O.window_partition(xn, ws).reshape(-1, C)
+    y = ops.layernorm(x.view(-1, C).to(dev), gm.to(dev), bt.to(dev), mode=1, B=B, H=H, W=W, ws=ws, shift=shift)
+    assert y.shape == ref.shape
+    assert (y.cpu() - ref).abs().max() < 2e-5
+
+
+def test_layernorm_patch_merging(dev):
+    """swin.py:327-334"""
+    B, H, W, C = 2, 6, 10, 32
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, H * W, C, generator=g)
+    gm, bt = torch.randn(4 * C, generator=g), torch.randn(4 * C, generator=g)
+    xv = x.view(B, H, W, C)
+    cat = torch.cat([xv[:, 0::2, 0::2], xv[:, 1::2, 0::2], xv[:, 0::2, 1::2], xv[:, 1::2, 1::2]], -1).view(-1, 4 * C)
+    ref = F.layer_norm(cat, (4 * C,), gm, bt)
+    y = ops.layernorm(x.view(-1, C).to(dev), gm.to(dev), bt.to(dev), mode=2, B=B, H=H, W=W)
+    assert (y.cpu() - ref).abs().max() < 2e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 20, 256), (129, 96, 128), (1000, 384, 64), (5, 1, 256), (257, 130, 2304)])
+@pytest.mark.parametrize("act", [ops.RBA_ACT_NONE, ops.RBA_ACT_RELU, ops.RBA_ACT_GELU])
+def test_gemm_ffma(dev, M, N, K, act):
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / math.sqrt(K)
+    bias = torch.randn(N, generator=g)
+    res = torch.randn(M, N, generator=g)
+    ap, av = planes(a, dev)
+    wp, wv = planes(w, dev)
+    z = (av.double() @ wv.double().t() + bias.double()).float()
+    z = {0: z, 1: F.relu(z), 2: F.gelu(z)}[act] + res
+    c, cp = ops.gemm(ap, wp, bias=bias.to(dev), act=act, residual=res.to(dev), out_planes=True)
+    assert (c.cpu() - z).abs().max() < 2e-5 * max(1.0, float(z.abs().max()))
+    assert (unplanes(cp) - z).abs().max() < 1e-4 * max(1.0, float(z.abs().max()))
+
+
+def test_gemm_batched_row_bias(dev):
+    """mask einsum form: per-image A (Q,K) x per-image W (HW,K), bias per row (mask2former_transformer_decoder.py:479)."""
+    Bn, Q, HW, K = 3, 100, 200, 64
+    g = torch.Generator().manual_seed(5)
+    a, w, b = torch.randn(Bn, Q, K, generator=g), torch.randn(Bn, HW, K, generator=g), torch.randn(Bn, Q, generator=g)
+    ap, av = planes(a, dev)
+    wp, wv = planes(w, dev)
+    ref = (torch.einsum("bqk,bpk->bqp", av.double(), wv.double()) + b.double()[:, :, None]).float()
+    c = ops.gemm(ap, wp, bias=b.to(dev), bias_per_row=True)
+    assert c.shape == ref.shape
+    assert (c.cpu() - ref).abs().max() < 5e-5
+
+
+@pytest.mark.parametrize("H,W,shift", [(24, 36, 0), (30, 41, 6)])
+def test_gemm_swin_scatter(dev, H, W, shift):
+    """proj + window_reverse + roll back + crop + residual (swin.py:169,277-292)."""
+    B, C, ws = 2, 64, 12
+    nWh, nWw = -(-H // ws), -(-W // ws)
+    rows = B * nWh * nWw * ws * ws
+    g = torch.Generator().manual_seed(6)
+    a = torch.randn(rows, C, generator=g)
+    w = torch.randn(C, C, generator=g) / 8
+    bias = torch.randn(C, generator=g)
+    shortcut = torch.randn(B * H * W, C, generator=g)
+    ap, av = planes(a, dev)
+    wp, wv = planes(w, dev)
+    y = (av.double() @ wv.double().t() + bias.double()).float()
+    y = O.window_reverse(y.view(-1, ws, ws, C), ws, nWh * ws, nWw * ws)
+    if shift:
+        y = torch.roll(y, shifts=(shift, shift), dims=(1, 2))
+    ref = shortcut + y[:, :H, :W, :].reshape(B * H * W, C)
+    c = ops.gemm(ap, wp, bias=bias.to(dev), residual=shortcut.to(dev), swin=(B, H, W, ws, shift))
+    assert (c.cpu() - ref).abs().max() < 5e-5
+
+
+def test_conv3x3(dev):
+    """msdeformattn.py:281-290 output_conv (bias-free), NHWC planes in, NHWC fp32 out."""
+    B, H, W, Cin, Cout = 2, 9, 13, 32, 64
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(B, H, W, Cin, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(9 * Cin)
+    xp, xv = planes(x, dev)
+    wk = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()       # k = (ky*3+kx)*Cin + ci
+    wp, wkv = planes(wk, dev)
+    wv = wkv.view(Cout, 3, 3, Cin).permute(0, 3, 1, 2)
+    ref = F.conv2d(xv.permute(0, 3, 1, 2).double(), wv.double(), padding=1).permute(0, 2, 3, 1).float()
+    y = ops.conv3x3(xp, wp)
+    assert (y.cpu() - ref).abs().max() < 5e-5
+
+
+@pytest.mark.parametrize("H,W,shift", [(24, 24, 0), (30, 41, 6), (12, 12, 6)])
+def test_window_attention(dev, H, W, shift):
+    """swin.py:145-168 on given qkv."""
+    B, heads, ws = 2, 2, 12
+    C = heads * 32
+    nWh, nWw = -(-H // ws), -(-W // ws)
+    nW = nWh * nWw
+    g = torch.Generator().manual_seed(8)
+    qkv = torch.randn(B * nW, ws * ws, 3 * C, generator=g)
+    table = torch.randn((2 * ws - 1) ** 2, heads, generator=g)
+    q, k, v = qkv.reshape(B * nW, ws * ws, 3, heads, 32).permute(2, 0, 3, 1, 4)
+    attn = (q * 32 ** -0.5) @ k.transpose(-2, -1)
+    idx = O.relative_position_index(ws)
+    attn = attn + table[idx.view(-1)].view(ws * ws, ws * ws, -1).permute(2, 0, 1).unsqueeze(0)
+    if shift:
+        mask = O.shift_attn_mask(H, W, ws, shift)
+        attn = (attn.view(B, nW, heads, ws * ws, ws * ws) + mask.unsqueeze(1).unsqueeze(0)).view(-1, heads, ws * ws, ws * ws)
+    ref = (attn.softmax(-1) @ v).transpose(1, 2).reshape(B * nW * ws * ws, C)
+    out = ops.window_attn(qkv.view(-1, 3 * C).to(dev), table.to(dev), B, H, W, C, heads, ws, shift)
+    assert (unplanes(out) - ref).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("Lk,masked", [(100, False), (77, True), (2048, True)])
+def test_mha(dev, Lk, masked):
+    """nn.MultiheadAttention core as used by the decoder (mask2former_transformer_decoder.py:52-53,110-113)."""
+    B, Lq, E, heads = 2, 100, 256, 8
+    g = torch.Generator().manual_seed(9)
+    q, k, v = torch.randn(B, Lq, E, generator=g), torch.randn(B, Lk, E, generator=g), torch.randn(B, Lk, E, generator=g)
+    mask = None
+    if masked:
+        mask = torch.rand(B, Lq, Lk, generator=g) < 0.6
+        mask[0, 3] = True
+        mask[0, 3, 5] = False                   # a single open key
+    qh = q.view(B, Lq, heads, 32).transpose(1, 2) * 32 ** -0.5
+    kh = k.view(B, Lk, heads, 32).transpose(1, 2)
+    vh = v.view(B, Lk, heads, 32).transpose(1, 2)
+    s = qh @ kh.transpose(-1, -2)
+    if masked:
+        s = s.masked_fill(mask[:, None], float("-inf"))
+    ref = (s.softmax(-1) @ vh).transpose(1, 2).reshape(B * Lq, E)
+    out = ops.mha(q.to(dev), k.to(dev), v.to(dev), mask.to(torch.uint8).to(dev) if masked else None, heads)
+    assert (unplanes(out) - ref).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("with_prev,relu", [(False, False), (True, False), (False, True)])
+def test_groupnorm_fused(dev, with_prev, relu):
+    """GroupNorm(32) (+ bilinear x2 up of the previous FPN level) (+ ReLU), msdeformattn.py:356-360."""
+    B, H, W, C = 2, 10, 14, 256
+    g = torch.Generator().manual_seed(10)
+    x = torch.randn(B, H, W, C, generator=g) * 2 + 0.5
+    gm, bt = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    prev = torch.randn(B, H // 2, W // 2, C, generator=g) if with_prev else None
+    ref = F.group_norm(x.permute(0, 3, 1, 2), 32, gm, bt)
+    if with_prev:
+        ref = ref + F.interpolate(prev.permute(0, 3, 1, 2), size=(H, W), mode="bilinear", align_corners=False)
+    if relu:
+        ref = F.relu(ref)
+    ref = ref.permute(0, 2, 3, 1)
+    y, p = ops.groupnorm(x.to(dev), gm.to(dev), bt.to(dev), prev=prev.to(dev) if with_prev else None, relu=relu,
+                         want_planes=True)
+    assert (y.cpu() - ref).abs().max() < 3e-5
+    assert (unplanes(p) - ref).abs().max() < 2e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.uint8, torch.float32])
+def test_patch_embed(dev, dtype):
+    """maskformer_model.py:255-257 + swin.py:479-495"""
+    B, H, W, C = 2, 30, 45, 32
+    Hp, Wp = 32, 64
+    g = torch.Generator().manual_seed(11)
+    img = torch.randint(0, 256, (B, 3, H, W), dtype=torch.uint8, generator=g).to(dtype)
+    cw, cb = torch.randn(C, 3, 4, 4, generator=g) / 7, torch.randn(C, generator=g)
+    gm, bt = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    mean, std = [123.675, 116.28, 103.53], [58.395, 57.12, 57.375]
+    x = (img.float() - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)
+    x = F.pad(x, (0, Wp - W, 0, Hp - H))
+    ref = F.layer_norm(F.conv2d(x, cw, cb, stride=4).flatten(2).transpose(1, 2), (C,), gm, bt)
+    tok = ops.patch_embed(img.to(dev), Hp, Wp, mean, std, cw.to(dev), cb.to(dev), gm.to(dev), bt.to(dev))
+    assert (tok.cpu() - ref).abs().max() < 3e-5
+
+
+@pytest.mark.parametrize("h,w,th,tw", [(32, 64, 4, 8), (16, 24, 4, 6), (16, 24, 8, 12), (16, 24, 2, 3)])
+def test_attn_mask(dev, h, w, th, tw):
+    B, Q = 2, 10
+    g = torch.Generator().manual_seed(12)
+    m = torch.randn(B, Q, h, w, generator=g)
+    m[0, 1] = m[0, 1].abs() + 0.1               # all-open row
+    m[1, 2] = -m[1, 2].abs() - 0.1              # all-blocked row -> reset to open (:433)
+    am = F.interpolate(m, size=(th, tw), mode="bilinear", align_corners=False)
+    ref = (am.sigmoid().flatten(2) < 0.5)
+    ref[torch.where(ref.sum(-1) == ref.shape[-1])] = False
+    out = ops.attn_mask(m.to(dev), (th, tw)).cpu().bool()
+    # values whose interpolated logit is within float round-off of 0 may legitimately flip
+    near0 = am.flatten(2).abs() < 1e-6
+    assert ((out != ref) & ~near0).sum() == 0
+    assert not out[1, 2].any() and not out[0, 1].any()
+
+
+def test_msda_reference_test_shapes(dev):
+    """Same shapes / seed / tolerance as the reference's own ops/test.py:24-63 check_forward_equal_with_pytorch_float."""
+    fix = load_golden("msda.pt")
+    for f in (fix, fix["big"]):
+        shapes = f["shapes"]
+        lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+        out = ops.ms_deform_attn_forward(f["value"].to(dev), shapes.to(dev), lsi.to(dev), f["loc"].to(dev), f["aw"].to(dev), 2)
+        assert torch.allclose(out.cpu(), f["out"], rtol=1e-2, atol=1e-3)      # reference tolerance (ops/test.py:59)
+        assert (out.cpu() - f["out"]).abs().max() < 1e-5                      # ours
+    with pytest.raises(ops.RbaError):                                        # batch % im2col_step (ms_deform_attn_cuda.cu:55-57)
+        f = fix["big"]
+        v3 = torch.cat([f["value"], f["value"][:1]]).to(dev)
+        l3 = torch.cat([f["loc"], f["loc"][:1]]).to(dev)
+        a3 = torch.cat([f["aw"], f["aw"][:1]]).to(dev)
+        ops.ms_deform_attn_forward(v3, f["shapes"], lsi, l3, a3, 2)
+
+
+def test_score_golden_and_edges(dev):
+    fix = load_golden("score.pt")
+    for nm, f in fix.items():
+        rba, sem = ops.score_fused(f["masks"].to(dev), f["logits"].to(dev), (f["H"], f["W"]), want_sem_seg=True)
+        assert (sem.cpu() - f["sem_seg"]).abs().max() < 2e-5, nm
+        assert (rba.cpu() - f["rba"]).abs().max() < 2e-5, nm
+        rba2 = ops.score_fused(f["masks"].to(dev), f["logits"].to(dev), (f["H"], f["W"]))
+        assert torch.equal(rba2, rba)
+    # empty batch
+    e = ops.score_fused(torch.empty(0, 100, 4, 4, device=dev), torch.empty(0, 100, 20, device=dev), (16, 16))
+    assert e.shape == (0, 16, 16)
+    with pytest.raises(ops.RbaError):
+        ops.score_fused(torch.zeros(1, 100, 4, 4, device=dev), torch.zeros(1, 100, 20, device=dev), (17, 16))
+
+
+def test_score_full_size_properties(dev):
+    """BASELINE size (8 x 100 x 256 x 512 -> 8 x 1024 x 2048): size-independent properties + oracle on crops."""
+    B, Q, K, h, w = 2, 100, 19, 256, 512
+    g = torch.Generator().manual_seed(13)
+    masks = (torch.randn(B, Q, h, w, generator=g) * 0.99 - 0.54)
+    logits = torch.randn(B, Q, K + 1, generator=g)
+    rba, sem = ops.score_fused(masks.to(dev), logits.to(dev), (4 * h, 4 * w), want_sem_seg=True)
+    rba, sem = rba.cpu(), sem.cpu()
+    assert rba.shape == (B, 4 * h, 4 * w) and torch.isfinite(rba).all()
+    assert (rba <= 0).all() and (rba >= -K).all()
+    assert (rba - (-sem.tanh().sum(1))).abs().max() < 1e-5            # rba is consistent with its own sem_seg
+    p = logits.softmax(-1)[..., :-1]
+    assert (sem.sum(1) <= p.sum(-1).sum(-1)[:, None, None] + 1e-3).all()  # sigmoid <= 1
+    # oracle on random 32x32 output crops (bilinear x4 is local: a crop needs a 1-pixel low-res halo)
+    for (b, y0, x0) in [(0, 0, 0), (1, 4 * h - 32, 4 * w - 32), (0, 512, 1000), (1, 100, 4)]:
+        ly0, lx0 = max(y0 // 4 - 1, 0), max(x0 // 4 - 1, 0)
+        ly1, lx1 = min((y0 + 32) // 4 + 1, h), min((x0 + 32) // 4 + 1, w)
+        up = F.interpolate(masks[b:b + 1], size=(4 * h, 4 * w), mode="bilinear", align_corners=False)[0, :, y0:y0 + 32, x0:x0 + 32]
+        ref = O.semantic_inference(logits[b], up)
+        assert (sem[b, :, y0:y0 + 32, x0:x0 + 32] - ref).abs().max() < 2e-5
+        assert ly1 > ly0 and lx1 > lx0
+    # constant mask logits: sem_seg[c] = sum_q p[q,c] * sigmoid(m_q) everywhere
+    mc = torch.linspace(-3, 3, Q).view(1, Q, 1, 1).expand(1, Q, 8, 8).contiguous()
+    r, s = ops.score_fused(mc.to(dev), logits[:1].to(dev), (32, 32), want_sem_seg=True)
+    expect = (p[0] * torch.sigmoid(torch.linspace(-3, 3, Q))[:, None]).sum(0)
+    assert (s.cpu()[0] - expect[:, None, None]).abs().max() < 1e-5

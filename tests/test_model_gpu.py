@@ -1,0 +1,132 @@
+"""GPU parity of the whole hot path against (a) the committed golden outputs of the unmodified reference and
+(b) the oracle's stage-boundary tensors, through the reference-facing interface (rba_b200.MaskFormer) and the
+engine C ABI.  Bar: 1e-3 max-abs (north star), on pred_logits, pred_masks, pre-tanh sem_seg and rba."""
+import pytest
+import torch
+
+import rba_oracle as O
+from conftest import TOL, load_golden
+from golden_cases import CASES, case_images, case_model_config, state_checksum
+import rba_b200
+from rba_b200 import weights
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(mc, sd, dev, taps=False):
+    e = rba_b200.Engine(mc, dev.index).load_state_dict(sd)
+    if taps:
+        e.set_option("taps", 1)
+    return e
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_forward_matches_reference_golden(dev, name):
+    fix = load_golden(f"model_{name}.pt")
+    case = fix["case"]
+    mc = case_model_config(case)
+    sd = weights.init_state_dict(mc, seed=case["seed"], perturb=case["perturb"])
+    assert abs(state_checksum(sd) - fix["state_checksum"]) <= 1e-6 * fix["state_checksum"]
+    imgs = torch.stack(case_images(case)).to(dev)
+    e = _engine(mc, sd, dev)
+    out = e.forward(imgs, rba=True, sem_seg=True, logits=True, masks=True)
+    torch.cuda.synchronize()
+    errs = {
+        "pred_logits": (out["pred_logits"].cpu() - fix["pred_logits"]).abs().max().item(),
+        "pred_masks": (out["pred_masks"].cpu() - fix["pred_masks"]).abs().max().item(),
+        "sem_seg": (out["sem_seg"].cpu()[:, :, ::4, ::4] - fix["sem_seg_s4"]).abs().max().item(),
+        "rba": (out["rba"].cpu() - fix["rba"]).abs().max().item(),
+    }
+    print(name, errs)
+    for k, v in errs.items():
+        assert v < TOL, (k, v)
+
+
+def test_stage_taps_match_oracle(dev):
+    """Every stage boundary: res2..res5, encoder output, FPN levels, decoder state."""
+    case = CASES["tiny_1dl"]
+    mc = case_model_config(case)
+    sd = weights.init_state_dict(mc, seed=case["seed"], perturb=case["perturb"])
+    imgs = case_images(case)
+    ref = O.forward(sd, mc, imgs, want_taps=True)
+    e = _engine(mc, sd, dev, taps=True)
+    out = e.forward(torch.stack(imgs).to(dev), rba=True, logits=True, masks=True)
+    B = len(imgs)
+    t = ref["taps"]
+    for i, k in enumerate(["res2", "res3", "res4", "res5"]):
+        r = t[k].permute(0, 2, 3, 1).reshape(B, -1, t[k].shape[1])
+        g = e.tap(k).cpu().view_as(r)
+        assert (g - r).abs().max() < 2e-4, k
+    enc = t[f"enc_l{mc.enc_layers - 1}"]
+    assert (e.tap("enc_out").cpu().view_as(enc) - enc).abs().max() < 5e-4
+    for k in ["res4", "res3", "res2"]:
+        r = t[f"fpn_{k}"].permute(0, 2, 3, 1)
+        assert (e.tap(f"fpn_{k}").cpu().view_as(r) - r).abs().max() < 5e-4, k
+    dec = t[f"dec{mc.dec_layers - 1}_out"].transpose(0, 1)
+    assert (e.tap("dec_out").cpu().view_as(dec) - dec).abs().max() < TOL
+    assert (out["pred_masks"].cpu() - ref["pred_masks"]).abs().max() < TOL
+
+
+def test_maskformer_module_interface(dev):
+    """model([{'image': ...}]) -> [{'sem_seg': (K,H,W)}] + get_RbA arithmetic (evaluate_ood.py:108-150)."""
+    case = CASES["tiny_1dl"]
+    mc = case_model_config(case)
+    sd = weights.init_state_dict(mc, seed=case["seed"], perturb=case["perturb"])
+    fix = load_golden("model_tiny_1dl.pt")
+    model = rba_b200.MaskFormer(mc)
+    missing = model.load_state_dict(sd)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    assert list(model.state_dict().keys()) == list(sd.keys())
+    model.to(dev)
+    model.eval()
+    x = case_images(case)[0]
+    with torch.no_grad():
+        out = model([{"image": x.to(dev)}])
+    logits = out[0]["sem_seg"]
+    assert logits.shape == (mc.num_classes, x.shape[1], x.shape[2]) and logits.device.type == "cuda"
+    rba = -logits.tanh().sum(dim=0)                                   # evaluate_ood.py:148-150, unchanged
+    assert (rba.cpu() - fix["rba"][0]).abs().max() < TOL
+    fused = model.rba([{"image": x.to(dev)}])[0]
+    assert (fused - rba).abs().max() < 1e-5
+    with pytest.raises(rba_b200.RbaError):
+        model([{"image": x.to(dev)}], return_ood_pred=True)
+    with pytest.raises(rba_b200.RbaError):
+        model.train()
+
+
+def test_batch_invariance_and_graph_replay(dev):
+    """Images are independent units: a batch equals per-image runs bitwise; CUDA-graph replay equals eager."""
+    case = CASES["tiny_3lvl"]
+    mc = case_model_config(case)
+    sd = weights.init_state_dict(mc, seed=case["seed"], perturb=case["perturb"])
+    imgs = torch.stack(case_images(case)).to(dev)
+    e = _engine(mc, sd, dev)
+    both = e.forward(imgs, rba=True)["rba"].clone()
+    one = [e.forward(imgs[i:i + 1].contiguous(), rba=True)["rba"].clone() for i in range(imgs.shape[0])]
+    assert torch.equal(both, torch.cat(one))
+    static_in, static_out, g = e.graphed(imgs, rba=True)
+    static_in.copy_(imgs)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(static_out["rba"], both)
+    static_in.copy_(imgs.flip(0))
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(static_out["rba"], both.flip(0))
+
+
+def test_errors_are_loud(dev):
+    mc = rba_b200.config.tiny_test()
+    sd = weights.init_state_dict(mc, seed=0)
+    e = rba_b200.Engine(mc, dev.index)
+    with pytest.raises(rba_b200.RbaError):
+        e.forward(torch.zeros(1, 3, 64, 64, dtype=torch.uint8, device=dev))      # not loaded
+    bad = dict(sd)
+    bad.pop("backbone.norm2.weight")
+    with pytest.raises(rba_b200.RbaError, match="backbone.norm2.weight"):
+        rba_b200.Engine(mc, dev.index).load_state_dict(bad)
+    e.load_state_dict(sd)
+    with pytest.raises(rba_b200.RbaError):
+        e.forward(torch.zeros(1, 3, 64, 64, dtype=torch.float16, device=dev))
+    with pytest.raises(rba_b200.RbaError):
+        e.forward(torch.zeros(1, 3, 64, 64, dtype=torch.uint8))                   # CPU tensor
