@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py — images/s of the RbA hot path (Mask2Former Swin-B 1dl forward + Rejected-by-All score) at
+1024x2048, BASELINE.json configs[1] ("Swin-B 1dl, batch 8x1024x2048 synthetic, 1xB200").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--height H] [--width W]
+
+A "step" = one pass of the hot path over one batch of B synthetic uint8 images per GPU: patch-embed ... decoder ...
+fused score -> (B,H,W) anomaly-score maps (what evaluate_ood.get_RbA returns).  Random-init weights of the
+ckpts/swin_b_1dl architecture (no network for checkpoints), synthetic uint8 images.
+
+  value  images/s with inputs resident in HBM (CUDA-graph replay of rba_forward; N>1: one process per GPU, images
+         sharded, + ONE NCCL all-gather of the score maps per step), device-timed with CUDA events, max over ranks.
+  e2e    the same metric through the public call with HOST buffers: pinned H2D of the uint8 batch + forward +
+         D2H of the score maps inside the timed region.
+  roofline     the fused mask-upsample+sigmoid+contraction+tanh score kernel (the kernel BASELINE's metric names),
+               timed alone with CUDA events on its launch stream on inputs > L2 (420 MB at B=8).
+  cpu_baseline the oracle port (oracle/rba_oracle.py, PyTorch CPU fp32, all host threads) on a bounded sample.
+
+`--impl reference` times that CPU port of the reference's path as the reference arm (rank 0 only).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "images/sec at 1024x2048 Swin-B 1dl (Mask2Former forward + RbA score)"
+UNIT = "images/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")
+    ap.add_argument("--height", type=int, default=1024)
+    ap.add_argument("--width", type=int, default=2048)
+    ap.add_argument("--model", default="swin_b_1dl", choices=["swin_b_1dl", "swin_l_1dl", "tiny"])
+    ap.add_argument("--backend", default=os.environ.get("RBA_GEMM_BACKEND", "auto"), choices=["auto", "ffma", "tc"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-images", type=int, default=1)
+    return ap.parse_args()
+
+
+def model_config(name):
+    from rba_b200 import config
+    return {"swin_b_1dl": config.swin_b_1dl, "swin_l_1dl": config.swin_l_1dl, "tiny": config.tiny_test}[name]()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks (pynvml; nvidia-smi CSV fallback)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU port (oracle) timing — cpu_baseline leg and the reference arm
+# ------------------------------------------------------------------------------------------------
+def cpu_port_images_per_s(mc, H, W, n_images, warmup, steps, budget_s=240.0):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import rba_oracle as O
+    from rba_b200 import weights
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd = weights.init_state_dict(mc, seed=0)
+    g = torch.Generator().manual_seed(1)
+    imgs = [torch.randint(0, 256, (3, H, W), dtype=torch.uint8, generator=g) for _ in range(n_images)]
+    t_start = time.perf_counter()
+    for _ in range(warmup):
+        O.forward(sd, mc, imgs)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        out = O.forward(sd, mc, imgs)
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s:
+            break
+    assert torch.isfinite(out["rba"][0]).all()
+    total = sum(times)
+    return n_images * len(times) / total, len(times), total / len(times), threads
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    mc = model_config(args.model)
+    warm = min(args.warmup, 1)
+    ips, steps, sec_per_step, threads = cpu_port_images_per_s(mc, args.height, args.width, args.cpu_sample_images, warm, args.steps)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.model} Mask2Former forward + RbA score, {args.height}x{args.width}, "
+                               f"{args.cpu_sample_images} image/step (bounded sample of the 8-image batch)"},
+        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{steps} step(s) x {args.cpu_sample_images} image(s) at {args.height}x{args.width}; "
+                                   "oracle/rba_oracle.py = PyTorch-CPU fp32 restatement of the reference modules "
+                                   "(the reference itself cannot travel to the GPU box)"},
+        "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import rba_b200
+    from rba_b200 import ops, weights
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    mc = model_config(args.model)
+    B, H, W = args.batch, args.height, args.width
+    sd = weights.init_state_dict(mc, seed=0)
+    eng = rba_b200.Engine(mc, local).load_state_dict(sd)
+    backend = args.backend
+    if backend == "auto":
+        backend = os.environ.get("RBA_BENCH_BACKEND", "ffma")
+    eng.set_gemm_backend(backend)
+    del sd
+
+    g = torch.Generator().manual_seed(1 + rank)
+    host_imgs = [torch.randint(0, 256, (B, 3, H, W), dtype=torch.uint8, generator=g).pin_memory() for _ in range(2)]
+    dev_imgs = [h.to(dev) for h in host_imgs]
+    host_out = torch.empty((B, H, W), dtype=torch.float32).pin_memory()
+    gathered = torch.empty((world * B, H, W), dtype=torch.float32, device=dev) if world > 1 else None
+
+    # one eager forward: warms position tables / function attributes and counts this library's launches per step
+    n0 = rba_b200.launch_count()
+    out = eng.forward(dev_imgs[0], rba=True, logits=True, masks=True)
+    torch.cuda.synchronize()
+    launches_per_step = rba_b200.launch_count() - n0
+    pred_masks, pred_logits = out["pred_masks"].clone(), out["pred_logits"].clone()
+    assert torch.isfinite(out["rba"]).all(), "non-finite scores"
+
+    use_graph = not args.no_graph
+    if use_graph:
+        try:
+            static_in, static_out, graph = eng.graphed(dev_imgs[0], rba=True)
+        except Exception as e:  # report, then fall back to eager launches (same kernels)
+            if rank == 0:
+                print(f"[bench] CUDA graph capture failed ({e}); timing eager launches", file=sys.stderr)
+            use_graph = False
+    if not use_graph:
+        static_in = torch.empty_like(dev_imgs[0])
+        static_out = eng.alloc_outputs(B, H, W, rba=True)
+
+    def step_device(i):
+        static_in.copy_(dev_imgs[i & 1], non_blocking=True)      # alternate inputs (device-resident)
+        if use_graph:
+            graph.replay()
+        else:
+            eng.forward_into(static_in, static_out)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, static_out["rba"])
+
+    def step_e2e(i):
+        static_in.copy_(host_imgs[i & 1], non_blocking=True)     # H2D from pinned memory
+        if use_graph:
+            graph.replay()
+        else:
+            eng.forward_into(static_in, static_out)
+        host_out.copy_(static_out["rba"], non_blocking=True)     # D2H of the step's result
+        torch.cuda.current_stream().synchronize()                # the caller reads the scores every step
+
+    def timed(fn, warmup, steps):
+        for i in range(warmup):
+            fn(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    clocks = ClockSampler(local)
+    clocks.start()
+    ms_total = timed(step_device, args.warmup, args.steps)
+    clk = clocks.stop()
+    ms_e2e = timed(step_e2e, max(1, args.warmup // 2), args.steps)
+    value = world * B * args.steps / (ms_total * 1e-3)
+    e2e = world * B * args.steps / (ms_e2e * 1e-3)
+
+    # ---- roofline of the fused score kernel (timed alone, inputs 52 MB/img > L2 at B >= 3) ----
+    Q, K = mc.num_queries, mc.num_classes
+    h4, w4 = pred_masks.shape[-2:]
+    for _ in range(3):
+        ops.score_fused(pred_masks, pred_logits, (H, W))
+    torch.cuda.synchronize()
+    reps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        ops.score_fused(pred_masks, pred_logits, (H, W))
+    e1.record()
+    torch.cuda.synchronize()
+    k_ms = e0.elapsed_time(e1) / reps
+    alg_bytes = B * (4 * Q * h4 * w4 + 4 * Q * (K + 1) + 4 * H * W)
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    roofline = {"kernel": "rba_score_kernel<19> (x4 bilinear + sigmoid + (Q,K) contraction + tanh + sum)", "bound": "hbm",
+                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst, kernel timed alone)" if peaks else "fallback 6.65 TB/s",
+                "traffic": None, "ms_per_launch": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "note": "fp32 semantics make this kernel FMA/MUFU-bound, not HBM-bound (SURVEY §0.5): "
+                        "2*K*Q FLOP + Q sigmoid per output pixel vs 29 B/pixel"}
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        ips, steps, sps, threads = cpu_port_images_per_s(mc, H, W, args.cpu_sample_images, 0, 1)
+        cpu_baseline = {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"{steps} step x {args.cpu_sample_images} image at {H}x{W} ({sps:.1f} s); oracle/rba_oracle.py, "
+                                  "PyTorch-CPU fp32 restatement of the reference modules"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (GEMM operands as bf16 hi+lo split planes, fp32 accumulate)", "data": "synthetic",
+        "config": {"workload": f"{args.model} Mask2Former forward + RbA score, batch {B}x{H}x{W} uint8 per GPU "
+                               "(BASELINE.json configs[1])",
+                   "gemm_backend": backend, "cuda_graph": use_graph,
+                   "l2": "activations are several GB per step (>> 126 MB L2); two input batches alternate",
+                   "parallelism": f"dp{world}: images sharded, weights replicated" + (", one NCCL all-gather of score maps per step" if world > 1 else "")},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * 3 * H * W, "d2h_bytes_per_step": B * H * W * 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "gpu_launches_per_step": int(launches_per_step),
+        "clocks": clk, "roofline": roofline,
+    }
+    if cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

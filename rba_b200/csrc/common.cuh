@@ -39,6 +39,12 @@ extern std::atomic<int64_t> g_launches;
       return ::rba::fail(RBA_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
   } while (0)
 
+#define RBA_TRY_(expr)             \
+  do {                             \
+    int _rc = (expr);              \
+    if (_rc != RBA_OK) return _rc; \
+  } while (0)
+
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- bf16 split planes ----

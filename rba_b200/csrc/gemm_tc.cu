@@ -1,13 +1,430 @@
-// tcgen05 bf16x3 GEMM backend (placeholder until the TMA/TMEM kernel lands; the entry points fail loudly).
+// tcgen05 bf16x3 GEMM / implicit-GEMM 3x3 convolution (sm_100a).
+//
+//   C[M,N] = act(A[M,K] * W[N,K]^T + bias) (+ residual)      A, W: bf16 split planes (hi, lo), K contiguous
+//
+// fp32-class accuracy on 5th-gen tensor cores: every K=16 step issues three tcgen05.mma (kind::f16, bf16 inputs,
+// fp32 accumulate in TMEM) into the SAME accumulator: A_hi*W_hi + A_hi*W_lo + A_lo*W_hi.  The dropped terms
+// (lo*lo and the 2^-18 split residuals) are ~1e-5 relative per product, random-signed; 1e-3 end-to-end parity needs
+// better than TF32 and this gives ~17 mantissa bits at 2/3 of the single-pass bf16 rate with the
+// operand bytes of ONE fp32 matrix (hi+lo = 4 B/element).
+//
+// Structure (one CTA per 128 x BN output tile, 192 threads):
+//   warp 0   TMA producer: cp.async.bulk.tensor (128B swizzle) of the 4 planes' 64-wide K blocks into a 3-stage ring,
+//            completion on mbarrier `full[s]` (expect_tx).
+//   warp 1   TMEM allocator + MMA issuer: one elected thread, 12 tcgen05.mma per K block, tcgen05.commit -> `empty[s]`,
+//            final commit -> `acc_full`.
+//   warps 2-5 epilogue: tcgen05.ld (32 lanes x 32 columns per warp and step) -> bias / GELU / ReLU / residual /
+//            Swin window-reverse row map -> fp32 and/or split-plane stores.
+// The conv variant loads A through a 4-D tensor map over the NHWC planes: a tile is an 8x16 pixel patch, each of the
+// 9 taps is the same box shifted by (dy-1, dx-1) with TMA out-of-bounds zero fill as the padding.
+#include <cuda.h>
+
+#include <cstring>
+#include <mutex>
+
 #include "common.cuh"
 
 namespace rba {
+
+constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 3, TC_THREADS = 192;
+constexpr int TC_CONV_TH = 8, TC_CONV_TW = 16;   // conv M tile = 8 x 16 output pixels
+
+struct TcParams {
+  int M, N, K;
+  int nkb;                         // K blocks of 64 (conv: 9 * Cin/64)
+  const float* bias; int bias_per_row; int64_t bias_bs;
+  int act;
+  const float* residual;
+  float* c; int64_t ldc; int64_t c_bs;
+  uint16_t* c_hi; uint16_t* c_lo; int64_t ldcp; int64_t cp_bs;
+  int swin_map; SwinGeom geom;
+  int a_batched, w_batched;
+  // conv
+  int cH, cW, cCin, tilesW, tilesH;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of 128 B, 8-row groups
+// 1024 B apart (SBO), LBO unused for swizzled K-major, version 1, layout_type 2.
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);        // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                            // leading byte offset (ignored), bits [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset = 1024 B, bits [32,46)
+  d |= (uint64_t)1 << 46;                            // version = 1 (Blackwell), bits [46,48)
+  d |= (uint64_t)2 << 61;                            // SWIZZLE_128B, bits [61,64)
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16: D fp32, A/B bf16, both K-major, M x N.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------------------
+template <int BN>
+struct TcSmem {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;      // one plane of A per stage (16 KB)
+  static constexpr int W_BYTES = BN * TC_BK * 2;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
+  static constexpr int TOTAL = TC_STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, bool CONV>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, const TcParams p) {
+  using S = TcSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * S::STAGE_BYTES);
+  uint64_t* full = bars;                     // [TC_STAGES]
+  uint64_t* empty = bars + TC_STAGES;        // [TC_STAGES]
+  uint64_t* acc_full = bars + 2 * TC_STAGES; // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bz = blockIdx.z;
+  const int n0 = blockIdx.x * BN;
+  int m0 = blockIdx.y * TC_BM;
+  // conv: blockIdx.y enumerates (b, tile_h, tile_w) patches of 8x16 pixels
+  int cvb = 0, cvh0 = 0, cvw0 = 0;
+  if (CONV) {
+    int t = blockIdx.y;
+    cvw0 = (t % p.tilesW) * TC_CONV_TW;
+    t /= p.tilesW;
+    cvh0 = (t % p.tilesH) * TC_CONV_TH;
+    cvb = t / p.tilesH;
+    m0 = 0;
+  }
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmW_hi); prefetch_tmap(&tmW_lo);
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {   // TMEM allocation: BN fp32 columns x 128 lanes (power of two >= 32)
+    constexpr uint32_t cols = BN < 32 ? 32 : BN;
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        const int s = kb % TC_STAGES;
+        const uint32_t ph = (kb / TC_STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* st = smem + s * S::STAGE_BYTES;
+        mbar_expect_tx(&full[s], S::STAGE_BYTES);
+        if (CONV) {
+          const int cpb = p.cCin / TC_BK;                 // channel blocks per tap
+          const int tap = kb / cpb, cblk = kb - tap * cpb;
+          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+          tma_load_4d(st, &tmA_hi, &full[s], cblk * TC_BK, cvw0 + dx, cvh0 + dy, cvb);
+          tma_load_4d(st + S::A_BYTES, &tmA_lo, &full[s], cblk * TC_BK, cvw0 + dx, cvh0 + dy, cvb);
+        } else {
+          tma_load_3d(st, &tmA_hi, &full[s], kb * TC_BK, m0, p.a_batched ? bz : 0);
+          tma_load_3d(st + S::A_BYTES, &tmA_lo, &full[s], kb * TC_BK, m0, p.a_batched ? bz : 0);
+        }
+        tma_load_3d(st + 2 * S::A_BYTES, &tmW_hi, &full[s], kb * TC_BK, n0, p.w_batched ? bz : 0);
+        tma_load_3d(st + 2 * S::A_BYTES + S::W_BYTES, &tmW_lo, &full[s], kb * TC_BK, n0, p.w_batched ? bz : 0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(TC_BM, BN);
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        const int s = kb % TC_STAGES;
+        const uint32_t ph = (kb / TC_STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t base = smem_u32(smem + s * S::STAGE_BYTES);
+        const uint64_t a_hi = make_sdesc(base), a_lo = make_sdesc(base + S::A_BYTES);
+        const uint64_t w_hi = make_sdesc(base + 2 * S::A_BYTES), w_lo = make_sdesc(base + 2 * S::A_BYTES + S::W_BYTES);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          const uint64_t adv = (uint64_t)(k * 32 >> 4);    // +32 B along K inside the 128 B swizzle span
+          umma_bf16(tmem_base, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
+          umma_bf16(tmem_base, a_hi + adv, w_lo + adv, idesc, 1);
+          umma_bf16(tmem_base, a_lo + adv, w_hi + adv, idesc, 1);
+        }
+        umma_commit(&empty[s]);                           // frees the smem stage when these MMAs retire
+      }
+      umma_commit(acc_full);                              // accumulator complete
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 <-> TMEM lane quadrants (warp % 4)) =====================
+    const int quad = warp & 3;
+    const int row_in_tile = quad * 32 + lane;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    int64_t orow = -1;                                    // output row (or -1: nothing to store)
+    int m_logical = m0 + row_in_tile;
+    if (CONV) {
+      const int hh = cvh0 + row_in_tile / TC_CONV_TW, ww = cvw0 + row_in_tile % TC_CONV_TW;
+      if (hh < p.cH && ww < p.cW) orow = ((int64_t)cvb * p.cH + hh) * p.cW + ww;
+    } else if (m_logical < p.M) {
+      orow = m_logical;
+      if (p.swin_map) orow = swin_row_to_token(p.geom, m_logical);
+    }
+    const float* bias = p.bias ? p.bias + bz * p.bias_bs : nullptr;
+    float* c = p.c ? p.c + bz * p.c_bs : nullptr;
+    const int64_t ldr = p.c ? p.ldc : p.ldcp;
+    const float* res = p.residual ? p.residual + bz * (p.c ? p.c_bs : p.cp_bs) : nullptr;
+    uint16_t* c_hi = p.c_hi ? p.c_hi + bz * p.cp_bs : nullptr;
+    uint16_t* c_lo = p.c_lo ? p.c_lo + bz * p.cp_bs : nullptr;
+    const bool vec_c = (p.ldc & 3) == 0, vec_p = (p.ldcp & 3) == 0, vec_r = (ldr & 3) == 0;
+    const float brow = (bias && p.bias_per_row && orow >= 0 && !CONV) ? bias[m_logical] : 0.f;
+#pragma unroll 1
+    for (int cb = 0; cb < BN / 32; ++cb) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cb * 32), v);   // warp-collective
+      tmem_ld_wait();
+      const int nb = n0 + cb * 32;
+      if (orow < 0 || nb >= p.N) continue;
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const int n = nb + j4 * 4;
+        if (n >= p.N) break;
+        float t[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float x = __uint_as_float(v[j4 * 4 + j]);
+          if (bias) x += p.bias_per_row ? brow : ((n + j < p.N) ? bias[n + j] : 0.f);
+          t[j] = apply_act_rt(x, p.act);
+        }
+        const bool fullv = n + 3 < p.N;
+        if (res) {
+          if (fullv && vec_r) {
+            float4 r4 = *reinterpret_cast<const float4*>(res + orow * ldr + n);
+            t[0] += r4.x; t[1] += r4.y; t[2] += r4.z; t[3] += r4.w;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (n + j < p.N) t[j] += res[orow * ldr + n + j];
+          }
+        }
+        if (c) {
+          if (fullv && vec_c) *reinterpret_cast<float4*>(c + orow * p.ldc + n) = make_float4(t[0], t[1], t[2], t[3]);
+          else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (n + j < p.N) c[orow * p.ldc + n + j] = t[j];
+          }
+        }
+        if (c_hi) {
+          if (fullv && vec_p) store_split4(c_hi, c_lo, orow * p.ldcp + n, t[0], t[1], t[2], t[3]);
+          else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (n + j < p.N) store_split1(c_hi, c_lo, orow * p.ldcp + n + j, t[j]);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    constexpr uint32_t cols = BN < 32 ? 32 : BN;
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(cols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+// bf16 [batch][rows][K] (row pitch ld elements, batch pitch bs elements) -> 3-D map, box = (64, box_rows, 1), 128B swizzle
+static int make_map_3d(CUtensorMap* m, const uint16_t* ptr, int64_t K, int64_t rows, int64_t ld, int64_t batch, int64_t bs,
+                       int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(RBA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)(batch > 0 ? batch : 1)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(bs > 0 ? bs : rows * ld) * 2};
+  cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(RBA_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed with %d (K=%lld rows=%lld ld=%lld)", (int)r,
+                                     (long long)K, (long long)rows, (long long)ld);
+  return RBA_OK;
+}
+// bf16 NHWC [B][H][W][C] -> 4-D map, box = (64 ch, 16 w, 8 h, 1)
+static int make_map_nhwc(CUtensorMap* m, const uint16_t* ptr, int B, int H, int W, int C) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(RBA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)TC_BK, TC_CONV_TW, TC_CONV_TH, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(RBA_ERR_CUDA, "cuTensorMapEncodeTiled(4d) failed with %d", (int)r);
+  return RBA_OK;
+}
+
+template <int BN, bool CONV>
+static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
+                     const TcParams& p, dim3 grid, cudaStream_t st) {
+  constexpr int smem = TcSmem<BN>::TOTAL;
+  static bool attr_done = false;
+  if (!attr_done) {
+    RBA_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_done = true;
+  }
+  gemm_tc_kernel<BN, CONV><<<grid, TC_THREADS, smem, st>>>(a_hi, a_lo, w_hi, w_lo, p);
+  RBA_LAUNCHED();
+  return RBA_OK;
+}
+
+static void fill_epilogue(TcParams& p, const rba_gemm_args& a) {
+  p.bias = a.bias; p.bias_per_row = a.bias_per_row; p.bias_bs = a.bias_bstride;
+  p.act = a.act; p.residual = a.residual;
+  p.c = a.c; p.ldc = a.ldc; p.c_bs = a.c_bstride;
+  p.c_hi = a.c_hi; p.c_lo = a.c_lo; p.ldcp = a.ldcp; p.cp_bs = a.cp_bstride;
+  p.swin_map = a.swin_map;
+  p.geom = make_swin_geom(a.sw_H > 0 ? a.sw_H : 1, a.sw_W > 0 ? a.sw_W : 1, a.sw_ws > 0 ? a.sw_ws : 1, a.sw_shift);
+}
+
 int gemm_tc_launch(const rba_gemm_args& a, cudaStream_t st) {
-  (void)a; (void)st;
-  return fail(RBA_ERR_STATE, "gemm: RBA_GEMM_TC backend not built in this revision");
+  RBA_CHECK(a.K % 8 == 0, "gemm(tc): K must be a multiple of 8");
+  RBA_CHECK(((uintptr_t)a.a_hi & 15) == 0 && ((uintptr_t)a.a_lo & 15) == 0 && ((uintptr_t)a.w_hi & 15) == 0 &&
+                ((uintptr_t)a.w_lo & 15) == 0, "gemm(tc): operand planes must be 16-byte aligned");
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = a.M; p.N = a.N; p.K = a.K;
+  p.nkb = (a.K + TC_BK - 1) / TC_BK;
+  fill_epilogue(p, a);
+  p.a_batched = a.batch > 1 && a.a_bstride != 0;
+  p.w_batched = a.batch > 1 && a.w_bstride != 0;
+  const int BN = a.N > 64 ? 128 : 64;
+  CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
+  RBA_TRY_(make_map_3d(&ta_hi, a.a_hi, a.K, a.M, a.lda, p.a_batched ? a.batch : 1, a.a_bstride, TC_BM));
+  RBA_TRY_(make_map_3d(&ta_lo, a.a_lo, a.K, a.M, a.lda, p.a_batched ? a.batch : 1, a.a_bstride, TC_BM));
+  RBA_TRY_(make_map_3d(&tw_hi, a.w_hi, a.K, a.N, a.ldw, p.w_batched ? a.batch : 1, a.w_bstride, BN));
+  RBA_TRY_(make_map_3d(&tw_lo, a.w_lo, a.K, a.N, a.ldw, p.w_batched ? a.batch : 1, a.w_bstride, BN));
+  dim3 grid((unsigned)cdiv(a.N, BN), (unsigned)cdiv(a.M, TC_BM), (unsigned)a.batch);
+  if (BN == 128) return launch_tc<128, false>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
+  return launch_tc<64, false>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
 }
-int conv3x3_tc_launch(const uint16_t*, const uint16_t*, const uint16_t*, const uint16_t*, int, int, int, int, int, float*,
-                      cudaStream_t) {
-  return fail(RBA_ERR_STATE, "conv3x3: RBA_GEMM_TC backend not built in this revision");
+
+int conv3x3_tc_launch(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* w_hi, const uint16_t* w_lo, int B, int H,
+                      int W, int Cin, int Cout, float* y, cudaStream_t st) {
+  RBA_CHECK(Cin % TC_BK == 0, "conv3x3(tc): Cin must be a multiple of 64 (got %d)", Cin);
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = B * H * W; p.N = Cout; p.K = 9 * Cin;
+  p.nkb = 9 * (Cin / TC_BK);
+  p.c = y; p.ldc = Cout;
+  p.geom = make_swin_geom(1, 1, 1, 0);
+  p.cH = H; p.cW = W; p.cCin = Cin;
+  p.tilesW = (int)cdiv(W, TC_CONV_TW); p.tilesH = (int)cdiv(H, TC_CONV_TH);
+  CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
+  RBA_TRY_(make_map_nhwc(&ta_hi, x_hi, B, H, W, Cin));
+  RBA_TRY_(make_map_nhwc(&ta_lo, x_lo, B, H, W, Cin));
+  const int BN = Cout > 64 ? 128 : 64;
+  RBA_TRY_(make_map_3d(&tw_hi, w_hi, 9 * Cin, Cout, 9 * Cin, 1, 0, BN));
+  RBA_TRY_(make_map_3d(&tw_lo, w_lo, 9 * Cin, Cout, 9 * Cin, 1, 0, BN));
+  const int64_t tiles = (int64_t)B * p.tilesH * p.tilesW;
+  RBA_CHECK(tiles <= 65535, "conv3x3(tc): too many tiles for one launch (%lld)", (long long)tiles);
+  dim3 grid((unsigned)cdiv(Cout, BN), (unsigned)tiles, 1);
+  if (BN == 128) return launch_tc<128, true>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
+  return launch_tc<64, true>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
 }
+
 }  // namespace rba

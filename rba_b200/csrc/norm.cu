@@ -301,64 +301,73 @@ int groupnorm(const float* x, int64_t x_bs, const float* gamma, const float* bet
 // ------------------------------------------------------------------------------------------------
 // Patch embedding: normalise + zero pad + 4x4/4 conv + LayerNorm (maskformer_model.py:255-257, swin.py:479-495)
 // ------------------------------------------------------------------------------------------------
-// One warp per token; the 48 (=3*4*4) normalised inputs are loaded by lanes 0..47->(2 rounds), broadcast through
-// shared memory; each lane produces C/32 output channels; conv weights [C][48] are read through L1 (24 KB for C=128).
+// One warp per token, persistent CTAs: the conv weights are staged ONCE per CTA in shared memory, transposed to
+// [48][C] so that lanes read consecutive channels (conflict-free); the 48 (=3*4*4) normalised inputs of a token are
+// broadcast through shared memory; each lane produces C/32 output channels and the LayerNorm is a warp reduction.
 template <typename T>
 __global__ void __launch_bounds__(256)
 patch_embed_kernel(const T* __restrict__ img, int B, int H, int W, int Hp, int Wp, float m0, float m1, float m2, float s0,
                    float s1, float s2, const float* __restrict__ cw, const float* __restrict__ cb,
                    const float* __restrict__ gamma, const float* __restrict__ beta, int C, float* __restrict__ tokens) {
-  __shared__ float sIn[8][48];
+  extern __shared__ float pe_smem[];
+  float* sW = pe_smem;                 // [48][C]
+  float* sIn = pe_smem + 48 * C;       // [8][48]
+  for (int e = threadIdx.x; e < 48 * C; e += blockDim.x) {
+    int c = e / 48, k = e - c * 48;
+    sW[k * C + c] = cw[e];
+  }
+  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Th = Hp >> 2, Tw = Wp >> 2;
   const int64_t ntok = (int64_t)B * Th * Tw;
-  const int64_t tok = (int64_t)blockIdx.x * 8 + warp;
-  if (tok >= ntok) return;
-  const int tx = (int)(tok % Tw);
-  int64_t t = tok / Tw;
-  const int ty = (int)(t % Th);
-  const int b = (int)(t / Th);
-  for (int e = lane; e < 48; e += 32) {
-    int ch = e >> 4, ky = (e >> 2) & 3, kx = e & 3;
-    int yy = ty * 4 + ky, xx = tx * 4 + kx;
-    float v = 0.f;                                  // ImageList pads the NORMALISED image with 0
-    if (yy < H && xx < W) {
-      float raw = (float)img[(((int64_t)b * 3 + ch) * H + yy) * W + xx];
-      float mean = ch == 0 ? m0 : (ch == 1 ? m1 : m2);
-      float sd = ch == 0 ? s0 : (ch == 1 ? s1 : s2);
-      v = (raw - mean) / sd;
+  float* in = sIn + warp * 48;
+  for (int64_t tok = (int64_t)blockIdx.x * 8 + warp; tok < ntok; tok += (int64_t)gridDim.x * 8) {
+    const int tx = (int)(tok % Tw);
+    int64_t t = tok / Tw;
+    const int ty = (int)(t % Th);
+    const int b = (int)(t / Th);
+    __syncwarp();
+    for (int e = lane; e < 48; e += 32) {
+      int ch = e >> 4, ky = (e >> 2) & 3, kx = e & 3;
+      int yy = ty * 4 + ky, xx = tx * 4 + kx;
+      float v = 0.f;                                  // ImageList pads the NORMALISED image with 0
+      if (yy < H && xx < W) {
+        float raw = (float)img[(((int64_t)b * 3 + ch) * H + yy) * W + xx];
+        float mean = ch == 0 ? m0 : (ch == 1 ? m1 : m2);
+        float sd = ch == 0 ? s0 : (ch == 1 ? s1 : s2);
+        v = (raw - mean) / sd;
+      }
+      in[e] = v;
     }
-    sIn[warp][e] = v;
-  }
-  __syncwarp();
-  constexpr int MAXC = 8;                           // C <= 256
-  float o[MAXC];
-  float sum = 0.f;
+    __syncwarp();
+    constexpr int MAXC = 8;                           // C <= 256
+    float o[MAXC];
+    float sum = 0.f;
 #pragma unroll
-  for (int k = 0; k < MAXC; ++k) {
-    int c = lane + 32 * k;
-    o[k] = 0.f;
-    if (c < C) {
-      float acc = cb[c];
-      const float* wr = cw + (int64_t)c * 48;
+    for (int k = 0; k < MAXC; ++k) {
+      int c = lane + 32 * k;
+      o[k] = 0.f;
+      if (c < C) {
+        float acc = cb[c];
 #pragma unroll
-      for (int e = 0; e < 48; ++e) acc = fmaf(wr[e], sIn[warp][e], acc);
-      o[k] = acc;
-      sum += acc;
+        for (int e = 0; e < 48; ++e) acc = fmaf(sW[e * C + c], in[e], acc);
+        o[k] = acc;
+        sum += acc;
+      }
     }
-  }
-  const float mean = warp_sum(sum) / (float)C;
-  float sq = 0.f;
+    const float mean = warp_sum(sum) / (float)C;
+    float sq = 0.f;
 #pragma unroll
-  for (int k = 0; k < MAXC; ++k) {
-    int c = lane + 32 * k;
-    if (c < C) { float d = o[k] - mean; sq += d * d; }
-  }
-  const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)C + 1e-5f);
+    for (int k = 0; k < MAXC; ++k) {
+      int c = lane + 32 * k;
+      if (c < C) { float d = o[k] - mean; sq += d * d; }
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)C + 1e-5f);
 #pragma unroll
-  for (int k = 0; k < MAXC; ++k) {
-    int c = lane + 32 * k;
-    if (c < C) tokens[tok * C + c] = (o[k] - mean) * rstd * gamma[c] + beta[c];
+    for (int k = 0; k < MAXC; ++k) {
+      int c = lane + 32 * k;
+      if (c < C) tokens[tok * C + c] = (o[k] - mean) * rstd * gamma[c] + beta[c];
+    }
   }
 }
 
@@ -370,12 +379,15 @@ int patch_embed(const void* images, int img_dtype, int B, int H, int W, int Hp, 
   RBA_CHECK(C <= 256, "patch_embed: C=%d > 256", C);
   const int64_t ntok = (int64_t)B * (Hp / 4) * (Wp / 4);
   if (ntok == 0) return RBA_OK;
-  dim3 grid((unsigned)cdiv(ntok, 8));
+  dim3 grid((unsigned)std::min<int64_t>(cdiv(ntok, 8), 148 * 8));
+  const size_t smem = (size_t)(48 * C + 8 * 48) * sizeof(float);
+  RBA_CUDA(cudaFuncSetAttribute(patch_embed_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RBA_CUDA(cudaFuncSetAttribute(patch_embed_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (img_dtype == RBA_IMG_U8)
-    patch_embed_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)images, B, H, W, Hp, Wp, mean[0], mean[1], mean[2],
+    patch_embed_kernel<uint8_t><<<grid, 256, smem, st>>>((const uint8_t*)images, B, H, W, Hp, Wp, mean[0], mean[1], mean[2],
                                                       stdv[0], stdv[1], stdv[2], conv_w, conv_b, gamma, beta, C, tokens);
   else if (img_dtype == RBA_IMG_F32)
-    patch_embed_kernel<float><<<grid, 256, 0, st>>>((const float*)images, B, H, W, Hp, Wp, mean[0], mean[1], mean[2],
+    patch_embed_kernel<float><<<grid, 256, smem, st>>>((const float*)images, B, H, W, Hp, Wp, mean[0], mean[1], mean[2],
                                                     stdv[0], stdv[1], stdv[2], conv_w, conv_b, gamma, beta, C, tokens);
   else return fail(RBA_ERR_INVALID, "patch_embed: bad image dtype %d", img_dtype);
   RBA_LAUNCHED();

@@ -208,11 +208,11 @@ static int launch_score(const float* masks, const float* logits, int B, int Q, i
 extern "C" int rba_score_fused(const float* pred_masks, const float* pred_logits, int B, int Q, int K, int h, int w,
                                int H, int W, float* rba_out, float* sem_seg, void* stream) {
   using namespace rba;
+  if (B == 0) return RBA_OK;   // empty batch: nothing to do (empty tensors carry null pointers)
   RBA_CHECK(pred_masks && pred_logits && rba_out, "rba_score_fused: null pointer");
   RBA_CHECK(B >= 0 && Q > 0 && h > 0 && w > 0, "rba_score_fused: bad shape B=%d Q=%d h=%d w=%d", B, Q, h, w);
   RBA_CHECK(H > 0 && W > 0 && H <= 4 * h && W <= 4 * w, "rba_score_fused: output (%d,%d) exceeds 4x(%d,%d)", H, W, h, w);
   RBA_CHECK(Q <= 2048, "rba_score_fused: Q=%d too large", Q);
-  if (B == 0) return RBA_OK;
   cudaStream_t st = (cudaStream_t)stream;
   switch (K) {
     case 19: return launch_score<19>(pred_masks, pred_logits, B, Q, h, w, H, W, rba_out, sem_seg, st);

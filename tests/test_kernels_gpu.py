@@ -302,3 +302,72 @@ def test_score_full_size_properties(dev):
     r, s = ops.score_fused(mc.to(dev), logits[:1].to(dev), (32, 32), want_sem_seg=True)
     expect = (p[0] * torch.sigmoid(torch.linspace(-3, 3, Q))[:, None]).sum(0)
     assert (s.cpu()[0] - expect[:, None, None]).abs().max() < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# tcgen05 bf16x3 backend: same contract as the FFMA kernel; tolerance = bf16x3 truncation (~1e-5 relative / product)
+# ------------------------------------------------------------------------------------------------
+TC_TOL = 2e-4
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 20, 256), (129, 96, 128), (1000, 384, 64), (5, 1, 256), (257, 130, 2304),
+                                   (128, 128, 32), (700, 512, 512)])
+@pytest.mark.parametrize("act", [ops.RBA_ACT_NONE, ops.RBA_ACT_GELU])
+def test_gemm_tc(dev, M, N, K, act):
+    g = torch.Generator().manual_seed(M + N + K + 1)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / math.sqrt(K)
+    bias = torch.randn(N, generator=g)
+    res = torch.randn(M, N, generator=g)
+    ap, av = planes(a, dev)
+    wp, wv = planes(w, dev)
+    z = (av.double() @ wv.double().t() + bias.double()).float()
+    z = {0: z, 2: F.gelu(z)}[act] + res
+    c, cp = ops.gemm(ap, wp, bias=bias.to(dev), act=act, residual=res.to(dev), out_planes=True, backend=ops.RBA_GEMM_TC)
+    torch.cuda.synchronize()
+    assert (c.cpu() - z).abs().max() < TC_TOL * max(1.0, float(z.abs().max()))
+    assert (unplanes(cp) - z).abs().max() < 2 * TC_TOL * max(1.0, float(z.abs().max()))
+    # and against the exact-arithmetic kernel on the same planes
+    c2 = ops.gemm(ap, wp, bias=bias.to(dev), act=act, residual=res.to(dev), backend=ops.RBA_GEMM_FFMA)
+    assert (c - c2).abs().max() < TC_TOL * max(1.0, float(z.abs().max()))
+
+
+def test_gemm_tc_batched_and_swin(dev):
+    Bn, Q, HW, K = 3, 100, 300, 256
+    g = torch.Generator().manual_seed(21)
+    a, w, b = torch.randn(Bn, Q, K, generator=g), torch.randn(Bn, HW, K, generator=g) / 16, torch.randn(Bn, Q, generator=g)
+    ap, av = planes(a, dev)
+    wp, wv = planes(w, dev)
+    ref = (torch.einsum("bqk,bpk->bqp", av.double(), wv.double()) + b.double()[:, :, None]).float()
+    c = ops.gemm(ap, wp, bias=b.to(dev), bias_per_row=True, backend=ops.RBA_GEMM_TC)
+    assert (c.cpu() - ref).abs().max() < TC_TOL * max(1.0, float(ref.abs().max()))
+    # swin scatter epilogue
+    B, H, W, C, ws, shift = 2, 30, 41, 64, 12, 6
+    nWh, nWw = -(-H // ws), -(-W // ws)
+    rows = B * nWh * nWw * ws * ws
+    a = torch.randn(rows, C, generator=g)
+    w = torch.randn(C, C, generator=g) / 8
+    bias = torch.randn(C, generator=g)
+    shortcut = torch.randn(B * H * W, C, generator=g)
+    ap, av = planes(a, dev)
+    wp, wv = planes(w, dev)
+    y = (av.double() @ wv.double().t() + bias.double()).float()
+    y = torch.roll(O.window_reverse(y.view(-1, ws, ws, C), ws, nWh * ws, nWw * ws), shifts=(shift, shift), dims=(1, 2))
+    ref = shortcut + y[:, :H, :W, :].reshape(B * H * W, C)
+    c = ops.gemm(ap, wp, bias=bias.to(dev), residual=shortcut.to(dev), swin=(B, H, W, ws, shift), backend=ops.RBA_GEMM_TC)
+    assert (c.cpu() - ref).abs().max() < TC_TOL * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("H,W", [(16, 32), (9, 13)])
+def test_conv3x3_tc(dev, H, W):
+    B, Cin, Cout = 2, 64, 128
+    g = torch.Generator().manual_seed(22)
+    x = torch.randn(B, H, W, Cin, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(9 * Cin)
+    xp, xv = planes(x, dev)
+    wk = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+    wp, wkv = planes(wk, dev)
+    wv = wkv.view(Cout, 3, 3, Cin).permute(0, 3, 1, 2)
+    ref = F.conv2d(xv.permute(0, 3, 1, 2).double(), wv.double(), padding=1).permute(0, 2, 3, 1).float()
+    y = ops.conv3x3(xp, wp, backend=ops.RBA_GEMM_TC)
+    assert (y.cpu() - ref).abs().max() < TC_TOL * max(1.0, float(ref.abs().max()))

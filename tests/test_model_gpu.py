@@ -130,3 +130,26 @@ def test_errors_are_loud(dev):
         e.forward(torch.zeros(1, 3, 64, 64, dtype=torch.float16, device=dev))
     with pytest.raises(rba_b200.RbaError):
         e.forward(torch.zeros(1, 3, 64, 64, dtype=torch.uint8))                   # CPU tensor
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_forward_tc_backend_matches_reference_golden(dev, name):
+    """Same bar with every GEMM / 3x3 conv on tcgen05 tensor cores (bf16x3 split precision)."""
+    fix = load_golden(f"model_{name}.pt")
+    case = fix["case"]
+    mc = case_model_config(case)
+    sd = weights.init_state_dict(mc, seed=case["seed"], perturb=case["perturb"])
+    imgs = torch.stack(case_images(case)).to(dev)
+    e = _engine(mc, sd, dev)
+    e.set_gemm_backend("tc")
+    out = e.forward(imgs, rba=True, sem_seg=True, logits=True, masks=True)
+    torch.cuda.synchronize()
+    errs = {
+        "pred_logits": (out["pred_logits"].cpu() - fix["pred_logits"]).abs().max().item(),
+        "pred_masks": (out["pred_masks"].cpu() - fix["pred_masks"]).abs().max().item(),
+        "sem_seg": (out["sem_seg"].cpu()[:, :, ::4, ::4] - fix["sem_seg_s4"]).abs().max().item(),
+        "rba": (out["rba"].cpu() - fix["rba"]).abs().max().item(),
+    }
+    print(name, "tc", errs)
+    for k, v in errs.items():
+        assert v < TOL, (k, v)
