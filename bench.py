@@ -177,7 +177,7 @@ def run_ours(args):
     eng = rba_b200.Engine(mc, local).load_state_dict(sd)
     backend = args.backend
     if backend == "auto":
-        backend = os.environ.get("RBA_BENCH_BACKEND", "ffma")
+        backend = os.environ.get("RBA_BENCH_BACKEND", "tc")
     eng.set_gemm_backend(backend)
     del sd
 

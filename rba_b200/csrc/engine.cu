@@ -88,7 +88,7 @@ struct rba_model {
   int device = 0;
   bool finalized = false;
   bool taps_enabled = false;
-  int gemm_backend = RBA_GEMM_FFMA;
+  int gemm_backend = RBA_GEMM_TC;   // tcgen05 bf16x3; RBA_GEMM_BACKEND=ffma selects the exact fp32 FMA kernels
   std::unordered_map<std::string, DevTensor> w;
   std::unordered_map<std::string, Planes> wp;      // split planes of GEMM weights, by key
   std::vector<void*> owned;                         // cudaMalloc'ed blocks (weights, derived)
@@ -182,6 +182,7 @@ extern "C" int rba_model_create(const rba_config* cfg, int device, rba_model** o
   m->device = device;
   const char* be = getenv("RBA_GEMM_BACKEND");
   if (be && std::string(be) == "tc") m->gemm_backend = RBA_GEMM_TC;
+  if (be && std::string(be) == "ffma") m->gemm_backend = RBA_GEMM_FFMA;
   *out = m;
   return RBA_OK;
 }
