@@ -1,0 +1,60 @@
+"""Data-parallel scoring over the GPUs of one box.
+
+Images are independent units: weights are replicated, image i goes to rank i % world, and the ONLY exchange on
+the path is one all-gather of the per-image score maps (what evaluate_ood's OODEvaluator consumes on rank 0,
+support.py:353-399).  One process per GPU (torchrun), NCCL for CUDA tensors; the same code runs over gloo on CPU
+tensors so the host logic is testable without GPUs."""
+import torch
+import torch.distributed as dist
+
+
+def shard_indices(n_items, rank, world):
+    """Round-robin: item i -> rank i % world (SURVEY §8e 'image i -> rank i mod 8')."""
+    return list(range(rank, n_items, world))
+
+
+def gather_scores(local_scores, n_items, rank=None, world=None, group=None):
+    """local_scores: (n_local, H, W) tensor for items shard_indices(n_items, rank, world), in that order.
+    Returns the (n_items, H, W) tensor in the ORIGINAL item order on every rank.  One all_gather; ranks with one
+    item fewer pad with a zero map that is dropped on reassembly."""
+    if world is None:
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if rank is None:
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+    per = -(-n_items // world)                       # ceil
+    H, W = local_scores.shape[-2:]
+    buf = local_scores.new_zeros((per, H, W))
+    n_local = len(shard_indices(n_items, rank, world))
+    if local_scores.shape[0] != n_local:
+        raise ValueError(f"rank {rank} holds {local_scores.shape[0]} maps, expected {n_local}")
+    buf[:n_local].copy_(local_scores)
+    if world == 1:
+        return buf[:n_items]
+    out = local_scores.new_empty((world * per, H, W))
+    dist.all_gather_into_tensor(out, buf, group=group)
+    out = out.view(world, per, H, W)
+    order = torch.empty((n_items, H, W), dtype=out.dtype, device=out.device)
+    for r in range(world):
+        idx = shard_indices(n_items, r, world)
+        if idx:
+            order[torch.as_tensor(idx, device=out.device)] = out[r, :len(idx)]
+    return order
+
+
+def score_sharded(score_fn, images, rank=None, world=None, group=None, batch=8):
+    """images: sequence of (3,H,W) tensors (same size).  score_fn(list_of_images) -> (n,H,W) score maps
+    (e.g. rba_b200.MaskFormer.rba on this rank's GPU).  Returns all score maps in input order on every rank."""
+    if world is None:
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if rank is None:
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+    mine = shard_indices(len(images), rank, world)
+    outs = []
+    for i in range(0, len(mine), batch):
+        outs.append(score_fn([images[j] for j in mine[i:i + batch]]))
+    if outs:
+        local = torch.cat(outs)
+    else:
+        ref = images[0]
+        local = torch.zeros((0, ref.shape[-2], ref.shape[-1]), dtype=torch.float32, device=ref.device)
+    return gather_scores(local, len(images), rank, world, group)
