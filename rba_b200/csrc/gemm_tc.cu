@@ -26,7 +26,7 @@
 
 namespace rba {
 
-constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 3, TC_THREADS = 192;
+constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 3;
 constexpr int TC_CONV_TH = 8, TC_CONV_TW = 16;   // conv M tile = 8 x 16 output pixels
 
 struct TcParams {
@@ -41,6 +41,8 @@ struct TcParams {
   int a_batched, w_batched;
   // conv
   int cH, cW, cCin, tilesW, tilesH;
+  // persistent tile schedule
+  int tilesM, tilesN, ntiles;
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -53,6 +55,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
@@ -131,51 +136,72 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ---------------------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------------------
+// Persistent: grid = min(#tiles, #SMs); every role loops over the tiles t = blockIdx.x, +gridDim.x, ... with n fastest
+// (CTAs running at the same time share A rows and all of W through L2).  The smem ring runs continuously across
+// tiles; the accumulator is double buffered in TMEM (2 x BN fp32 columns) so the epilogue of tile i overlaps the
+// loads and MMAs of tile i+1.
+constexpr int TC_EPI_WARPS = 8;                         // 2 warps per TMEM lane quadrant, each takes BN/2 columns
+constexpr int TC_THREADS2 = (2 + TC_EPI_WARPS) * 32;    // 320
+
 template <int BN>
 struct TcSmem {
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;      // one plane of A per stage (16 KB)
   static constexpr int W_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
-  static constexpr int TOTAL = TC_STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int BIAS_BYTES = TC_EPI_WARPS * (BN / 2) * 4;
+  static constexpr int TOTAL = TC_STAGES * STAGE_BYTES + BIAS_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+struct TileCoord {
+  int m0, n0, bz;           // GEMM
+  int cvb, cvh0, cvw0;      // conv
 };
 
 template <int BN, bool CONV>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int t) {
+  TileCoord c;
+  const int tn = t % p.tilesN;
+  int r = t / p.tilesN;
+  c.n0 = tn * BN;
+  c.m0 = 0; c.bz = 0; c.cvb = 0; c.cvh0 = 0; c.cvw0 = 0;
+  if (CONV) {
+    c.cvw0 = (r % p.tilesW) * TC_CONV_TW;
+    r /= p.tilesW;
+    c.cvh0 = (r % p.tilesH) * TC_CONV_TH;
+    c.cvb = r / p.tilesH;
+  } else {
+    c.m0 = (r % p.tilesM) * TC_BM;
+    c.bz = r / p.tilesM;
+  }
+  return c;
+}
+
+template <int BN, bool CONV>
+__global__ void __launch_bounds__(TC_THREADS2, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, const TcParams p) {
   using S = TcSmem<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * S::STAGE_BYTES);
-  uint64_t* full = bars;                     // [TC_STAGES]
-  uint64_t* empty = bars + TC_STAGES;        // [TC_STAGES]
-  uint64_t* acc_full = bars + 2 * TC_STAGES; // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
+  float* sbias = reinterpret_cast<float*>(smem + TC_STAGES * S::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * S::STAGE_BYTES + S::BIAS_BYTES);
+  uint64_t* full = bars;                          // [TC_STAGES]
+  uint64_t* empty = bars + TC_STAGES;             // [TC_STAGES]
+  uint64_t* acc_full = bars + 2 * TC_STAGES;      // [2]
+  uint64_t* acc_empty = bars + 2 * TC_STAGES + 2; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
+  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int bz = blockIdx.z;
-  const int n0 = blockIdx.x * BN;
-  int m0 = blockIdx.y * TC_BM;
-  // conv: blockIdx.y enumerates (b, tile_h, tile_w) patches of 8x16 pixels
-  int cvb = 0, cvh0 = 0, cvw0 = 0;
-  if (CONV) {
-    int t = blockIdx.y;
-    cvw0 = (t % p.tilesW) * TC_CONV_TW;
-    t /= p.tilesW;
-    cvh0 = (t % p.tilesH) * TC_CONV_TH;
-    cvb = t / p.tilesH;
-    m0 = 0;
-  }
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmW_hi); prefetch_tmap(&tmW_lo);
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(acc_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], TC_EPI_WARPS); }
     fence_barrier_init();
   }
-  if (warp == 1) {   // TMEM allocation: BN fp32 columns x 128 lanes (power of two >= 32)
-    constexpr uint32_t cols = BN < 32 ? 32 : BN;
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(cols) : "memory");
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -186,115 +212,151 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      for (int kb = 0; kb < p.nkb; ++kb) {
-        const int s = kb % TC_STAGES;
-        const uint32_t ph = (kb / TC_STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        uint8_t* st = smem + s * S::STAGE_BYTES;
-        mbar_expect_tx(&full[s], S::STAGE_BYTES);
-        if (CONV) {
-          const int cpb = p.cCin / TC_BK;                 // channel blocks per tap
-          const int tap = kb / cpb, cblk = kb - tap * cpb;
-          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-          tma_load_4d(st, &tmA_hi, &full[s], cblk * TC_BK, cvw0 + dx, cvh0 + dy, cvb);
-          tma_load_4d(st + S::A_BYTES, &tmA_lo, &full[s], cblk * TC_BK, cvw0 + dx, cvh0 + dy, cvb);
-        } else {
-          tma_load_3d(st, &tmA_hi, &full[s], kb * TC_BK, m0, p.a_batched ? bz : 0);
-          tma_load_3d(st + S::A_BYTES, &tmA_lo, &full[s], kb * TC_BK, m0, p.a_batched ? bz : 0);
+      uint32_t it = 0;                                 // running K-block counter (ring position)
+      for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+        const TileCoord tc = tile_coord<BN, CONV>(p, t);
+        for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+          const int s = it % TC_STAGES;
+          const uint32_t ph = (it / TC_STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* st = smem + s * S::STAGE_BYTES;
+          mbar_expect_tx(&full[s], S::STAGE_BYTES);
+          if (CONV) {
+            const int cpb = p.cCin / TC_BK;               // channel blocks per tap
+            const int tap = kb / cpb, cblk = kb - tap * cpb;
+            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            tma_load_4d(st, &tmA_hi, &full[s], cblk * TC_BK, tc.cvw0 + dx, tc.cvh0 + dy, tc.cvb);
+            tma_load_4d(st + S::A_BYTES, &tmA_lo, &full[s], cblk * TC_BK, tc.cvw0 + dx, tc.cvh0 + dy, tc.cvb);
+          } else {
+            tma_load_3d(st, &tmA_hi, &full[s], kb * TC_BK, tc.m0, p.a_batched ? tc.bz : 0);
+            tma_load_3d(st + S::A_BYTES, &tmA_lo, &full[s], kb * TC_BK, tc.m0, p.a_batched ? tc.bz : 0);
+          }
+          tma_load_3d(st + 2 * S::A_BYTES, &tmW_hi, &full[s], kb * TC_BK, tc.n0, p.w_batched ? tc.bz : 0);
+          tma_load_3d(st + 2 * S::A_BYTES + S::W_BYTES, &tmW_lo, &full[s], kb * TC_BK, tc.n0, p.w_batched ? tc.bz : 0);
         }
-        tma_load_3d(st + 2 * S::A_BYTES, &tmW_hi, &full[s], kb * TC_BK, n0, p.w_batched ? bz : 0);
-        tma_load_3d(st + 2 * S::A_BYTES + S::W_BYTES, &tmW_lo, &full[s], kb * TC_BK, n0, p.w_batched ? bz : 0);
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(TC_BM, BN);
-      for (int kb = 0; kb < p.nkb; ++kb) {
-        const int s = kb % TC_STAGES;
-        const uint32_t ph = (kb / TC_STAGES) & 1;
-        mbar_wait(&full[s], ph);
+      uint32_t it = 0, lt = 0;                           // ring position, local tile counter
+      for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++lt) {
+        const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
+        mbar_wait(&acc_empty[as], aph ^ 1);              // epilogue has drained this accumulator buffer
         tc_fence_after();
-        const uint32_t base = smem_u32(smem + s * S::STAGE_BYTES);
-        const uint64_t a_hi = make_sdesc(base), a_lo = make_sdesc(base + S::A_BYTES);
-        const uint64_t w_hi = make_sdesc(base + 2 * S::A_BYTES), w_lo = make_sdesc(base + 2 * S::A_BYTES + S::W_BYTES);
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+          const int s = it % TC_STAGES;
+          const uint32_t ph = (it / TC_STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t base = smem_u32(smem + s * S::STAGE_BYTES);
+          const uint64_t a_hi = make_sdesc(base), a_lo = make_sdesc(base + S::A_BYTES);
+          const uint64_t w_hi = make_sdesc(base + 2 * S::A_BYTES), w_lo = make_sdesc(base + 2 * S::A_BYTES + S::W_BYTES);
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          const uint64_t adv = (uint64_t)(k * 32 >> 4);    // +32 B along K inside the 128 B swizzle span
-          umma_bf16(tmem_base, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
-          umma_bf16(tmem_base, a_hi + adv, w_lo + adv, idesc, 1);
-          umma_bf16(tmem_base, a_lo + adv, w_hi + adv, idesc, 1);
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);  // +32 B along K inside the 128 B swizzle span
+            umma_bf16(tmem_d, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
+            umma_bf16(tmem_d, a_hi + adv, w_lo + adv, idesc, 1);
+            umma_bf16(tmem_d, a_lo + adv, w_hi + adv, idesc, 1);
+          }
+          umma_commit(&empty[s]);                         // frees the smem stage when these MMAs retire
         }
-        umma_commit(&empty[s]);                           // frees the smem stage when these MMAs retire
+        umma_commit(&acc_full[as]);                       // accumulator complete
       }
-      umma_commit(acc_full);                              // accumulator complete
     }
   } else {
-    // ===================== epilogue (warps 2..5 <-> TMEM lane quadrants (warp % 4)) =====================
-    const int quad = warp & 3;
+    // ===================== epilogue: warps 2..9; TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4 =====
+    const int ew = warp - 2;
+    const int quad = warp & 3, half = ew >> 2;
+    constexpr int HC = BN / 2;                            // columns per warp
+    float* mybias = sbias + ew * HC;
     const int row_in_tile = quad * 32 + lane;
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    int64_t orow = -1;                                    // output row (or -1: nothing to store)
-    int m_logical = m0 + row_in_tile;
-    if (CONV) {
-      const int hh = cvh0 + row_in_tile / TC_CONV_TW, ww = cvw0 + row_in_tile % TC_CONV_TW;
-      if (hh < p.cH && ww < p.cW) orow = ((int64_t)cvb * p.cH + hh) * p.cW + ww;
-    } else if (m_logical < p.M) {
-      orow = m_logical;
-      if (p.swin_map) orow = swin_row_to_token(p.geom, m_logical);
-    }
-    const float* bias = p.bias ? p.bias + bz * p.bias_bs : nullptr;
-    float* c = p.c ? p.c + bz * p.c_bs : nullptr;
-    const int64_t ldr = p.c ? p.ldc : p.ldcp;
-    const float* res = p.residual ? p.residual + bz * (p.c ? p.c_bs : p.cp_bs) : nullptr;
-    uint16_t* c_hi = p.c_hi ? p.c_hi + bz * p.cp_bs : nullptr;
-    uint16_t* c_lo = p.c_lo ? p.c_lo + bz * p.cp_bs : nullptr;
-    const bool vec_c = (p.ldc & 3) == 0, vec_p = (p.ldcp & 3) == 0, vec_r = (ldr & 3) == 0;
-    const float brow = (bias && p.bias_per_row && orow >= 0 && !CONV) ? bias[m_logical] : 0.f;
+    uint32_t lt = 0;
+    for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++lt) {
+      const TileCoord tc = tile_coord<BN, CONV>(p, t);
+      const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
+      const int bz = tc.bz;
+      const int nbase = tc.n0 + half * HC;
+      int64_t orow = -1;                                  // output row (or -1: nothing to store)
+      const int m_logical = tc.m0 + row_in_tile;
+      if (CONV) {
+        const int hh = tc.cvh0 + row_in_tile / TC_CONV_TW, ww = tc.cvw0 + row_in_tile % TC_CONV_TW;
+        if (hh < p.cH && ww < p.cW) orow = ((int64_t)tc.cvb * p.cH + hh) * p.cW + ww;
+      } else if (m_logical < p.M) {
+        orow = m_logical;
+        if (p.swin_map) orow = swin_row_to_token(p.geom, m_logical);
+      }
+      const float* bias = p.bias ? p.bias + bz * p.bias_bs : nullptr;
+      float* c = p.c ? p.c + bz * p.c_bs : nullptr;
+      const int64_t ldr = p.c ? p.ldc : p.ldcp;
+      const float* res = p.residual ? p.residual + bz * (p.c ? p.c_bs : p.cp_bs) : nullptr;
+      uint16_t* c_hi = p.c_hi ? p.c_hi + bz * p.cp_bs : nullptr;
+      uint16_t* c_lo = p.c_lo ? p.c_lo + bz * p.cp_bs : nullptr;
+      const bool vec_c = (p.ldc & 3) == 0, vec_p = (p.ldcp & 3) == 0, vec_r = (ldr & 3) == 0;
+      // stage this warp's slice of the column bias while the MMAs of this tile are still running
+      float brow = 0.f;
+      if (bias) {
+        if (p.bias_per_row) {
+          if (orow >= 0 && !CONV) brow = bias[m_logical];
+        } else {
+          __syncwarp();
+          for (int j = lane; j < HC; j += 32) mybias[j] = (nbase + j < p.N) ? bias[nbase + j] : 0.f;
+          __syncwarp();
+        }
+      }
+      mbar_wait(&acc_full[as], aph);
+      tc_fence_after();
 #pragma unroll 1
-    for (int cb = 0; cb < BN / 32; ++cb) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cb * 32), v);   // warp-collective
-      tmem_ld_wait();
-      const int nb = n0 + cb * 32;
-      if (orow < 0 || nb >= p.N) continue;
-#pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) {
-        const int n = nb + j4 * 4;
-        if (n >= p.N) break;
-        float t[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float x = __uint_as_float(v[j4 * 4 + j]);
-          if (bias) x += p.bias_per_row ? brow : ((n + j < p.N) ? bias[n + j] : 0.f);
-          t[j] = apply_act_rt(x, p.act);
+      for (int cb = 0; cb < HC / 32; ++cb) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + half * HC + cb * 32), v);
+        tmem_ld_wait();
+        if (cb == HC / 32 - 1) {                          // all of this warp's TMEM reads for the tile are done
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[as]);
         }
-        const bool fullv = n + 3 < p.N;
-        if (res) {
-          if (fullv && vec_r) {
-            float4 r4 = *reinterpret_cast<const float4*>(res + orow * ldr + n);
-            t[0] += r4.x; t[1] += r4.y; t[2] += r4.z; t[3] += r4.w;
-          } else {
+        const int nb = nbase + cb * 32;
+        if (orow < 0 || nb >= p.N) continue;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (n + j < p.N) t[j] += res[orow * ldr + n + j];
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const int n = nb + j4 * 4;
+          if (n >= p.N) break;
+          float tt[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float x = __uint_as_float(v[j4 * 4 + j]);
+            if (bias) x += p.bias_per_row ? brow : mybias[cb * 32 + j4 * 4 + j];
+            tt[j] = apply_act_rt(x, p.act);
           }
-        }
-        if (c) {
-          if (fullv && vec_c) *reinterpret_cast<float4*>(c + orow * p.ldc + n) = make_float4(t[0], t[1], t[2], t[3]);
-          else {
+          const bool fullv = n + 3 < p.N;
+          if (res) {
+            if (fullv && vec_r) {
+              float4 r4 = *reinterpret_cast<const float4*>(res + orow * ldr + n);
+              tt[0] += r4.x; tt[1] += r4.y; tt[2] += r4.z; tt[3] += r4.w;
+            } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (n + j < p.N) c[orow * p.ldc + n + j] = t[j];
+              for (int j = 0; j < 4; ++j)
+                if (n + j < p.N) tt[j] += res[orow * ldr + n + j];
+            }
           }
-        }
-        if (c_hi) {
-          if (fullv && vec_p) store_split4(c_hi, c_lo, orow * p.ldcp + n, t[0], t[1], t[2], t[3]);
-          else {
+          if (c) {
+            if (fullv && vec_c) *reinterpret_cast<float4*>(c + orow * p.ldc + n) = make_float4(tt[0], tt[1], tt[2], tt[3]);
+            else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (n + j < p.N) store_split1(c_hi, c_lo, orow * p.ldcp + n + j, t[j]);
+              for (int j = 0; j < 4; ++j)
+                if (n + j < p.N) c[orow * p.ldc + n + j] = tt[j];
+            }
+          }
+          if (c_hi) {
+            if (fullv && vec_p) store_split4(c_hi, c_lo, orow * p.ldcp + n, tt[0], tt[1], tt[2], tt[3]);
+            else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (n + j < p.N) store_split1(c_hi, c_lo, orow * p.ldcp + n + j, tt[j]);
+            }
           }
         }
       }
@@ -304,8 +366,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    constexpr uint32_t cols = BN < 32 ? 32 : BN;
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(cols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -358,6 +419,16 @@ static int make_map_nhwc(CUtensorMap* m, const uint16_t* ptr, int B, int H, int 
   return RBA_OK;
 }
 
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
 template <int BN, bool CONV>
 static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
                      const TcParams& p, dim3 grid, cudaStream_t st) {
@@ -367,7 +438,7 @@ static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUt
     RBA_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_done = true;
   }
-  gemm_tc_kernel<BN, CONV><<<grid, TC_THREADS, smem, st>>>(a_hi, a_lo, w_hi, w_lo, p);
+  gemm_tc_kernel<BN, CONV><<<grid, TC_THREADS2, smem, st>>>(a_hi, a_lo, w_hi, w_lo, p);
   RBA_LAUNCHED();
   return RBA_OK;
 }
@@ -398,7 +469,11 @@ int gemm_tc_launch(const rba_gemm_args& a, cudaStream_t st) {
   RBA_TRY_(make_map_3d(&ta_lo, a.a_lo, a.K, a.M, a.lda, p.a_batched ? a.batch : 1, a.a_bstride, TC_BM));
   RBA_TRY_(make_map_3d(&tw_hi, a.w_hi, a.K, a.N, a.ldw, p.w_batched ? a.batch : 1, a.w_bstride, BN));
   RBA_TRY_(make_map_3d(&tw_lo, a.w_lo, a.K, a.N, a.ldw, p.w_batched ? a.batch : 1, a.w_bstride, BN));
-  dim3 grid((unsigned)cdiv(a.N, BN), (unsigned)cdiv(a.M, TC_BM), (unsigned)a.batch);
+  p.tilesM = (int)cdiv(a.M, TC_BM); p.tilesN = (int)cdiv(a.N, BN);
+  const int64_t nt = (int64_t)p.tilesM * p.tilesN * a.batch;
+  RBA_CHECK(nt < (1LL << 31), "gemm(tc): too many tiles");
+  p.ntiles = (int)nt;
+  dim3 grid((unsigned)std::min<int64_t>(nt, num_sms()));
   if (BN == 128) return launch_tc<128, false>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
   return launch_tc<64, false>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
 }
@@ -420,9 +495,11 @@ int conv3x3_tc_launch(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t
   const int BN = Cout > 64 ? 128 : 64;
   RBA_TRY_(make_map_3d(&tw_hi, w_hi, 9 * Cin, Cout, 9 * Cin, 1, 0, BN));
   RBA_TRY_(make_map_3d(&tw_lo, w_lo, 9 * Cin, Cout, 9 * Cin, 1, 0, BN));
-  const int64_t tiles = (int64_t)B * p.tilesH * p.tilesW;
-  RBA_CHECK(tiles <= 65535, "conv3x3(tc): too many tiles for one launch (%lld)", (long long)tiles);
-  dim3 grid((unsigned)cdiv(Cout, BN), (unsigned)tiles, 1);
+  p.tilesM = 1; p.tilesN = (int)cdiv(Cout, BN);
+  const int64_t nt = (int64_t)B * p.tilesH * p.tilesW * p.tilesN;
+  RBA_CHECK(nt < (1LL << 31), "conv3x3(tc): too many tiles");
+  p.ntiles = (int)nt;
+  dim3 grid((unsigned)std::min<int64_t>(nt, num_sms()));
   if (BN == 128) return launch_tc<128, true>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
   return launch_tc<64, true>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
 }

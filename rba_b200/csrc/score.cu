@@ -32,6 +32,26 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// Single-MUFU helpers: ex2.approx / rcp.approx are accurate to ~2 ulp, far inside the 1e-3 parity budget.
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// sigmoid(u) = 1 / (1 + 2^(-u*log2e)); the exponent is clamped so 1+e stays finite (u > -87)
+__device__ __forceinline__ float fast_sigmoid(float u) {
+  return fast_rcp(1.0f + fast_ex2(fminf(-1.4426950408889634f * u, 126.0f)));
+}
+// tanh(x) for x >= 0 (sem_seg is a sum of non-negative terms): 1 - 2/(1 + e^(2x)); abs error ~1e-7
+__device__ __forceinline__ float fast_tanh_pos(float x) {
+  return 1.0f - 2.0f * fast_rcp(1.0f + fast_ex2(fminf(2.8853900817779268f * x, 126.0f)));
+}
+
 // PyTorch area_pixel_compute_source_index (align_corners=False, scale 1/4) for output index o:
 // src = max((o+0.5)/4 - 0.5, 0); i0 = floor(src); l1 = src - i0.
 __device__ __forceinline__ void up4_coeff(int o, int& i0, float& l1) {
@@ -134,7 +154,7 @@ rba_score_kernel(const float* __restrict__ masks, const float* __restrict__ logi
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         float u = wx0[i] * col[i >> 1] + wx1[i] * col[(i >> 1) + 1];
-        sg[i] = __frcp_rn(1.0f + __expf(-u));          // sigmoid, maskformer_model.py:383
+        sg[i] = fast_sigmoid(u);                       // sigmoid, maskformer_model.py:383
       }
       const float4* pq = reinterpret_cast<const float4*>(sP + (size_t)(chunk * SC_QC + qq) * SC_KP);
       float p[SC_KP];
@@ -160,7 +180,7 @@ rba_score_kernel(const float* __restrict__ masks, const float* __restrict__ logi
   for (int i = 0; i < 4; ++i) {
     float s = 0.f;
 #pragma unroll
-    for (int c = 0; c < K; ++c) s += tanhf(acc[i][c]);
+    for (int c = 0; c < K; ++c) s += fast_tanh_pos(acc[i][c]);   // evaluate_ood.py:150
     r[i] = -s;
   }
   const bool vec = ((W & 3) == 0) && (x0 + 3 < W);
