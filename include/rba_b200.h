@@ -80,7 +80,8 @@ int rba_model_load_tensor(rba_model* m, const char* key, const float* data, cons
  * buffers (bf16 split planes of the weights, re-laid-out conv filters, fused projection matrices). */
 int rba_model_finalize(rba_model* m);
 /* Options: "taps" (0/1: keep stage-boundary tensors of the next forwards for rba_model_get_tap),
- * "gemm_backend" (RBA_GEMM_FFMA / RBA_GEMM_TC, see below). */
+ * "gemm_backend" (RBA_GEMM_FFMA / RBA_GEMM_TC, see below), "attn_backend" (1 = tensor-core window attention,
+ * 0 = fp32 CUDA-core kernel). */
 int rba_model_set_option(rba_model* m, const char* name, int value);
 /* Max batch / padded image size the workspace is sized for; (re)allocates device workspace. */
 int rba_model_reserve(rba_model* m, int batch, int height, int width);
@@ -162,6 +163,10 @@ int rba_k_layernorm(const float* x, const float* gamma, const float* beta, int m
  * bias_table [(2ws-1)^2, heads]; shift>0 adds the -100 region mask of swin.py:413-440 (computed analytically). */
 int rba_k_window_attn(const float* qkv, const float* bias_table, int B, int H, int W, int C, int heads, int ws, int shift,
                       uint16_t* out_hi, uint16_t* out_lo, void* stream);
+
+/* Tensor-core variant (mma.sync m16n8k16, bf16x3): qkv given as split planes [rows, 3C] (what the QKV GEMM writes). */
+int rba_k_window_attn_planes(const uint16_t* qkv_hi, const uint16_t* qkv_lo, const float* bias_table, int B, int H, int W,
+                             int C, int heads, int ws, int shift, uint16_t* out_hi, uint16_t* out_lo, void* stream);
 
 /* nn.MultiheadAttention core for the decoder (mask2former_transformer_decoder.py:52-53,110-113):
  * q [B,Lq,E], k,v [B,Lk,E] fp32 (already projected, q NOT yet scaled), mask (B,Lq,Lk) uint8 (1 = blocked, shared by

@@ -4,10 +4,15 @@ import torch
 
 from rba_b200 import config as rcfg
 
+# Seeds are chosen so that the reference's own boolean attention-mask decisions (sigmoid(interp(mask)) < 0.5,
+# mask2former_transformer_decoder.py:483-486) are WELL CONDITIONED: the closest decision is >= 1e-3 away from its
+# threshold (fixture field "am_margin", checked in tests/test_oracle_golden.py).  With a razor-edge decision (e.g.
+# margin 1.8e-5 for tiny_3lvl seed 12) any implementation whose mask logits differ by round-off flips it and the
+# outputs change by O(0.1) — such inputs cannot pin parity to 1e-3 for ANY implementation, the reference included.
 CASES = {
     # name: preset, encoder levels, decoder layers, weight seed / perturbation, image seed and sizes
     "tiny_1dl": dict(preset="tiny", levels=1, dec_layers=1, seed=11, perturb=0.02, img_seed=1, sizes=[(70, 100)]),
-    "tiny_3lvl": dict(preset="tiny", levels=3, dec_layers=3, seed=12, perturb=0.02, img_seed=2, sizes=[(64, 96), (64, 96)]),
+    "tiny_3lvl": dict(preset="tiny", levels=3, dec_layers=3, seed=248, perturb=0.02, img_seed=2, sizes=[(64, 96), (64, 96)]),
     "swin_b_1dl": dict(preset="swin_b_1dl", levels=1, dec_layers=1, seed=13, perturb=0.02, img_seed=3, sizes=[(96, 160)]),
 }
 

@@ -57,14 +57,16 @@ def main():
         out = model([{"image": im} for im in images])
         sem = torch.stack([o["sem_seg"] for o in out])
         rba = -sem.tanh().sum(1)                                     # evaluate_ood.py:148-150
+        import rba_oracle as O
+        margin = O.forward(sd, mc, images, want_taps=True)["taps"]["am_margin"]
         fix = {
-            "case": case, "state_checksum": state_checksum(sd),
+            "case": case, "state_checksum": state_checksum(sd), "am_margin": margin,
             "pred_logits": caps["head"]["pred_logits"].clone(), "pred_masks": caps["head"]["pred_masks"].clone(),
             "rba": rba.clone(), "sem_seg_s4": sem[:, :, ::4, ::4].clone(),
             "torch_version": torch.__version__, "reference": "NazirNayal8/RbA @ /root/reference (unmodified modules under oracle/ref_shims)",
         }
         torch.save(fix, os.path.join(OUT, f"model_{name}.pt"))
-        print(name, "pred_masks", tuple(fix["pred_masks"].shape), "rba range", float(rba.min()), float(rba.max()))
+        print(name, "pred_masks", tuple(fix["pred_masks"].shape), "rba range", float(rba.min()), float(rba.max()), "am_margin", margin)
 
     # ---- MSDeformAttn: shapes / seed / value scaling of the reference's own ops/test.py:24-47 (CPU RNG) ----
     core = ref_loader.msda_core_pytorch()

@@ -385,7 +385,7 @@ def multihead_attention(sd, p, query, key, value, nheads, attn_mask=None):
     return F.linear(o, sd[p + "out_proj.weight"], sd[p + "out_proj.bias"])
 
 
-def prediction_heads(sd, p, output, mask_features, target_size, nheads):
+def prediction_heads(sd, p, output, mask_features, target_size, nheads, taps=None):
     """mask2former_transformer_decoder.py:472-489"""
     D = output.shape[-1]
     dec = F.layer_norm(output, (D,), sd[p + "decoder_norm.weight"], sd[p + "decoder_norm.bias"]).transpose(0, 1)
@@ -397,6 +397,8 @@ def prediction_heads(sd, p, output, mask_features, target_size, nheads):
             me = F.relu(me)
     masks = torch.einsum("bqc,bchw->bqhw", me, mask_features)
     am = F.interpolate(masks, size=target_size, mode="bilinear", align_corners=False)
+    if taps is not None:   # distance of the closest boolean decision (sigmoid(x) < 0.5 <=> x < 0) from its threshold
+        taps["am_margin"] = min(taps.get("am_margin", float("inf")), float(am.abs().min()))
     am = (am.sigmoid().flatten(2).unsqueeze(1).repeat(1, nheads, 1, 1).flatten(0, 1) < 0.5).bool()
     return cls, masks, am
 
@@ -416,7 +418,7 @@ def transformer_decoder_forward(sd, cfg, multi_scale, mask_features, p="sem_seg_
     bs = src[0].shape[1]
     qe = sd[p + "query_embed.weight"].unsqueeze(1).repeat(1, bs, 1)
     out = sd[p + "query_feat.weight"].unsqueeze(1).repeat(1, bs, 1)
-    cls, masks, am = prediction_heads(sd, p, out, mask_features, sizes[0], cfg.nheads)
+    cls, masks, am = prediction_heads(sd, p, out, mask_features, sizes[0], cfg.nheads, taps)
     if taps is not None:
         taps["head0_logits"], taps["head0_masks"] = cls, masks
     for i in range(cfg.dec_layers):
@@ -437,7 +439,8 @@ def transformer_decoder_forward(sd, cfg, multi_scale, mask_features, p="sem_seg_
         out = F.layer_norm(out + t2, (D,), sd[q + "norm.weight"], sd[q + "norm.bias"])
         if taps is not None:
             taps[f"dec{i}_out"] = out
-        cls, masks, am = prediction_heads(sd, p, out, mask_features, sizes[(i + 1) % nl], cfg.nheads)
+        cls, masks, am = prediction_heads(sd, p, out, mask_features, sizes[(i + 1) % nl], cfg.nheads,
+                                          taps if i + 1 < cfg.dec_layers else None)   # the last mask is never used
     return cls, masks
 
 

@@ -63,6 +63,7 @@ PROTOTYPES = {
     "rba_k_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                                 c_void_p, c_void_p, c_void_p, c_void_p]),
     "rba_k_window_attn": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "rba_k_window_attn_planes": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "rba_k_mha": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "rba_k_groupnorm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int,
                                 c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -165,6 +165,214 @@ int window_attn(const float* qkv, const float* bias_table, int B, int H, int W, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Swin window attention on the legacy tensor path (mma.sync m16n8k16, bf16x3 split precision)
+// ------------------------------------------------------------------------------------------------
+// Same contract as window_attn_kernel, but q/k/v arrive as bf16 split planes (written by the QKV GEMM epilogue) and
+// both contractions run on tensor cores: S = q k^T and O = P v each as hi*hi + hi*lo + lo*hi with fp32 accumulation.
+// 144 = 9 x 16 query rows = 18 x 8 key columns, so the warp-level m16n8k16 shape tiles a 12x12 window exactly (the
+// tcgen05 shapes, M in {64,128,256}, do not).  One CTA per (window, head), 9 warps, warp w owns query rows 16w..16w+15:
+// S fragments (72 fp32/thread) stay in registers through bias/mask/softmax and are re-packed in place as the A operand
+// of P.v (FlashAttention-2 register reuse).  K and V^T fragments come from shared memory via ldmatrix(.trans).
+constexpr int WM_PITCH = 40;                         // bf16 per smem row (32 used): 80 B pitch, conflict-free ldmatrix
+constexpr int WM_PLANE = WA_N * WM_PITCH;            // one 144 x 32 operand plane
+constexpr int WM_THREADS = 288;
+
+__device__ __forceinline__ void ldsm_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const void* p) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const void* p) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(a));
+}
+__device__ __forceinline__ void mma_bf16(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem));
+}
+// packs two fp32 into bf16x2 hi and the bf16x2 of the residuals
+__device__ __forceinline__ void split_pack2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  __nv_bfloat16 hx, lx, hy, ly;
+  split2(x, hx, lx);
+  split2(y, hy, ly);
+  hi = (uint32_t)__bfloat16_as_ushort(hx) | ((uint32_t)__bfloat16_as_ushort(hy) << 16);
+  lo = (uint32_t)__bfloat16_as_ushort(lx) | ((uint32_t)__bfloat16_as_ushort(ly) << 16);
+}
+
+__global__ void __launch_bounds__(WM_THREADS, 1)
+window_attn_mma_kernel(const uint16_t* __restrict__ qkv_hi, const uint16_t* __restrict__ qkv_lo,
+                       const float* __restrict__ bias_table, int C, int heads, int nWh, int nWw, int shift, float scale,
+                       uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo) {
+  extern __shared__ __align__(16) uint8_t wm_smem[];
+  // planes: 0 q_hi, 1 q_lo, 2 k_hi, 3 k_lo, 4 v_hi, 5 v_lo
+  uint16_t* sOp = reinterpret_cast<uint16_t*>(wm_smem);
+  float* sB = reinterpret_cast<float*>(wm_smem + 6 * WM_PLANE * 2);     // [529] relative position bias of this head
+  int* sCol = reinterpret_cast<int*>(sB + 532);                          // [144] (ci*23 + cj) | region << 16
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int head = blockIdx.y;
+  const int64_t win = blockIdx.x;
+  const int ww = (int)(win % nWw), wh = (int)((win / nWw) % nWh);
+  const int Hp = nWh * WA_WS, Wp = nWw * WA_WS;
+
+  // ---- stage q/k/v planes: 144 rows x 64 B per operand plane ----
+  {
+    const int64_t rowbase = win * WA_N;
+    for (int e = tid; e < 6 * WA_N * 4; e += WM_THREADS) {
+      const int chunk = e & 3;                     // 16 B chunk within the 64 B row segment
+      int t = e >> 2;
+      const int r = t % WA_N;
+      const int pl = t / WA_N;                     // 0..5
+      const int part = pl >> 1;                    // q, k, v
+      const uint16_t* src = ((pl & 1) ? qkv_lo : qkv_hi) + (rowbase + r) * (int64_t)(3 * C) + part * C + head * WA_D + chunk * 8;
+      cp_async16(sOp + pl * WM_PLANE + r * WM_PITCH + chunk * 8, src);
+    }
+    asm volatile("cp.async.commit_group;" ::);
+  }
+  for (int e = tid; e < 23 * 23; e += WM_THREADS) sB[e] = bias_table[(int64_t)e * heads + head];
+  for (int c = tid; c < WA_N; c += WM_THREADS) {
+    const int ci = c / WA_WS, cj = c - ci * WA_WS;
+    const int hs = wh * WA_WS + ci, wsx = ww * WA_WS + cj;
+    const int rh = hs < Hp - WA_WS ? 0 : (hs < Hp - shift ? 1 : 2);
+    const int rw = wsx < Wp - WA_WS ? 0 : (wsx < Wp - shift ? 1 : 2);
+    sCol[c] = (ci * 23 + cj) | ((rh * 3 + rw) << 16);
+  }
+  asm volatile("cp.async.wait_group 0;" ::);
+  __syncthreads();
+
+  const uint16_t* sQh = sOp, *sQl = sOp + WM_PLANE, *sKh = sOp + 2 * WM_PLANE, *sKl = sOp + 3 * WM_PLANE;
+  const uint16_t* sVh = sOp + 4 * WM_PLANE, *sVl = sOp + 5 * WM_PLANE;
+  const int g = lane >> 2, tq = lane & 3;
+  const int r0 = warp * 16;
+
+  // ---- Q fragments (2 k-steps x hi/lo) ----
+  uint32_t qh[2][4], ql[2][4];
+  {
+    const int row = r0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+    const int col = (lane >> 4) * 8;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      ldsm_x4(qh[ks][0], qh[ks][1], qh[ks][2], qh[ks][3], sQh + row * WM_PITCH + ks * 16 + col);
+      ldsm_x4(ql[ks][0], ql[ks][1], ql[ks][2], ql[ks][3], sQl + row * WM_PITCH + ks * 16 + col);
+    }
+  }
+  // ---- S = q k^T (bf16x3) ----
+  float sacc[18][4];
+#pragma unroll
+  for (int nb = 0; nb < 18; ++nb) {
+    sacc[nb][0] = sacc[nb][1] = sacc[nb][2] = sacc[nb][3] = 0.f;
+    uint32_t kh[4], kl[4];
+    const int krow = nb * 8 + (lane & 7), kcol = (lane >> 3) * 8;
+    ldsm_x4(kh[0], kh[1], kh[2], kh[3], sKh + krow * WM_PITCH + kcol);
+    ldsm_x4(kl[0], kl[1], kl[2], kl[3], sKl + krow * WM_PITCH + kcol);
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      mma_bf16(sacc[nb], qh[ks], kh[2 * ks], kh[2 * ks + 1]);
+      mma_bf16(sacc[nb], qh[ks], kl[2 * ks], kl[2 * ks + 1]);
+      mma_bf16(sacc[nb], ql[ks], kh[2 * ks], kh[2 * ks + 1]);
+    }
+  }
+  // ---- scale, relative position bias, shift mask, softmax (rows g and g+8 of this warp's 16) ----
+  float inv_sum[2];
+#pragma unroll
+  for (int hrow = 0; hrow < 2; ++hrow) {
+    const int r = r0 + g + hrow * 8;
+    const int ri = r / WA_WS, rj = r - ri * WA_WS;
+    const int rterm = ri * 23 + rj + (WA_WS - 1) * 23 + (WA_WS - 1);
+    const int hs = wh * WA_WS + ri, wsx = ww * WA_WS + rj;
+    const int rid = (hs < Hp - WA_WS ? 0 : (hs < Hp - shift ? 1 : 2)) * 3 + (wsx < Wp - WA_WS ? 0 : (wsx < Wp - shift ? 1 : 2));
+    float mx = -INFINITY;
+#pragma unroll
+    for (int nb = 0; nb < 18; ++nb)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int cinfo = sCol[nb * 8 + tq * 2 + j];
+        float sv = sacc[nb][hrow * 2 + j] * scale + sB[rterm - (cinfo & 0xffff)];
+        if (shift > 0 && rid != (cinfo >> 16)) sv += -100.0f;
+        sacc[nb][hrow * 2 + j] = sv;
+        mx = fmaxf(mx, sv);
+      }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    float sum = 0.f;
+#pragma unroll
+    for (int nb = 0; nb < 18; ++nb)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float e = __expf(sacc[nb][hrow * 2 + j] - mx);
+        sacc[nb][hrow * 2 + j] = e;
+        sum += e;
+      }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    inv_sum[hrow] = 1.0f / sum;
+  }
+  // ---- O = P v (bf16x3); P is normalised after the contraction ----
+  float oacc[4][4];
+#pragma unroll
+  for (int nd = 0; nd < 4; ++nd) oacc[nd][0] = oacc[nd][1] = oacc[nd][2] = oacc[nd][3] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < 9; ++kk) {
+    uint32_t ph[4], pl[4];
+    split_pack2(sacc[2 * kk][0], sacc[2 * kk][1], ph[0], pl[0]);          // row g,   keys kk*16 + 2t, +1
+    split_pack2(sacc[2 * kk][2], sacc[2 * kk][3], ph[1], pl[1]);          // row g+8
+    split_pack2(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1], ph[2], pl[2]);  // row g,   keys kk*16 + 8 + 2t, +1
+    split_pack2(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3], ph[3], pl[3]);  // row g+8
+    const int vrow = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {                                     // pairs of 8-wide d blocks
+      uint32_t vh[4], vl[4];
+      const int vcol = np * 16 + (lane >> 4) * 8;
+      ldsm_x4_t(vh[0], vh[1], vh[2], vh[3], sVh + vrow * WM_PITCH + vcol);
+      ldsm_x4_t(vl[0], vl[1], vl[2], vl[3], sVl + vrow * WM_PITCH + vcol);
+#pragma unroll
+      for (int q2 = 0; q2 < 2; ++q2) {
+        float* o = oacc[np * 2 + q2];
+        mma_bf16(o, ph, vh[2 * q2], vh[2 * q2 + 1]);
+        mma_bf16(o, ph, vl[2 * q2], vl[2 * q2 + 1]);
+        mma_bf16(o, pl, vh[2 * q2], vh[2 * q2 + 1]);
+      }
+    }
+  }
+  // ---- store (attn @ v).transpose(1,2).reshape(B_, N, C) as split planes ----
+#pragma unroll
+  for (int hrow = 0; hrow < 2; ++hrow) {
+    const int64_t orow = win * WA_N + r0 + g + hrow * 8;
+    const int64_t ob = orow * C + head * WA_D + tq * 2;
+#pragma unroll
+    for (int nd = 0; nd < 4; ++nd) {
+      uint32_t hi, lo;
+      split_pack2(oacc[nd][hrow * 2] * inv_sum[hrow], oacc[nd][hrow * 2 + 1] * inv_sum[hrow], hi, lo);
+      *reinterpret_cast<uint32_t*>(out_hi + ob + nd * 8) = hi;
+      *reinterpret_cast<uint32_t*>(out_lo + ob + nd * 8) = lo;
+    }
+  }
+}
+
+int window_attn_planes(const uint16_t* qkv_hi, const uint16_t* qkv_lo, const float* bias_table, int B, int H, int W, int C,
+                       int heads, int ws, int shift, uint16_t* out_hi, uint16_t* out_lo, cudaStream_t st) {
+  RBA_CHECK(qkv_hi && qkv_lo && bias_table && out_hi && out_lo, "window_attn_planes: null pointer");
+  RBA_CHECK(ws == WA_WS, "window_attn_planes: only window_size 12 is built (got %d)", ws);
+  RBA_CHECK(heads > 0 && C == heads * WA_D, "window_attn_planes: head_dim must be 32 (C=%d heads=%d)", C, heads);
+  RBA_CHECK(shift >= 0 && shift < ws, "window_attn_planes: bad shift %d", shift);
+  SwinGeom g = make_swin_geom(H, W, ws, shift);
+  const int64_t nwin = (int64_t)B * g.nWh * g.nWw;
+  if (nwin == 0) return RBA_OK;
+  RBA_CHECK(nwin < (1LL << 31), "window_attn_planes: too many windows");
+  const size_t smem = (size_t)6 * WM_PLANE * 2 + 532 * 4 + WA_N * 4;
+  RBA_CUDA(cudaFuncSetAttribute(window_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)nwin, (unsigned)heads);
+  window_attn_mma_kernel<<<grid, WM_THREADS, smem, st>>>(qkv_hi, qkv_lo, bias_table, C, heads, g.nWh, g.nWw, shift,
+                                                         1.0f / sqrtf((float)WA_D), out_hi, out_lo);
+  RBA_LAUNCHED();
+  return RBA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Decoder multi-head attention core (nn.MultiheadAttention, mask2former_transformer_decoder.py:52-53,110-113)
 // ------------------------------------------------------------------------------------------------
 // One warp per (b, head, query); keys are streamed in chunks of 32 (lane <-> key for the scores, lane <-> dim for
@@ -293,6 +501,12 @@ int attn_mask(const float* masks, int B, int Q, int h, int w, int th, int tw, ui
 extern "C" int rba_k_window_attn(const float* qkv, const float* bias_table, int B, int H, int W, int C, int heads, int ws,
                                  int shift, uint16_t* out_hi, uint16_t* out_lo, void* stream) {
   return rba::window_attn(qkv, bias_table, B, H, W, C, heads, ws, shift, out_hi, out_lo, (cudaStream_t)stream);
+}
+
+extern "C" int rba_k_window_attn_planes(const uint16_t* qkv_hi, const uint16_t* qkv_lo, const float* bias_table, int B, int H,
+                                        int W, int C, int heads, int ws, int shift, uint16_t* out_hi, uint16_t* out_lo,
+                                        void* stream) {
+  return rba::window_attn_planes(qkv_hi, qkv_lo, bias_table, B, H, W, C, heads, ws, shift, out_hi, out_lo, (cudaStream_t)stream);
 }
 
 extern "C" int rba_k_mha(const float* q, const float* k, const float* v, const uint8_t* mask, int B, int Lq, int Lk, int E,

@@ -88,6 +88,7 @@ struct rba_model {
   int device = 0;
   bool finalized = false;
   bool taps_enabled = false;
+  int attn_backend = 1;             // 1: tensor-core window attention (mma.sync bf16x3), 0: fp32 CUDA-core kernel
   int gemm_backend = RBA_GEMM_TC;   // tcgen05 bf16x3; RBA_GEMM_BACKEND=ffma selects the exact fp32 FMA kernels
   std::unordered_map<std::string, DevTensor> w;
   std::unordered_map<std::string, Planes> wp;      // split planes of GEMM weights, by key
@@ -196,6 +197,10 @@ extern "C" int rba_model_set_option(rba_model* m, const char* name, int value) {
   else if (n == "gemm_backend") {
     RBA_CHECK(value == RBA_GEMM_FFMA || value == RBA_GEMM_TC, "bad gemm backend %d", value);
     m->gemm_backend = value;
+  } else if (n == "attn_backend") {
+    RBA_CHECK(value == 0 || value == 1, "bad attn backend %d", value);
+    m->attn_backend = value;
+    m->rB = m->rH = m->rW = 0;
   } else return fail(RBA_ERR_INVALID, "unknown option '%s'", name);
   return RBA_OK;
 }
@@ -478,12 +483,20 @@ static int forward_impl(rba_model* m, const void* images, int img_dtype, int B, 
       Planes a1 = A.planes(RW * C);
       RBA_RUN(layernorm(x, F.W(p + "norm1.weight"), F.W(p + "norm1.bias"), 1, B, Hs, Wsz, C, ws, shift, eps, nullptr, a1.hi,
                         a1.lo, st));
-      float* qkv = A.f32(RW * 3 * C);
-      RBA_TRY(F.lin(a1, C, RW, C, F.P(p + "attn.qkv.weight"), 3 * C, F.W(p + "attn.qkv.bias"), RBA_ACT_NONE, nullptr, qkv,
-                    3 * C));
       Planes ao = A.planes(RW * C);
-      RBA_RUN(window_attn(qkv, F.W(p + "attn.relative_position_bias_table"), B, Hs, Wsz, C, heads, ws, shift, ao.hi, ao.lo,
-                          st));
+      if (m->attn_backend == 1) {
+        Planes qkv = A.planes(RW * 3 * C);
+        RBA_TRY(F.lin(a1, C, RW, C, F.P(p + "attn.qkv.weight"), 3 * C, F.W(p + "attn.qkv.bias"), RBA_ACT_NONE, nullptr, nullptr, 0,
+                      qkv, 3 * C));
+        RBA_RUN(window_attn_planes(qkv.hi, qkv.lo, F.W(p + "attn.relative_position_bias_table"), B, Hs, Wsz, C, heads, ws, shift,
+                                   ao.hi, ao.lo, st));
+      } else {
+        float* qkv = A.f32(RW * 3 * C);
+        RBA_TRY(F.lin(a1, C, RW, C, F.P(p + "attn.qkv.weight"), 3 * C, F.W(p + "attn.qkv.bias"), RBA_ACT_NONE, nullptr, qkv,
+                      3 * C));
+        RBA_RUN(window_attn(qkv, F.W(p + "attn.relative_position_bias_table"), B, Hs, Wsz, C, heads, ws, shift, ao.hi, ao.lo,
+                            st));
+      }
       {  // x = shortcut + window_reverse(proj(attn))  (swin.py:169,277-292): scatter epilogue, in place
         rba_gemm_args ga;
         memset(&ga, 0, sizeof(ga));

@@ -167,6 +167,17 @@ def window_attn(qkv, bias_table, B, H, W, C, heads, ws, shift):
     return hi, lo
 
 
+def window_attn_planes(qkv, bias_table, B, H, W, C, heads, ws, shift):
+    """Tensor-core window attention; qkv = (hi, lo) planes [rows, 3C]."""
+    q_hi, q_lo = qkv
+    _chk_cuda(q_hi, q_lo, bias_table)
+    rows = q_hi.shape[0]
+    hi = torch.empty((rows, C), dtype=torch.bfloat16, device=q_hi.device)
+    lo = torch.empty((rows, C), dtype=torch.bfloat16, device=q_hi.device)
+    _lib.check(_lib.lib().rba_k_window_attn_planes(_p(q_hi), _p(q_lo), _p(bias_table), B, H, W, C, heads, ws, shift, _p(hi), _p(lo), _stream()))
+    return hi, lo
+
+
 def mha(q, k, v, mask, heads):
     """q (B,Lq,E), k/v (B,Lk,E) fp32 projected; mask (B,Lq,Lk) uint8 (1 = blocked) or None -> planes (B*Lq, E)."""
     _chk_cuda(q, k, v, mask)

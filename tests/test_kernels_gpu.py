@@ -371,3 +371,27 @@ def test_conv3x3_tc(dev, H, W):
     ref = F.conv2d(xv.permute(0, 3, 1, 2).double(), wv.double(), padding=1).permute(0, 2, 3, 1).float()
     y = ops.conv3x3(xp, wp, backend=ops.RBA_GEMM_TC)
     assert (y.cpu() - ref).abs().max() < TC_TOL * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("H,W,shift", [(24, 24, 0), (30, 41, 6), (12, 12, 6)])
+def test_window_attention_tensor_core(dev, H, W, shift):
+    """swin.py:145-168 with q/k/v as split planes, both contractions on mma.sync (bf16x3)."""
+    B, heads, ws = 2, 2, 12
+    C = heads * 32
+    nWh, nWw = -(-H // ws), -(-W // ws)
+    nW = nWh * nWw
+    g = torch.Generator().manual_seed(18)
+    qkv = torch.randn(B * nW, ws * ws, 3 * C, generator=g) * 1.5
+    table = torch.randn((2 * ws - 1) ** 2, heads, generator=g)
+    qp, qv = planes(qkv.view(-1, 3 * C), dev)
+    qkv = qv.view(B * nW, ws * ws, 3 * C)
+    q, k, v = qkv.reshape(B * nW, ws * ws, 3, heads, 32).permute(2, 0, 3, 1, 4)
+    attn = (q * 32 ** -0.5) @ k.transpose(-2, -1)
+    idx = O.relative_position_index(ws)
+    attn = attn + table[idx.view(-1)].view(ws * ws, ws * ws, -1).permute(2, 0, 1).unsqueeze(0)
+    if shift:
+        mask = O.shift_attn_mask(H, W, ws, shift)
+        attn = (attn.view(B, nW, heads, ws * ws, ws * ws) + mask.unsqueeze(1).unsqueeze(0)).view(-1, heads, ws * ws, ws * ws)
+    ref = (attn.softmax(-1) @ v).transpose(1, 2).reshape(B * nW * ws * ws, C)
+    out = ops.window_attn_planes(qp, table.to(dev), B, H, W, C, heads, ws, shift)
+    assert (unplanes(out) - ref).abs().max() < 3e-4

@@ -19,7 +19,9 @@ def test_oracle_matches_reference_golden(name):
     sd = weights.init_state_dict(mc, seed=case["seed"], perturb=case["perturb"])
     assert abs(state_checksum(sd) - fix["state_checksum"]) <= 1e-6 * fix["state_checksum"], "weight RNG drifted"
     torch.set_num_threads(max(1, min(8, torch.get_num_threads())))
-    out = O.forward(sd, mc, case_images(case))
+    out = O.forward(sd, mc, case_images(case), want_taps=True)
+    # the case is well conditioned: no boolean attention-mask decision sits within 1e-3 of its threshold
+    assert fix["am_margin"] >= 1e-3 and abs(out["taps"]["am_margin"] - fix["am_margin"]) < 1e-4
     assert (out["pred_logits"] - fix["pred_logits"]).abs().max() < ORACLE_TOL
     assert (out["pred_masks"] - fix["pred_masks"]).abs().max() < ORACLE_TOL
     sem = torch.stack(out["sem_seg"])
