@@ -131,6 +131,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  __nv_bfloat16 ha, la, hb, lb;
+  split2(a, ha, la);
+  split2(b, hb, lb);
+  hi = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+  lo = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -140,15 +147,15 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // (CTAs running at the same time share A rows and all of W through L2).  The smem ring runs continuously across
 // tiles; the accumulator is double buffered in TMEM (2 x BN fp32 columns) so the epilogue of tile i overlaps the
 // loads and MMAs of tile i+1.
-constexpr int TC_EPI_WARPS = 8;                         // 2 warps per TMEM lane quadrant, each takes BN/2 columns
-constexpr int TC_THREADS2 = (2 + TC_EPI_WARPS) * 32;    // 320
+constexpr int TC_EPI_WARPS = 16;                        // 4 warps per TMEM lane quadrant, each takes 32 columns
+constexpr int TC_THREADS2 = (2 + TC_EPI_WARPS) * 32;    // 576
 
 template <int BN>
 struct TcSmem {
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;      // one plane of A per stage (16 KB)
   static constexpr int W_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
-  static constexpr int BIAS_BYTES = TC_EPI_WARPS * (BN / 2) * 4;
+  static constexpr int BIAS_BYTES = TC_EPI_WARPS * 32 * 4;
   static constexpr int TOTAL = TC_STAGES * STAGE_BYTES + BIAS_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
@@ -197,7 +204,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmW_hi); prefetch_tmap(&tmW_lo);
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], TC_EPI_WARPS); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], (BN / 32) * 4); }   // one arrival per active epilogue warp
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -267,98 +274,114 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
     }
   } else {
-    // ===================== epilogue: warps 2..9; TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4 =====
+    // ===================== epilogue: warps 2..17; TMEM lane quadrant = warp % 4, 32-column group = (warp - 2) / 4 =====
+    // Each warp owns a 32-row x 32-column block of every tile.  Everything that does not depend on the accumulator
+    // (output row, bias slice, residual row segment) is fetched BEFORE waiting on acc_full so that global latency
+    // overlaps the MMAs of the tile; the TMEM buffer is released right after the single tcgen05.ld.
     const int ew = warp - 2;
-    const int quad = warp & 3, half = ew >> 2;
-    constexpr int HC = BN / 2;                            // columns per warp
-    float* mybias = sbias + ew * HC;
-    const int row_in_tile = quad * 32 + lane;
-    uint32_t lt = 0;
-    for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++lt) {
-      const TileCoord tc = tile_coord<BN, CONV>(p, t);
-      const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
-      const int bz = tc.bz;
-      const int nbase = tc.n0 + half * HC;
-      int64_t orow = -1;                                  // output row (or -1: nothing to store)
-      const int m_logical = tc.m0 + row_in_tile;
-      if (CONV) {
-        const int hh = tc.cvh0 + row_in_tile / TC_CONV_TW, ww = tc.cvw0 + row_in_tile % TC_CONV_TW;
-        if (hh < p.cH && ww < p.cW) orow = ((int64_t)tc.cvb * p.cH + hh) * p.cW + ww;
-      } else if (m_logical < p.M) {
-        orow = m_logical;
-        if (p.swin_map) orow = swin_row_to_token(p.geom, m_logical);
-      }
-      const float* bias = p.bias ? p.bias + bz * p.bias_bs : nullptr;
-      float* c = p.c ? p.c + bz * p.c_bs : nullptr;
-      const int64_t ldr = p.c ? p.ldc : p.ldcp;
-      const float* res = p.residual ? p.residual + bz * (p.c ? p.c_bs : p.cp_bs) : nullptr;
-      uint16_t* c_hi = p.c_hi ? p.c_hi + bz * p.cp_bs : nullptr;
-      uint16_t* c_lo = p.c_lo ? p.c_lo + bz * p.cp_bs : nullptr;
-      const bool vec_c = (p.ldc & 3) == 0, vec_p = (p.ldcp & 3) == 0, vec_r = (ldr & 3) == 0;
-      // stage this warp's slice of the column bias while the MMAs of this tile are still running
-      float brow = 0.f;
-      if (bias) {
-        if (p.bias_per_row) {
-          if (orow >= 0 && !CONV) brow = bias[m_logical];
-        } else {
-          __syncwarp();
-          for (int j = lane; j < HC; j += 32) mybias[j] = (nbase + j < p.N) ? bias[nbase + j] : 0.f;
-          __syncwarp();
+    const int quad = warp & 3, cg = ew >> 2;
+    if (cg * 32 < BN) {
+      float* mybias = sbias + ew * 32;
+      const int row_in_tile = quad * 32 + lane;
+      uint32_t lt = 0;
+      for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++lt) {
+        const TileCoord tc = tile_coord<BN, CONV>(p, t);
+        const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
+        const int bz = tc.bz;
+        const int nb = tc.n0 + cg * 32;                     // first column of this warp's block
+        int64_t orow = -1;                                  // output row (or -1: nothing to store)
+        const int m_logical = tc.m0 + row_in_tile;
+        if (CONV) {
+          const int hh = tc.cvh0 + row_in_tile / TC_CONV_TW, ww = tc.cvw0 + row_in_tile % TC_CONV_TW;
+          if (hh < p.cH && ww < p.cW) orow = ((int64_t)tc.cvb * p.cH + hh) * p.cW + ww;
+        } else if (m_logical < p.M) {
+          orow = m_logical;
+          if (p.swin_map) orow = swin_row_to_token(p.geom, m_logical);
         }
-      }
-      mbar_wait(&acc_full[as], aph);
-      tc_fence_after();
-#pragma unroll 1
-      for (int cb = 0; cb < HC / 32; ++cb) {
+        const float* bias = p.bias ? p.bias + bz * p.bias_bs : nullptr;
+        float* c = p.c ? p.c + bz * p.c_bs : nullptr;
+        const int64_t ldr = p.c ? p.ldc : p.ldcp;
+        const float* res = p.residual ? p.residual + bz * (p.c ? p.c_bs : p.cp_bs) : nullptr;
+        uint16_t* c_hi = p.c_hi ? p.c_hi + bz * p.cp_bs : nullptr;
+        uint16_t* c_lo = p.c_lo ? p.c_lo + bz * p.cp_bs : nullptr;
+        const bool active = orow >= 0 && nb < p.N;
+        const bool full32 = nb + 31 < p.N;
+        // ---- prefetch (independent of the accumulator) ----
+        float brow = 0.f;
+        if (bias) {
+          if (p.bias_per_row) {
+            if (orow >= 0 && !CONV) brow = bias[m_logical];
+          } else {
+            __syncwarp();
+            mybias[lane] = (nb + lane < p.N) ? bias[nb + lane] : 0.f;
+            __syncwarp();
+          }
+        }
+        float4 r4[8];
+        const bool res_vec = res && active && full32 && ((ldr & 3) == 0);
+        if (res_vec) {
+          const float4* rp = reinterpret_cast<const float4*>(res + orow * ldr + nb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r4[j] = rp[j];
+        }
+        // ---- accumulator ----
+        __syncwarp();
+        mbar_wait(&acc_full[as], aph);
+        tc_fence_after();
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + half * HC + cb * 32), v);
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + cg * 32), v);
         tmem_ld_wait();
-        if (cb == HC / 32 - 1) {                          // all of this warp's TMEM reads for the tile are done
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[as]);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[as]);         // this warp is done with the TMEM buffer
+        if (active) {
+        float x[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float t0 = __uint_as_float(v[j]);
+          if (bias) t0 += p.bias_per_row ? brow : mybias[j];
+          x[j] = apply_act_rt(t0, p.act);
         }
-        const int nb = nbase + cb * 32;
-        if (orow < 0 || nb >= p.N) continue;
+        if (res_vec) {
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const int n = nb + j4 * 4;
-          if (n >= p.N) break;
-          float tt[4];
+          for (int j = 0; j < 8; ++j) { x[4 * j] += r4[j].x; x[4 * j + 1] += r4[j].y; x[4 * j + 2] += r4[j].z; x[4 * j + 3] += r4[j].w; }
+        } else if (res) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float x = __uint_as_float(v[j4 * 4 + j]);
-            if (bias) x += p.bias_per_row ? brow : mybias[cb * 32 + j4 * 4 + j];
-            tt[j] = apply_act_rt(x, p.act);
-          }
-          const bool fullv = n + 3 < p.N;
-          if (res) {
-            if (fullv && vec_r) {
-              float4 r4 = *reinterpret_cast<const float4*>(res + orow * ldr + n);
-              tt[0] += r4.x; tt[1] += r4.y; tt[2] += r4.z; tt[3] += r4.w;
-            } else {
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < p.N) x[j] += res[orow * ldr + nb + j];
+        }
+        if (c) {
+          float* cp = c + orow * p.ldc + nb;
+          if (full32 && (p.ldc & 3) == 0) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (n + j < p.N) tt[j] += res[orow * ldr + n + j];
-            }
-          }
-          if (c) {
-            if (fullv && vec_c) *reinterpret_cast<float4*>(c + orow * p.ldc + n) = make_float4(tt[0], tt[1], tt[2], tt[3]);
-            else {
+            for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(cp)[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+          } else {
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (n + j < p.N) c[orow * p.ldc + n + j] = tt[j];
-            }
-          }
-          if (c_hi) {
-            if (fullv && vec_p) store_split4(c_hi, c_lo, orow * p.ldcp + n, tt[0], tt[1], tt[2], tt[3]);
-            else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (n + j < p.N) store_split1(c_hi, c_lo, orow * p.ldcp + n + j, tt[j]);
-            }
+            for (int j = 0; j < 32; ++j)
+              if (nb + j < p.N) cp[j] = x[j];
           }
         }
+        if (c_hi) {
+          const int64_t ob = orow * p.ldcp + nb;
+          if (full32 && (p.ldcp & 7) == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {                   // 8 columns -> one 16-byte store per plane
+              uint4 H, L;
+              split_pack2(x[8 * j], x[8 * j + 1], H.x, L.x);
+              split_pack2(x[8 * j + 2], x[8 * j + 3], H.y, L.y);
+              split_pack2(x[8 * j + 4], x[8 * j + 5], H.z, L.z);
+              split_pack2(x[8 * j + 6], x[8 * j + 7], H.w, L.w);
+              *reinterpret_cast<uint4*>(c_hi + ob + 8 * j) = H;
+              *reinterpret_cast<uint4*>(c_lo + ob + 8 * j) = L;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nb + j < p.N) store_split1(c_hi, c_lo, ob + j, x[j]);
+          }
+        }
+        }  // active
+        __syncwarp();                                       // reconverge before the next tile's .aligned TMEM ops
       }
     }
     tc_fence_before();
