@@ -275,7 +275,7 @@ def run_ours(args):
         peaks = json.load(open(pk))
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    roofline = {"kernel": "rba_score_kernel<19> (x4 bilinear + sigmoid + (Q,K) contraction + tanh + sum)", "bound": "hbm",
+    roofline = {"kernel": "rba_score_mma_kernel<19> (x4 bilinear + sigmoid + (Q,K) contraction on mma.sync fp16 hi/lo + tanh + sum)", "bound": "hbm",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst, kernel timed alone)" if peaks else "fallback 6.65 TB/s",
                 "traffic": None, "ms_per_launch": k_ms, "algorithmic_bytes_per_launch": alg_bytes,

@@ -26,7 +26,7 @@
 
 namespace rba {
 
-constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 3;
+constexpr int TC_BM = 128, TC_BK = 64;
 constexpr int TC_CONV_TH = 8, TC_CONV_TW = 16;   // conv M tile = 8 x 16 output pixels
 
 struct TcParams {
@@ -152,11 +152,13 @@ constexpr int TC_THREADS2 = (2 + TC_EPI_WARPS) * 32;    // 576
 
 template <int BN>
 struct TcSmem {
+  static constexpr int STAGES = BN > 128 ? 2 : 3;        // 96 KB stages for BN = 256, 64 KB (48 KB) otherwise
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;      // one plane of A per stage (16 KB)
   static constexpr int W_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
-  static constexpr int BIAS_BYTES = TC_EPI_WARPS * 32 * 4;
-  static constexpr int TOTAL = TC_STAGES * STAGE_BYTES + BIAS_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int NG = BN > 128 ? BN / 128 : 1;     // 128-column groups per tile (epilogue passes)
+  static constexpr int BIAS_BYTES = TC_EPI_WARPS * 32 * NG * 4;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BIAS_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
 struct TileCoord {
@@ -188,6 +190,7 @@ __global__ void __launch_bounds__(TC_THREADS2, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, const TcParams p) {
   using S = TcSmem<BN>;
+  constexpr int TC_STAGES = S::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* sbias = reinterpret_cast<float*>(smem + TC_STAGES * S::STAGE_BYTES);
@@ -204,7 +207,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmW_hi); prefetch_tmap(&tmW_lo);
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], (BN / 32) * 4); }   // one arrival per active epilogue warp
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], (BN >= 128 ? 4 : BN / 32) * 4); }   // one arrival per active epilogue warp
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -281,14 +284,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int ew = warp - 2;
     const int quad = warp & 3, cg = ew >> 2;
     if (cg * 32 < BN) {
-      float* mybias = sbias + ew * 32;
+      constexpr int NG = S::NG;
+      float* mybias = sbias + ew * 32 * NG;
       const int row_in_tile = quad * 32 + lane;
       uint32_t lt = 0;
       for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++lt) {
         const TileCoord tc = tile_coord<BN, CONV>(p, t);
         const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
         const int bz = tc.bz;
-        const int nb = tc.n0 + cg * 32;                     // first column of this warp's block
         int64_t orow = -1;                                  // output row (or -1: nothing to store)
         const int m_logical = tc.m0 + row_in_tile;
         if (CONV) {
@@ -304,19 +307,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const float* res = p.residual ? p.residual + bz * (p.c ? p.c_bs : p.cp_bs) : nullptr;
         uint16_t* c_hi = p.c_hi ? p.c_hi + bz * p.cp_bs : nullptr;
         uint16_t* c_lo = p.c_lo ? p.c_lo + bz * p.cp_bs : nullptr;
-        const bool active = orow >= 0 && nb < p.N;
-        const bool full32 = nb + 31 < p.N;
-        // ---- prefetch (independent of the accumulator) ----
         float brow = 0.f;
         if (bias) {
           if (p.bias_per_row) {
             if (orow >= 0 && !CONV) brow = bias[m_logical];
           } else {
             __syncwarp();
-            mybias[lane] = (nb + lane < p.N) ? bias[nb + lane] : 0.f;
+#pragma unroll
+            for (int g2 = 0; g2 < NG; ++g2) {
+              const int n = tc.n0 + g2 * 128 + cg * 32 + lane;
+              mybias[g2 * 32 + lane] = (n < p.N) ? bias[n] : 0.f;
+            }
             __syncwarp();
           }
         }
+#pragma unroll 1
+        for (int g2 = 0; g2 < NG; ++g2) {
+        const int nb = tc.n0 + g2 * 128 + cg * 32;          // first column of this warp's block
+        const bool active = orow >= 0 && nb < p.N;
+        const bool full32 = nb + 31 < p.N;
+        // ---- prefetch (independent of the accumulator) ----
         float4 r4[8];
         const bool res_vec = res && active && full32 && ((ldr & 3) == 0);
         if (res_vec) {
@@ -326,20 +336,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
         // ---- accumulator ----
         __syncwarp();
-        mbar_wait(&acc_full[as], aph);
-        tc_fence_after();
+        if (g2 == 0) {
+          mbar_wait(&acc_full[as], aph);
+          tc_fence_after();
+        }
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + cg * 32), v);
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + g2 * 128 + cg * 32), v);
         tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[as]);         // this warp is done with the TMEM buffer
+        if (g2 == NG - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[as]);       // this warp is done with the TMEM buffer
+        }
         if (active) {
         float x[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           float t0 = __uint_as_float(v[j]);
-          if (bias) t0 += p.bias_per_row ? brow : mybias[j];
+          if (bias) t0 += p.bias_per_row ? brow : mybias[g2 * 32 + j];
           x[j] = apply_act_rt(t0, p.act);
         }
         if (res_vec) {
@@ -381,7 +395,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           }
         }
         }  // active
-        __syncwarp();                                       // reconverge before the next tile's .aligned TMEM ops
+        __syncwarp();                                       // reconverge before the next .aligned TMEM op
+        }  // g2
       }
     }
     tc_fence_before();
@@ -442,6 +457,8 @@ static int make_map_nhwc(CUtensorMap* m, const uint16_t* ptr, int B, int H, int 
   return RBA_OK;
 }
 
+static const bool g_tc_bn256 = []() { const char* e = getenv("RBA_TC_BN256"); return !(e && e[0] == '0'); }();
+
 static int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -486,7 +503,8 @@ int gemm_tc_launch(const rba_gemm_args& a, cudaStream_t st) {
   fill_epilogue(p, a);
   p.a_batched = a.batch > 1 && a.a_bstride != 0;
   p.w_batched = a.batch > 1 && a.w_bstride != 0;
-  const int BN = a.N > 64 ? 128 : 64;
+  int BN = a.N > 64 ? 128 : 64;
+  if (a.N % 256 == 0 && g_tc_bn256) BN = 256;
   CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
   RBA_TRY_(make_map_3d(&ta_hi, a.a_hi, a.K, a.M, a.lda, p.a_batched ? a.batch : 1, a.a_bstride, TC_BM));
   RBA_TRY_(make_map_3d(&ta_lo, a.a_lo, a.K, a.M, a.lda, p.a_batched ? a.batch : 1, a.a_bstride, TC_BM));
@@ -497,6 +515,7 @@ int gemm_tc_launch(const rba_gemm_args& a, cudaStream_t st) {
   RBA_CHECK(nt < (1LL << 31), "gemm(tc): too many tiles");
   p.ntiles = (int)nt;
   dim3 grid((unsigned)std::min<int64_t>(nt, num_sms()));
+  if (BN == 256) return launch_tc<256, false>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
   if (BN == 128) return launch_tc<128, false>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
   return launch_tc<64, false>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
 }

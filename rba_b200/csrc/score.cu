@@ -13,6 +13,8 @@
 // (4 rows x 34 cols per query) is staged through shared memory with cp.async, double buffered over
 // chunks of QC queries.  Class probabilities (Q x K, padded to 20 floats/row) live in shared memory and
 // are read as broadcast float4s.  Accumulators: 4 pixels x K classes per thread in registers.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace rba {
@@ -207,6 +209,200 @@ rba_score_kernel(const float* __restrict__ masks, const float* __restrict__ logi
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tensor-core variant: the (Q x K) contraction runs on mma.sync (m16n8k16, fp16 hi/lo split = fp32-class accuracy:
+// sigma = s_hi + s_lo, p = p_hi + p_lo, products s_hi*p_hi + s_hi*p_lo + s_lo*p_hi, fp32 accumulate), which frees the
+// FMA pipe: what remains per (pixel, query) is the bilinear tap combination, two MUFU ops (ex2, rcp) and the fp16
+// split.  The sigma values are produced directly in the A-fragment layout (no shared-memory staging of the operand):
+// MMA row g <-> pixel (x0+g, y), row g+8 <-> pixel (x0+g, y+1) — two vertically adjacent pixels that share all four
+// low-resolution taps — and the k index is the query.  Class probabilities (B operand, [K pad 24] x [Q pad 112]) live in
+// registers for the whole CTA.  CTA = 4 output rows x 128 columns, 8 warps = 2 row pairs x 4 column groups of 32 px.
+// ------------------------------------------------------------------------------------------------
+constexpr int SM_KS = 7;                    // k16 steps: Q padded to 112
+constexpr int SM_QP = SM_KS * 16;
+constexpr int SM_NT = 3;                    // n8 tiles: K padded to 24
+constexpr int SM_QS = 120;                  // shared-memory pitch (words) of one query row: = 24 mod 32, so the 8-word
+                                            // spans read by the 4 lanes of a quad never collide across quads
+constexpr int SM_PR = 3, SM_PC = 34;        // patch rows / columns per CTA
+constexpr int SM_TW = 128, SM_TH = 4;
+constexpr int SM_PS = 122;                  // patch pitch (words) per (row, col): even (8-byte loads), = 26 mod 32 so the
+                                            // column-major staging writes are at most 2-way conflicted
+constexpr int SM_PATCH_WORDS = SM_PR * SM_PC * SM_PS;       // patch [row][col][query] fp32
+constexpr int SM_B_WORDS = 24 * SM_QS;                      // probabilities [class][query pair]{hi.x2, lo.x2} (2 words/pair)
+
+__device__ __forceinline__ uint32_t pack_f16x2(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
+__device__ __forceinline__ void split_f16x2(float e0, float e1, uint32_t& hi, uint32_t& lo) {
+  hi = pack_f16x2(e0, e1);
+  const __half2 h = *reinterpret_cast<const __half2*>(&hi);
+  const float2 f = __half22float2(h);
+  lo = pack_f16x2(e0 - f.x, e1 - f.y);
+}
+__device__ __forceinline__ void mma_f16(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int K, bool WRITE_SEM>
+__global__ void __launch_bounds__(256, 3)
+rba_score_mma_kernel(const float* __restrict__ masks, const float* __restrict__ logits, int Q, int h, int w, int H, int W,
+                     float* __restrict__ rba, float* __restrict__ sem) {
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  float* sPatch = reinterpret_cast<float*>(sm_raw);                       // [3][34][SM_PS]: query innermost
+  uint32_t* sB = reinterpret_cast<uint32_t*>(sm_raw) + SM_PATCH_WORDS;    // [24][SM_QS]: word 2*(q/2) = hi pair, +1 = lo pair
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  const int b = blockIdx.z;
+  const int X0 = blockIdx.x * SM_TW, Y0 = blockIdx.y * SM_TH;
+  const int lx0 = X0 / 4 - 1, ly0 = Y0 / 4 - 1;
+  const float* mb = masks + (size_t)b * Q * h * w;
+
+  // ---- stage the low-res patch transposed to [row][col][query] (padded queries read as 0) ----
+  for (int e = tid; e < SM_QP * SM_PR * SM_PC; e += 256) {
+    const int pc = e % SM_PC;
+    const int t = e / SM_PC;
+    const int pr = t % SM_PR, q = t / SM_PR;
+    float* dst = sPatch + (pr * SM_PC + pc) * SM_PS + q;
+    if (q < Q) {
+      const int gy = min(max(ly0 + pr, 0), h - 1), gx = min(max(lx0 + pc, 0), w - 1);
+      cp_async4(dst, mb + ((size_t)q * h + gy) * w + gx);
+    } else {
+      *dst = 0.f;
+    }
+  }
+  cp_async_commit();
+  // ---- class probabilities -> fp16 hi/lo pairs, [class][query pair] ----
+  for (int e = tid; e < SM_B_WORDS; e += 256) sB[e] = 0u;
+  __syncthreads();
+  for (int q = tid; q < Q; q += 256) {
+    const float* lg = logits + ((size_t)b * Q + q) * (K + 1);
+    float m = lg[0];
+#pragma unroll
+    for (int c = 1; c <= K; ++c) m = fmaxf(m, lg[c]);
+    float e[K + 1];
+    float ssum = 0.f;
+#pragma unroll
+    for (int c = 0; c <= K; ++c) { e[c] = expf(lg[c] - m); ssum += e[c]; }
+    const float inv = 1.0f / ssum;
+    __half* sBh = reinterpret_cast<__half*>(sB);
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      const float pv = e[c] * inv;
+      const __half hh = __float2half_rn(pv);
+      // halves of class row c: pair p = q/2 occupies halves [4p .. 4p+3] = {hi(q even), hi(q odd), lo(even), lo(odd)}
+      const int base = (c * SM_QS + (q >> 1) * 2) * 2 + (q & 1);
+      sBh[base] = hh;
+      sBh[base + 2] = __float2half_rn(pv - __half2float(hh));
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+
+  // ---- per-warp geometry ----
+  const int rp = warp >> 2, xg = warp & 3;
+  const int y = Y0 + 2 * rp;                              // rows y, y+1 share their two low-res rows
+  int iy0, iyb; float l1a, l1b;
+  up4_coeff(y, iy0, l1a);
+  up4_coeff(y + 1, iyb, l1b);
+  const int prA = iy0 - ly0, prB = min(iy0 + 1, h - 1) - ly0;
+  // weights pre-multiplied by -log2(e): sigmoid(u) = 1 / (1 + 2^(-u log2 e))
+  const float NL2E = -1.4426950408889634f;
+  const float wyA0 = (1.f - l1a) * NL2E, wyA1 = l1a * NL2E;   // row y
+  const float wyB0 = (1.f - l1b) * NL2E, wyB1 = l1b * NL2E;   // row y + 1
+  const uint32_t* bbase = sB + g * SM_QS + tq * 2;             // + nt*8*SM_QS + ks*16 (+8)
+
+#pragma unroll 1
+  for (int ti = 0; ti < 4; ++ti) {
+    const int x = X0 + 32 * xg + 8 * ti + g;
+    int ix0; float lx1;
+    up4_coeff(min(x, 4 * w - 1), ix0, lx1);
+    ix0 = min(ix0, w - 1);
+    const float wx0 = 1.f - lx1, wx1 = lx1;
+    const int pcA = ix0 - lx0, pcB = min(ix0 + 1, w - 1) - lx0;
+    // the four taps of this pixel pair, query-contiguous rows
+    const float* t00 = sPatch + (prA * SM_PC + pcA) * SM_PS + tq * 2;
+    const float* t01 = sPatch + (prA * SM_PC + pcB) * SM_PS + tq * 2;
+    const float* t10 = sPatch + (prB * SM_PC + pcA) * SM_PS + tq * 2;
+    const float* t11 = sPatch + (prB * SM_PC + pcB) * SM_PS + tq * 2;
+    float acc[SM_NT][4];
+#pragma unroll
+    for (int nt = 0; nt < SM_NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll 1
+    for (int ks = 0; ks < SM_KS; ++ks) {
+      uint32_t ah[4], al[4];
+#pragma unroll
+      for (int hq = 0; hq < 2; ++hq) {                    // queries 16ks + 2t + {0,1} (+8 for hq = 1)
+        const int qo = ks * 16 + hq * 8;
+        const float2 a = *reinterpret_cast<const float2*>(t00 + qo);
+        const float2 bq = *reinterpret_cast<const float2*>(t01 + qo);
+        const float2 c = *reinterpret_cast<const float2*>(t10 + qo);
+        const float2 d = *reinterpret_cast<const float2*>(t11 + qo);
+        const float h0x = wx0 * a.x + wx1 * bq.x, h0y = wx0 * a.y + wx1 * bq.y;
+        const float h1x = wx0 * c.x + wx1 * d.x, h1y = wx0 * c.y + wx1 * d.y;
+        const float sAx = fast_rcp(1.0f + fast_ex2(wyA0 * h0x + wyA1 * h1x));   // row y
+        const float sAy = fast_rcp(1.0f + fast_ex2(wyA0 * h0y + wyA1 * h1y));
+        const float sBx = fast_rcp(1.0f + fast_ex2(wyB0 * h0x + wyB1 * h1x));   // row y + 1
+        const float sBy = fast_rcp(1.0f + fast_ex2(wyB0 * h0y + wyB1 * h1y));
+        split_f16x2(sAx, sAy, ah[2 * hq], al[2 * hq]);             // MMA row g
+        split_f16x2(sBx, sBy, ah[2 * hq + 1], al[2 * hq + 1]);     // MMA row g + 8
+      }
+#pragma unroll
+      for (int nt = 0; nt < SM_NT; ++nt) {
+        const uint2 b0 = *reinterpret_cast<const uint2*>(bbase + nt * 8 * SM_QS + ks * 16);       // {hi, lo} of k = 2t, 2t+1
+        const uint2 b1 = *reinterpret_cast<const uint2*>(bbase + nt * 8 * SM_QS + ks * 16 + 8);   // k = 2t+8, 2t+9
+        mma_f16(acc[nt], ah, b0.x, b1.x);
+        mma_f16(acc[nt], ah, b0.y, b1.y);
+        mma_f16(acc[nt], al, b0.x, b1.x);
+      }
+    }
+    // ---- epilogue: acc[nt][j] = sem_seg[class 8nt+2t+j] of pixel (x, y); acc[nt][2+j] of pixel (x, y+1) ----
+    float ra = 0.f, rb = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < SM_NT; ++nt)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = nt * 8 + tq * 2 + j;
+        if (c < K) {
+          ra += fast_tanh_pos(acc[nt][j]);
+          rb += fast_tanh_pos(acc[nt][2 + j]);
+          if (WRITE_SEM && x < W) {
+            if (y < H) sem[(((size_t)b * K + c) * H + y) * W + x] = acc[nt][j];
+            if (y + 1 < H) sem[(((size_t)b * K + c) * H + y + 1) * W + x] = acc[nt][2 + j];
+          }
+        }
+      }
+    ra += __shfl_xor_sync(0xffffffffu, ra, 1);
+    ra += __shfl_xor_sync(0xffffffffu, ra, 2);
+    rb += __shfl_xor_sync(0xffffffffu, rb, 1);
+    rb += __shfl_xor_sync(0xffffffffu, rb, 2);
+    if (x < W) {
+      if (tq == 0 && y < H) rba[((size_t)b * H + y) * W + x] = -ra;
+      if (tq == 1 && y + 1 < H) rba[((size_t)b * H + y + 1) * W + x] = -rb;
+    }
+  }
+}
+
+template <int K>
+static int launch_score_mma(const float* masks, const float* logits, int B, int Q, int h, int w, int H, int W, float* rba,
+                            float* sem, cudaStream_t st) {
+  dim3 grid((unsigned)cdiv(4 * w, SM_TW), (unsigned)cdiv(4 * h, SM_TH), (unsigned)B);
+  const size_t smem = (size_t)(SM_PATCH_WORDS + SM_B_WORDS) * 4;
+  if (sem) {
+    RBA_CUDA(cudaFuncSetAttribute(rba_score_mma_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rba_score_mma_kernel<K, true><<<grid, 256, smem, st>>>(masks, logits, Q, h, w, H, W, rba, sem);
+  } else {
+    RBA_CUDA(cudaFuncSetAttribute(rba_score_mma_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rba_score_mma_kernel<K, false><<<grid, 256, smem, st>>>(masks, logits, Q, h, w, H, W, rba, sem);
+  }
+  RBA_LAUNCHED();
+  return RBA_OK;
+}
+
 template <int K>
 static int launch_score(const float* masks, const float* logits, int B, int Q, int h, int w, int H, int W, float* rba,
                         float* sem, cudaStream_t st) {
@@ -234,6 +430,9 @@ extern "C" int rba_score_fused(const float* pred_masks, const float* pred_logits
   RBA_CHECK(H > 0 && W > 0 && H <= 4 * h && W <= 4 * w, "rba_score_fused: output (%d,%d) exceeds 4x(%d,%d)", H, W, h, w);
   RBA_CHECK(Q <= 2048, "rba_score_fused: Q=%d too large", Q);
   cudaStream_t st = (cudaStream_t)stream;
+  static const bool use_mma = []() { const char* e = getenv("RBA_SCORE_MMA"); return !(e && e[0] == '0'); }();
+  if (use_mma && K == 19 && Q > SM_QP - 16 && Q <= SM_QP)      // tensor-core path: Q padded to 112 (100 queries)
+    return launch_score_mma<19>(pred_masks, pred_logits, B, Q, h, w, H, W, rba_out, sem_seg, st);
   switch (K) {
     case 19: return launch_score<19>(pred_masks, pred_logits, B, Q, h, w, H, W, rba_out, sem_seg, st);
     case 13: return launch_score<13>(pred_masks, pred_logits, B, Q, h, w, H, W, rba_out, sem_seg, st);  // StreetHazards

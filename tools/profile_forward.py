@@ -29,12 +29,19 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
     eng.forward_into(img, out)
     torch.cuda.synchronize()
 tot = defaultdict(lambda: [0, 0.0])
+seq = []
 for ev in prof.events():
     if ev.device_type == torch.autograd.DeviceType.CUDA:
         name = ev.name.split("(")[0][:80]
+        seq.append((ev.time_range.start, name, ev.device_time_total if hasattr(ev, "device_time_total") else ev.cuda_time_total))
         tot[name][0] += 1
         tot[name][1] += ev.device_time_total if hasattr(ev, "device_time_total") else ev.cuda_time_total
 total = sum(v[1] for v in tot.values())
 print(f"batch {a.batch} {a.height}x{a.width} backend {a.backend}: total kernel time {total/1e3:.2f} ms = {total/1e3/a.batch:.2f} ms/img")
 for name, (n, us) in sorted(tot.items(), key=lambda kv: -kv[1][1])[:30]:
     print(f"{name:80s} {n:6d} {us/1e3:10.3f} ms {100*us/total:6.2f}%")
+
+if os.environ.get("RBA_PROFILE_SEQ"):
+    print("--- launch sequence (us) ---")
+    for i, (t0, name, us) in enumerate(sorted(seq)):
+        print(f"{i:4d} {us:10.1f} {name[:60]}")
