@@ -204,20 +204,110 @@ __device__ __forceinline__ void split_pack2(float x, float y, uint32_t& hi, uint
   lo = (uint32_t)__bfloat16_as_ushort(lx) | ((uint32_t)__bfloat16_as_ushort(ly) << 16);
 }
 
-__global__ void __launch_bounds__(WM_THREADS, 1)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// One key chunk [NB0*8, (NB0+NBN)*8) of the online-softmax attention for this warp's 16 query rows.
+// m / l: running row max (log2 domain) and row sum for rows g and g+8; oacc: unnormalised output accumulators.
+template <int NB0, int NBN, bool MASK>
+__device__ __forceinline__ void wm_chunk(const uint16_t* sKh, const uint16_t* sKl, const uint16_t* sVh, const uint16_t* sVl,
+                                         const float* sB, const int* sCol, const uint32_t (&qh)[2][4],
+                                         const uint32_t (&ql)[2][4], int lane, int g, int tq, const int (&rterm)[2],
+                                         const int (&rid)[2], float scale2, float (&m)[2], float (&l)[2],
+                                         float (&oacc)[4][4]) {
+  static_assert(NBN % 2 == 0, "chunks are whole k16 steps");
+  float sacc[NBN][4];
+#pragma unroll
+  for (int nb = 0; nb < NBN; ++nb) {
+    sacc[nb][0] = sacc[nb][1] = sacc[nb][2] = sacc[nb][3] = 0.f;
+    uint32_t kh[4], kl[4];
+    const int krow = (NB0 + nb) * 8 + (lane & 7), kcol = (lane >> 3) * 8;
+    ldsm_x4(kh[0], kh[1], kh[2], kh[3], sKh + krow * WM_PITCH + kcol);
+    ldsm_x4(kl[0], kl[1], kl[2], kl[3], sKl + krow * WM_PITCH + kcol);
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      mma_bf16(sacc[nb], qh[ks], kh[2 * ks], kh[2 * ks + 1]);
+      mma_bf16(sacc[nb], qh[ks], kl[2 * ks], kl[2 * ks + 1]);
+      mma_bf16(sacc[nb], ql[ks], kh[2 * ks], kh[2 * ks + 1]);
+    }
+  }
+  // scale + relative position bias (+ shift mask), all in the log2 domain; online softmax update
+#pragma unroll
+  for (int hrow = 0; hrow < 2; ++hrow) {
+    float mx = m[hrow];
+#pragma unroll
+    for (int nb = 0; nb < NBN; ++nb)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int cinfo = sCol[(NB0 + nb) * 8 + tq * 2 + j];
+        float sv = fmaf(sacc[nb][hrow * 2 + j], scale2, sB[rterm[hrow] - (cinfo & 0xffff)]);
+        if (MASK && rid[hrow] != (cinfo >> 16)) sv += -100.0f * 1.4426950408889634f;
+        sacc[nb][hrow * 2 + j] = sv;
+        mx = fmaxf(mx, sv);
+      }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    const float alpha = ex2_approx(m[hrow] - mx);               // 0 on the first chunk (m = -inf)
+    float sum = 0.f;
+#pragma unroll
+    for (int nb = 0; nb < NBN; ++nb)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float e = ex2_approx(sacc[nb][hrow * 2 + j] - mx);
+        sacc[nb][hrow * 2 + j] = e;
+        sum += e;
+      }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    l[hrow] = l[hrow] * alpha + sum;
+    m[hrow] = mx;
+#pragma unroll
+    for (int nd = 0; nd < 4; ++nd) { oacc[nd][hrow * 2] *= alpha; oacc[nd][hrow * 2 + 1] *= alpha; }
+  }
+  // O += P v
+#pragma unroll
+  for (int kk = 0; kk < NBN / 2; ++kk) {
+    uint32_t ph[4], pl[4];
+    split_pack2(sacc[2 * kk][0], sacc[2 * kk][1], ph[0], pl[0]);          // row g,   keys 16kk + 2t, +1
+    split_pack2(sacc[2 * kk][2], sacc[2 * kk][3], ph[1], pl[1]);          // row g+8
+    split_pack2(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1], ph[2], pl[2]);  // row g,   keys 16kk + 8 + 2t, +1
+    split_pack2(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3], ph[3], pl[3]);  // row g+8
+    const int vrow = (NB0 / 2 + kk) * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {                                     // pairs of 8-wide d blocks
+      uint32_t vh[4], vl[4];
+      const int vcol = np * 16 + (lane >> 4) * 8;
+      ldsm_x4_t(vh[0], vh[1], vh[2], vh[3], sVh + vrow * WM_PITCH + vcol);
+      ldsm_x4_t(vl[0], vl[1], vl[2], vl[3], sVl + vrow * WM_PITCH + vcol);
+#pragma unroll
+      for (int q2 = 0; q2 < 2; ++q2) {
+        float* o = oacc[np * 2 + q2];
+        mma_bf16(o, ph, vh[2 * q2], vh[2 * q2 + 1]);
+        mma_bf16(o, ph, vl[2 * q2], vl[2 * q2 + 1]);
+        mma_bf16(o, pl, vh[2 * q2], vh[2 * q2 + 1]);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(WM_THREADS, 2)
 window_attn_mma_kernel(const uint16_t* __restrict__ qkv_hi, const uint16_t* __restrict__ qkv_lo,
                        const float* __restrict__ bias_table, int C, int heads, int nWh, int nWw, int shift, float scale,
                        uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo) {
   extern __shared__ __align__(16) uint8_t wm_smem[];
   // planes: 0 q_hi, 1 q_lo, 2 k_hi, 3 k_lo, 4 v_hi, 5 v_lo
   uint16_t* sOp = reinterpret_cast<uint16_t*>(wm_smem);
-  float* sB = reinterpret_cast<float*>(wm_smem + 6 * WM_PLANE * 2);     // [529] relative position bias of this head
+  float* sB = reinterpret_cast<float*>(wm_smem + 6 * WM_PLANE * 2);     // [529] relative position bias * log2(e)
   int* sCol = reinterpret_cast<int*>(sB + 532);                          // [144] (ci*23 + cj) | region << 16
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int head = blockIdx.y;
   const int64_t win = blockIdx.x;
   const int ww = (int)(win % nWw), wh = (int)((win / nWw) % nWh);
   const int Hp = nWh * WA_WS, Wp = nWw * WA_WS;
+  constexpr float LOG2E = 1.4426950408889634f;
 
   // ---- stage q/k/v planes: 144 rows x 64 B per operand plane ----
   {
@@ -233,7 +323,7 @@ window_attn_mma_kernel(const uint16_t* __restrict__ qkv_hi, const uint16_t* __re
     }
     asm volatile("cp.async.commit_group;" ::);
   }
-  for (int e = tid; e < 23 * 23; e += WM_THREADS) sB[e] = bias_table[(int64_t)e * heads + head];
+  for (int e = tid; e < 23 * 23; e += WM_THREADS) sB[e] = bias_table[(int64_t)e * heads + head] * LOG2E;
   for (int c = tid; c < WA_N; c += WM_THREADS) {
     const int ci = c / WA_WS, cj = c - ci * WA_WS;
     const int hs = wh * WA_WS + ci, wsx = ww * WA_WS + cj;
@@ -260,93 +350,39 @@ window_attn_mma_kernel(const uint16_t* __restrict__ qkv_hi, const uint16_t* __re
       ldsm_x4(ql[ks][0], ql[ks][1], ql[ks][2], ql[ks][3], sQl + row * WM_PITCH + ks * 16 + col);
     }
   }
-  // ---- S = q k^T (bf16x3) ----
-  float sacc[18][4];
-#pragma unroll
-  for (int nb = 0; nb < 18; ++nb) {
-    sacc[nb][0] = sacc[nb][1] = sacc[nb][2] = sacc[nb][3] = 0.f;
-    uint32_t kh[4], kl[4];
-    const int krow = nb * 8 + (lane & 7), kcol = (lane >> 3) * 8;
-    ldsm_x4(kh[0], kh[1], kh[2], kh[3], sKh + krow * WM_PITCH + kcol);
-    ldsm_x4(kl[0], kl[1], kl[2], kl[3], sKl + krow * WM_PITCH + kcol);
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-      mma_bf16(sacc[nb], qh[ks], kh[2 * ks], kh[2 * ks + 1]);
-      mma_bf16(sacc[nb], qh[ks], kl[2 * ks], kl[2 * ks + 1]);
-      mma_bf16(sacc[nb], ql[ks], kh[2 * ks], kh[2 * ks + 1]);
-    }
-  }
-  // ---- scale, relative position bias, shift mask, softmax (rows g and g+8 of this warp's 16) ----
-  float inv_sum[2];
+  int rterm[2], rid[2];
 #pragma unroll
   for (int hrow = 0; hrow < 2; ++hrow) {
     const int r = r0 + g + hrow * 8;
     const int ri = r / WA_WS, rj = r - ri * WA_WS;
-    const int rterm = ri * 23 + rj + (WA_WS - 1) * 23 + (WA_WS - 1);
+    rterm[hrow] = ri * 23 + rj + (WA_WS - 1) * 23 + (WA_WS - 1);
     const int hs = wh * WA_WS + ri, wsx = ww * WA_WS + rj;
-    const int rid = (hs < Hp - WA_WS ? 0 : (hs < Hp - shift ? 1 : 2)) * 3 + (wsx < Wp - WA_WS ? 0 : (wsx < Wp - shift ? 1 : 2));
-    float mx = -INFINITY;
-#pragma unroll
-    for (int nb = 0; nb < 18; ++nb)
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int cinfo = sCol[nb * 8 + tq * 2 + j];
-        float sv = sacc[nb][hrow * 2 + j] * scale + sB[rterm - (cinfo & 0xffff)];
-        if (shift > 0 && rid != (cinfo >> 16)) sv += -100.0f;
-        sacc[nb][hrow * 2 + j] = sv;
-        mx = fmaxf(mx, sv);
-      }
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-    float sum = 0.f;
-#pragma unroll
-    for (int nb = 0; nb < 18; ++nb)
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const float e = __expf(sacc[nb][hrow * 2 + j] - mx);
-        sacc[nb][hrow * 2 + j] = e;
-        sum += e;
-      }
-    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-    inv_sum[hrow] = 1.0f / sum;
+    rid[hrow] = (hs < Hp - WA_WS ? 0 : (hs < Hp - shift ? 1 : 2)) * 3 + (wsx < Wp - WA_WS ? 0 : (wsx < Wp - shift ? 1 : 2));
   }
-  // ---- O = P v (bf16x3); P is normalised after the contraction ----
+  float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
   float oacc[4][4];
 #pragma unroll
   for (int nd = 0; nd < 4; ++nd) oacc[nd][0] = oacc[nd][1] = oacc[nd][2] = oacc[nd][3] = 0.f;
-#pragma unroll
-  for (int kk = 0; kk < 9; ++kk) {
-    uint32_t ph[4], pl[4];
-    split_pack2(sacc[2 * kk][0], sacc[2 * kk][1], ph[0], pl[0]);          // row g,   keys kk*16 + 2t, +1
-    split_pack2(sacc[2 * kk][2], sacc[2 * kk][3], ph[1], pl[1]);          // row g+8
-    split_pack2(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1], ph[2], pl[2]);  // row g,   keys kk*16 + 8 + 2t, +1
-    split_pack2(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3], ph[3], pl[3]);  // row g+8
-    const int vrow = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-#pragma unroll
-    for (int np = 0; np < 2; ++np) {                                     // pairs of 8-wide d blocks
-      uint32_t vh[4], vl[4];
-      const int vcol = np * 16 + (lane >> 4) * 8;
-      ldsm_x4_t(vh[0], vh[1], vh[2], vh[3], sVh + vrow * WM_PITCH + vcol);
-      ldsm_x4_t(vl[0], vl[1], vl[2], vl[3], sVl + vrow * WM_PITCH + vcol);
-#pragma unroll
-      for (int q2 = 0; q2 < 2; ++q2) {
-        float* o = oacc[np * 2 + q2];
-        mma_bf16(o, ph, vh[2 * q2], vh[2 * q2 + 1]);
-        mma_bf16(o, ph, vl[2 * q2], vl[2 * q2 + 1]);
-        mma_bf16(o, pl, vh[2 * q2], vh[2 * q2 + 1]);
-      }
-    }
+  const float scale2 = scale * LOG2E;
+  // only windows in the last window row / column see more than one shift region (swin.py:416-431)
+  const bool need_mask = shift > 0 && (wh == nWh - 1 || ww == nWw - 1);
+  if (need_mask) {
+    wm_chunk<0, 10, true>(sKh, sKl, sVh, sVl, sB, sCol, qh, ql, lane, g, tq, rterm, rid, scale2, m, l, oacc);
+    wm_chunk<10, 8, true>(sKh, sKl, sVh, sVl, sB, sCol, qh, ql, lane, g, tq, rterm, rid, scale2, m, l, oacc);
+  } else {
+    wm_chunk<0, 10, false>(sKh, sKl, sVh, sVl, sB, sCol, qh, ql, lane, g, tq, rterm, rid, scale2, m, l, oacc);
+    wm_chunk<10, 8, false>(sKh, sKl, sVh, sVl, sB, sCol, qh, ql, lane, g, tq, rterm, rid, scale2, m, l, oacc);
   }
   // ---- store (attn @ v).transpose(1,2).reshape(B_, N, C) as split planes ----
 #pragma unroll
   for (int hrow = 0; hrow < 2; ++hrow) {
+    const float inv = 1.0f / l[hrow];
     const int64_t orow = win * WA_N + r0 + g + hrow * 8;
     const int64_t ob = orow * C + head * WA_D + tq * 2;
 #pragma unroll
     for (int nd = 0; nd < 4; ++nd) {
       uint32_t hi, lo;
-      split_pack2(oacc[nd][hrow * 2] * inv_sum[hrow], oacc[nd][hrow * 2 + 1] * inv_sum[hrow], hi, lo);
+      split_pack2(oacc[nd][hrow * 2] * inv, oacc[nd][hrow * 2 + 1] * inv, hi, lo);
       *reinterpret_cast<uint32_t*>(out_hi + ob + nd * 8) = hi;
       *reinterpret_cast<uint32_t*>(out_lo + ob + nd * 8) = lo;
     }
