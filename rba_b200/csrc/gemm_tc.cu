@@ -43,6 +43,7 @@ struct TcParams {
   int cH, cW, cCin, tilesW, tilesH;
   // persistent tile schedule
   int tilesM, tilesN, ntiles;
+  int debug;   // RBA_TC_DEBUG: 1 = skip global stores, 2 = skip the whole epilogue after the TMEM load (profiling aid)
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -150,15 +151,20 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 constexpr int TC_EPI_WARPS = 16;                        // 4 warps per TMEM lane quadrant, each takes 32 columns
 constexpr int TC_THREADS2 = (2 + TC_EPI_WARPS) * 32;    // 576
 
-template <int BN>
+// STG = "store-staged" configuration for store-bound shapes (K <= 256): a 2-stage operand ring leaves room for a
+// 4 KB per-warp staging buffer through which the epilogue turns its row-per-lane registers into coalesced 16-byte
+// global stores (4 full lines per instruction instead of 32 partial ones).
+template <int BN, bool STG = false>
 struct TcSmem {
-  static constexpr int STAGES = BN > 128 ? 2 : 3;        // 96 KB stages for BN = 256, 64 KB (48 KB) otherwise
+  static constexpr int STAGES = (BN > 128 || STG) ? 2 : 3;   // 96 KB stages for BN = 256, 64 KB (48 KB) otherwise
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;      // one plane of A per stage (16 KB)
   static constexpr int W_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
   static constexpr int NG = BN > 128 ? BN / 128 : 1;     // 128-column groups per tile (epilogue passes)
   static constexpr int BIAS_BYTES = TC_EPI_WARPS * 32 * NG * 4;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BIAS_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int OROW_BYTES = TC_EPI_WARPS * 32 * 8;
+  static constexpr int STG_BYTES = STG ? TC_EPI_WARPS * 4096 : 0;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BIAS_BYTES + OROW_BYTES + STG_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
 struct TileCoord {
@@ -185,16 +191,45 @@ __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int t) {
   return c;
 }
 
-template <int BN, bool CONV>
+// erf via Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7) on the FMA + XU pipes: the exact-erf GELU of swin.py:25 is
+// evaluated 4C times per token, and libdevice erff (~30 instructions with branches) made the fc1 epilogue the
+// bottleneck of the whole GEMM.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+  const float erf_abs = fmaf(-poly, e, 1.0f);            // erf(|x|/sqrt2)
+  const float erf_s = copysignf(erf_abs, x);
+  return 0.5f * x * (1.0f + erf_s);
+}
+template <int ACT>
+__device__ __forceinline__ float tc_act(float x) {
+  if (ACT == RBA_ACT_RELU) return fmaxf(x, 0.f);
+  if (ACT == RBA_ACT_GELU) return gelu_fast(x);
+  return x;
+}
+
+// ACT: RBA_ACT_*; OUTP: false = fp32 output (c), true = split-plane output (c_hi/c_lo) [both: handled by the fp32 variant
+// falling back to scalar plane stores].
+template <int BN, bool CONV, int ACT, bool OUTP, bool STG>
 __global__ void __launch_bounds__(TC_THREADS2, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, const TcParams p) {
-  using S = TcSmem<BN>;
+  using S = TcSmem<BN, STG>;
   constexpr int TC_STAGES = S::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* sbias = reinterpret_cast<float*>(smem + TC_STAGES * S::STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * S::STAGE_BYTES + S::BIAS_BYTES);
+  int64_t* sorow = reinterpret_cast<int64_t*>(smem + TC_STAGES * S::STAGE_BYTES + S::BIAS_BYTES);
+  uint8_t* sstage = smem + TC_STAGES * S::STAGE_BYTES + S::BIAS_BYTES + S::OROW_BYTES;   // [16 warps][4 KB] (STG only)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sstage + S::STG_BYTES);
   uint64_t* full = bars;                          // [TC_STAGES]
   uint64_t* empty = bars + TC_STAGES;             // [TC_STAGES]
   uint64_t* acc_full = bars + 2 * TC_STAGES;      // [2]
@@ -286,6 +321,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (cg * 32 < BN) {
       constexpr int NG = S::NG;
       float* mybias = sbias + ew * 32 * NG;
+      int64_t* my_orow = sorow + ew * 32;
+      uint8_t* mystage = sstage + ew * 4096;
       const int row_in_tile = quad * 32 + lane;
       uint32_t lt = 0;
       for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++lt) {
@@ -321,12 +358,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             __syncwarp();
           }
         }
+        if (STG) {
+          __syncwarp();
+          my_orow[lane] = orow;
+          __syncwarp();
+        }
 #pragma unroll 1
         for (int g2 = 0; g2 < NG; ++g2) {
-        const int nb = tc.n0 + g2 * 128 + cg * 32;          // first column of this warp's block
+        const int nb = tc.n0 + g2 * 128 + cg * 32;          // first column of this warp's 32x32 block
         const bool active = orow >= 0 && nb < p.N;
         const bool full32 = nb + 31 < p.N;
-        // ---- prefetch (independent of the accumulator) ----
+        // ---- prefetch the residual row segment (independent of the accumulator) ----
         float4 r4[8];
         const bool res_vec = res && active && full32 && ((ldr & 3) == 0);
         if (res_vec) {
@@ -348,53 +390,119 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[as]);       // this warp is done with the TMEM buffer
         }
-        if (active) {
+        if ((p.debug & 2) || nb >= p.N) { __syncwarp(); continue; }   // warp-uniform
+        // ---- bias, activation, residual in the TMEM layout (lane <-> row, register j <-> column nb + j) ----
         float x[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float t0 = __uint_as_float(v[j]);
-          if (bias) t0 += p.bias_per_row ? brow : mybias[g2 * 32 + j];
-          x[j] = apply_act_rt(t0, p.act);
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+        if (bias) {
+          if (p.bias_per_row) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] += brow;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = *reinterpret_cast<const float4*>(mybias + g2 * 32 + 4 * j);
+              x[4 * j] += b4.x; x[4 * j + 1] += b4.y; x[4 * j + 2] += b4.z; x[4 * j + 3] += b4.w;
+            }
+          }
+        }
+        if (ACT != RBA_ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = tc_act<ACT>(x[j]);
         }
         if (res_vec) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) { x[4 * j] += r4[j].x; x[4 * j + 1] += r4[j].y; x[4 * j + 2] += r4[j].z; x[4 * j + 3] += r4[j].w; }
-        } else if (res) {
-#pragma unroll
+        } else if (res && active) {
+#pragma unroll 1
           for (int j = 0; j < 32; ++j)
             if (nb + j < p.N) x[j] += res[orow * ldr + nb + j];
         }
-        if (c) {
-          float* cp = c + orow * p.ldc + nb;
-          if (full32 && (p.ldc & 3) == 0) {
+        // ---- stores ----
+        const bool staged = STG && full32 && ((OUTP ? (p.ldcp & 7) : (p.ldc & 3)) == 0) && !(!OUTP && c_hi);   // warp-uniform
+        if (p.debug & 1) {
+        } else if (staged) {
+          // Row-per-lane registers -> swizzled shared-memory tile -> coalesced 16-byte global stores.
+          if (!OUTP) {
+            // tile: 32 rows x 128 B; 16-byte chunk j of row r lives at chunk (j ^ (r & 7))
+            float4* st4 = reinterpret_cast<float4*>(mystage);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(cp)[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-          } else {
+            for (int j = 0; j < 8; ++j) st4[lane * 8 + (j ^ (lane & 7))] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+            __syncwarp();
+            const int cidx = lane & 7;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < p.N) cp[j] = x[j];
-          }
-        }
-        if (c_hi) {
-          const int64_t ob = orow * p.ldcp + nb;
-          if (full32 && (p.ldcp & 7) == 0) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {                   // 8 columns -> one 16-byte store per plane
-              uint4 H, L;
-              split_pack2(x[8 * j], x[8 * j + 1], H.x, L.x);
-              split_pack2(x[8 * j + 2], x[8 * j + 3], H.y, L.y);
-              split_pack2(x[8 * j + 4], x[8 * j + 5], H.z, L.z);
-              split_pack2(x[8 * j + 6], x[8 * j + 7], H.w, L.w);
-              *reinterpret_cast<uint4*>(c_hi + ob + 8 * j) = H;
-              *reinterpret_cast<uint4*>(c_lo + ob + 8 * j) = L;
+            for (int i = 0; i < 8; ++i) {                   // 4 rows x 128 B per instruction
+              const int rr = i * 4 + (lane >> 3);
+              const int64_t o = my_orow[rr];
+              const float4 val = st4[rr * 8 + (cidx ^ (rr & 7))];
+              if (o >= 0) *reinterpret_cast<float4*>(c + o * p.ldc + nb + cidx * 4) = val;
             }
           } else {
+            // two tiles (hi, lo): 32 rows x 64 B; chunk j of row r lives at chunk (j ^ ((r >> 1) & 3))
+            uint4* sh4 = reinterpret_cast<uint4*>(mystage);
+            uint4* sl4 = sh4 + 128;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < p.N) store_split1(c_hi, c_lo, ob + j, x[j]);
+            for (int j = 0; j < 4; ++j) {
+              uint4 Hh, Ll;
+              split_pack2(x[8 * j], x[8 * j + 1], Hh.x, Ll.x);
+              split_pack2(x[8 * j + 2], x[8 * j + 3], Hh.y, Ll.y);
+              split_pack2(x[8 * j + 4], x[8 * j + 5], Hh.z, Ll.z);
+              split_pack2(x[8 * j + 6], x[8 * j + 7], Hh.w, Ll.w);
+              const int pc = j ^ ((lane >> 1) & 3);
+              sh4[lane * 4 + pc] = Hh;
+              sl4[lane * 4 + pc] = Ll;
+            }
+            __syncwarp();
+            const int cidx = lane & 3;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {                   // 8 rows x 64 B per instruction and plane
+              const int rr = i * 8 + (lane >> 2);
+              const int64_t o = my_orow[rr];
+              const int pc = cidx ^ ((rr >> 1) & 3);
+              const uint4 hv = sh4[rr * 4 + pc], lv = sl4[rr * 4 + pc];
+              if (o >= 0) {
+                *reinterpret_cast<uint4*>(c_hi + o * p.ldcp + nb + cidx * 8) = hv;
+                *reinterpret_cast<uint4*>(c_lo + o * p.ldcp + nb + cidx * 8) = lv;
+              }
+            }
+          }
+        } else if (active) {
+          if (!OUTP) {
+            float* cp = c + orow * p.ldc + nb;
+            if (full32 && (p.ldc & 3) == 0) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(cp)[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+            } else {
+#pragma unroll 1
+              for (int j = 0; j < 32; ++j)
+                if (nb + j < p.N) cp[j] = x[j];
+            }
+            if (c_hi) {                                     // rare: both outputs requested
+#pragma unroll 1
+              for (int j = 0; j < 32; ++j)
+                if (nb + j < p.N) store_split1(c_hi, c_lo, orow * p.ldcp + nb + j, x[j]);
+            }
+          } else {
+            const int64_t ob = orow * p.ldcp + nb;
+            if (full32 && (p.ldcp & 7) == 0) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {                 // 8 columns -> one 16-byte store per plane
+                uint4 Hh, Ll;
+                split_pack2(x[8 * j], x[8 * j + 1], Hh.x, Ll.x);
+                split_pack2(x[8 * j + 2], x[8 * j + 3], Hh.y, Ll.y);
+                split_pack2(x[8 * j + 4], x[8 * j + 5], Hh.z, Ll.z);
+                split_pack2(x[8 * j + 6], x[8 * j + 7], Hh.w, Ll.w);
+                *reinterpret_cast<uint4*>(c_hi + ob + 8 * j) = Hh;
+                *reinterpret_cast<uint4*>(c_lo + ob + 8 * j) = Ll;
+              }
+            } else {
+#pragma unroll 1
+              for (int j = 0; j < 32; ++j)
+                if (nb + j < p.N) store_split1(c_hi, c_lo, ob + j, x[j]);
+            }
           }
         }
-        }  // active
         __syncwarp();                                       // reconverge before the next .aligned TMEM op
         }  // g2
       }
@@ -457,7 +565,7 @@ static int make_map_nhwc(CUtensorMap* m, const uint16_t* ptr, int B, int H, int 
   return RBA_OK;
 }
 
-static const bool g_tc_bn256 = []() { const char* e = getenv("RBA_TC_BN256"); return !(e && e[0] == '0'); }();
+static const bool g_tc_bn256 = []() { const char* e = getenv("RBA_TC_BN256"); return e && e[0] == '1'; }();
 
 static int num_sms() {
   static int n = 0;
@@ -469,21 +577,52 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, bool CONV>
-static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
-                     const TcParams& p, dim3 grid, cudaStream_t st) {
-  constexpr int smem = TcSmem<BN>::TOTAL;
+template <int BN, bool CONV, int ACT, bool OUTP, bool STG>
+static int launch_tc3(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
+                      const TcParams& p, dim3 grid, cudaStream_t st) {
+  constexpr int smem = TcSmem<BN, STG>::TOTAL;
   static bool attr_done = false;
   if (!attr_done) {
-    RBA_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    RBA_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CONV, ACT, OUTP, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_done = true;
   }
-  gemm_tc_kernel<BN, CONV><<<grid, TC_THREADS2, smem, st>>>(a_hi, a_lo, w_hi, w_lo, p);
+  gemm_tc_kernel<BN, CONV, ACT, OUTP, STG><<<grid, TC_THREADS2, smem, st>>>(a_hi, a_lo, w_hi, w_lo, p);
   RBA_LAUNCHED();
   return RBA_OK;
 }
 
+static const int g_tc_stg_maxk = []() { const char* e = getenv("RBA_TC_STG_MAXK"); return e ? atoi(e) : 256; }();
+
+template <int BN, bool CONV, int ACT, bool OUTP>
+static int launch_tc2(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
+                      const TcParams& p, dim3 grid, cudaStream_t st) {
+  // store-bound shapes (short K loop, BN = 128): 2-stage ring + staged coalesced stores
+  if (BN == 128 && !CONV && p.K <= g_tc_stg_maxk) return launch_tc3<BN, CONV, ACT, OUTP, (BN == 128 && !CONV)>(a_hi, a_lo, w_hi, w_lo, p, grid, st);
+  return launch_tc3<BN, CONV, ACT, OUTP, false>(a_hi, a_lo, w_hi, w_lo, p, grid, st);
+}
+
+template <int BN, bool CONV>
+static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
+                     const TcParams& p, dim3 grid, cudaStream_t st) {
+  const bool outp = p.c == nullptr;                       // planes only
+  if (CONV) return launch_tc2<BN, CONV, RBA_ACT_NONE, false>(a_hi, a_lo, w_hi, w_lo, p, grid, st);
+  switch (p.act) {
+    case RBA_ACT_RELU:
+      return outp ? launch_tc2<BN, false, RBA_ACT_RELU, true>(a_hi, a_lo, w_hi, w_lo, p, grid, st)
+                  : launch_tc2<BN, false, RBA_ACT_RELU, false>(a_hi, a_lo, w_hi, w_lo, p, grid, st);
+    case RBA_ACT_GELU:
+      return outp ? launch_tc2<BN, false, RBA_ACT_GELU, true>(a_hi, a_lo, w_hi, w_lo, p, grid, st)
+                  : launch_tc2<BN, false, RBA_ACT_GELU, false>(a_hi, a_lo, w_hi, w_lo, p, grid, st);
+    default:
+      return outp ? launch_tc2<BN, false, RBA_ACT_NONE, true>(a_hi, a_lo, w_hi, w_lo, p, grid, st)
+                  : launch_tc2<BN, false, RBA_ACT_NONE, false>(a_hi, a_lo, w_hi, w_lo, p, grid, st);
+  }
+}
+
+static const int g_tc_debug = []() { const char* e = getenv("RBA_TC_DEBUG"); return e ? atoi(e) : 0; }();
+
 static void fill_epilogue(TcParams& p, const rba_gemm_args& a) {
+  p.debug = g_tc_debug;
   p.bias = a.bias; p.bias_per_row = a.bias_per_row; p.bias_bs = a.bias_bstride;
   p.act = a.act; p.residual = a.residual;
   p.c = a.c; p.ldc = a.ldc; p.c_bs = a.c_bstride;
