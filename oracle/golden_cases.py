@@ -14,6 +14,7 @@ CASES = {
     "tiny_1dl": dict(preset="tiny", levels=1, dec_layers=1, seed=11, perturb=0.02, img_seed=1, sizes=[(70, 100)]),
     "tiny_3lvl": dict(preset="tiny", levels=3, dec_layers=3, seed=248, perturb=0.02, img_seed=2, sizes=[(64, 96), (64, 96)]),
     "swin_b_1dl": dict(preset="swin_b_1dl", levels=1, dec_layers=1, seed=13, perturb=0.02, img_seed=3, sizes=[(96, 160)]),
+    "swin_l_1dl": dict(preset="swin_l_1dl", levels=1, dec_layers=1, seed=17, perturb=0.02, img_seed=4, sizes=[(64, 96)]),
 }
 
 

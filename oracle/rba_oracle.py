@@ -87,11 +87,11 @@ def relative_position_index(ws):
     return rel.sum(-1)
 
 
-def shift_attn_mask(H, W, ws, shift):
+def shift_attn_mask(H, W, ws, shift, device=None):
     """swin.py:413-440 — (nW, ws*ws, ws*ws) of {0, -100}."""
     Hp = int(math.ceil(H / ws)) * ws
     Wp = int(math.ceil(W / ws)) * ws
-    img_mask = torch.zeros((1, Hp, Wp, 1))
+    img_mask = torch.zeros((1, Hp, Wp, 1), device=device)
     cnt = 0
     for h in (slice(0, -ws), slice(-ws, -shift), slice(-shift, None)):
         for w in (slice(0, -ws), slice(-ws, -shift), slice(-shift, None)):
@@ -112,7 +112,7 @@ def window_attention(sd, p, x, mask, num_heads, ws):
     attn = q @ k.transpose(-2, -1)
     idx = sd.get(p + "relative_position_index", None)
     if idx is None:
-        idx = relative_position_index(ws)
+        idx = relative_position_index(ws).to(x.device)
     bias = sd[p + "relative_position_bias_table"][idx.view(-1)].view(N, N, -1).permute(2, 0, 1).contiguous()
     attn = attn + bias.unsqueeze(0)
     if mask is not None:
@@ -184,7 +184,7 @@ def swin_forward(sd, cfg, x, p="backbone."):
     ws = cfg.window_size
     for i, depth in enumerate(cfg.depths):
         Ci = C * 2 ** i
-        mask = shift_attn_mask(Wh, Ww, ws, ws // 2)
+        mask = shift_attn_mask(Wh, Ww, ws, ws // 2, device=x.device)
         for j in range(depth):
             x = swin_block(sd, f"{p}layers.{i}.blocks.{j}.", x, Wh, Ww, cfg.num_heads[i], ws,
                            0 if j % 2 == 0 else ws // 2, mask)
@@ -201,15 +201,15 @@ def swin_forward(sd, cfg, x, p="backbone."):
 # --------------------------------------------------------------------------------------
 
 
-def position_embedding_sine(B, H, W, num_pos_feats, temperature=10000, scale=2 * math.pi):
+def position_embedding_sine(B, H, W, num_pos_feats, temperature=10000, scale=2 * math.pi, device=None):
     """transformer_decoder/position_encoding.py:29-52 with mask=None, normalize=True."""
-    not_mask = torch.ones((B, H, W), dtype=torch.bool)
+    not_mask = torch.ones((B, H, W), dtype=torch.bool, device=device)
     y_embed = not_mask.cumsum(1, dtype=torch.float32)
     x_embed = not_mask.cumsum(2, dtype=torch.float32)
     eps = 1e-6
     y_embed = y_embed / (y_embed[:, -1:, :] + eps) * scale
     x_embed = x_embed / (x_embed[:, :, -1:] + eps) * scale
-    dim_t = torch.arange(num_pos_feats, dtype=torch.float32)
+    dim_t = torch.arange(num_pos_feats, dtype=torch.float32, device=device)
     dim_t = temperature ** (2 * (dim_t // 2) / num_pos_feats)
     pos_x = x_embed[:, :, :, None] / dim_t
     pos_y = y_embed[:, :, :, None] / dim_t
@@ -281,25 +281,25 @@ def msdeform_attn(sd, p, query, reference_points, src, spatial_shapes, n_heads, 
     off = off.view(N, Lq, n_heads, n_levels, n_points, 2)
     aw = F.linear(query, sd[p + "attention_weights.weight"], sd[p + "attention_weights.bias"])
     aw = F.softmax(aw.view(N, Lq, n_heads, n_levels * n_points), -1).view(N, Lq, n_heads, n_levels, n_points)
-    normalizer = torch.tensor([[w, h] for h, w in spatial_shapes], dtype=torch.float32)
+    normalizer = torch.tensor([[w, h] for h, w in spatial_shapes], dtype=torch.float32, device=query.device)
     loc = reference_points[:, :, None, :, None, :] + off / normalizer[None, None, None, :, None, :]
     core = msda_bilinear_gather if explicit else msda_core_grid_sample
     out = core(value, spatial_shapes, loc, aw)
     return F.linear(out, sd[p + "output_proj.weight"], sd[p + "output_proj.bias"])
 
 
-def encoder_reference_points(spatial_shapes, B):
+def encoder_reference_points(spatial_shapes, B, device=None):
     """msdeformattn.py:150-162 with valid_ratios == 1 (masks are all-False, :71)."""
     refs = []
     for H_, W_ in spatial_shapes:
-        ry, rx = torch.meshgrid(torch.linspace(0.5, H_ - 0.5, H_, dtype=torch.float32),
-                                torch.linspace(0.5, W_ - 0.5, W_, dtype=torch.float32), indexing="ij")
-        ry = ry.reshape(-1)[None] / (torch.ones(B, 1) * H_)
-        rx = rx.reshape(-1)[None] / (torch.ones(B, 1) * W_)
+        ry, rx = torch.meshgrid(torch.linspace(0.5, H_ - 0.5, H_, dtype=torch.float32, device=device),
+                                torch.linspace(0.5, W_ - 0.5, W_, dtype=torch.float32, device=device), indexing="ij")
+        ry = ry.reshape(-1)[None] / (torch.ones(B, 1, device=device) * H_)
+        rx = rx.reshape(-1)[None] / (torch.ones(B, 1, device=device) * W_)
         refs.append(torch.stack((rx, ry), -1))
     ref = torch.cat(refs, 1)  # B, S, 2
     L = len(spatial_shapes)
-    return ref[:, :, None] * torch.ones(B, 1, L, 2)
+    return ref[:, :, None] * torch.ones(B, 1, L, 2, device=device)
 
 
 def pixel_decoder_forward(sd, cfg, feats, p="sem_seg_head.pixel_decoder.", explicit_msda=False, taps=None):
@@ -315,13 +315,13 @@ def pixel_decoder_forward(sd, cfg, feats, p="sem_seg_head.pixel_decoder.", expli
         y = F.conv2d(x, sd[f"{p}input_proj.{idx}.0.weight"], sd[f"{p}input_proj.{idx}.0.bias"])
         y = F.group_norm(y, 32, sd[f"{p}input_proj.{idx}.1.weight"], sd[f"{p}input_proj.{idx}.1.bias"])
         srcs.append(y)
-        pos.append(position_embedding_sine(x.shape[0], x.shape[2], x.shape[3], D // 2))
+        pos.append(position_embedding_sine(x.shape[0], x.shape[2], x.shape[3], D // 2, device=x.device))
     B = srcs[0].shape[0]
     spatial_shapes = [(s.shape[2], s.shape[3]) for s in srcs]
     src_flat = torch.cat([s.flatten(2).transpose(1, 2) for s in srcs], 1)
     lvl_pos = torch.cat([pe.flatten(2).transpose(1, 2) + sd[p + "transformer.level_embed"][l].view(1, 1, -1)
                          for l, pe in enumerate(pos)], 1)
-    ref = encoder_reference_points(spatial_shapes, B)
+    ref = encoder_reference_points(spatial_shapes, B, device=src_flat.device)
     out = src_flat
     L = len(spatial_shapes)
     if taps is not None:
@@ -411,7 +411,7 @@ def transformer_decoder_forward(sd, cfg, multi_scale, mask_features, p="sem_seg_
     for i in range(nl):
         x = multi_scale[i]
         sizes.append(x.shape[-2:])
-        pos.append(position_embedding_sine(x.shape[0], x.shape[2], x.shape[3], D // 2).flatten(2).permute(2, 0, 1))
+        pos.append(position_embedding_sine(x.shape[0], x.shape[2], x.shape[3], D // 2, device=x.device).flatten(2).permute(2, 0, 1))
         if (p + f"input_proj.{i}.weight") in sd:          # :353-358 (empty Sequential when in_channels == hidden_dim)
             x = F.conv2d(x, sd[p + f"input_proj.{i}.weight"], sd[p + f"input_proj.{i}.bias"])
         src.append((x.flatten(2) + sd[p + "level_embed.weight"][i][None, :, None]).permute(2, 0, 1))
@@ -472,8 +472,9 @@ def score_from_head_outputs(pred_logits, pred_masks, padded_hw, image_hw):
 def preprocess(images, cfg):
     """maskformer_model.py:255-257: (x - mean)/std per image, zero-pad bottom/right to a multiple of
     SIZE_DIVISIBILITY (detectron2 ImageList.from_tensors, pad_value 0)."""
-    mean = torch.tensor(cfg.pixel_mean).view(-1, 1, 1)
-    std = torch.tensor(cfg.pixel_std).view(-1, 1, 1)
+    dev = images[0].device
+    mean = torch.tensor(cfg.pixel_mean, device=dev).view(-1, 1, 1)
+    std = torch.tensor(cfg.pixel_std, device=dev).view(-1, 1, 1)
     ims = [(x.float() - mean) / std for x in images]
     sizes = [(x.shape[-2], x.shape[-1]) for x in ims]
     s = cfg.size_divisibility
@@ -481,7 +482,7 @@ def preprocess(images, cfg):
     Wm = max(w for _, w in sizes)
     if s > 1:
         Hm, Wm = (Hm + s - 1) // s * s, (Wm + s - 1) // s * s
-    out = torch.zeros(len(ims), 3, Hm, Wm)
+    out = torch.zeros(len(ims), 3, Hm, Wm, device=dev)
     for i, x in enumerate(ims):
         out[i, :, :x.shape[-2], :x.shape[-1]] = x
     return out, sizes

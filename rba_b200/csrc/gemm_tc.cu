@@ -591,7 +591,7 @@ static int launch_tc3(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CU
   return RBA_OK;
 }
 
-static const int g_tc_stg_maxk = []() { const char* e = getenv("RBA_TC_STG_MAXK"); return e ? atoi(e) : 256; }();
+static const int g_tc_stg_maxk = []() { const char* e = getenv("RBA_TC_STG_MAXK"); return e ? atoi(e) : 512; }();
 
 template <int BN, bool CONV, int ACT, bool OUTP>
 static int launch_tc2(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
