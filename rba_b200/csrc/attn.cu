@@ -195,14 +195,6 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem));
 }
-// packs two fp32 into bf16x2 hi and the bf16x2 of the residuals
-__device__ __forceinline__ void split_pack2(float x, float y, uint32_t& hi, uint32_t& lo) {
-  __nv_bfloat16 hx, lx, hy, ly;
-  split2(x, hx, lx);
-  split2(y, hy, ly);
-  hi = (uint32_t)__bfloat16_as_ushort(hx) | ((uint32_t)__bfloat16_as_ushort(hy) << 16);
-  lo = (uint32_t)__bfloat16_as_ushort(lx) | ((uint32_t)__bfloat16_as_ushort(ly) << 16);
-}
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float r;

@@ -57,19 +57,21 @@ __device__ __forceinline__ float bf16_bits_to_float(uint16_t b) { return __uint_
 __device__ __forceinline__ float bf16lo(uint32_t packed) { return __uint_as_float(packed << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t packed) { return __uint_as_float(packed & 0xffff0000u); }
 
+// Two values -> packed bf16x2 hi word and bf16x2 lo (residual) word, element `a` in the low half.
+// cvt.rn.bf16x2.f32 converts and packs a pair in one instruction.
+__device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+  const float ra = a - __uint_as_float(hi << 16);
+  const float rb = b - __uint_as_float(hi & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
+}
+
 // Stores 4 consecutive values as split planes (8-byte stores, idx must be a multiple of 4).
 __device__ __forceinline__ void store_split4(uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int64_t idx,
                                              float a, float b, float c, float d) {
-  __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-  split2(a, h0, l0);
-  split2(b, h1, l1);
-  split2(c, h2, l2);
-  split2(d, h3, l3);
   uint2 H, L;
-  H.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-  H.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
-  L.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-  L.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+  split_pack2(a, b, H.x, L.x);
+  split_pack2(c, d, H.y, L.y);
   *reinterpret_cast<uint2*>(hi + idx) = H;
   *reinterpret_cast<uint2*>(lo + idx) = L;
 }

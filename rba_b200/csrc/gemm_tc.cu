@@ -132,13 +132,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  __nv_bfloat16 ha, la, hb, lb;
-  split2(a, ha, la);
-  split2(b, hb, lb);
-  hi = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
-  lo = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
-}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -225,7 +218,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   using S = TcSmem<BN, STG>;
   constexpr int TC_STAGES = S::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align to 1024 B (128B-swizzle atoms) with pointer arithmetic on the __shared__ array so that the compiler keeps the
+  // shared address space (LDS/STS instead of generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* sbias = reinterpret_cast<float*>(smem + TC_STAGES * S::STAGE_BYTES);
   int64_t* sorow = reinterpret_cast<int64_t*>(smem + TC_STAGES * S::STAGE_BYTES + S::BIAS_BYTES);
   uint8_t* sstage = smem + TC_STAGES * S::STAGE_BYTES + S::BIAS_BYTES + S::OROW_BYTES;   // [16 warps][4 KB] (STG only)
