@@ -410,7 +410,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 8; ++j) { x[4 * j] += r4[j].x; x[4 * j + 1] += r4[j].y; x[4 * j + 2] += r4[j].z; x[4 * j + 3] += r4[j].w; }
         } else if (res && active) {
-#pragma unroll 1
+#pragma unroll
           for (int j = 0; j < 32; ++j)
             if (nb + j < p.N) x[j] += res[orow * ldr + nb + j];
         }
@@ -469,12 +469,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
               for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(cp)[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
             } else {
-#pragma unroll 1
+#pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (nb + j < p.N) cp[j] = x[j];
             }
             if (c_hi) {                                     // rare: both outputs requested
-#pragma unroll 1
+#pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (nb + j < p.N) store_split1(c_hi, c_lo, orow * p.ldcp + nb + j, x[j]);
             }
@@ -492,7 +492,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 *reinterpret_cast<uint4*>(c_lo + ob + 8 * j) = Ll;
               }
             } else {
-#pragma unroll 1
+#pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (nb + j < p.N) store_split1(c_hi, c_lo, ob + j, x[j]);
             }

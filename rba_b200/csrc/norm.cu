@@ -301,72 +301,98 @@ int groupnorm(const float* x, int64_t x_bs, const float* gamma, const float* bet
 // ------------------------------------------------------------------------------------------------
 // Patch embedding: normalise + zero pad + 4x4/4 conv + LayerNorm (maskformer_model.py:255-257, swin.py:479-495)
 // ------------------------------------------------------------------------------------------------
-// One warp per token, persistent CTAs: the conv weights are staged ONCE per CTA in shared memory, transposed to
-// [48][C] so that lanes read consecutive channels (conflict-free); the 48 (=3*4*4) normalised inputs of a token are
-// broadcast through shared memory; each lane produces C/32 output channels and the LayerNorm is a warp reduction.
-template <typename T>
+// Persistent CTAs, one warp per PAIR of horizontally adjacent tokens: the conv weights are staged once per CTA in shared
+// memory transposed to [48][C]; lane l owns channels 4l..4l+3 (and 128+4l.. for C > 128), so each weight read is one
+// conflict-free 16-byte load reused for both tokens; the 48 (=3*4*4) normalised inputs per token are broadcast through
+// shared memory; the LayerNorm is a warp reduction.
+template <typename T, int G>   // G = channel groups of 128 (C <= 128*G)
 __global__ void __launch_bounds__(256)
 patch_embed_kernel(const T* __restrict__ img, int B, int H, int W, int Hp, int Wp, float m0, float m1, float m2, float s0,
                    float s1, float s2, const float* __restrict__ cw, const float* __restrict__ cb,
                    const float* __restrict__ gamma, const float* __restrict__ beta, int C, float* __restrict__ tokens) {
-  extern __shared__ float pe_smem[];
-  float* sW = pe_smem;                 // [48][C]
-  float* sIn = pe_smem + 48 * C;       // [8][48]
-  for (int e = threadIdx.x; e < 48 * C; e += blockDim.x) {
-    int c = e / 48, k = e - c * 48;
-    sW[k * C + c] = cw[e];
+  extern __shared__ __align__(16) float pe_smem[];
+  const int CP = 128 * G;              // padded channel count in smem
+  float* sW = pe_smem;                 // [48][CP]
+  float* sIn = pe_smem + 48 * CP;      // [8 warps][2 tokens][48]
+  for (int e = threadIdx.x; e < 48 * CP; e += blockDim.x) {
+    const int k = e / CP, c = e - k * CP;
+    sW[e] = (c < C) ? cw[c * 48 + k] : 0.f;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Th = Hp >> 2, Tw = Wp >> 2;
-  const int64_t ntok = (int64_t)B * Th * Tw;
-  float* in = sIn + warp * 48;
-  for (int64_t tok = (int64_t)blockIdx.x * 8 + warp; tok < ntok; tok += (int64_t)gridDim.x * 8) {
-    const int tx = (int)(tok % Tw);
-    int64_t t = tok / Tw;
+  const int64_t npair = (int64_t)B * Th * (Tw >> 1);           // Tw is even (Wp is a multiple of 32)
+  float* in = sIn + warp * 96;
+  for (int64_t pr = (int64_t)blockIdx.x * 8 + warp; pr < npair; pr += (int64_t)gridDim.x * 8) {
+    const int tx = (int)(pr % (Tw >> 1)) * 2;
+    int64_t t = pr / (Tw >> 1);
     const int ty = (int)(t % Th);
     const int b = (int)(t / Th);
     __syncwarp();
-    for (int e = lane; e < 48; e += 32) {
-      int ch = e >> 4, ky = (e >> 2) & 3, kx = e & 3;
-      int yy = ty * 4 + ky, xx = tx * 4 + kx;
-      float v = 0.f;                                  // ImageList pads the NORMALISED image with 0
+    for (int e = lane; e < 96; e += 32) {                      // e = ch*32 + ky*8 + kx8 : 8 consecutive pixels per (ch, ky)
+      const int ch = e >> 5, ky = (e >> 3) & 3, kx8 = e & 7;
+      const int yy = ty * 4 + ky, xx = tx * 4 + kx8;
+      float v = 0.f;                                            // ImageList pads the NORMALISED image with 0
       if (yy < H && xx < W) {
-        float raw = (float)img[(((int64_t)b * 3 + ch) * H + yy) * W + xx];
-        float mean = ch == 0 ? m0 : (ch == 1 ? m1 : m2);
-        float sd = ch == 0 ? s0 : (ch == 1 ? s1 : s2);
+        const float raw = (float)img[(((int64_t)b * 3 + ch) * H + yy) * W + xx];
+        const float mean = ch == 0 ? m0 : (ch == 1 ? m1 : m2);
+        const float sd = ch == 0 ? s0 : (ch == 1 ? s1 : s2);
         v = (raw - mean) / sd;
       }
-      in[e] = v;
+      in[(kx8 >> 2) * 48 + ch * 16 + ky * 4 + (kx8 & 3)] = v;  // token (kx8 >> 2), conv index ch*16 + ky*4 + kx
     }
     __syncwarp();
-    constexpr int MAXC = 8;                           // C <= 256
-    float o[MAXC];
-    float sum = 0.f;
+    float acc[2][4 * G];
 #pragma unroll
-    for (int k = 0; k < MAXC; ++k) {
-      int c = lane + 32 * k;
-      o[k] = 0.f;
-      if (c < C) {
-        float acc = cb[c];
+    for (int gch = 0; gch < G; ++gch) {
+      const int c0 = gch * 128 + 4 * lane;
+      float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c0 < C) bb = *reinterpret_cast<const float4*>(cb + c0);
 #pragma unroll
-        for (int e = 0; e < 48; ++e) acc = fmaf(sW[e * C + c], in[e], acc);
-        o[k] = acc;
-        sum += acc;
+      for (int tk = 0; tk < 2; ++tk) { acc[tk][4 * gch] = bb.x; acc[tk][4 * gch + 1] = bb.y; acc[tk][4 * gch + 2] = bb.z; acc[tk][4 * gch + 3] = bb.w; }
+    }
+#pragma unroll 4
+    for (int e = 0; e < 48; ++e) {
+      const float i0 = in[e], i1 = in[48 + e];
+#pragma unroll
+      for (int gch = 0; gch < G; ++gch) {
+        const float4 w4 = *reinterpret_cast<const float4*>(sW + e * CP + gch * 128 + 4 * lane);
+        acc[0][4 * gch] = fmaf(w4.x, i0, acc[0][4 * gch]); acc[0][4 * gch + 1] = fmaf(w4.y, i0, acc[0][4 * gch + 1]);
+        acc[0][4 * gch + 2] = fmaf(w4.z, i0, acc[0][4 * gch + 2]); acc[0][4 * gch + 3] = fmaf(w4.w, i0, acc[0][4 * gch + 3]);
+        acc[1][4 * gch] = fmaf(w4.x, i1, acc[1][4 * gch]); acc[1][4 * gch + 1] = fmaf(w4.y, i1, acc[1][4 * gch + 1]);
+        acc[1][4 * gch + 2] = fmaf(w4.z, i1, acc[1][4 * gch + 2]); acc[1][4 * gch + 3] = fmaf(w4.w, i1, acc[1][4 * gch + 3]);
       }
     }
-    const float mean = warp_sum(sum) / (float)C;
-    float sq = 0.f;
 #pragma unroll
-    for (int k = 0; k < MAXC; ++k) {
-      int c = lane + 32 * k;
-      if (c < C) { float d = o[k] - mean; sq += d * d; }
-    }
-    const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)C + 1e-5f);
+    for (int tk = 0; tk < 2; ++tk) {
+      float sum = 0.f;
 #pragma unroll
-    for (int k = 0; k < MAXC; ++k) {
-      int c = lane + 32 * k;
-      if (c < C) tokens[tok * C + c] = (o[k] - mean) * rstd * gamma[c] + beta[c];
+      for (int j = 0; j < 4 * G; ++j) {
+        const int c = (j >> 2) * 128 + 4 * lane + (j & 3);
+        if (c < C) sum += acc[tk][j];
+      }
+      const float mean = warp_sum(sum) / (float)C;
+      float sq = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4 * G; ++j) {
+        const int c = (j >> 2) * 128 + 4 * lane + (j & 3);
+        if (c < C) { const float d = acc[tk][j] - mean; sq += d * d; }
+      }
+      const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)C + 1e-5f);
+      const int64_t tok = ((int64_t)b * Th + ty) * Tw + tx + tk;
+#pragma unroll
+      for (int gch = 0; gch < G; ++gch) {
+        const int c0 = gch * 128 + 4 * lane;
+        if (c0 < C) {
+          const float4 g4 = *reinterpret_cast<const float4*>(gamma + c0), b4 = *reinterpret_cast<const float4*>(beta + c0);
+          float4 o;
+          o.x = (acc[tk][4 * gch] - mean) * rstd * g4.x + b4.x;
+          o.y = (acc[tk][4 * gch + 1] - mean) * rstd * g4.y + b4.y;
+          o.z = (acc[tk][4 * gch + 2] - mean) * rstd * g4.z + b4.z;
+          o.w = (acc[tk][4 * gch + 3] - mean) * rstd * g4.w + b4.w;
+          *reinterpret_cast<float4*>(tokens + tok * C + c0) = o;
+        }
+      }
     }
   }
 }
@@ -375,21 +401,23 @@ int patch_embed(const void* images, int img_dtype, int B, int H, int W, int Hp, 
                 const float* stdv, const float* conv_w, const float* conv_b, const float* gamma, const float* beta, int C,
                 float* tokens, cudaStream_t st) {
   RBA_CHECK(images && conv_w && conv_b && gamma && beta && tokens, "patch_embed: null pointer");
-  RBA_CHECK(Hp % 4 == 0 && Wp % 4 == 0 && Hp >= H && Wp >= W, "patch_embed: bad padded size");
-  RBA_CHECK(C <= 256, "patch_embed: C=%d > 256", C);
-  const int64_t ntok = (int64_t)B * (Hp / 4) * (Wp / 4);
-  if (ntok == 0) return RBA_OK;
-  dim3 grid((unsigned)std::min<int64_t>(cdiv(ntok, 8), 148 * 8));
-  const size_t smem = (size_t)(48 * C + 8 * 48) * sizeof(float);
-  RBA_CUDA(cudaFuncSetAttribute(patch_embed_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  RBA_CUDA(cudaFuncSetAttribute(patch_embed_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (img_dtype == RBA_IMG_U8)
-    patch_embed_kernel<uint8_t><<<grid, 256, smem, st>>>((const uint8_t*)images, B, H, W, Hp, Wp, mean[0], mean[1], mean[2],
-                                                      stdv[0], stdv[1], stdv[2], conv_w, conv_b, gamma, beta, C, tokens);
-  else if (img_dtype == RBA_IMG_F32)
-    patch_embed_kernel<float><<<grid, 256, smem, st>>>((const float*)images, B, H, W, Hp, Wp, mean[0], mean[1], mean[2],
-                                                    stdv[0], stdv[1], stdv[2], conv_w, conv_b, gamma, beta, C, tokens);
+  RBA_CHECK(Hp % 8 == 0 && Wp % 8 == 0 && Hp >= H && Wp >= W, "patch_embed: padded size must be a multiple of 8");
+  RBA_CHECK(C <= 256 && C % 4 == 0, "patch_embed: C=%d unsupported", C);
+  const int64_t npair = (int64_t)B * (Hp / 4) * (Wp / 8);
+  if (npair == 0) return RBA_OK;
+  dim3 grid((unsigned)std::min<int64_t>(cdiv(npair, 8), 148 * 4));
+  const int G = C > 128 ? 2 : 1;
+  const size_t smem = (size_t)(48 * 128 * G + 8 * 96) * sizeof(float);
+#define RBA_PE(T, GG)                                                                                                   \
+  do {                                                                                                                  \
+    RBA_CUDA(cudaFuncSetAttribute(patch_embed_kernel<T, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    patch_embed_kernel<T, GG><<<grid, 256, smem, st>>>((const T*)images, B, H, W, Hp, Wp, mean[0], mean[1], mean[2],   \
+                                                       stdv[0], stdv[1], stdv[2], conv_w, conv_b, gamma, beta, C, tokens); \
+  } while (0)
+  if (img_dtype == RBA_IMG_U8) { if (G == 1) RBA_PE(uint8_t, 1); else RBA_PE(uint8_t, 2); }
+  else if (img_dtype == RBA_IMG_F32) { if (G == 1) RBA_PE(float, 1); else RBA_PE(float, 2); }
   else return fail(RBA_ERR_INVALID, "patch_embed: bad image dtype %d", img_dtype);
+#undef RBA_PE
   RBA_LAUNCHED();
   return RBA_OK;
 }
