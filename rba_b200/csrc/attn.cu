@@ -295,8 +295,10 @@ window_attn_mma_kernel(const uint16_t* __restrict__ qkv_hi, const uint16_t* __re
   float* sB = reinterpret_cast<float*>(wm_smem + 6 * WM_PLANE * 2);     // [529] relative position bias * log2(e)
   int* sCol = reinterpret_cast<int*>(sB + 532);                          // [144] (ci*23 + cj) | region << 16
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int head = blockIdx.y;
-  const int64_t win = blockIdx.x;
+  // heads fastest: the CTAs of one window run together, so the 128-byte lines that hold two heads' 64-byte q/k/v
+  // segments are fetched from HBM once
+  const int head = blockIdx.x % heads;
+  const int64_t win = blockIdx.x / heads;
   const int ww = (int)(win % nWw), wh = (int)((win / nWw) % nWh);
   const int Hp = nWh * WA_WS, Wp = nWw * WA_WS;
   constexpr float LOG2E = 1.4426950408889634f;
@@ -393,7 +395,8 @@ int window_attn_planes(const uint16_t* qkv_hi, const uint16_t* qkv_lo, const flo
   RBA_CHECK(nwin < (1LL << 31), "window_attn_planes: too many windows");
   const size_t smem = (size_t)6 * WM_PLANE * 2 + 532 * 4 + WA_N * 4;
   RBA_CUDA(cudaFuncSetAttribute(window_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)nwin, (unsigned)heads);
+  RBA_CHECK(nwin * heads < (1LL << 31), "window_attn_planes: grid too large");
+  dim3 grid((unsigned)(nwin * heads));
   window_attn_mma_kernel<<<grid, WM_THREADS, smem, st>>>(qkv_hi, qkv_lo, bias_table, C, heads, g.nWh, g.nWw, shift,
                                                          1.0f / sqrtf((float)WA_D), out_hi, out_lo);
   RBA_LAUNCHED();
