@@ -275,10 +275,16 @@ def run_ours(args):
         peaks = json.load(open(pk))
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    # DRAM traffic of this kernel from the committed `ncu --set full` capture (dram__bytes_read.sum + dram__bytes_write.sum,
+    # per image; profiles/r1_score_kernel_traffic.json), scaled to this launch's batch
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r1_score_kernel_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp))["dram_bytes_per_image"] * B
     roofline = {"kernel": "rba_score_mma_kernel<19> (x4 bilinear + sigmoid + (Q,K) contraction on mma.sync fp16 hi/lo + tanh + sum)", "bound": "hbm",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst, kernel timed alone)" if peaks else "fallback 6.65 TB/s",
-                "traffic": None, "ms_per_launch": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "traffic": traffic, "ms_per_launch": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "note": "fp32 semantics make this kernel FMA/MUFU-bound, not HBM-bound (SURVEY §0.5): "
                         "2*K*Q FLOP + Q sigmoid per output pixel vs 29 B/pixel"}
 
