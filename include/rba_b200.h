@@ -105,6 +105,15 @@ int rba_model_get_tap(rba_model* m, const char* name, float* dst, int64_t capaci
 int rba_score_fused(const float* pred_masks, const float* pred_logits, int B, int Q, int K, int h, int w, int H,
                     int W, float* rba, float* sem_seg, void* stream);
 
+/* ---- fused mask einsum + score (SURVEY §8d "Variant A": the kernel the engine runs for rba-only calls) ----
+ * Same result as  pred_masks = einsum("bqc,bchw->bqhw", mask_embed, features) + bias[:, :, None, None]
+ * (mask2former_transformer_decoder.py:479) followed by rba_score_fused, without materialising pred_masks.
+ * mask_embed (B,Q,D) and features (B,h,w,D) [NHWC] are bf16 split planes (see above); bias (B,Q) fp32 or NULL;
+ * pred_logits (B,Q,K+1).  Limits: Q <= 104, K <= 24, D a multiple of 64.  sem_seg may be NULL. */
+int rba_einsum_score_fused(const uint16_t* embed_hi, const uint16_t* embed_lo, const float* bias, const uint16_t* feat_hi,
+                           const uint16_t* feat_lo, const float* pred_logits, int B, int Q, int K, int D, int h, int w,
+                           int H, int W, float* rba, float* sem_seg, void* stream);
+
 /* ---- MSDeformAttn forward, same argument meaning as the reference FFI ----
  * value (B,S,M,D) fp32 (device); spatial_shapes (L,2) int64 (H_l,W_l) and level_start_index (L) int64 are HOST
  * arrays (shape metadata: the reference reads them on the host too, ms_deform_attn_cuda.cu:44-52 sizes);

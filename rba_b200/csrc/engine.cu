@@ -90,6 +90,7 @@ struct rba_model {
   bool taps_enabled = false;
   int attn_backend = 1;             // 1: tensor-core window attention (mma.sync bf16x3), 0: fp32 CUDA-core kernel
   int gemm_backend = RBA_GEMM_TC;   // tcgen05 bf16x3; RBA_GEMM_BACKEND=ffma selects the exact fp32 FMA kernels
+  int fused_score = 1;              // 1: last mask einsum + score in one kernel (score_fused.cu) when pred_masks is not asked for
   std::unordered_map<std::string, DevTensor> w;
   std::unordered_map<std::string, Planes> wp;      // split planes of GEMM weights, by key
   std::vector<void*> owned;                         // cudaMalloc'ed blocks (weights, derived)
@@ -184,6 +185,8 @@ extern "C" int rba_model_create(const rba_config* cfg, int device, rba_model** o
   const char* be = getenv("RBA_GEMM_BACKEND");
   if (be && std::string(be) == "tc") m->gemm_backend = RBA_GEMM_TC;
   if (be && std::string(be) == "ffma") m->gemm_backend = RBA_GEMM_FFMA;
+  const char* fs = getenv("RBA_FUSED_SCORE");
+  if (fs && fs[0] == '0') m->fused_score = 0;
   *out = m;
   return RBA_OK;
 }
@@ -200,6 +203,10 @@ extern "C" int rba_model_set_option(rba_model* m, const char* name, int value) {
   } else if (n == "attn_backend") {
     RBA_CHECK(value == 0 || value == 1, "bad attn backend %d", value);
     m->attn_backend = value;
+    m->rB = m->rH = m->rW = 0;
+  } else if (n == "fused_score") {
+    RBA_CHECK(value == 0 || value == 1, "bad fused_score %d", value);
+    m->fused_score = value;
     m->rB = m->rH = m->rW = 0;
   } else return fail(RBA_ERR_INVALID, "unknown option '%s'", name);
   return RBA_OK;
@@ -672,7 +679,14 @@ static int forward_impl(rba_model* m, const void* images, int img_dtype, int B, 
   for (int l = 0; l < L; ++l) maxS = std::max(maxS, lv.H[l] * lv.W[l]);
   uint8_t* am = (uint8_t*)A.alloc((size_t)BQ * maxS);
 
-  auto heads = [&](int target_level) -> int {   // forward_prediction_heads (:472-489)
+  // The last prediction head feeds only the score: its mask einsum is fused into the score kernel (score_fused.cu)
+  // unless the caller wants pred_masks itself.
+  const bool fuse_last = m->fused_score && !pred_masks_out && F.backend == RBA_GEMM_TC &&
+                         einsum_score_supported(Q, c.num_classes, D) && (rba_out || sem_seg);
+  Planes ef = A.planes(BQ * D);                 // E' = mask_embed . Wmf (kept for the fused kernel)
+  float* bq = A.f32(BQ);                        // b' = mask_embed . bmf
+
+  auto heads = [&](int target_level, bool last) -> int {   // forward_prediction_heads (:472-489)
     const size_t mk = A.mark();
     Planes dn = A.planes(BQ * D);
     RBA_RUN(layernorm(out, F.W(pr + "decoder_norm.weight"), F.W(pr + "decoder_norm.bias"), 0, 1, 1, (int)BQ, D, 0, 0, eps,
@@ -686,12 +700,10 @@ static int forward_impl(rba_model* m, const void* images, int img_dtype, int B, 
     RBA_TRY(F.lin(m2, D, BQ, D, F.P(pr + "mask_embed.layers.2.weight"), c.mask_dim, F.W(pr + "mask_embed.layers.2.bias"),
                   RBA_ACT_NONE, nullptr, nullptr, 0, me, c.mask_dim));
     // fold mask_features: E' = E Wmf, b' = E bmf
-    Planes ef = A.planes(BQ * D);
-    float* bq = A.f32(BQ);
     RBA_TRY(F.lin(me, c.mask_dim, BQ, c.mask_dim, F.P(pd + "mask_features.weightT"), D, nullptr, RBA_ACT_NONE, nullptr, nullptr,
                   0, ef, D));
     RBA_TRY(F.lin(me, c.mask_dim, BQ, c.mask_dim, F.P(pd + "mask_features.bias_row"), 1, nullptr, RBA_ACT_NONE, nullptr, bq, 1));
-    {  // masks[b] (Q, HW) = E'[b] (Q, D) . y[b]^T (HW, D) + b'[b]   (einsum "bqc,bchw->bqhw", :479)
+    if (!(last && fuse_last)) {  // masks[b] (Q, HW) = E'[b] (Q, D) . y[b]^T (HW, D) + b'[b]   (einsum "bqc,bchw->bqhw", :479)
       rba_gemm_args ga;
       memset(&ga, 0, sizeof(ga));
       ga.a_hi = ef.hi; ga.a_lo = ef.lo; ga.lda = D; ga.a_bstride = (int64_t)Q * D;
@@ -701,13 +713,13 @@ static int forward_impl(rba_model* m, const void* images, int img_dtype, int B, 
       ga.c = masks; ga.ldc = HWm; ga.c_bstride = (int64_t)Q * HWm;
       ga.backend = F.backend;
       RBA_RUN(gemm(ga, st));
+      if (!last) RBA_RUN(attn_mask(masks, B, Q, mH, mW, lv.H[target_level], lv.W[target_level], am, st));
     }
-    RBA_RUN(attn_mask(masks, B, Q, mH, mW, lv.H[target_level], lv.W[target_level], am, st));
     A.release(mk);
     return RBA_OK;
   };
 
-  RBA_TRY(heads(0));
+  RBA_TRY(heads(0, c.dec_layers == 0));
   const float* qe = F.W(pr + "query_embed.weight");
   for (int i = 0; i < c.dec_layers; ++i) {
     const int l = i % L;
@@ -765,7 +777,7 @@ static int forward_impl(rba_model* m, const void* images, int img_dtype, int B, 
       RBA_RUN(layernorm(t, F.W(ff + "norm.weight"), F.W(ff + "norm.bias"), 0, 1, 1, (int)BQ, D, 0, 0, eps, out, nullptr, nullptr, st));
     }
     A.release(mk);
-    RBA_TRY(heads((i + 1) % L));
+    RBA_TRY(heads((i + 1) % L, i == c.dec_layers - 1));
   }
   F.tap("dec_out", out, BQ * D);
 
@@ -776,7 +788,10 @@ static int forward_impl(rba_model* m, const void* images, int img_dtype, int B, 
   if (rba_out || sem_seg) {
     float* ro = rba_out;
     if (!ro) ro = A.f32((int64_t)B * H * W);
-    RBA_RUN(rba_score_fused(masks, cls, B, Q, c.num_classes, mH, mW, H, W, ro, sem_seg, (void*)st));
+    if (fuse_last)
+      RBA_RUN(einsum_score_launch(ef.hi, ef.lo, bq, ypl.hi, ypl.lo, cls, B, Q, c.num_classes, D, mH, mW, H, W, ro, sem_seg, st));
+    else
+      RBA_RUN(rba_score_fused(masks, cls, B, Q, c.num_classes, mH, mW, H, W, ro, sem_seg, (void*)st));
   }
   if (!dry && A.overflow) return fail(RBA_ERR_STATE, "workspace overflow (reserved %zu, needed %zu)", A.cap, A.peak);
   return RBA_OK;

@@ -1,0 +1,429 @@
+// Fused mask einsum + RbA score: ONE pass from the pixel decoder's feature planes to the score map
+// (SURVEY §8d "Variant A"; the kernel BASELINE.json's metric names).
+//
+// Replaces, per image (mask2former_transformer_decoder.py:479, maskformer_model.py:294-299,381-386,
+// evaluate_ood.py:148-150; the mask_features 1x1 conv of msdeformattn.py:254-260 is already folded into E'):
+//   m[q,i,j]   = sum_c E'[q,c] y[i,j,c] + b'[q]                          einsum "bqc,bchw->bqhw"   (tcgen05, bf16x3)
+//   u[q,Y,X]   = bilinear x4 (align_corners=False) of m                   F.interpolate             (mma.sync tf32)
+//   s[k,Y,X]   = sum_q softmax(logits[q,:])[k] * sigmoid(u[q,Y,X])        semantic_inference        (mma.sync f16 hi/lo)
+//   rba[Y,X]   = -sum_k tanh(s[k,Y,X])                                    get_RbA
+// Neither the (Q,h,w) mask logits, nor the (Q,4h,4w) upsampled masks, nor (unless asked for) the (K,4h,4w) sem_seg
+// ever reach HBM.  Algorithmic HBM bytes per image: 4*D*h*w (feature planes) + 4*Q*D + 4*Q*(K+2) + 4*H*W.
+//
+// Persistent kernel, one CTA per SM, 18 warps.  A tile is an 8 x 16 patch of low-resolution pixels (M = 128 rows of the
+// einsum GEMM) whose 7 x 15 interior cells each own the 4 x 4 output pixels that interpolate between the cell's four
+// corner taps; neighbouring tiles overlap by one low-res row/column (22 % redundant GEMM work, no halo exchange).
+//   warp 0      TMA producer: feature planes through a 4-D NHWC map (out-of-bounds rows/cols zero-filled) and E' planes,
+//               K blocks of 64 channels into a 2-stage mbarrier ring.
+//   warp 1      MMA issuer: 3 tcgen05.mma (hi*hi, hi*lo, lo*hi) per K=16 step into a 128 x 112 fp32 TMEM accumulator.
+//   warps 2-17  drain TMEM -> shared memory as patch[pixel][query] (scaled by -log2 e, bias added), then per cell:
+//               interpolation as a 16x8x8 tf32 MMA (A = the 16 pixels' tap weights, exact in tf32; B = the four taps of
+//               8 queries as tf32 hi|lo), sigmoid on the MUFU pipe (ex2 + rcp), the C fragment re-used in place as the A
+//               fragment of the (pixel x query) x (query x class) contraction on f16 hi/lo MMAs, tanh + class sum with
+//               quad shuffles.  The MMAs of tile i+1 overlap the score phase of tile i (the accumulator is drained first).
+#include <cuda_fp16.h>
+
+#include "tcgen05.cuh"
+
+namespace rba {
+
+constexpr int FS_NQ = 112;                                  // MMA N: queries padded to a multiple of 16
+constexpr int FS_QP = 104;                                  // patch pitch (words): queries kept; = 8 (mod 32)
+constexpr int FS_ROWSTRIDE = TC_CONV_TW * FS_QP + 16;       // 1680 words: = 16 (mod 32) -> the 4 taps hit 4 bank groups
+constexpr int FS_BR = TC_CONV_TH - 1, FS_BC = TC_CONV_TW - 1, FS_NBLK = FS_BR * FS_BC;   // 7 x 15 cells
+constexpr int FS_STAGES = 2;
+constexpr int FS_A_BYTES = TC_BM * TC_BK * 2;               // 16 KB: one plane of the feature tile per K block
+constexpr int FS_E_BYTES = FS_NQ * TC_BK * 2;               // 14 KB: one plane of E'
+constexpr int FS_STAGE_BYTES = 2 * FS_A_BYTES + 2 * FS_E_BYTES;
+constexpr int FS_PATCH_BYTES = TC_CONV_TH * FS_ROWSTRIDE * 4;
+constexpr int FS_KS = 7;                                    // k16 steps in the probability layout
+constexpr int FS_NT = 3;                                    // n8 class tiles (K <= 24)
+constexpr int FS_P_BYTES = FS_NT * 8 * FS_KS * 4 * 16;      // [class][k16 step][tq] x {b0_hi, b1_hi, b0_lo, b1_lo}
+constexpr int FS_BIAS_BYTES = 512;
+constexpr int FS_CW = 16;                                   // compute warps
+constexpr int FS_THREADS = (2 + FS_CW) * 32;
+constexpr int FS_SMEM = FS_STAGES * FS_STAGE_BYTES + FS_PATCH_BYTES + FS_P_BYTES + FS_BIAS_BYTES + 128 + 1024;
+constexpr uint32_t FS_TMEM_COLS = 128;
+
+struct FsParams {
+  const float* logits;   // (B, Q, K+1)
+  const float* bias;     // (B, Q) or null
+  float* rba;            // (B, H, W)
+  float* sem;            // (B, K, H, W) or null
+  int B, Q, K, h, w, H, W;
+  int nkb;               // D / 64
+  int tilesX, tilesY, ntiles;
+};
+
+__device__ __forceinline__ float fs_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fs_ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// u = -x log2(e): sigmoid(x) = 1 / (1 + 2^u); 2^u -> +inf gives rcp(inf) = 0
+__device__ __forceinline__ float fs_sigmoid_scaled(float u) { return fs_rcp(1.0f + fs_ex2(u)); }
+// tanh(x), x >= 0: 1 - 2 / (1 + e^(2x))
+__device__ __forceinline__ float fs_tanh_pos(float x) { return 1.0f - 2.0f * fs_rcp(1.0f + fs_ex2(2.8853900817779268f * x)); }
+
+__device__ __forceinline__ uint32_t fs_pack_f16x2(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
+__device__ __forceinline__ void fs_split_f16x2(float e0, float e1, uint32_t& hi, uint32_t& lo) {
+  hi = fs_pack_f16x2(e0, e1);
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  lo = fs_pack_f16x2(e0 - f.x, e1 - f.y);
+}
+__device__ __forceinline__ void fs_mma_tf32(float* d, uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%4,%5}, {%6,%7}, {%8,%8,%8,%8};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a0), "r"(a1), "r"(b0), "r"(b1), "f"(0.0f));
+}
+__device__ __forceinline__ void fs_mma_f16(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void fs_mma_f16_k8(float* c, uint32_t a0, uint32_t a1, uint32_t b0) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(b0));
+}
+__device__ __forceinline__ void fs_bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(FS_CW * 32) : "memory"); }
+
+// Interpolated, scaled logits of 16 pixels x 8 queries: one LDS (this lane's tap of query g), tf32 hi|lo, one MMA.
+__device__ __forceinline__ void fs_interp8(const float* tp, uint32_t a0, uint32_t a1, float* u) {
+  const float v = *tp;
+  const uint32_t hi = __float_as_uint(v) & 0xffffe000u;
+  const float lo = v - __uint_as_float(hi);
+  fs_mma_tf32(u, a0, a1, hi, __float_as_uint(lo));
+}
+
+template <bool WRITE_SEM>
+__global__ void __launch_bounds__(FS_THREADS, 1)
+rba_einsum_score_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constant__ CUtensorMap tmY_lo,
+                        const __grid_constant__ CUtensorMap tmE_hi, const __grid_constant__ CUtensorMap tmE_lo,
+                        const FsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* sPatch = reinterpret_cast<float*>(smem + FS_STAGES * FS_STAGE_BYTES);
+  uint4* sP = reinterpret_cast<uint4*>(smem + FS_STAGES * FS_STAGE_BYTES + FS_PATCH_BYTES);
+  float* sBias = reinterpret_cast<float*>(smem + FS_STAGES * FS_STAGE_BYTES + FS_PATCH_BYTES + FS_P_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FS_STAGES * FS_STAGE_BYTES + FS_PATCH_BYTES + FS_P_BYTES + FS_BIAS_BYTES);
+  uint64_t* full = bars;                    // [FS_STAGES]
+  uint64_t* empty = bars + FS_STAGES;       // [FS_STAGES]
+  uint64_t* acc_full = bars + 2 * FS_STAGES;
+  uint64_t* acc_empty = bars + 2 * FS_STAGES + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * FS_STAGES + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmY_hi); prefetch_tmap(&tmY_lo); prefetch_tmap(&tmE_hi); prefetch_tmap(&tmE_lo);
+    for (int s = 0; s < FS_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, FS_CW);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(FS_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+        const int tx = t % p.tilesX;
+        const int r = t / p.tilesX;
+        const int ty = r % p.tilesY, b = r / p.tilesY;
+        const int r0 = FS_BR * ty - 1, c0 = FS_BC * tx - 1;
+        for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+          const int s = it % FS_STAGES;
+          const uint32_t ph = (it / FS_STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* st = smem + s * FS_STAGE_BYTES;
+          mbar_expect_tx(&full[s], FS_STAGE_BYTES);
+          tma_load_4d(st, &tmY_hi, &full[s], kb * TC_BK, c0, r0, b);
+          tma_load_4d(st + FS_A_BYTES, &tmY_lo, &full[s], kb * TC_BK, c0, r0, b);
+          tma_load_3d(st + 2 * FS_A_BYTES, &tmE_hi, &full[s], kb * TC_BK, 0, b);
+          tma_load_3d(st + 2 * FS_A_BYTES + FS_E_BYTES, &tmE_lo, &full[s], kb * TC_BK, 0, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(TC_BM, FS_NQ);
+      uint32_t it = 0, lt = 0;
+      for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++lt) {
+        mbar_wait(acc_empty, (lt & 1) ^ 1);              // the previous tile's accumulator has been drained
+        tc_fence_after();
+        for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+          const int s = it % FS_STAGES;
+          const uint32_t ph = (it / FS_STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t base = smem_u32(smem + s * FS_STAGE_BYTES);
+          const uint64_t a_hi = make_sdesc(base), a_lo = make_sdesc(base + FS_A_BYTES);
+          const uint64_t e_hi = make_sdesc(base + 2 * FS_A_BYTES), e_lo = make_sdesc(base + 2 * FS_A_BYTES + FS_E_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+            umma_bf16(tmem_base, a_hi + adv, e_hi + adv, idesc, (kb | k) != 0);
+            umma_bf16(tmem_base, a_hi + adv, e_lo + adv, idesc, 1);
+            umma_bf16(tmem_base, a_lo + adv, e_hi + adv, idesc, 1);
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(acc_full);
+      }
+    }
+  } else {
+    // ===================== drain + score: warps 2..17 =====================
+    const int cw = warp - 2;
+    const int ctid = cw * 32 + lane;                       // 0..511
+    const int qd = warp & 3, jq = cw >> 2;                 // TMEM lane quadrant of this warp; index among its 4 warps
+    const int g = lane >> 2, tq = lane & 3;
+    const int tr = tq >> 1, tcn = tq & 1;                  // tap row / column select of this lane
+    const float SCALE = -1.4426950408889634f;
+    const int ngroups = (p.Q + 7) >> 3, nfull = ngroups >> 1, tail = ngroups & 1;
+    int cur_b = -1;
+    uint32_t lt = 0;
+    for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++lt) {
+      const int tx = t % p.tilesX;
+      const int rr = t / p.tilesX;
+      const int ty = rr % p.tilesY, b = rr / p.tilesY;
+      const int r0 = FS_BR * ty - 1, c0 = FS_BC * tx - 1;
+      if (b != cur_b) {
+        // ---- per image: class probabilities as f16 hi/lo MMA B fragments, scaled bias ----
+        cur_b = b;
+        for (int e = ctid; e < FS_P_BYTES / 16; e += FS_CW * 32) sP[e] = make_uint4(0u, 0u, 0u, 0u);
+        if (ctid < FS_NQ) sBias[ctid] = (p.bias && ctid < p.Q) ? p.bias[(size_t)b * p.Q + ctid] * SCALE : 0.f;
+        fs_bar_compute();
+        if (ctid < p.Q) {
+          const int q = ctid;
+          const float* lg = p.logits + ((size_t)b * p.Q + q) * (p.K + 1);
+          float m = lg[0];
+          for (int c = 1; c <= p.K; ++c) m = fmaxf(m, lg[c]);
+          float ssum = 0.f;
+          for (int c = 0; c <= p.K; ++c) ssum += expf(lg[c] - m);
+          const float inv = 1.0f / ssum;
+          const int ks = q >> 4, r = q & 15;
+          const int hoff = (r >> 3) * 2 + (r & 1);         // half index inside the 16-byte entry (hi); lo = +4
+          __half* base = reinterpret_cast<__half*>(sP) + ((size_t)ks * 4 + ((r & 7) >> 1)) * 8 + hoff;
+          for (int c = 0; c < p.K; ++c) {
+            const float pv = expf(lg[c] - m) * inv;
+            const __half hh = __float2half_rn(pv);
+            __half* d = base + (size_t)c * FS_KS * 4 * 8;
+            d[0] = hh;
+            d[4] = __float2half_rn(pv - __half2float(hh));
+          }
+        }
+        fs_bar_compute();
+      }
+      // ---- drain the accumulator: TMEM lane = low-res pixel, column = query ----
+      mbar_wait(acc_full, lt & 1);
+      tc_fence_after();
+      {
+        const int m = qd * 32 + lane;
+        float* prow = sPatch + (m >> 4) * FS_ROWSTRIDE + (m & 15) * FS_QP;
+        for (int chunk = jq; chunk * 16 < FS_QP; chunk += 4) {
+          const int q0 = chunk * 16;
+          uint32_t v[16];
+          const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)q0;
+          if (q0 + 16 <= FS_QP) {
+            tmem_ld16(taddr, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 b4 = *reinterpret_cast<const float4*>(sBias + q0 + 4 * j);
+              float4 o;
+              o.x = fmaf(__uint_as_float(v[4 * j]), SCALE, b4.x);
+              o.y = fmaf(__uint_as_float(v[4 * j + 1]), SCALE, b4.y);
+              o.z = fmaf(__uint_as_float(v[4 * j + 2]), SCALE, b4.z);
+              o.w = fmaf(__uint_as_float(v[4 * j + 3]), SCALE, b4.w);
+              *reinterpret_cast<float4*>(prow + q0 + 4 * j) = o;
+            }
+          } else {
+            tmem_ld8(taddr, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const float4 b4 = *reinterpret_cast<const float4*>(sBias + q0 + 4 * j);
+              float4 o;
+              o.x = fmaf(__uint_as_float(v[4 * j]), SCALE, b4.x);
+              o.y = fmaf(__uint_as_float(v[4 * j + 1]), SCALE, b4.y);
+              o.z = fmaf(__uint_as_float(v[4 * j + 2]), SCALE, b4.z);
+              o.w = fmaf(__uint_as_float(v[4 * j + 3]), SCALE, b4.w);
+              *reinterpret_cast<float4*>(prow + q0 + 4 * j) = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);               // the MMAs of the next tile may start
+      fs_bar_compute();                                    // patch complete
+
+      // ---- score phase: one 4x4 output cell per warp iteration ----
+      for (int blk = cw; blk < FS_NBLK; blk += FS_CW) {
+        const int br = blk / FS_BC, bc = blk - br * FS_BC;
+        const int i = r0 + br, j = c0 + bc;                // low-res coordinates of the cell's top-left tap
+        if (i > p.h - 1 || j > p.w - 1) continue;
+        const int y0 = 4 * i + 2, x0 = 4 * j + 2;          // the cell's 4x4 output pixels
+        if (y0 >= p.H || x0 >= p.W) continue;
+        // tap weights (align_corners=False, scale 4): l1 = 1/8 + d/4 on the lower/right tap; image borders clamp
+        const int dyA = g >> 2, dx = g & 3;
+        const float lyA = 0.125f + 0.25f * (float)dyA, lyB = lyA + 0.5f, lxx = 0.125f + 0.25f * (float)dx;
+        float wyA = tr ? lyA : 1.f - lyA, wyB = tr ? lyB : 1.f - lyB, wx = tcn ? lxx : 1.f - lxx;
+        if (i < 0) wyA = wyB = tr ? 1.f : 0.f;
+        if (i == p.h - 1) wyA = wyB = tr ? 0.f : 1.f;
+        if (j < 0) wx = tcn ? 1.f : 0.f;
+        if (j == p.w - 1) wx = tcn ? 0.f : 1.f;
+        const uint32_t a0 = __float_as_uint(wyA * wx), a1 = __float_as_uint(wyB * wx);
+        const float* tp = sPatch + (br + tr) * FS_ROWSTRIDE + (bc + tcn) * FS_QP + g;
+        const uint4* bp = sP + (size_t)g * FS_KS * 4 + tq;
+
+        float acc[FS_NT][4];
+#pragma unroll
+        for (int nt = 0; nt < FS_NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll 1
+        for (int ks = 0; ks < nfull; ++ks) {
+          float u0[4], u1[4];
+          fs_interp8(tp + ks * 16, a0, a1, u0);            // queries 16ks + {2tq, 2tq+1}: rows g (u[0..1]), g+8 (u[2..3])
+          fs_interp8(tp + ks * 16 + 8, a0, a1, u1);        // queries 16ks + 8 + {2tq, 2tq+1}
+          uint32_t ah[4], al[4];
+          fs_split_f16x2(fs_sigmoid_scaled(u0[0]), fs_sigmoid_scaled(u0[1]), ah[0], al[0]);
+          fs_split_f16x2(fs_sigmoid_scaled(u0[2]), fs_sigmoid_scaled(u0[3]), ah[1], al[1]);
+          fs_split_f16x2(fs_sigmoid_scaled(u1[0]), fs_sigmoid_scaled(u1[1]), ah[2], al[2]);
+          fs_split_f16x2(fs_sigmoid_scaled(u1[2]), fs_sigmoid_scaled(u1[3]), ah[3], al[3]);
+          uint4 bv[FS_NT];
+#pragma unroll
+          for (int nt = 0; nt < FS_NT; ++nt) bv[nt] = bp[(size_t)nt * 8 * FS_KS * 4 + ks * 4];
+          // consecutive MMAs target different accumulators (no back-to-back dependent HMMAs)
+#pragma unroll
+          for (int nt = 0; nt < FS_NT; ++nt) fs_mma_f16(acc[nt], ah, bv[nt].x, bv[nt].y);
+#pragma unroll
+          for (int nt = 0; nt < FS_NT; ++nt) fs_mma_f16(acc[nt], ah, bv[nt].z, bv[nt].w);
+#pragma unroll
+          for (int nt = 0; nt < FS_NT; ++nt) fs_mma_f16(acc[nt], al, bv[nt].x, bv[nt].y);
+        }
+        if (tail) {
+          float u0[4];
+          fs_interp8(tp + nfull * 16, a0, a1, u0);
+          uint32_t ah0, al0, ah1, al1;
+          fs_split_f16x2(fs_sigmoid_scaled(u0[0]), fs_sigmoid_scaled(u0[1]), ah0, al0);
+          fs_split_f16x2(fs_sigmoid_scaled(u0[2]), fs_sigmoid_scaled(u0[3]), ah1, al1);
+          uint4 bv[FS_NT];
+#pragma unroll
+          for (int nt = 0; nt < FS_NT; ++nt) bv[nt] = bp[(size_t)nt * 8 * FS_KS * 4 + nfull * 4];
+#pragma unroll
+          for (int nt = 0; nt < FS_NT; ++nt) fs_mma_f16_k8(acc[nt], ah0, ah1, bv[nt].x);
+#pragma unroll
+          for (int nt = 0; nt < FS_NT; ++nt) fs_mma_f16_k8(acc[nt], ah0, ah1, bv[nt].z);
+#pragma unroll
+          for (int nt = 0; nt < FS_NT; ++nt) fs_mma_f16_k8(acc[nt], al0, al1, bv[nt].x);
+        }
+        // ---- epilogue: acc[nt][e] = sem_seg[class 8nt+2tq+e] of pixel A (row g), acc[nt][2+e] of pixel B (row g+8) ----
+        const int yA = y0 + dyA, yB = yA + 2, x = x0 + dx;
+        const bool okx = x >= 0 && x < p.W;
+        const bool okA = okx && yA >= 0 && yA < p.H, okB = okx && yB >= 0 && yB < p.H;
+        float ra = 0.f, rb = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < FS_NT; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            ra += fs_tanh_pos(acc[nt][e]);                 // padded classes hold exactly 0: tanh = 0
+            rb += fs_tanh_pos(acc[nt][2 + e]);
+            if (WRITE_SEM) {
+              const int c = nt * 8 + tq * 2 + e;
+              if (c < p.K) {
+                if (okA) p.sem[(((size_t)b * p.K + c) * p.H + yA) * p.W + x] = acc[nt][e];
+                if (okB) p.sem[(((size_t)b * p.K + c) * p.H + yB) * p.W + x] = acc[nt][2 + e];
+              }
+            }
+          }
+        ra += __shfl_xor_sync(0xffffffffu, ra, 1);
+        ra += __shfl_xor_sync(0xffffffffu, ra, 2);
+        rb += __shfl_xor_sync(0xffffffffu, rb, 1);
+        rb += __shfl_xor_sync(0xffffffffu, rb, 2);
+        if (tq == 0 && okA) p.rba[((size_t)b * p.H + yA) * p.W + x] = -ra;
+        if (tq == 1 && okB) p.rba[((size_t)b * p.H + yB) * p.W + x] = -rb;
+      }
+      fs_bar_compute();                                    // patch (and, at an image change, sP) free for the next tile
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(FS_TMEM_COLS) : "memory");
+  }
+}
+
+int einsum_score_supported(int Q, int K, int D) { return Q > 0 && Q <= FS_QP && K > 0 && K <= FS_NT * 8 && K + 1 <= 64 && D % TC_BK == 0; }
+
+int einsum_score_launch(const uint16_t* e_hi, const uint16_t* e_lo, const float* bias, const uint16_t* y_hi,
+                        const uint16_t* y_lo, const float* logits, int B, int Q, int K, int D, int h, int w, int H, int W,
+                        float* rba, float* sem, cudaStream_t st) {
+  RBA_CHECK(einsum_score_supported(Q, K, D), "einsum_score: unsupported Q=%d (<= %d) K=%d (<= %d) D=%d (multiple of %d)", Q,
+            FS_QP, K, FS_NT * 8, D, TC_BK);
+  RBA_CHECK(((uintptr_t)e_hi & 15) == 0 && ((uintptr_t)e_lo & 15) == 0 && ((uintptr_t)y_hi & 15) == 0 && ((uintptr_t)y_lo & 15) == 0,
+            "einsum_score: operand planes must be 16-byte aligned");
+  FsParams p;
+  memset(&p, 0, sizeof(p));
+  p.logits = logits; p.bias = bias; p.rba = rba; p.sem = sem;
+  p.B = B; p.Q = Q; p.K = K; p.h = h; p.w = w; p.H = H; p.W = W;
+  p.nkb = D / TC_BK;
+  p.tilesX = (int)cdiv(w + 1, FS_BC); p.tilesY = (int)cdiv(h + 1, FS_BR);
+  const int64_t nt = (int64_t)B * p.tilesX * p.tilesY;
+  RBA_CHECK(nt < (1LL << 31), "einsum_score: too many tiles");
+  p.ntiles = (int)nt;
+  CUtensorMap ty_hi, ty_lo, te_hi, te_lo;
+  RBA_TRY_(make_map_nhwc(&ty_hi, y_hi, B, h, w, D));
+  RBA_TRY_(make_map_nhwc(&ty_lo, y_lo, B, h, w, D));
+  RBA_TRY_(make_map_3d(&te_hi, e_hi, D, Q, D, B, (int64_t)Q * D, FS_NQ));
+  RBA_TRY_(make_map_3d(&te_lo, e_lo, D, Q, D, B, (int64_t)Q * D, FS_NQ));
+  dim3 grid((unsigned)std::min<int64_t>(nt, num_sms()));
+  if (sem) {
+    static bool done = false;
+    if (!done) { RBA_CUDA(cudaFuncSetAttribute(rba_einsum_score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM)); done = true; }
+    rba_einsum_score_kernel<true><<<grid, FS_THREADS, FS_SMEM, st>>>(ty_hi, ty_lo, te_hi, te_lo, p);
+  } else {
+    static bool done = false;
+    if (!done) { RBA_CUDA(cudaFuncSetAttribute(rba_einsum_score_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM)); done = true; }
+    rba_einsum_score_kernel<false><<<grid, FS_THREADS, FS_SMEM, st>>>(ty_hi, ty_lo, te_hi, te_lo, p);
+  }
+  RBA_LAUNCHED();
+  return RBA_OK;
+}
+
+}  // namespace rba
+
+// mask_embed (B,Q,D) and features (B,h,w,D) as bf16 split planes; bias (B,Q) fp32 or NULL; pred_logits (B,Q,K+1).
+extern "C" int rba_einsum_score_fused(const uint16_t* embed_hi, const uint16_t* embed_lo, const float* bias,
+                                      const uint16_t* feat_hi, const uint16_t* feat_lo, const float* pred_logits, int B, int Q,
+                                      int K, int D, int h, int w, int H, int W, float* rba_out, float* sem_seg, void* stream) {
+  using namespace rba;
+  if (B == 0) return RBA_OK;
+  RBA_CHECK(embed_hi && embed_lo && feat_hi && feat_lo && pred_logits && rba_out, "rba_einsum_score_fused: null pointer");
+  RBA_CHECK(B > 0 && h > 0 && w > 0, "rba_einsum_score_fused: bad shape B=%d h=%d w=%d", B, h, w);
+  RBA_CHECK(H > 0 && W > 0 && H <= 4 * h && W <= 4 * w, "rba_einsum_score_fused: output (%d,%d) exceeds 4x(%d,%d)", H, W, h, w);
+  return einsum_score_launch(embed_hi, embed_lo, bias, feat_hi, feat_lo, pred_logits, B, Q, K, D, h, w, H, W, rba_out, sem_seg,
+                             (cudaStream_t)stream);
+}

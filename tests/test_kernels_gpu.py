@@ -304,6 +304,64 @@ def test_score_full_size_properties(dev):
     assert (s.cpu()[0] - expect[:, None, None]).abs().max() < 1e-5
 
 
+def _einsum_score_reference(E, Fm, bias, logits, H, W):
+    """fp64 einsum (mask2former_transformer_decoder.py:479) on the exact values the planes hold, then the oracle."""
+    masks = torch.einsum("bqc,bhwc->bqhw", E.double(), Fm.double())
+    if bias is not None:
+        masks = masks + bias.double()[:, :, None, None]
+    masks = masks.float()
+    h, w = Fm.shape[1:3]
+    sems, rbas = [], []
+    for b in range(E.shape[0]):
+        sem, r = O.score_from_head_outputs(logits[b], masks[b], (4 * h, 4 * w), (H, W))
+        sems.append(sem)
+        rbas.append(r)
+    return torch.stack(sems), torch.stack(rbas), masks
+
+
+@pytest.mark.parametrize("B,Q,K,D,h,w,crop", [(2, 100, 19, 256, 20, 37, (0, 0)), (1, 100, 19, 256, 8, 16, (3, 5)),
+                                               (1, 37, 3, 64, 5, 3, (0, 1)), (3, 104, 13, 128, 15, 31, (1, 0)),
+                                               (1, 100, 19, 256, 64, 128, (0, 0))])
+def test_einsum_score_fused(dev, B, Q, K, D, h, w, crop):
+    """Fused mask einsum + x4 upsample + semantic_inference + RbA (score_fused.cu) against the oracle on the same
+    inputs: several tiles per image, image borders, cropped outputs, Q not a multiple of 8/16, batch > 1."""
+    g = torch.Generator().manual_seed(B * 1000 + Q + h + w)
+    E = torch.randn(B, Q, D, generator=g) / math.sqrt(D) * 2.0
+    Fm = torch.randn(B, h, w, D, generator=g)
+    bias = torch.randn(B, Q, generator=g) * 0.5 - 0.5
+    logits = torch.randn(B, Q, K + 1, generator=g)
+    H, W = 4 * h - crop[0], 4 * w - crop[1]
+    (e_hi, e_lo), Ex = planes(E.view(B * Q, D), dev)
+    (f_hi, f_lo), Fx = planes(Fm.view(-1, D), dev)
+    e_pl = (e_hi.view(B, Q, D), e_lo.view(B, Q, D))
+    f_pl = (f_hi.view(B, h, w, D), f_lo.view(B, h, w, D))
+    sem_ref, rba_ref, masks = _einsum_score_reference(Ex.view(B, Q, D), Fx.view(B, h, w, D), bias, logits, H, W)
+    rba, sem = ops.einsum_score_fused(e_pl, f_pl, logits.to(dev), (H, W), bias=bias.to(dev), want_sem_seg=True)
+    assert (sem.cpu() - sem_ref).abs().max() < 5e-5, float((sem.cpu() - sem_ref).abs().max())
+    assert (rba.cpu() - rba_ref).abs().max() < 5e-5
+    rba2 = ops.einsum_score_fused(e_pl, f_pl, logits.to(dev), (H, W), bias=bias.to(dev))
+    assert torch.equal(rba2, rba)
+    # same answer as the two-kernel path (GEMM -> pred_masks -> rba_score_fused)
+    rba3 = ops.score_fused(masks.to(dev), logits.to(dev), (H, W))
+    assert (rba3 - rba).abs().max() < 5e-5
+    # no bias
+    sem_ref0, rba_ref0, _ = _einsum_score_reference(Ex.view(B, Q, D), Fx.view(B, h, w, D), None, logits, H, W)
+    rba0 = ops.einsum_score_fused(e_pl, f_pl, logits.to(dev), (H, W))
+    assert (rba0.cpu() - rba_ref0).abs().max() < 5e-5
+
+
+def test_einsum_score_fused_limits(dev):
+    z = lambda *s: torch.zeros(*s, dtype=torch.bfloat16, device=dev)  # noqa: E731
+    with pytest.raises(ops.RbaError):      # Q > 104
+        ops.einsum_score_fused((z(1, 105, 64), z(1, 105, 64)), (z(1, 4, 4, 64), z(1, 4, 4, 64)), torch.zeros(1, 105, 4, device=dev), (16, 16))
+    with pytest.raises(ops.RbaError):      # D not a multiple of 64
+        ops.einsum_score_fused((z(1, 10, 32), z(1, 10, 32)), (z(1, 4, 4, 32), z(1, 4, 4, 32)), torch.zeros(1, 10, 4, device=dev), (16, 16))
+    with pytest.raises(ops.RbaError):      # output larger than 4x
+        ops.einsum_score_fused((z(1, 10, 64), z(1, 10, 64)), (z(1, 4, 4, 64), z(1, 4, 4, 64)), torch.zeros(1, 10, 4, device=dev), (17, 16))
+    e = ops.einsum_score_fused((z(0, 10, 64), z(0, 10, 64)), (z(0, 4, 4, 64), z(0, 4, 4, 64)), torch.zeros(0, 10, 4, device=dev), (16, 16))
+    assert e.shape == (0, 16, 16)
+
+
 # ------------------------------------------------------------------------------------------------
 # tcgen05 bf16x3 backend: same contract as the FFMA kernel; tolerance = bf16x3 truncation (~1e-5 relative / product)
 # ------------------------------------------------------------------------------------------------

@@ -153,3 +153,34 @@ def test_forward_tc_backend_matches_reference_golden(dev, name):
     print(name, "tc", errs)
     for k, v in errs.items():
         assert v < TOL, (k, v)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_forward_fused_score_matches_reference_golden(dev, name):
+    """The product path of model.rba() / model(): last mask einsum fused into the score kernel (pred_masks never
+    materialised), against the same golden outputs of the unmodified reference; and against the two-kernel path."""
+    fix = load_golden(f"model_{name}.pt")
+    case = fix["case"]
+    mc = case_model_config(case)
+    sd = weights.init_state_dict(mc, seed=case["seed"], perturb=case["perturb"])
+    imgs = torch.stack(case_images(case)).to(dev)
+    e = _engine(mc, sd, dev)
+    n0 = rba_b200.launch_count()
+    out = e.forward(imgs, rba=True, sem_seg=True, logits=True)          # no pred_masks -> fused kernel
+    n_fused = rba_b200.launch_count() - n0
+    torch.cuda.synchronize()
+    errs = {
+        "pred_logits": (out["pred_logits"].cpu() - fix["pred_logits"]).abs().max().item(),
+        "sem_seg": (out["sem_seg"].cpu()[:, :, ::4, ::4] - fix["sem_seg_s4"]).abs().max().item(),
+        "rba": (out["rba"].cpu() - fix["rba"]).abs().max().item(),
+    }
+    print(name, "fused", errs)
+    for k, v in errs.items():
+        assert v < TOL, (k, v)
+    e.set_option("fused_score", 0)
+    n0 = rba_b200.launch_count()
+    two = e.forward(imgs, rba=True, sem_seg=True)
+    n_two = rba_b200.launch_count() - n0
+    assert n_fused == n_two - 1, (n_fused, n_two)                        # one GEMM launch less
+    assert (two["rba"] - out["rba"]).abs().max() < 1e-4
+    assert (two["sem_seg"] - out["sem_seg"]).abs().max() < 1e-4
