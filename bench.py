@@ -12,8 +12,8 @@ ckpts/swin_b_1dl architecture (no network for checkpoints), synthetic uint8 imag
          sharded, + ONE NCCL all-gather of the score maps per step), device-timed with CUDA events, max over ranks.
   e2e    the same metric through the public call with HOST buffers: pinned H2D of the uint8 batch + forward +
          D2H of the score maps inside the timed region.
-  roofline     the fused mask-upsample+sigmoid+contraction+tanh score kernel (the kernel BASELINE's metric names),
-               timed alone with CUDA events on its launch stream on inputs > L2 (420 MB at B=8).
+  roofline     the fused mask-einsum + upsample + sigmoid + contraction + tanh score kernel (the kernel BASELINE's metric
+               names; score_fused.cu), timed alone with CUDA events on its launch stream on inputs > L2 (1.07 GB at B=8).
   cpu_baseline the oracle port (oracle/rba_oracle.py, PyTorch CPU fp32, all host threads) on a bounded sample.
 
 `--impl reference` times that CPU port of the reference's path as the reference arm (rank 0 only).
@@ -189,10 +189,9 @@ def run_ours(args):
 
     # one eager forward: warms position tables / function attributes and counts this library's launches per step
     n0 = rba_b200.launch_count()
-    out = eng.forward(dev_imgs[0], rba=True, logits=True, masks=True)
+    out = eng.forward(dev_imgs[0], rba=True)
     torch.cuda.synchronize()
     launches_per_step = rba_b200.launch_count() - n0
-    pred_masks, pred_logits = out["pred_masks"].clone(), out["pred_logits"].clone()
     assert torch.isfinite(out["rba"]).all(), "non-finite scores"
 
     use_graph = not args.no_graph
@@ -254,21 +253,33 @@ def run_ours(args):
     value = world * B * args.steps / (ms_total * 1e-3)
     e2e = world * B * args.steps / (ms_e2e * 1e-3)
 
-    # ---- roofline of the fused score kernel (timed alone, inputs 52 MB/img > L2 at B >= 3) ----
-    Q, K = mc.num_queries, mc.num_classes
-    h4, w4 = pred_masks.shape[-2:]
+    # ---- roofline of the fused mask-einsum + RbA score kernel (score_fused.cu), timed alone on the stream it is launched
+    # on; its inputs (feature planes 134 MB/img) exceed L2 at every batch size ----
+    Q, K, D = mc.num_queries, mc.num_classes, mc.conv_dim
+    Hp, Wp = eng.padded_hw(H, W)
+    h4, w4 = Hp // 4, Wp // 4
+    gk = torch.Generator(device=dev).manual_seed(2)
+    # synthetic operands with the statistics of the real ones (mask logits ~ N(-0.54, 0.99^2))
+    feat = torch.randn(B * h4 * w4, D, device=dev, generator=gk)
+    emb = torch.randn(B * Q, D, device=dev, generator=gk) * (0.99 / D ** 0.5)
+    f_pl = tuple(t.view(B, h4, w4, D) for t in ops.split_planes(feat))
+    e_pl = tuple(t.view(B, Q, D) for t in ops.split_planes(emb))
+    del feat, emb
+    kbias = torch.full((B, Q), -0.54, device=dev)
+    klogits = torch.randn(B, Q, K + 1, device=dev, generator=gk)
     for _ in range(3):
-        ops.score_fused(pred_masks, pred_logits, (H, W))
+        ops.einsum_score_fused(e_pl, f_pl, klogits, (H, W), bias=kbias)
     torch.cuda.synchronize()
     reps = 10
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        ops.score_fused(pred_masks, pred_logits, (H, W))
+        ops.einsum_score_fused(e_pl, f_pl, klogits, (H, W), bias=kbias)
     e1.record()
     torch.cuda.synchronize()
     k_ms = e0.elapsed_time(e1) / reps
-    alg_bytes = B * (4 * Q * h4 * w4 + 4 * Q * (K + 1) + 4 * H * W)
+    # SURVEY §8d "Variant A": feature planes + mask embeddings + class logits + bias in, score map out
+    alg_bytes = B * (4 * D * h4 * w4 + 4 * Q * D + 4 * Q * (K + 1) + 4 * Q + 4 * H * W)
     peaks = {}
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
@@ -276,17 +287,18 @@ def run_ours(args):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     # DRAM traffic of this kernel from the committed `ncu --set full` capture (dram__bytes_read.sum + dram__bytes_write.sum,
-    # per image; profiles/r1_score_kernel_traffic.json), scaled to this launch's batch
+    # per image; profiles/r1_fused_score_traffic.json), scaled to this launch's batch
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r1_score_kernel_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r1_fused_score_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp))["dram_bytes_per_image"] * B
-    roofline = {"kernel": "rba_score_mma_kernel<19> (x4 bilinear + sigmoid + (Q,K) contraction on mma.sync fp16 hi/lo + tanh + sum)", "bound": "hbm",
+    roofline = {"kernel": "rba_einsum_score_kernel (tcgen05 mask einsum -> x4 bilinear on tf32 MMA -> sigmoid -> (Q,K) contraction "
+                          "on f16 hi/lo MMA -> tanh -> class sum; one HBM pass)", "bound": "hbm",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst, kernel timed alone)" if peaks else "fallback 6.65 TB/s",
                 "traffic": traffic, "ms_per_launch": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                "note": "fp32 semantics make this kernel FMA/MUFU-bound, not HBM-bound (SURVEY §0.5): "
-                        "2*K*Q FLOP + Q sigmoid per output pixel vs 29 B/pixel"}
+                "note": "fp32 semantics make this kernel issue/MUFU-bound, not HBM-bound (SURVEY §0.5): per output pixel "
+                        "Q sigmoids of individually interpolated logits (2 MUFU each) + 2*K*Q contraction FLOP vs 68 B"}
 
     if world > 1:
         dist.barrier()

@@ -40,7 +40,8 @@ constexpr int FS_KS = 7;                                    // k16 steps in the 
 constexpr int FS_NT = 3;                                    // n8 class tiles (K <= 24)
 constexpr int FS_P_BYTES = FS_NT * 8 * FS_KS * 4 * 16;      // [class][k16 step][tq] x {b0_hi, b1_hi, b0_lo, b1_lo}
 constexpr int FS_BIAS_BYTES = 512;
-constexpr int FS_CW = 16;                                   // compute warps
+constexpr int FS_CW = 16;                                   // compute warps (4 per scheduler)
+constexpr int FS_CWQ = FS_CW / 4;                            // compute warps per TMEM lane quadrant
 constexpr int FS_THREADS = (2 + FS_CW) * 32;
 constexpr int FS_SMEM = FS_STAGES * FS_STAGE_BYTES + FS_PATCH_BYTES + FS_P_BYTES + FS_BIAS_BYTES + 128 + 1024;
 constexpr uint32_t FS_TMEM_COLS = 128;
@@ -53,6 +54,7 @@ struct FsParams {
   int B, Q, K, h, w, H, W;
   int nkb;               // D / 64
   int tilesX, tilesY, ntiles;
+  int debug;             // RBA_FS_DEBUG (profiling aid): 16 = skip the score phase (times TMA + einsum GEMM + drain alone)
 };
 
 __device__ __forceinline__ float fs_rcp(float x) {
@@ -80,20 +82,28 @@ __device__ __forceinline__ void fs_split_f16x2(float e0, float e1, uint32_t& hi,
   const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hi));
   lo = fs_pack_f16x2(e0 - f.x, e1 - f.y);
 }
+// Compile-time ablation (profiling aid, RBA_FS_ABL): 1 no contraction MMAs, 2 sigmoid -> FMA, 4 no f16 split, 8 no tanh
+template <int ABL>
+__device__ __forceinline__ float fs_sig(float u) { return (ABL & 2) ? fmaf(u, 0.01f, 0.5f) : fs_sigmoid_scaled(u); }
+template <int ABL>
+__device__ __forceinline__ void fs_split(float e0, float e1, uint32_t& hi, uint32_t& lo) {
+  if (ABL & 4) { hi = __float_as_uint(e0); lo = __float_as_uint(e1); return; }
+  fs_split_f16x2(e0, e1, hi, lo);
+}
 __device__ __forceinline__ void fs_mma_tf32(float* d, uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1) {
-  asm volatile(
+  asm(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%4,%5}, {%6,%7}, {%8,%8,%8,%8};"
       : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
       : "r"(a0), "r"(a1), "r"(b0), "r"(b1), "f"(0.0f));
 }
 __device__ __forceinline__ void fs_mma_f16(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
-  asm volatile(
+  asm(
       "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ void fs_mma_f16_k8(float* c, uint32_t a0, uint32_t a1, uint32_t b0) {
-  asm volatile(
+  asm(
       "mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a0), "r"(a1), "r"(b0));
@@ -108,7 +118,7 @@ __device__ __forceinline__ void fs_interp8(const float* tp, uint32_t a0, uint32_
   fs_mma_tf32(u, a0, a1, hi, __float_as_uint(lo));
 }
 
-template <bool WRITE_SEM>
+template <bool WRITE_SEM, int ABL = 0>
 __global__ void __launch_bounds__(FS_THREADS, 1)
 rba_einsum_score_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constant__ CUtensorMap tmY_lo,
                         const __grid_constant__ CUtensorMap tmE_hi, const __grid_constant__ CUtensorMap tmE_lo,
@@ -155,7 +165,7 @@ rba_einsum_score_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid
         for (int kb = 0; kb < p.nkb; ++kb, ++it) {
           const int s = it % FS_STAGES;
           const uint32_t ph = (it / FS_STAGES) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
+          mbar_wait_sleep(&empty[s], ph ^ 1);
           uint8_t* st = smem + s * FS_STAGE_BYTES;
           mbar_expect_tx(&full[s], FS_STAGE_BYTES);
           tma_load_4d(st, &tmY_hi, &full[s], kb * TC_BK, c0, r0, b);
@@ -171,12 +181,12 @@ rba_einsum_score_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid
       constexpr uint32_t idesc = make_idesc(TC_BM, FS_NQ);
       uint32_t it = 0, lt = 0;
       for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++lt) {
-        mbar_wait(acc_empty, (lt & 1) ^ 1);              // the previous tile's accumulator has been drained
+        mbar_wait_sleep(acc_empty, (lt & 1) ^ 1);              // the previous tile's accumulator has been drained
         tc_fence_after();
         for (int kb = 0; kb < p.nkb; ++kb, ++it) {
           const int s = it % FS_STAGES;
           const uint32_t ph = (it / FS_STAGES) & 1;
-          mbar_wait(&full[s], ph);
+          mbar_wait_sleep(&full[s], ph);
           tc_fence_after();
           const uint32_t base = smem_u32(smem + s * FS_STAGE_BYTES);
           const uint64_t a_hi = make_sdesc(base), a_lo = make_sdesc(base + FS_A_BYTES);
@@ -194,14 +204,20 @@ rba_einsum_score_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid
       }
     }
   } else {
-    // ===================== drain + score: warps 2..17 =====================
+    // ===================== drain + score: warps 2..2+FS_CW-1 =====================
     const int cw = warp - 2;
-    const int ctid = cw * 32 + lane;                       // 0..511
+    const int ctid = cw * 32 + lane;
     const int qd = warp & 3, jq = cw >> 2;                 // TMEM lane quadrant of this warp; index among its 4 warps
     const int g = lane >> 2, tq = lane & 3;
     const int tr = tq >> 1, tcn = tq & 1;                  // tap row / column select of this lane
     const float SCALE = -1.4426950408889634f;
+    const int dbg = p.debug;
     const int ngroups = (p.Q + 7) >> 3, nfull = ngroups >> 1, tail = ngroups & 1;
+    // interior tap weights (align_corners=False, scale 4): l1 = 1/8 + d/4 on the lower / right tap
+    const int dyA = g >> 2, dx = g & 3;
+    const float lyA = 0.125f + 0.25f * (float)dyA, lyB = lyA + 0.5f, lxx = 0.125f + 0.25f * (float)dx;
+    const float wyA_in = tr ? lyA : 1.f - lyA, wyB_in = tr ? lyB : 1.f - lyB, wx_in = tcn ? lxx : 1.f - lxx;
+    const uint4* const bp = sP + (size_t)g * FS_KS * 4 + tq;
     int cur_b = -1;
     uint32_t lt = 0;
     for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++lt) {
@@ -242,7 +258,7 @@ rba_einsum_score_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid
       {
         const int m = qd * 32 + lane;
         float* prow = sPatch + (m >> 4) * FS_ROWSTRIDE + (m & 15) * FS_QP;
-        for (int chunk = jq; chunk * 16 < FS_QP; chunk += 4) {
+        for (int chunk = jq; chunk * 16 < FS_QP; chunk += FS_CWQ) {
           const int q0 = chunk * 16;
           uint32_t v[16];
           const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)q0;
@@ -280,55 +296,66 @@ rba_einsum_score_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid
       if (lane == 0) mbar_arrive(acc_empty);               // the MMAs of the next tile may start
       fs_bar_compute();                                    // patch complete
 
-      // ---- score phase: one 4x4 output cell per warp iteration ----
-      for (int blk = cw; blk < FS_NBLK; blk += FS_CW) {
-        const int br = blk / FS_BC, bc = blk - br * FS_BC;
+      // ---- score phase: one 4x4 output cell per warp iteration; cell index advances by 16 = one row + one column ----
+      float* const rba_b = p.rba + (size_t)b * p.H * p.W;
+      int br = cw / FS_BC, bc = cw - br * FS_BC;
+      for (int blk = cw; blk < FS_NBLK; blk += FS_CW, br += FS_CW / FS_BC, bc += FS_CW % FS_BC) {
+        if (bc >= FS_BC) { bc -= FS_BC; ++br; }
+        if (dbg & 16) continue;
         const int i = r0 + br, j = c0 + bc;                // low-res coordinates of the cell's top-left tap
         if (i > p.h - 1 || j > p.w - 1) continue;
         const int y0 = 4 * i + 2, x0 = 4 * j + 2;          // the cell's 4x4 output pixels
         if (y0 >= p.H || x0 >= p.W) continue;
-        // tap weights (align_corners=False, scale 4): l1 = 1/8 + d/4 on the lower/right tap; image borders clamp
-        const int dyA = g >> 2, dx = g & 3;
-        const float lyA = 0.125f + 0.25f * (float)dyA, lyB = lyA + 0.5f, lxx = 0.125f + 0.25f * (float)dx;
-        float wyA = tr ? lyA : 1.f - lyA, wyB = tr ? lyB : 1.f - lyB, wx = tcn ? lxx : 1.f - lxx;
+        // tap weights: interior cells use the phase weights; at the image border the clamped source index puts
+        // all the weight on the in-range tap (the out-of-range tap was zero-filled by TMA)
+        float wyA = wyA_in, wyB = wyB_in, wx = wx_in;
         if (i < 0) wyA = wyB = tr ? 1.f : 0.f;
         if (i == p.h - 1) wyA = wyB = tr ? 0.f : 1.f;
         if (j < 0) wx = tcn ? 1.f : 0.f;
         if (j == p.w - 1) wx = tcn ? 0.f : 1.f;
         const uint32_t a0 = __float_as_uint(wyA * wx), a1 = __float_as_uint(wyB * wx);
         const float* tp = sPatch + (br + tr) * FS_ROWSTRIDE + (bc + tcn) * FS_QP + g;
-        const uint4* bp = sP + (size_t)g * FS_KS * 4 + tq;
 
         float acc[FS_NT][4];
 #pragma unroll
         for (int nt = 0; nt < FS_NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+        // software pipeline: the interpolation (LDS -> tf32 MMA) of step ks+1 is issued before the sigmoid / split /
+        // contraction of step ks, so the MUFU chain of one step overlaps the MMA latency of the next
+        float u0[4], u1[4];
+        fs_interp8(tp, a0, a1, u0);                        // queries 16ks + {2tq, 2tq+1}: rows g (u[0..1]), g+8 (u[2..3])
+        fs_interp8(tp + 8, a0, a1, u1);                    // queries 16ks + 8 + {2tq, 2tq+1}
 #pragma unroll 1
         for (int ks = 0; ks < nfull; ++ks) {
-          float u0[4], u1[4];
-          fs_interp8(tp + ks * 16, a0, a1, u0);            // queries 16ks + {2tq, 2tq+1}: rows g (u[0..1]), g+8 (u[2..3])
-          fs_interp8(tp + ks * 16 + 8, a0, a1, u1);        // queries 16ks + 8 + {2tq, 2tq+1}
-          uint32_t ah[4], al[4];
-          fs_split_f16x2(fs_sigmoid_scaled(u0[0]), fs_sigmoid_scaled(u0[1]), ah[0], al[0]);
-          fs_split_f16x2(fs_sigmoid_scaled(u0[2]), fs_sigmoid_scaled(u0[3]), ah[1], al[1]);
-          fs_split_f16x2(fs_sigmoid_scaled(u1[0]), fs_sigmoid_scaled(u1[1]), ah[2], al[2]);
-          fs_split_f16x2(fs_sigmoid_scaled(u1[2]), fs_sigmoid_scaled(u1[3]), ah[3], al[3]);
+          float n0[4], n1[4];
+          fs_interp8(tp + ks * 16 + 16, a0, a1, n0);       // may run past the last query group: finite garbage, unused
+          fs_interp8(tp + ks * 16 + 24, a0, a1, n1);
           uint4 bv[FS_NT];
 #pragma unroll
           for (int nt = 0; nt < FS_NT; ++nt) bv[nt] = bp[(size_t)nt * 8 * FS_KS * 4 + ks * 4];
+          uint32_t ah[4], al[4];
+          fs_split<ABL>(fs_sig<ABL>(u0[0]), fs_sig<ABL>(u0[1]), ah[0], al[0]);
+          fs_split<ABL>(fs_sig<ABL>(u0[2]), fs_sig<ABL>(u0[3]), ah[1], al[1]);
+          fs_split<ABL>(fs_sig<ABL>(u1[0]), fs_sig<ABL>(u1[1]), ah[2], al[2]);
+          fs_split<ABL>(fs_sig<ABL>(u1[2]), fs_sig<ABL>(u1[3]), ah[3], al[3]);
           // consecutive MMAs target different accumulators (no back-to-back dependent HMMAs)
+          if (ABL & 1) {
+            acc[0][0] += __uint_as_float(ah[0] ^ al[1] ^ bv[0].x ^ bv[1].y ^ bv[2].z);
+            acc[1][0] += __uint_as_float(ah[2] ^ al[3] ^ ah[1] ^ ah[3] ^ al[0] ^ al[2]);
+          } else {
 #pragma unroll
-          for (int nt = 0; nt < FS_NT; ++nt) fs_mma_f16(acc[nt], ah, bv[nt].x, bv[nt].y);
+            for (int nt = 0; nt < FS_NT; ++nt) fs_mma_f16(acc[nt], ah, bv[nt].x, bv[nt].y);
 #pragma unroll
-          for (int nt = 0; nt < FS_NT; ++nt) fs_mma_f16(acc[nt], ah, bv[nt].z, bv[nt].w);
+            for (int nt = 0; nt < FS_NT; ++nt) fs_mma_f16(acc[nt], ah, bv[nt].z, bv[nt].w);
 #pragma unroll
-          for (int nt = 0; nt < FS_NT; ++nt) fs_mma_f16(acc[nt], al, bv[nt].x, bv[nt].y);
+            for (int nt = 0; nt < FS_NT; ++nt) fs_mma_f16(acc[nt], al, bv[nt].x, bv[nt].y);
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { u0[e] = n0[e]; u1[e] = n1[e]; }
         }
         if (tail) {
-          float u0[4];
-          fs_interp8(tp + nfull * 16, a0, a1, u0);
           uint32_t ah0, al0, ah1, al1;
-          fs_split_f16x2(fs_sigmoid_scaled(u0[0]), fs_sigmoid_scaled(u0[1]), ah0, al0);
-          fs_split_f16x2(fs_sigmoid_scaled(u0[2]), fs_sigmoid_scaled(u0[3]), ah1, al1);
+          fs_split<ABL>(fs_sig<ABL>(u0[0]), fs_sig<ABL>(u0[1]), ah0, al0);
+          fs_split<ABL>(fs_sig<ABL>(u0[2]), fs_sig<ABL>(u0[3]), ah1, al1);
           uint4 bv[FS_NT];
 #pragma unroll
           for (int nt = 0; nt < FS_NT; ++nt) bv[nt] = bp[(size_t)nt * 8 * FS_KS * 4 + nfull * 4];
@@ -339,7 +366,8 @@ rba_einsum_score_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid
 #pragma unroll
           for (int nt = 0; nt < FS_NT; ++nt) fs_mma_f16_k8(acc[nt], al0, al1, bv[nt].x);
         }
-        // ---- epilogue: acc[nt][e] = sem_seg[class 8nt+2tq+e] of pixel A (row g), acc[nt][2+e] of pixel B (row g+8) ----
+        // ---- epilogue: acc[nt][e] = sem_seg[class 8nt+2tq+e] of pixel A (row g), acc[nt][2+e] of pixel B (row g+8).
+        // sum_c tanh(s_c) = n - 2 sum_c 1/(1 + e^(2 s_c)); padded classes hold exactly 0 and contribute tanh(0) = 0 ----
         const int yA = y0 + dyA, yB = yA + 2, x = x0 + dx;
         const bool okx = x >= 0 && x < p.W;
         const bool okA = okx && yA >= 0 && yA < p.H, okB = okx && yB >= 0 && yB < p.H;
@@ -348,8 +376,9 @@ rba_einsum_score_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid
         for (int nt = 0; nt < FS_NT; ++nt)
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            ra += fs_tanh_pos(acc[nt][e]);                 // padded classes hold exactly 0: tanh = 0
-            rb += fs_tanh_pos(acc[nt][2 + e]);
+            if (ABL & 8) { ra += acc[nt][e]; rb += acc[nt][2 + e]; continue; }
+            ra += fs_rcp(1.0f + fs_ex2(2.8853900817779268f * acc[nt][e]));
+            rb += fs_rcp(1.0f + fs_ex2(2.8853900817779268f * acc[nt][2 + e]));
             if (WRITE_SEM) {
               const int c = nt * 8 + tq * 2 + e;
               if (c < p.K) {
@@ -362,8 +391,9 @@ rba_einsum_score_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid
         ra += __shfl_xor_sync(0xffffffffu, ra, 2);
         rb += __shfl_xor_sync(0xffffffffu, rb, 1);
         rb += __shfl_xor_sync(0xffffffffu, rb, 2);
-        if (tq == 0 && okA) p.rba[((size_t)b * p.H + yA) * p.W + x] = -ra;
-        if (tq == 1 && okB) p.rba[((size_t)b * p.H + yB) * p.W + x] = -rb;
+        // rba = -sum tanh = 2 sum r - 24
+        if (tq == 0 && okA) rba_b[(size_t)yA * p.W + x] = fmaf(2.0f, ra, -(float)(FS_NT * 8));
+        if (tq == 1 && okB) rba_b[(size_t)yB * p.W + x] = fmaf(2.0f, rb, -(float)(FS_NT * 8));
       }
       fs_bar_compute();                                    // patch (and, at an image change, sP) free for the next tile
     }
@@ -390,6 +420,7 @@ int einsum_score_launch(const uint16_t* e_hi, const uint16_t* e_lo, const float*
   p.logits = logits; p.bias = bias; p.rba = rba; p.sem = sem;
   p.B = B; p.Q = Q; p.K = K; p.h = h; p.w = w; p.H = H; p.W = W;
   p.nkb = D / TC_BK;
+  { const char* e = getenv("RBA_FS_DEBUG"); p.debug = e ? atoi(e) : 0; }
   p.tilesX = (int)cdiv(w + 1, FS_BC); p.tilesY = (int)cdiv(h + 1, FS_BR);
   const int64_t nt = (int64_t)B * p.tilesX * p.tilesY;
   RBA_CHECK(nt < (1LL << 31), "einsum_score: too many tiles");
@@ -405,9 +436,24 @@ int einsum_score_launch(const uint16_t* e_hi, const uint16_t* e_lo, const float*
     if (!done) { RBA_CUDA(cudaFuncSetAttribute(rba_einsum_score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM)); done = true; }
     rba_einsum_score_kernel<true><<<grid, FS_THREADS, FS_SMEM, st>>>(ty_hi, ty_lo, te_hi, te_lo, p);
   } else {
-    static bool done = false;
-    if (!done) { RBA_CUDA(cudaFuncSetAttribute(rba_einsum_score_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM)); done = true; }
-    rba_einsum_score_kernel<false><<<grid, FS_THREADS, FS_SMEM, st>>>(ty_hi, ty_lo, te_hi, te_lo, p);
+    static const int abl = []() { const char* e = getenv("RBA_FS_ABL"); return e ? atoi(e) : 0; }();
+#define RBA_FS_LAUNCH(A)                                                                                                   \
+  do {                                                                                                                     \
+    static bool done = false;                                                                                              \
+    if (!done) { RBA_CUDA(cudaFuncSetAttribute(rba_einsum_score_kernel<false, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM)); done = true; } \
+    rba_einsum_score_kernel<false, A><<<grid, FS_THREADS, FS_SMEM, st>>>(ty_hi, ty_lo, te_hi, te_lo, p);                   \
+  } while (0)
+    switch (abl) {
+      case 1: RBA_FS_LAUNCH(1); break;
+      case 2: RBA_FS_LAUNCH(2); break;
+      case 4: RBA_FS_LAUNCH(4); break;
+      case 8: RBA_FS_LAUNCH(8); break;
+      case 6: RBA_FS_LAUNCH(6); break;
+      case 7: RBA_FS_LAUNCH(7); break;
+      case 15: RBA_FS_LAUNCH(15); break;
+      default: RBA_FS_LAUNCH(0); break;
+    }
+#undef RBA_FS_LAUNCH
   }
   RBA_LAUNCHED();
   return RBA_OK;

@@ -8,9 +8,9 @@
 
 constexpr int ITERS = 2048, CHAINS = 8;
 
-enum Op { EX2, RCP, TANH, F2FP, HADD2F32, PRMT, LOP, FMNMX, FFMA, FADD, HMMA_F16, HMMA_BF16, HMMA_TF32, LDS32, MIX_SIG, NOPS };
-const char* names[] = {"MUFU.EX2", "MUFU.RCP", "MUFU.TANH", "F2FP.F16.F32.PACK", "HADD2.F32 (h->f)", "PRMT", "LOP3", "FMNMX",
-                       "FFMA", "FADD", "HMMA.16816.F32 f16", "HMMA.16816.F32 bf16", "HMMA.1688.F32.TF32", "LDS.32", "EX2+FADD+RCP"};
+enum Op { EX2, RCP, TANH, F2FP, F2FP_BF16, SPLIT_F16, SPLIT_BF16T, HADD2F32, PRMT, LOP, FMNMX, FFMA, FADD, HMMA_F16, HMMA_BF16, HMMA_TF32, LDS32, MIX_SIG, MIX_MUFU_HMMA, MIX_MUFU_FFMA4, NOPS };
+const char* names[] = {"MUFU.EX2", "MUFU.RCP", "MUFU.TANH", "F2FP.F16.F32.PACK", "F2FP.BF16.F32.PACK", "split f16 (6 ops)", "split bf16 trunc (6 ops)", "HADD2.F32 (h->f)", "PRMT", "LOP3", "FMNMX",
+                       "FFMA", "FADD", "HMMA.16816.F32 f16", "HMMA.16816.F32 bf16", "HMMA.1688.F32.TF32", "LDS.32", "EX2+FADD+RCP", "EX2+HMMA", "EX2+4xFFMA"};
 
 template <int OP>
 __global__ void __launch_bounds__(256) k(float* out, long long* clk, float seed) {
@@ -32,7 +32,25 @@ __global__ void __launch_bounds__(256) k(float* out, long long* clk, float seed)
       if (OP == EX2) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[c]));
       if (OP == RCP) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(x[c]));
       if (OP == TANH) asm volatile("tanh.approx.f32 %0, %0;" : "+f"(x[c]));
-      if (OP == F2FP) asm volatile("cvt.rn.f16x2.f32 %0, %1, %1;" : "=r"(u[c]) : "f"(x[c] ), "r"(u[c]));
+      if (OP == F2FP) { asm volatile("cvt.rn.f16x2.f32 %0, %1, %1;" : "=r"(u[c]) : "f"(x[c])); x[c] = __uint_as_float(u[c]); }
+      if (OP == F2FP_BF16) { asm volatile("cvt.rn.bf16x2.f32 %0, %1, %1;" : "=r"(u[c]) : "f"(x[c])); x[c] = __uint_as_float(u[c]); }
+      if (OP == SPLIT_F16) {
+        const float e0 = x[c], e1 = x[(c + 1) % CHAINS];
+        uint32_t hi, lo;
+        asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(e1), "f"(e0));
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+        asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(e1 - f.y), "f"(e0 - f.x));
+        u[c] ^= hi; x[c] = __uint_as_float(lo);
+      }
+      if (OP == SPLIT_BF16T) {
+        const float e0 = x[c], e1 = x[(c + 1) % CHAINS];
+        uint32_t hi, lo;
+        asm volatile("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(hi) : "r"(__float_as_uint(e0)), "r"(__float_as_uint(e1)));
+        const float l0 = e0 - __uint_as_float(__float_as_uint(e0) & 0xffff0000u);
+        const float l1 = e1 - __uint_as_float(__float_as_uint(e1) & 0xffff0000u);
+        asm volatile("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(lo) : "r"(__float_as_uint(l0)), "r"(__float_as_uint(l1)));
+        u[c] ^= hi; x[c] = __uint_as_float(lo);
+      }
       if (OP == HADD2F32) { asm volatile("{.reg .f16 lo, hi; mov.b32 {lo, hi}, %1; cvt.f32.f16 %0, lo;}" : "=f"(x[c]) : "r"(u[c])); u[c] = __float_as_uint(x[c]); }
       if (OP == PRMT) asm volatile("prmt.b32 %0, %0, %1, 0x7632;" : "+r"(u[c]) : "r"(u[(c + 1) % CHAINS]));
       if (OP == LOP) asm volatile("lop3.b32 %0, %0, %1, 0xffff0000, 0x6a;" : "+r"(u[c]) : "r"(u[(c + 1) % CHAINS]));
@@ -52,6 +70,19 @@ __global__ void __launch_bounds__(256) k(float* out, long long* clk, float seed)
                      : "+f"(acc[c][0]), "+f"(acc[c][1]), "+f"(acc[c][2]), "+f"(acc[c][3])
                      : "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]));
       if (OP == LDS32) { asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x[c]) : "r"((uint32_t)__cvta_generic_to_shared(&sm[(u[c] >> 7) & 1023]))); u[c] += __float_as_uint(x[c]); }
+      if (OP == MIX_MUFU_HMMA) {
+        asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[c]));
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(acc[c][0]), "+f"(acc[c][1]), "+f"(acc[c][2]), "+f"(acc[c][3])
+                     : "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]));
+      }
+      if (OP == MIX_MUFU_FFMA4) {
+        asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[c]));
+        asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(acc[c][0]) : "f"(seed));
+        asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(acc[c][1]) : "f"(seed));
+        asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(acc[c][2]) : "f"(seed));
+        asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(acc[c][3]) : "f"(seed));
+      }
       if (OP == MIX_SIG) {
         asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[c]));
         asm volatile("add.f32 %0, %0, 1.0;" : "+f"(x[c]));
@@ -85,7 +116,7 @@ void run(int sms, int ctas_per_sm) {
   long long* h = new long long[grid];
   cudaMemcpy(h, clk, grid * 8, cudaMemcpyDeviceToHost);
   double avg = 0; for (int i = 0; i < grid; ++i) avg += h[i]; avg /= grid;
-  const double per_op = (OP == MIX_SIG) ? 3.0 : 1.0;
+  const double per_op = (OP == MIX_SIG) ? 3.0 : (OP == MIX_MUFU_HMMA) ? 2.0 : (OP == MIX_MUFU_FFMA4) ? 5.0 : (OP == SPLIT_F16 || OP == SPLIT_BF16T) ? 6.0 : 1.0;
   const double winst_per_cta = 8.0 * ITERS * CHAINS * per_op;     // 8 warps
   // per-SM rate from the in-kernel clocks (each SM runs ctas_per_sm CTAs concurrently for ~avg clocks)
   printf("%-22s ctas/SM=%d  %.3f warp-inst/clk/SM  (%.1f lanes/clk/SM)  [%.3f ms, %.0f clk]\n", names[OP], ctas_per_sm,
@@ -98,9 +129,9 @@ int main() {
   const int sms = p.multiProcessorCount;
   printf("%s, %d SMs\n", p.name, sms);
   for (int c : {2, 4}) {
-    run<EX2>(sms, c); run<RCP>(sms, c); run<TANH>(sms, c); run<MIX_SIG>(sms, c); run<F2FP>(sms, c); run<HADD2F32>(sms, c);
+    run<EX2>(sms, c); run<RCP>(sms, c); run<TANH>(sms, c); run<MIX_SIG>(sms, c); run<F2FP>(sms, c); run<F2FP_BF16>(sms, c); run<SPLIT_F16>(sms, c); run<SPLIT_BF16T>(sms, c); run<HADD2F32>(sms, c);
     run<PRMT>(sms, c); run<LOP>(sms, c); run<FMNMX>(sms, c); run<FFMA>(sms, c); run<FADD>(sms, c);
-    run<HMMA_F16>(sms, c); run<HMMA_BF16>(sms, c); run<HMMA_TF32>(sms, c); run<LDS32>(sms, c);
+    run<HMMA_F16>(sms, c); run<HMMA_BF16>(sms, c); run<HMMA_TF32>(sms, c); run<LDS32>(sms, c); run<MIX_MUFU_HMMA>(sms, c); run<MIX_MUFU_FFMA4>(sms, c);
   }
   return 0;
 }
