@@ -184,3 +184,50 @@ def test_forward_fused_score_matches_reference_golden(dev, name):
     assert n_fused == n_two - 1, (n_fused, n_two)                        # one GEMM launch less
     assert (two["rba"] - out["rba"]).abs().max() < 1e-4
     assert (two["sem_seg"] - out["sem_seg"]).abs().max() < 1e-4
+
+
+def test_compat_plugin_flow_on_gpu(dev, tmp_path):
+    """evaluate_ood.get_model / get_RbA flow (evaluate_ood.py:108-150) through the drop-in plumbing, on the GPU box
+    (no reference checkout here): get_cfg -> merge_from_file -> build_model -> DetectionCheckpointer -> model(...)."""
+    import yaml
+    from rba_b200 import compat
+    compat.plug_in()
+    from detectron2.checkpoint import DetectionCheckpointer
+    from detectron2.config import get_cfg
+    from detectron2.modeling import build_model
+    case = CASES["tiny_1dl"]
+    mc = case_model_config(case)
+    sd = weights.init_state_dict(mc, seed=case["seed"], perturb=case["perturb"])
+    fix = load_golden("model_tiny_1dl.pt")
+    y = {"MODEL": {
+        "META_ARCHITECTURE": "MaskFormer", "DEVICE": "cuda", "WEIGHTS": "",
+        "PIXEL_MEAN": list(mc.pixel_mean), "PIXEL_STD": list(mc.pixel_std),
+        "BACKBONE": {"NAME": "D2SwinTransformer"},
+        "SWIN": {"EMBED_DIM": mc.embed_dim, "DEPTHS": list(mc.depths), "NUM_HEADS": list(mc.num_heads), "WINDOW_SIZE": 12,
+                 "MLP_RATIO": 4.0, "PATCH_SIZE": 4, "APE": False, "QKV_BIAS": True, "PATCH_NORM": True},
+        "SEM_SEG_HEAD": {"NAME": "MaskFormerHead", "PIXEL_DECODER_NAME": "MSDeformAttnPixelDecoder", "NORM": "GN",
+                         "CONVS_DIM": 256, "MASK_DIM": 256, "NUM_CLASSES": mc.num_classes,
+                         "IN_FEATURES": ["res2", "res3", "res4", "res5"],
+                         "DEFORMABLE_TRANSFORMER_ENCODER_IN_FEATURES": list(mc.transformer_in_features),
+                         "COMMON_STRIDE": 4, "TRANSFORMER_ENC_LAYERS": mc.enc_layers},
+        "MASK_FORMER": {"TRANSFORMER_DECODER_NAME": "MultiScaleMaskedTransformerDecoder", "PRE_NORM": False, "NHEADS": 8,
+                        "HIDDEN_DIM": 256, "DIM_FEEDFORWARD": 2048, "DEC_LAYERS": mc.dec_layers + 1,
+                        "NUM_OBJECT_QUERIES": mc.num_queries, "SIZE_DIVISIBILITY": 32}}}
+    cfg_path, ckpt_path = str(tmp_path / "config.yaml"), str(tmp_path / "model_final.pth")
+    with open(cfg_path, "w") as f:
+        yaml.safe_dump(y, f)
+    torch.save({"model": sd}, ckpt_path)
+    cfg = get_cfg()
+    cfg.merge_from_file(cfg_path)
+    cfg.merge_from_list(["OUTPUT_DIR", str(tmp_path / "out")])
+    cfg.freeze()
+    model = build_model(cfg)
+    assert isinstance(model, rba_b200.MaskFormer)
+    DetectionCheckpointer(model, save_dir=cfg.OUTPUT_DIR).resume_or_load(ckpt_path, resume=False)
+    model.to(dev)
+    model.eval()
+    x = case_images(case)[0]
+    with torch.no_grad():
+        out = model([{"image": x.to(dev)}])
+    rba = -out[0]["sem_seg"].tanh().sum(dim=0)
+    assert (rba.cpu() - fix["rba"][0]).abs().max() < TOL
