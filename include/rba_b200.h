@@ -109,10 +109,18 @@ int rba_score_fused(const float* pred_masks, const float* pred_logits, int B, in
  * Same result as  pred_masks = einsum("bqc,bchw->bqhw", mask_embed, features) + bias[:, :, None, None]
  * (mask2former_transformer_decoder.py:479) followed by rba_score_fused, without materialising pred_masks.
  * mask_embed (B,Q,D) and features (B,h,w,D) [NHWC] are bf16 split planes (see above); bias (B,Q) fp32 or NULL;
- * pred_logits (B,Q,K+1).  Limits: Q <= 104, K <= 24, D a multiple of 64.  sem_seg may be NULL. */
+ * pred_logits (B,Q,K+1).  Limits: Q <= 104, K + 1 <= 24, D a multiple of 64.
+ * score_func selects the per-pixel reduction written to `score` (evaluate_ood.py:143-159):
+ *   RBA_SCORE_RBA    -sum_c tanh(sem_seg[c])      (get_RbA)
+ *   RBA_SCORE_ENERGY -logsumexp_c(sem_seg[c])     (get_energy, --score_func pebal)
+ * include_void != 0 keeps the void column of the class softmax (semantic_inference_with_void,
+ * maskformer_model.py:388-392): sem_seg then has K+1 planes and the score runs over K+1 classes.
+ * sem_seg (B, K or K+1, H, W) may be NULL. */
+#define RBA_SCORE_RBA 0
+#define RBA_SCORE_ENERGY 1
 int rba_einsum_score_fused(const uint16_t* embed_hi, const uint16_t* embed_lo, const float* bias, const uint16_t* feat_hi,
                            const uint16_t* feat_lo, const float* pred_logits, int B, int Q, int K, int D, int h, int w,
-                           int H, int W, float* rba, float* sem_seg, void* stream);
+                           int H, int W, int score_func, int include_void, float* score, float* sem_seg, void* stream);
 
 /* ---- MSDeformAttn forward, same argument meaning as the reference FFI ----
  * value (B,S,M,D) fp32 (device); spatial_shapes (L,2) int64 (H_l,W_l) and level_start_index (L) int64 are HOST

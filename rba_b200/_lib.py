@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "librba_b200.so")
 RBA_IMG_U8, RBA_IMG_F32 = 0, 1
 RBA_ACT_NONE, RBA_ACT_RELU, RBA_ACT_GELU = 0, 1, 2
 RBA_GEMM_FFMA, RBA_GEMM_TC = 0, 1
+RBA_SCORE_RBA, RBA_SCORE_ENERGY = 0, 1
 
 
 class RbaError(RuntimeError):
@@ -56,7 +57,7 @@ PROTOTYPES = {
     "rba_model_get_tap": (c_int, [c_void_p, c_char_p, c_void_p, c_int64, POINTER(c_int64), c_void_p]),
     "rba_score_fused": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "rba_einsum_score_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
-                                       c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+                                       c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "rba_msda_forward": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64), c_void_p, c_void_p, c_int, c_int, c_int,
                                  c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "rba_k_split": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_int64, c_void_p]),

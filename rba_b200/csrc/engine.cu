@@ -91,6 +91,8 @@ struct rba_model {
   int attn_backend = 1;             // 1: tensor-core window attention (mma.sync bf16x3), 0: fp32 CUDA-core kernel
   int gemm_backend = RBA_GEMM_TC;   // tcgen05 bf16x3; RBA_GEMM_BACKEND=ffma selects the exact fp32 FMA kernels
   int fused_score = 1;              // 1: last mask einsum + score in one kernel (score_fused.cu) when pred_masks is not asked for
+  int score_func = RBA_SCORE_RBA;   // per-pixel reduction written to the score output (evaluate_ood.py:143-159)
+  int include_void = 0;             // 1: semantic_inference_with_void (maskformer_model.py:388-392): K+1 sem_seg planes
   std::unordered_map<std::string, DevTensor> w;
   std::unordered_map<std::string, Planes> wp;      // split planes of GEMM weights, by key
   std::vector<void*> owned;                         // cudaMalloc'ed blocks (weights, derived)
@@ -204,6 +206,12 @@ extern "C" int rba_model_set_option(rba_model* m, const char* name, int value) {
     RBA_CHECK(value == 0 || value == 1, "bad attn backend %d", value);
     m->attn_backend = value;
     m->rB = m->rH = m->rW = 0;
+  } else if (n == "score_func") {
+    RBA_CHECK(value == RBA_SCORE_RBA || value == RBA_SCORE_ENERGY, "bad score_func %d", value);
+    m->score_func = value;
+  } else if (n == "include_void") {
+    RBA_CHECK(value == 0 || value == 1, "bad include_void %d", value);
+    m->include_void = value;
   } else if (n == "fused_score") {
     RBA_CHECK(value == 0 || value == 1, "bad fused_score %d", value);
     m->fused_score = value;
@@ -681,8 +689,11 @@ static int forward_impl(rba_model* m, const void* images, int img_dtype, int B, 
 
   // The last prediction head feeds only the score: its mask einsum is fused into the score kernel (score_fused.cu)
   // unless the caller wants pred_masks itself.
-  const bool fuse_last = m->fused_score && !pred_masks_out && F.backend == RBA_GEMM_TC &&
+  const bool special = m->score_func != RBA_SCORE_RBA || m->include_void;   // only the fused kernel implements these
+  const bool fuse_last = (m->fused_score || special) && (!pred_masks_out || special) && F.backend == RBA_GEMM_TC &&
                          einsum_score_supported(Q, c.num_classes, D) && (rba_out || sem_seg);
+  if (special && (rba_out || sem_seg))
+    RBA_CHECK(fuse_last, "score_func / include_void need the tensor-core backend and Q <= 104, K + 1 <= 24");
   Planes ef = A.planes(BQ * D);                 // E' = mask_embed . Wmf (kept for the fused kernel)
   float* bq = A.f32(BQ);                        // b' = mask_embed . bmf
 
@@ -703,7 +714,7 @@ static int forward_impl(rba_model* m, const void* images, int img_dtype, int B, 
     RBA_TRY(F.lin(me, c.mask_dim, BQ, c.mask_dim, F.P(pd + "mask_features.weightT"), D, nullptr, RBA_ACT_NONE, nullptr, nullptr,
                   0, ef, D));
     RBA_TRY(F.lin(me, c.mask_dim, BQ, c.mask_dim, F.P(pd + "mask_features.bias_row"), 1, nullptr, RBA_ACT_NONE, nullptr, bq, 1));
-    if (!(last && fuse_last)) {  // masks[b] (Q, HW) = E'[b] (Q, D) . y[b]^T (HW, D) + b'[b]   (einsum "bqc,bchw->bqhw", :479)
+    if (!(last && fuse_last && !pred_masks_out)) {  // masks[b] (Q, HW) = E'[b] (Q, D) . y[b]^T (HW, D) + b'[b]   (einsum "bqc,bchw->bqhw", :479)
       rba_gemm_args ga;
       memset(&ga, 0, sizeof(ga));
       ga.a_hi = ef.hi; ga.a_lo = ef.lo; ga.lda = D; ga.a_bstride = (int64_t)Q * D;
@@ -789,7 +800,8 @@ static int forward_impl(rba_model* m, const void* images, int img_dtype, int B, 
     float* ro = rba_out;
     if (!ro) ro = A.f32((int64_t)B * H * W);
     if (fuse_last)
-      RBA_RUN(einsum_score_launch(ef.hi, ef.lo, bq, ypl.hi, ypl.lo, cls, B, Q, c.num_classes, D, mH, mW, H, W, ro, sem_seg, st));
+      RBA_RUN(einsum_score_launch(ef.hi, ef.lo, bq, ypl.hi, ypl.lo, cls, B, Q, c.num_classes, D, mH, mW, H, W, m->score_func,
+                                  m->include_void, ro, sem_seg, st));
     else
       RBA_RUN(rba_score_fused(masks, cls, B, Q, c.num_classes, mH, mW, H, W, ro, sem_seg, (void*)st));
   }

@@ -52,6 +52,8 @@ struct FsParams {
   float* rba;            // (B, H, W)
   float* sem;            // (B, K, H, W) or null
   int B, Q, K, h, w, H, W;
+  int Kc;                // class columns kept: K (semantic_inference) or K+1 (semantic_inference_with_void)
+  int score_func;        // RBA_SCORE_RBA: -sum_c tanh(s_c); RBA_SCORE_ENERGY: -logsumexp_c(s_c)
   int nkb;               // D / 64
   int tilesX, tilesY, ntiles;
   int debug;             // RBA_FS_DEBUG (profiling aid): 16 = skip the score phase (times TMA + einsum GEMM + drain alone)
@@ -242,7 +244,7 @@ rba_einsum_score_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid
           const int ks = q >> 4, r = q & 15;
           const int hoff = (r >> 3) * 2 + (r & 1);         // half index inside the 16-byte entry (hi); lo = +4
           __half* base = reinterpret_cast<__half*>(sP) + ((size_t)ks * 4 + ((r & 7) >> 1)) * 8 + hoff;
-          for (int c = 0; c < p.K; ++c) {
+          for (int c = 0; c < p.Kc; ++c) {
             const float pv = expf(lg[c] - m) * inv;
             const __half hh = __float2half_rn(pv);
             __half* d = base + (size_t)c * FS_KS * 4 * 8;
@@ -371,29 +373,60 @@ rba_einsum_score_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid
         const int yA = y0 + dyA, yB = yA + 2, x = x0 + dx;
         const bool okx = x >= 0 && x < p.W;
         const bool okA = okx && yA >= 0 && yA < p.H, okB = okx && yB >= 0 && yB < p.H;
-        float ra = 0.f, rb = 0.f;
+        if (WRITE_SEM) {
 #pragma unroll
-        for (int nt = 0; nt < FS_NT; ++nt)
+          for (int nt = 0; nt < FS_NT; ++nt)
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            if (ABL & 8) { ra += acc[nt][e]; rb += acc[nt][2 + e]; continue; }
-            ra += fs_rcp(1.0f + fs_ex2(2.8853900817779268f * acc[nt][e]));
-            rb += fs_rcp(1.0f + fs_ex2(2.8853900817779268f * acc[nt][2 + e]));
-            if (WRITE_SEM) {
+            for (int e = 0; e < 2; ++e) {
               const int c = nt * 8 + tq * 2 + e;
-              if (c < p.K) {
-                if (okA) p.sem[(((size_t)b * p.K + c) * p.H + yA) * p.W + x] = acc[nt][e];
-                if (okB) p.sem[(((size_t)b * p.K + c) * p.H + yB) * p.W + x] = acc[nt][2 + e];
+              if (c < p.Kc) {
+                if (okA) p.sem[(((size_t)b * p.Kc + c) * p.H + yA) * p.W + x] = acc[nt][e];
+                if (okB) p.sem[(((size_t)b * p.Kc + c) * p.H + yB) * p.W + x] = acc[nt][2 + e];
               }
             }
-          }
-        ra += __shfl_xor_sync(0xffffffffu, ra, 1);
-        ra += __shfl_xor_sync(0xffffffffu, ra, 2);
-        rb += __shfl_xor_sync(0xffffffffu, rb, 1);
-        rb += __shfl_xor_sync(0xffffffffu, rb, 2);
-        // rba = -sum tanh = 2 sum r - 24
-        if (tq == 0 && okA) rba_b[(size_t)yA * p.W + x] = fmaf(2.0f, ra, -(float)(FS_NT * 8));
-        if (tq == 1 && okB) rba_b[(size_t)yB * p.W + x] = fmaf(2.0f, rb, -(float)(FS_NT * 8));
+        }
+        if (p.score_func == RBA_SCORE_ENERGY) {
+          // -logsumexp over the kept classes (evaluate_ood.py:152-159): max and sum reduced over the quad
+          float ma = -1e30f, mb = -1e30f;
+#pragma unroll
+          for (int nt = 0; nt < FS_NT; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+              if (nt * 8 + tq * 2 + e < p.Kc) { ma = fmaxf(ma, acc[nt][e]); mb = fmaxf(mb, acc[nt][2 + e]); }
+          ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 1));
+          ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 2));
+          mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 1));
+          mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 2));
+          float sa = 0.f, sb = 0.f;
+#pragma unroll
+          for (int nt = 0; nt < FS_NT; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+              if (nt * 8 + tq * 2 + e < p.Kc) { sa += __expf(acc[nt][e] - ma); sb += __expf(acc[nt][2 + e] - mb); }
+          sa += __shfl_xor_sync(0xffffffffu, sa, 1);
+          sa += __shfl_xor_sync(0xffffffffu, sa, 2);
+          sb += __shfl_xor_sync(0xffffffffu, sb, 1);
+          sb += __shfl_xor_sync(0xffffffffu, sb, 2);
+          if (tq == 0 && okA) rba_b[(size_t)yA * p.W + x] = -(ma + logf(sa));
+          if (tq == 1 && okB) rba_b[(size_t)yB * p.W + x] = -(mb + logf(sb));
+        } else {
+          float ra = 0.f, rb = 0.f;
+#pragma unroll
+          for (int nt = 0; nt < FS_NT; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              if (ABL & 8) { ra += acc[nt][e]; rb += acc[nt][2 + e]; continue; }
+              ra += fs_rcp(1.0f + fs_ex2(2.8853900817779268f * acc[nt][e]));
+              rb += fs_rcp(1.0f + fs_ex2(2.8853900817779268f * acc[nt][2 + e]));
+            }
+          ra += __shfl_xor_sync(0xffffffffu, ra, 1);
+          ra += __shfl_xor_sync(0xffffffffu, ra, 2);
+          rb += __shfl_xor_sync(0xffffffffu, rb, 1);
+          rb += __shfl_xor_sync(0xffffffffu, rb, 2);
+          // rba = -sum tanh = 2 sum r - 24
+          if (tq == 0 && okA) rba_b[(size_t)yA * p.W + x] = fmaf(2.0f, ra, -(float)(FS_NT * 8));
+          if (tq == 1 && okB) rba_b[(size_t)yB * p.W + x] = fmaf(2.0f, rb, -(float)(FS_NT * 8));
+        }
       }
       fs_bar_compute();                                    // patch (and, at an image change, sP) free for the next tile
     }
@@ -406,19 +439,22 @@ rba_einsum_score_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid
   }
 }
 
-int einsum_score_supported(int Q, int K, int D) { return Q > 0 && Q <= FS_QP && K > 0 && K <= FS_NT * 8 && K + 1 <= 64 && D % TC_BK == 0; }
+int einsum_score_supported(int Q, int K, int D) { return Q > 0 && Q <= FS_QP && K > 0 && K + 1 <= FS_NT * 8 && D % TC_BK == 0; }
 
 int einsum_score_launch(const uint16_t* e_hi, const uint16_t* e_lo, const float* bias, const uint16_t* y_hi,
                         const uint16_t* y_lo, const float* logits, int B, int Q, int K, int D, int h, int w, int H, int W,
-                        float* rba, float* sem, cudaStream_t st) {
+                        int score_func, int include_void, float* rba, float* sem, cudaStream_t st) {
   RBA_CHECK(einsum_score_supported(Q, K, D), "einsum_score: unsupported Q=%d (<= %d) K=%d (<= %d) D=%d (multiple of %d)", Q,
-            FS_QP, K, FS_NT * 8, D, TC_BK);
+            FS_QP, K, FS_NT * 8 - 1, D, TC_BK);
+  RBA_CHECK(score_func == RBA_SCORE_RBA || score_func == RBA_SCORE_ENERGY, "einsum_score: unknown score function %d", score_func);
   RBA_CHECK(((uintptr_t)e_hi & 15) == 0 && ((uintptr_t)e_lo & 15) == 0 && ((uintptr_t)y_hi & 15) == 0 && ((uintptr_t)y_lo & 15) == 0,
             "einsum_score: operand planes must be 16-byte aligned");
   FsParams p;
   memset(&p, 0, sizeof(p));
   p.logits = logits; p.bias = bias; p.rba = rba; p.sem = sem;
   p.B = B; p.Q = Q; p.K = K; p.h = h; p.w = w; p.H = H; p.W = W;
+  p.Kc = include_void ? K + 1 : K;
+  p.score_func = score_func;
   p.nkb = D / TC_BK;
   { const char* e = getenv("RBA_FS_DEBUG"); p.debug = e ? atoi(e) : 0; }
   p.tilesX = (int)cdiv(w + 1, FS_BC); p.tilesY = (int)cdiv(h + 1, FS_BR);
@@ -461,15 +497,17 @@ int einsum_score_launch(const uint16_t* e_hi, const uint16_t* e_lo, const float*
 
 }  // namespace rba
 
-// mask_embed (B,Q,D) and features (B,h,w,D) as bf16 split planes; bias (B,Q) fp32 or NULL; pred_logits (B,Q,K+1).
+// mask_embed (B,Q,D) and features (B,h,w,D) as bf16 split planes; bias (B,Q) fp32 or NULL; pred_logits (B,Q,K+1);
+// sem_seg (B, K or K+1, H, W) or NULL.
 extern "C" int rba_einsum_score_fused(const uint16_t* embed_hi, const uint16_t* embed_lo, const float* bias,
                                       const uint16_t* feat_hi, const uint16_t* feat_lo, const float* pred_logits, int B, int Q,
-                                      int K, int D, int h, int w, int H, int W, float* rba_out, float* sem_seg, void* stream) {
+                                      int K, int D, int h, int w, int H, int W, int score_func, int include_void,
+                                      float* rba_out, float* sem_seg, void* stream) {
   using namespace rba;
   if (B == 0) return RBA_OK;
   RBA_CHECK(embed_hi && embed_lo && feat_hi && feat_lo && pred_logits && rba_out, "rba_einsum_score_fused: null pointer");
   RBA_CHECK(B > 0 && h > 0 && w > 0, "rba_einsum_score_fused: bad shape B=%d h=%d w=%d", B, h, w);
   RBA_CHECK(H > 0 && W > 0 && H <= 4 * h && W <= 4 * w, "rba_einsum_score_fused: output (%d,%d) exceeds 4x(%d,%d)", H, W, h, w);
-  return einsum_score_launch(embed_hi, embed_lo, bias, feat_hi, feat_lo, pred_logits, B, Q, K, D, h, w, H, W, rba_out, sem_seg,
-                             (cudaStream_t)stream);
+  return einsum_score_launch(embed_hi, embed_lo, bias, feat_hi, feat_lo, pred_logits, B, Q, K, D, h, w, H, W, score_func,
+                             include_void, rba_out, sem_seg, (cudaStream_t)stream);
 }

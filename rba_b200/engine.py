@@ -20,6 +20,7 @@ class Engine:
         _lib.check(_lib.lib().rba_model_create(ctypes.byref(cfg), self.device.index, ctypes.byref(self._h)))
         self._finalized = False
         self._graphs = {}
+        self._opts = {}
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -51,7 +52,19 @@ class Engine:
 
     def set_option(self, name, value):
         _lib.check(_lib.lib().rba_model_set_option(self._h, name.encode(), int(value)))
+        self._opts[name] = int(value)
         self._graphs.clear()
+
+    def set_score(self, func="rba", include_void=False):
+        """Per-pixel reduction of the score output: "rba" (evaluate_ood.get_RbA) or "energy"/"pebal" (get_energy);
+        include_void keeps the void column (semantic_inference_with_void): sem_seg gets K+1 planes."""
+        from .ops import SCORE_FUNCS
+        if func not in SCORE_FUNCS:
+            raise RbaError(f"unknown score function {func!r} (one of {sorted(SCORE_FUNCS)})")
+        if self._opts.get("score_func", 0) != SCORE_FUNCS[func]:
+            self.set_option("score_func", SCORE_FUNCS[func])
+        if self._opts.get("include_void", 0) != int(bool(include_void)):
+            self.set_option("include_void", int(bool(include_void)))
 
     def set_gemm_backend(self, name):
         """'tc': tcgen05 GEMMs + tensor-core window attention; 'ffma': exact fp32 CUDA-core kernels everywhere."""
@@ -73,7 +86,7 @@ class Engine:
         if rba:
             out["rba"] = torch.empty((B, H, W), dtype=torch.float32, device=dev)
         if sem_seg:
-            out["sem_seg"] = torch.empty((B, K, H, W), dtype=torch.float32, device=dev)
+            out["sem_seg"] = torch.empty((B, K + self._opts.get("include_void", 0), H, W), dtype=torch.float32, device=dev)
         if logits:
             out["pred_logits"] = torch.empty((B, Q, K + 1), dtype=torch.float32, device=dev)
         if masks:

@@ -120,11 +120,13 @@ class MaskFormer(nn.Module):
     def forward(self, batched_inputs, include_void=False, return_separately=False, return_aux=False,
                 return_ood_pred=False, **kwargs):
         """maskformer_model.py:227-356, eval + SEMANTIC_ON branch."""
-        if include_void or return_aux or return_ood_pred or kwargs.get("return_panoptic_ood"):
-            raise RbaError("include_void / return_aux / return_ood_pred / panoptic outputs are not built (SURVEY §8f-3)")
+        if return_aux or return_ood_pred or kwargs.get("return_panoptic_ood"):
+            raise RbaError("return_aux / return_ood_pred (DenseHybrid head) / panoptic outputs are not built (SURVEY §8f-3)")
         images = self._batch(batched_inputs)
         B, _, H, W = images.shape
-        out = self.engine().forward(images, rba=False, sem_seg=True, logits=return_separately, masks=return_separately)
+        eng = self.engine()
+        eng.set_score("rba", include_void=include_void)     # semantic_inference_with_void (maskformer_model.py:388-392)
+        out = eng.forward(images, rba=False, sem_seg=True, logits=return_separately, masks=return_separately)
         results = []
         for b, inp in enumerate(batched_inputs):
             r = out["sem_seg"][b]
@@ -142,8 +144,16 @@ class MaskFormer(nn.Module):
     def rba(self, batched_inputs):
         """Fused path: evaluate_ood.get_RbA (evaluate_ood.py:143-150) without materialising sem_seg.
         Returns a (B,H,W) tensor of anomaly scores."""
+        return self.score(batched_inputs, "rba")
+
+    @torch.no_grad()
+    def score(self, batched_inputs, score_func="rba"):
+        """Fused anomaly score of evaluate_ood.py --score_func: "rba" (get_RbA, :143-150) or "pebal"/"energy"
+        (get_energy, :152-159: -logsumexp over the class planes).  sem_seg is never materialised."""
         images = self._batch(batched_inputs)
-        return self.engine().forward(images, rba=True)["rba"]
+        eng = self.engine()
+        eng.set_score(score_func, include_void=False)
+        return eng.forward(images, rba=True)["rba"]
 
 
 def build_model(cfg):

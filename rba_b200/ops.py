@@ -52,10 +52,15 @@ def score_fused(pred_masks, pred_logits, out_hw, want_sem_seg=False):
     return (rba, sem) if want_sem_seg else rba
 
 
-def einsum_score_fused(mask_embed, features, pred_logits, out_hw, bias=None, want_sem_seg=False):
+SCORE_FUNCS = {"rba": _lib.RBA_SCORE_RBA, "energy": _lib.RBA_SCORE_ENERGY, "pebal": _lib.RBA_SCORE_ENERGY}
+
+
+def einsum_score_fused(mask_embed, features, pred_logits, out_hw, bias=None, want_sem_seg=False, score_func="rba",
+                       include_void=False):
     """einsum("bqc,bchw->bqhw") (mask2former_transformer_decoder.py:479) + score_fused in ONE kernel: pred_masks is
     never materialised.  mask_embed: (hi, lo) planes (B,Q,D); features: (hi, lo) planes (B,h,w,D) NHWC;
-    pred_logits (B,Q,K+1) fp32; bias (B,Q) fp32 or None -> rba (B,H,W) [, sem_seg (B,K,H,W)]."""
+    pred_logits (B,Q,K+1) fp32; bias (B,Q) fp32 or None -> score (B,H,W) [, sem_seg (B,K|K+1,H,W)].
+    score_func: "rba" (evaluate_ood.get_RbA) or "energy" (get_energy); include_void: semantic_inference_with_void."""
     e_hi, e_lo = mask_embed
     f_hi, f_lo = features
     _chk_cuda(e_hi, e_lo, f_hi, f_lo, pred_logits, bias)
@@ -63,10 +68,12 @@ def einsum_score_fused(mask_embed, features, pred_logits, out_hw, bias=None, wan
     _, h, w, _ = f_hi.shape
     K = pred_logits.shape[-1] - 1
     H, W = out_hw
+    Kc = K + 1 if include_void else K
     rba = torch.empty((B, H, W), dtype=torch.float32, device=f_hi.device)
-    sem = torch.empty((B, K, H, W), dtype=torch.float32, device=f_hi.device) if want_sem_seg else None
+    sem = torch.empty((B, Kc, H, W), dtype=torch.float32, device=f_hi.device) if want_sem_seg else None
     _lib.check(_lib.lib().rba_einsum_score_fused(_p(e_hi), _p(e_lo), _p(bias), _p(f_hi), _p(f_lo), _p(pred_logits), B, Q, K, D,
-                                                h, w, H, W, _p(rba), _p(sem), _stream()))
+                                                h, w, H, W, SCORE_FUNCS[score_func], int(bool(include_void)), _p(rba), _p(sem),
+                                                _stream()))
     return (rba, sem) if want_sem_seg else rba
 
 

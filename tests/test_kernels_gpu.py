@@ -350,6 +350,36 @@ def test_einsum_score_fused(dev, B, Q, K, D, h, w, crop):
     assert (rba0.cpu() - rba_ref0).abs().max() < 5e-5
 
 
+def test_einsum_score_fused_energy_and_void(dev):
+    """Other score heads on the same kernel: get_energy (evaluate_ood.py:152-159) and
+    semantic_inference_with_void (maskformer_model.py:388-392)."""
+    B, Q, K, D, h, w = 2, 100, 19, 256, 9, 20
+    g = torch.Generator().manual_seed(77)
+    E = torch.randn(B, Q, D, generator=g) / math.sqrt(D) * 2.0
+    Fm = torch.randn(B, h, w, D, generator=g)
+    bias = torch.randn(B, Q, generator=g) * 0.5 - 0.5
+    logits = torch.randn(B, Q, K + 1, generator=g)
+    H, W = 4 * h - 1, 4 * w
+    (e_hi, e_lo), Ex = planes(E.view(B * Q, D), dev)
+    (f_hi, f_lo), Fx = planes(Fm.view(-1, D), dev)
+    e_pl = (e_hi.view(B, Q, D), e_lo.view(B, Q, D))
+    f_pl = (f_hi.view(B, h, w, D), f_lo.view(B, h, w, D))
+    masks = (torch.einsum("bqc,bhwc->bqhw", Ex.view(B, Q, D).double(), Fx.view(B, h, w, D).double())
+             + bias.double()[:, :, None, None]).float()
+    up = F.interpolate(masks, size=(4 * h, 4 * w), mode="bilinear", align_corners=False)[:, :, :H, :W]
+    sem = torch.einsum("bqc,bqhw->bchw", logits.softmax(-1)[..., :-1], up.sigmoid())
+    sem_void = torch.einsum("bqc,bqhw->bchw", logits.softmax(-1), up.sigmoid())
+    en, s1 = ops.einsum_score_fused(e_pl, f_pl, logits.to(dev), (H, W), bias=bias.to(dev), want_sem_seg=True, score_func="energy")
+    assert (s1.cpu() - sem).abs().max() < 5e-5
+    assert (en.cpu() - (-torch.logsumexp(sem, dim=1))).abs().max() < 5e-5
+    rv, s2 = ops.einsum_score_fused(e_pl, f_pl, logits.to(dev), (H, W), bias=bias.to(dev), want_sem_seg=True, include_void=True)
+    assert s2.shape == (B, K + 1, H, W)
+    assert (s2.cpu() - sem_void).abs().max() < 5e-5
+    assert (rv.cpu() - (-sem_void.tanh().sum(1))).abs().max() < 5e-5
+    ev = ops.einsum_score_fused(e_pl, f_pl, logits.to(dev), (H, W), bias=bias.to(dev), score_func="pebal", include_void=True)
+    assert (ev.cpu() - (-torch.logsumexp(sem_void, dim=1))).abs().max() < 5e-5
+
+
 def test_einsum_score_fused_limits(dev):
     z = lambda *s: torch.zeros(*s, dtype=torch.bfloat16, device=dev)  # noqa: E731
     with pytest.raises(ops.RbaError):      # Q > 104

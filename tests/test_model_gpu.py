@@ -231,3 +231,28 @@ def test_compat_plugin_flow_on_gpu(dev, tmp_path):
         out = model([{"image": x.to(dev)}])
     rba = -out[0]["sem_seg"].tanh().sum(dim=0)
     assert (rba.cpu() - fix["rba"][0]).abs().max() < TOL
+
+
+def test_model_energy_score_and_include_void(dev):
+    """model.score(..., "pebal") == get_energy on the model's own sem_seg (evaluate_ood.py:152-159);
+    model(..., include_void=True) returns K+1 planes whose first K equal the default call (maskformer_model.py:381-392)."""
+    case = CASES["tiny_1dl"]
+    mc = case_model_config(case)
+    sd = weights.init_state_dict(mc, seed=case["seed"], perturb=case["perturb"])
+    model = rba_b200.MaskFormer(mc)
+    model.load_state_dict(sd)
+    model.to(dev).eval()
+    x = case_images(case)[0].to(dev)
+    sem = model([{"image": x}])[0]["sem_seg"]
+    energy = model.score([{"image": x}], "pebal")[0]
+    assert (energy - (-torch.logsumexp(sem, dim=0))).abs().max() < 1e-5
+    semv = model([{"image": x}], include_void=True)[0]["sem_seg"]
+    assert semv.shape[0] == mc.num_classes + 1
+    assert (semv[:-1] - sem).abs().max() < 1e-6
+    ref = O.forward(sd, mc, [x.cpu()])
+    cls = ref["pred_logits"][0].softmax(-1)
+    up = torch.nn.functional.interpolate(ref["pred_masks"], scale_factor=4, mode="bilinear", align_corners=False)[0]
+    void = torch.einsum("q,qhw->hw", cls[:, -1], up.sigmoid())[: x.shape[1], : x.shape[2]]
+    assert (semv[-1].cpu() - void).abs().max() < TOL
+    again = model.rba([{"image": x}])[0]                       # options reset to the default score
+    assert (again - (-sem.tanh().sum(0))).abs().max() < 1e-5
