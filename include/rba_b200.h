@@ -122,6 +122,17 @@ int rba_einsum_score_fused(const uint16_t* embed_hi, const uint16_t* embed_lo, c
                            const uint16_t* feat_lo, const float* pred_logits, int B, int Q, int K, int D, int h, int w,
                            int H, int W, int score_func, int include_void, float* score, float* sem_seg, void* stream);
 
+/* ---- streaming OoD metrics (replaces OODEvaluator.evaluate_ood / calculate_auroc, support.py:247-303, and the
+ * per-image host round trip of compute_anomaly_scores, support.py:353-399) ----
+ * A two-class histogram of order-preserving float keys (2 x 2^24 uint64 counters = rba_ood_hist_bytes() device bytes,
+ * zero-initialised by the caller) accumulates (score, label) pixels; finalize sweeps it.  Labels: 1 = OoD (positive),
+ * 0 = in-distribution, anything else ignored.  Result = sklearn roc_curve/auc/average_precision_score on scores
+ * quantised to 2^-15 relative resolution.  out (device): auroc, aupr, fpr95, n_ood, n_ind (doubles). */
+int64_t rba_ood_hist_bytes(void);
+int64_t rba_ood_workspace_bytes(void);
+int rba_ood_hist_update(const float* score, const void* label, int label_dtype_bytes, int64_t n, void* hist, void* stream);
+int rba_ood_hist_finalize(const void* hist, void* workspace, double* out, void* stream);
+
 /* ---- MSDeformAttn forward, same argument meaning as the reference FFI ----
  * value (B,S,M,D) fp32 (device); spatial_shapes (L,2) int64 (H_l,W_l) and level_start_index (L) int64 are HOST
  * arrays (shape metadata: the reference reads them on the host too, ms_deform_attn_cuda.cu:44-52 sizes);

@@ -7,6 +7,7 @@ from . import config, ops  # noqa: F401
 from ._lib import LIB_PATH, RbaError, launch_count  # noqa: F401
 from .config import ModelConfig, model_config_from_cfg, model_config_from_yaml  # noqa: F401
 from .engine import Engine  # noqa: F401
+from .metrics import OODEvaluator, StreamingOODMetrics, evaluate_ood  # noqa: F401
 from .modeling import MaskFormer, build_model  # noqa: F401
 
 __version__ = "0.1.0"

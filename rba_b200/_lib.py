@@ -58,6 +58,10 @@ PROTOTYPES = {
     "rba_score_fused": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "rba_einsum_score_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                        c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "rba_ood_hist_bytes": (c_int64, []),
+    "rba_ood_workspace_bytes": (c_int64, []),
+    "rba_ood_hist_update": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
+    "rba_ood_hist_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "rba_msda_forward": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64), c_void_p, c_void_p, c_int, c_int, c_int,
                                  c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "rba_k_split": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_int64, c_void_p]),
