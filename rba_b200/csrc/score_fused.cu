@@ -92,6 +92,57 @@ __device__ __forceinline__ void fs_split(float e0, float e1, uint32_t& hi, uint3
   if (ABL & 4) { hi = __float_as_uint(e0); lo = __float_as_uint(e1); return; }
   fs_split_f16x2(e0, e1, hi, lo);
 }
+// lo = x - float(h) in ONE instruction: sm_100 mixed-precision FMA (SASS FHFMA), h = one half of a packed f16x2 register
+__device__ __forceinline__ float fs_residual(float x, uint16_t h) {
+  float r;
+  const uint16_t m1 = 0xBC00;                               // -1.0h
+  asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(r) : "h"(h), "h"(m1), "f"(x));
+  return r;
+}
+__device__ __forceinline__ void fs_split_fast(float e0, float e1, uint32_t& hi, uint32_t& lo) {
+  hi = fs_pack_f16x2(e0, e1);
+  lo = fs_pack_f16x2(fs_residual(e0, (uint16_t)(hi & 0xffffu)), fs_residual(e1, (uint16_t)(hi >> 16)));
+}
+// Four sigmoids 1 / (1 + 2^u) with ONE reciprocal (the MUFU pipe is the binding resource of this kernel): the four
+// denominators are multiplied up, inverted once and divided back out (9 FMUL on the idle FMA pipe for 3 MUFU.RCP).
+// u is clamped at 30 so the product stays below 2^121; the clamp changes a sigmoid by < 2^-30.
+__device__ __forceinline__ void fs_sigmoid4(const float* u, float* s) {
+  const float a0 = 1.0f + fs_ex2(fminf(u[0], 30.f)), a1 = 1.0f + fs_ex2(fminf(u[1], 30.f));
+  const float a2 = 1.0f + fs_ex2(fminf(u[2], 30.f)), a3 = 1.0f + fs_ex2(fminf(u[3], 30.f));
+  const float ab = a0 * a1, cd = a2 * a3;
+  const float r = fs_rcp(ab * cd);
+  const float rab = r * cd, rcd = r * ab;
+  s[0] = rab * a1; s[1] = rab * a0; s[2] = rcd * a3; s[3] = rcd * a2;
+}
+// Two sigmoids with one reciprocal (u clamped at 60)
+__device__ __forceinline__ void fs_sigmoid2(float u0, float u1, float& s0, float& s1) {
+  const float a0 = 1.0f + fs_ex2(fminf(u0, 60.f)), a1 = 1.0f + fs_ex2(fminf(u1, 60.f));
+  const float r = fs_rcp(a0 * a1);
+  s0 = r * a1; s1 = r * a0;
+}
+// RCPM (RBA_FS_RCP): 0 one reciprocal per sigmoid, 1 per pair, 2 per quad.  Produces the f16 hi/lo A fragments of one k16 step.
+template <int ABL, int RCPM>
+__device__ __forceinline__ void fs_sig_frag(const float* u0, const float* u1, uint32_t* ah, uint32_t* al) {
+  if (ABL != 0 || RCPM == 0) {
+    fs_split<ABL>(fs_sig<ABL>(u0[0]), fs_sig<ABL>(u0[1]), ah[0], al[0]);
+    fs_split<ABL>(fs_sig<ABL>(u0[2]), fs_sig<ABL>(u0[3]), ah[1], al[1]);
+    fs_split<ABL>(fs_sig<ABL>(u1[0]), fs_sig<ABL>(u1[1]), ah[2], al[2]);
+    fs_split<ABL>(fs_sig<ABL>(u1[2]), fs_sig<ABL>(u1[3]), ah[3], al[3]);
+  } else {
+    float s0[4], s1[4];
+    if (RCPM == 3) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { s0[e] = fs_sigmoid_scaled(u0[e]); s1[e] = fs_sigmoid_scaled(u1[e]); }
+    } else if (RCPM == 1) {
+      fs_sigmoid2(u0[0], u0[1], s0[0], s0[1]); fs_sigmoid2(u0[2], u0[3], s0[2], s0[3]);
+      fs_sigmoid2(u1[0], u1[1], s1[0], s1[1]); fs_sigmoid2(u1[2], u1[3], s1[2], s1[3]);
+    } else {
+      fs_sigmoid4(u0, s0); fs_sigmoid4(u1, s1);
+    }
+    fs_split_fast(s0[0], s0[1], ah[0], al[0]); fs_split_fast(s0[2], s0[3], ah[1], al[1]);
+    fs_split_fast(s1[0], s1[1], ah[2], al[2]); fs_split_fast(s1[2], s1[3], ah[3], al[3]);
+  }
+}
 __device__ __forceinline__ void fs_mma_tf32(float* d, uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1) {
   asm(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%4,%5}, {%6,%7}, {%8,%8,%8,%8};"
@@ -120,7 +171,7 @@ __device__ __forceinline__ void fs_interp8(const float* tp, uint32_t a0, uint32_
   fs_mma_tf32(u, a0, a1, hi, __float_as_uint(lo));
 }
 
-template <bool WRITE_SEM, int ABL = 0>
+template <bool WRITE_SEM, int ABL = 0, int RCPM = 1>
 __global__ void __launch_bounds__(FS_THREADS, 1)
 rba_einsum_score_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constant__ CUtensorMap tmY_lo,
                         const __grid_constant__ CUtensorMap tmE_hi, const __grid_constant__ CUtensorMap tmE_lo,
@@ -335,10 +386,7 @@ rba_einsum_score_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid
 #pragma unroll
           for (int nt = 0; nt < FS_NT; ++nt) bv[nt] = bp[(size_t)nt * 8 * FS_KS * 4 + ks * 4];
           uint32_t ah[4], al[4];
-          fs_split<ABL>(fs_sig<ABL>(u0[0]), fs_sig<ABL>(u0[1]), ah[0], al[0]);
-          fs_split<ABL>(fs_sig<ABL>(u0[2]), fs_sig<ABL>(u0[3]), ah[1], al[1]);
-          fs_split<ABL>(fs_sig<ABL>(u1[0]), fs_sig<ABL>(u1[1]), ah[2], al[2]);
-          fs_split<ABL>(fs_sig<ABL>(u1[2]), fs_sig<ABL>(u1[3]), ah[3], al[3]);
+          fs_sig_frag<ABL, RCPM>(u0, u1, ah, al);
           // consecutive MMAs target different accumulators (no back-to-back dependent HMMAs)
           if (ABL & 1) {
             acc[0][0] += __uint_as_float(ah[0] ^ al[1] ^ bv[0].x ^ bv[1].y ^ bv[2].z);
@@ -356,8 +404,20 @@ rba_einsum_score_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid
         }
         if (tail) {
           uint32_t ah0, al0, ah1, al1;
-          fs_split<ABL>(fs_sig<ABL>(u0[0]), fs_sig<ABL>(u0[1]), ah0, al0);
-          fs_split<ABL>(fs_sig<ABL>(u0[2]), fs_sig<ABL>(u0[3]), ah1, al1);
+          if (ABL != 0 || RCPM == 0) {
+            fs_split<ABL>(fs_sig<ABL>(u0[0]), fs_sig<ABL>(u0[1]), ah0, al0);
+            fs_split<ABL>(fs_sig<ABL>(u0[2]), fs_sig<ABL>(u0[3]), ah1, al1);
+          } else {
+            float s0[4];
+            if (RCPM == 3) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) s0[e] = fs_sigmoid_scaled(u0[e]);
+            } else {
+              fs_sigmoid4(u0, s0);
+            }
+            fs_split_fast(s0[0], s0[1], ah0, al0);
+            fs_split_fast(s0[2], s0[3], ah1, al1);
+          }
           uint4 bv[FS_NT];
 #pragma unroll
           for (int nt = 0; nt < FS_NT; ++nt) bv[nt] = bp[(size_t)nt * 8 * FS_KS * 4 + nfull * 4];
@@ -469,25 +529,27 @@ int einsum_score_launch(const uint16_t* e_hi, const uint16_t* e_lo, const float*
   dim3 grid((unsigned)std::min<int64_t>(nt, num_sms()));
   if (sem) {
     static bool done = false;
-    if (!done) { RBA_CUDA(cudaFuncSetAttribute(rba_einsum_score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM)); done = true; }
-    rba_einsum_score_kernel<true><<<grid, FS_THREADS, FS_SMEM, st>>>(ty_hi, ty_lo, te_hi, te_lo, p);
+    if (!done) { RBA_CUDA(cudaFuncSetAttribute(rba_einsum_score_kernel<true, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM)); done = true; }
+    rba_einsum_score_kernel<true, 0, 1><<<grid, FS_THREADS, FS_SMEM, st>>>(ty_hi, ty_lo, te_hi, te_lo, p);
   } else {
     static const int abl = []() { const char* e = getenv("RBA_FS_ABL"); return e ? atoi(e) : 0; }();
-#define RBA_FS_LAUNCH(A)                                                                                                   \
+    static const int rcpm = []() { const char* e = getenv("RBA_FS_RCP"); return e ? atoi(e) : 1; }();
+#define RBA_FS_LAUNCH(A, R)                                                                                                  \
   do {                                                                                                                     \
     static bool done = false;                                                                                              \
-    if (!done) { RBA_CUDA(cudaFuncSetAttribute(rba_einsum_score_kernel<false, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM)); done = true; } \
-    rba_einsum_score_kernel<false, A><<<grid, FS_THREADS, FS_SMEM, st>>>(ty_hi, ty_lo, te_hi, te_lo, p);                   \
+    if (!done) { RBA_CUDA(cudaFuncSetAttribute(rba_einsum_score_kernel<false, A, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM)); done = true; } \
+    rba_einsum_score_kernel<false, A, R><<<grid, FS_THREADS, FS_SMEM, st>>>(ty_hi, ty_lo, te_hi, te_lo, p);                \
   } while (0)
-    switch (abl) {
-      case 1: RBA_FS_LAUNCH(1); break;
-      case 2: RBA_FS_LAUNCH(2); break;
-      case 4: RBA_FS_LAUNCH(4); break;
-      case 8: RBA_FS_LAUNCH(8); break;
-      case 6: RBA_FS_LAUNCH(6); break;
-      case 7: RBA_FS_LAUNCH(7); break;
-      case 15: RBA_FS_LAUNCH(15); break;
-      default: RBA_FS_LAUNCH(0); break;
+    switch (abl * 4 + (abl ? 0 : rcpm)) {
+      case 1 * 4: RBA_FS_LAUNCH(1, 0); break;
+      case 2 * 4: RBA_FS_LAUNCH(2, 0); break;
+      case 4 * 4: RBA_FS_LAUNCH(4, 0); break;
+      case 8 * 4: RBA_FS_LAUNCH(8, 0); break;
+      case 15 * 4: RBA_FS_LAUNCH(15, 0); break;
+      case 0: RBA_FS_LAUNCH(0, 0); break;
+      case 3: RBA_FS_LAUNCH(0, 3); break;
+      case 2: RBA_FS_LAUNCH(0, 2); break;
+      default: RBA_FS_LAUNCH(0, 1); break;
     }
 #undef RBA_FS_LAUNCH
   }

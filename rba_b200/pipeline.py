@@ -1,0 +1,119 @@
+"""Overlapped host->device->host scoring stream (pinned-memory prefetch and true batching).
+
+The reference's evaluation loop is batch-1 and synchronous: per image a blocking H2D, the forward, and a blocking
+`.cpu().numpy()` (support.py:353-399, evaluate_ood.py:143-150).  `ScoreStream` keeps the same per-batch semantics
+(uint8 CHW images in host memory -> float32 score maps in host memory) but runs the three legs on three CUDA streams:
+
+    copy-in stream   H2D of batch i+1 (pinned staging)       |
+    compute stream   rba_forward of batch i (CUDA graph)     |  all concurrent
+    copy-out stream  D2H of the scores of batch i-1          |
+
+so at steady state a step costs max(forward, H2D, D2H) instead of their sum.  Results come back in order, one step
+late; `close()`/exhausting the iterator drains the pipeline.  torch is only the carrier of buffers, streams and events.
+"""
+import torch
+
+from ._lib import RbaError
+
+
+class ScoreStream:
+    """eng: rba_b200.Engine with weights loaded.  B, H, W: fixed batch shape (the forward is captured once)."""
+
+    def __init__(self, eng, B, H, W, use_graph=True, post_forward=None):
+        if not torch.cuda.is_available():
+            raise RbaError("ScoreStream needs a CUDA device: the product path has no CPU fallback")
+        self.eng, self.B, self.H, self.W = eng, B, H, W
+        self.post_forward = post_forward      # callable(static_out) launched on the compute stream after each forward
+        dev = eng.device
+        self.dev = dev
+        proto = torch.empty((B, 3, H, W), dtype=torch.uint8, device=dev)
+        self.use_graph = use_graph
+        if use_graph:
+            self.static_in, self.static_out, self.graph = eng.graphed(proto, rba=True)
+        else:
+            eng.reserve(B, H, W)
+            self.static_in = proto
+            self.static_out = eng.alloc_outputs(B, H, W, rba=True)
+            self.graph = None
+        self.stage_in = [torch.empty_like(proto) for _ in range(2)]
+        self.stage_out = [torch.empty((B, H, W), dtype=torch.float32, device=dev) for _ in range(2)]
+        self.host_out = [torch.empty((B, H, W), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        ev = lambda: torch.cuda.Event()  # noqa: E731
+        self.ev_in_ready = [ev(), ev()]      # H2D into stage_in[k] finished
+        self.ev_in_free = [ev(), ev()]       # compute has consumed stage_in[k]
+        self.ev_c_done = [ev(), ev()]        # scores of this step are in stage_out[k]
+        self.ev_out_done = [ev(), ev()]      # D2H out of stage_out[k] finished
+        self.n_submitted = 0
+        self.n_collected = 0
+        self.h2d_bytes_per_step = proto.numel()
+        self.d2h_bytes_per_step = B * H * W * 4
+
+    # ---- one step = submit batch i, (maybe) collect batch i-1 ----
+    def submit(self, host_images):
+        """host_images: (B,3,H,W) uint8 tensor in PINNED host memory.  Asynchronous."""
+        if host_images.shape != self.stage_in[0].shape or host_images.dtype != torch.uint8:
+            raise RbaError(f"ScoreStream.submit: expected uint8 {tuple(self.stage_in[0].shape)}, got {host_images.dtype} {tuple(host_images.shape)}")
+        if not host_images.is_pinned():
+            raise RbaError("ScoreStream.submit: host batch must be in pinned memory (torch.Tensor.pin_memory())")
+        i = self.n_submitted
+        k = i & 1
+        comp = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(self.s_in):
+            if i >= 2:
+                self.s_in.wait_event(self.ev_in_free[k])
+            self.stage_in[k].copy_(host_images, non_blocking=True)
+            self.ev_in_ready[k].record(self.s_in)
+        comp.wait_event(self.ev_in_ready[k])
+        self.static_in.copy_(self.stage_in[k], non_blocking=True)
+        self.ev_in_free[k].record(comp)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.eng.forward_into(self.static_in, self.static_out)
+        if self.post_forward is not None:
+            self.post_forward(self.static_out)
+        if i >= 2:
+            comp.wait_event(self.ev_out_done[k])          # the D2H that last read stage_out[k]
+        self.stage_out[k].copy_(self.static_out["rba"], non_blocking=True)
+        self.ev_c_done[k].record(comp)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self.ev_c_done[k])
+            self.host_out[k].copy_(self.stage_out[k], non_blocking=True)
+            self.ev_out_done[k].record(self.s_out)
+        self.n_submitted += 1
+
+    def collect(self):
+        """Blocks until the oldest un-collected batch's scores are in host memory; returns the (B,H,W) pinned tensor
+        (valid until two more batches have been submitted)."""
+        if self.n_collected >= self.n_submitted:
+            raise RbaError("ScoreStream.collect: nothing in flight")
+        k = self.n_collected & 1
+        self.ev_out_done[k].synchronize()
+        self.n_collected += 1
+        return self.host_out[k]
+
+    def step(self, host_images):
+        """Submit batch i; return the scores of batch i-1 (None on the first call)."""
+        prev = None
+        if self.n_submitted - self.n_collected >= 2:
+            raise RbaError("ScoreStream.step: collect() the previous result first")
+        self.submit(host_images)
+        if self.n_submitted - self.n_collected == 2:
+            prev = self.collect()
+        return prev
+
+    def drain(self):
+        out = []
+        while self.n_collected < self.n_submitted:
+            out.append(self.collect())
+        return out
+
+    def run(self, host_batches):
+        """Generator: yields one (B,H,W) host score tensor per input batch, in order."""
+        for hb in host_batches:
+            r = self.step(hb)
+            if r is not None:
+                yield r
+        for r in self.drain():
+            yield r

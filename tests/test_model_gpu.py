@@ -256,3 +256,29 @@ def test_model_energy_score_and_include_void(dev):
     assert (semv[-1].cpu() - void).abs().max() < TOL
     again = model.rba([{"image": x}])[0]                       # options reset to the default score
     assert (again - (-sem.tanh().sum(0))).abs().max() < 1e-5
+
+
+def test_score_stream_overlapped_pipeline(dev):
+    """rba_b200.ScoreStream (pinned H2D / forward / D2H on three streams): results, in order and bitwise, equal the
+    synchronous forward of the same batches; misuse fails loudly."""
+    case = CASES["tiny_1dl"]
+    mc = case_model_config(case)
+    sd = weights.init_state_dict(mc, seed=case["seed"], perturb=case["perturb"])
+    e = _engine(mc, sd, dev)
+    g = torch.Generator().manual_seed(11)
+    B, H, W = 2, 64, 96
+    batches = [torch.randint(0, 256, (B, 3, H, W), dtype=torch.uint8, generator=g).pin_memory() for _ in range(5)]
+    want = [e.forward(b.to(dev), rba=True)["rba"].cpu() for b in batches]
+    for use_graph in (True, False):
+        stream = rba_b200.ScoreStream(e, B, H, W, use_graph=use_graph)
+        got = [r.clone() for r in stream.run(batches)]
+        assert len(got) == len(want)
+        for a, b in zip(got, want):
+            assert torch.equal(a, b)
+        assert stream.h2d_bytes_per_step == B * 3 * H * W and stream.d2h_bytes_per_step == B * H * W * 4
+    with pytest.raises(rba_b200.RbaError):
+        stream.submit(torch.zeros((B, 3, H, W), dtype=torch.uint8))          # not pinned
+    with pytest.raises(rba_b200.RbaError):
+        stream.submit(torch.zeros((B, 3, H + 32, W), dtype=torch.uint8).pin_memory())
+    with pytest.raises(rba_b200.RbaError):
+        stream.collect()

@@ -1,3 +1,9 @@
 #!/bin/bash
-timeout 300 python -m pytest tests/test_kernels_gpu.py -m gpu -q --tb=short -x -k "einsum_score" 2>&1 | tail -1
-for d in ${@:-0 1 2 4 8 6 7 15}; do echo -n "RBA_FS_ABL=$d: "; RBA_FS_ABL=$d python tools/fused_score_only.py 8 10 2>&1 | tail -1; done
+# Ablation timings of the fused kernel (B=8): which phase bounds it
+OUT=gpurun_out/${1:-fsabl}; mkdir -p $OUT
+export PYTHONUNBUFFERED=1
+{
+echo "default";            python tools/fused_score_only.py 8 20 2>&1 | tail -1
+echo "RBA_FS_DEBUG=16 (no score phase: TMA + einsum GEMM + drain only)"; RBA_FS_DEBUG=16 python tools/fused_score_only.py 8 20 2>&1 | tail -1
+for a in 1 2 4 8 15; do echo "RBA_FS_ABL=$a"; RBA_FS_ABL=$a python tools/fused_score_only.py 8 20 2>&1 | tail -1; done
+} | tee $OUT/ablation.txt

@@ -8,9 +8,9 @@
 
 constexpr int ITERS = 2048, CHAINS = 8;
 
-enum Op { EX2, RCP, TANH, F2FP, F2FP_BF16, SPLIT_F16, SPLIT_BF16T, HADD2F32, PRMT, LOP, FMNMX, FFMA, FADD, HMMA_F16, HMMA_BF16, HMMA_TF32, LDS32, MIX_SIG, MIX_MUFU_HMMA, MIX_MUFU_FFMA4, NOPS };
+enum Op { EX2, RCP, TANH, F2FP, F2FP_BF16, SPLIT_F16, SPLIT_BF16T, HADD2F32, PRMT, LOP, FMNMX, FFMA, FADD, HMMA_F16, HMMA_BF16, HMMA_TF32, LDS32, MIX_SIG, MIX_MUFU_HMMA, MIX_MUFU_FFMA4, FHFMA_OP, HMMA_F16_K8, NOPS };
 const char* names[] = {"MUFU.EX2", "MUFU.RCP", "MUFU.TANH", "F2FP.F16.F32.PACK", "F2FP.BF16.F32.PACK", "split f16 (6 ops)", "split bf16 trunc (6 ops)", "HADD2.F32 (h->f)", "PRMT", "LOP3", "FMNMX",
-                       "FFMA", "FADD", "HMMA.16816.F32 f16", "HMMA.16816.F32 bf16", "HMMA.1688.F32.TF32", "LDS.32", "EX2+FADD+RCP", "EX2+HMMA", "EX2+4xFFMA"};
+                       "FFMA", "FADD", "HMMA.16816.F32 f16", "HMMA.16816.F32 bf16", "HMMA.1688.F32.TF32", "LDS.32", "EX2+FADD+RCP", "EX2+HMMA", "EX2+4xFFMA", "FHFMA (f32 += f16*f16)", "HMMA.1688.F32 f16"};
 
 template <int OP>
 __global__ void __launch_bounds__(256) k(float* out, long long* clk, float seed) {
@@ -83,6 +83,11 @@ __global__ void __launch_bounds__(256) k(float* out, long long* clk, float seed)
         asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(acc[c][2]) : "f"(seed));
         asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(acc[c][3]) : "f"(seed));
       }
+      if (OP == FHFMA_OP) asm volatile("{.reg .f16 lo, hi; mov.b32 {lo, hi}, %1; fma.rn.f32.f16 %0, lo, hi, %0;}" : "+f"(x[c]) : "r"(u[c]));
+      if (OP == HMMA_F16_K8)
+        asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                     : "+f"(acc[c][0]), "+f"(acc[c][1]), "+f"(acc[c][2]), "+f"(acc[c][3])
+                     : "r"(u[0]), "r"(u[1]), "r"(u[4]));
       if (OP == MIX_SIG) {
         asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[c]));
         asm volatile("add.f32 %0, %0, 1.0;" : "+f"(x[c]));
@@ -131,7 +136,7 @@ int main() {
   for (int c : {2, 4}) {
     run<EX2>(sms, c); run<RCP>(sms, c); run<TANH>(sms, c); run<MIX_SIG>(sms, c); run<F2FP>(sms, c); run<F2FP_BF16>(sms, c); run<SPLIT_F16>(sms, c); run<SPLIT_BF16T>(sms, c); run<HADD2F32>(sms, c);
     run<PRMT>(sms, c); run<LOP>(sms, c); run<FMNMX>(sms, c); run<FFMA>(sms, c); run<FADD>(sms, c);
-    run<HMMA_F16>(sms, c); run<HMMA_BF16>(sms, c); run<HMMA_TF32>(sms, c); run<LDS32>(sms, c); run<MIX_MUFU_HMMA>(sms, c); run<MIX_MUFU_FFMA4>(sms, c);
+    run<HMMA_F16>(sms, c); run<HMMA_BF16>(sms, c); run<HMMA_TF32>(sms, c); run<LDS32>(sms, c); run<MIX_MUFU_HMMA>(sms, c); run<MIX_MUFU_FFMA4>(sms, c); run<FHFMA_OP>(sms, c); run<HMMA_F16_K8>(sms, c);
   }
   return 0;
 }
