@@ -10,6 +10,7 @@
  *
  * Reference interfaces replaced (paths relative to the reference repo root):
  *   rba_msda_forward          <- MultiScaleDeformableAttention.ms_deform_attn_forward
+ *   rba_msda_backward         <- MultiScaleDeformableAttention.ms_deform_attn_backward
  *                                (mask2former/modeling/pixel_decoder/ops/src/vision.cpp:18-21,
  *                                 src/ms_deform_attn.h:25-45, src/cuda/ms_deform_attn_cuda.cu:25-84)
  *   rba_score_fused           <- F.interpolate x4 + MaskFormer.semantic_inference + get_RbA
@@ -142,6 +143,16 @@ int rba_ood_hist_finalize(const void* hist, void* workspace, double* out, void* 
 int rba_msda_forward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
                      const float* sampling_loc, const float* attn_weight, int B, int S, int M, int D, int Lq, int L,
                      int P, int im2col_step, float* out, void* stream);
+
+/* ---- MSDeformAttn backward: `ms_deform_attn_backward` of the same FFI (ops/src/vision.cpp:20,
+ * ops/src/ms_deform_attn.h:44-66, ops/src/cuda/ms_deform_attn_cuda.cu:87-153) ----
+ * grad_output (B,Lq,M*D) fp32.  Outputs (device): grad_value (B,S,M,D) -- zeroed inside, then accumulated with atomics --
+ * grad_sampling_loc (B,Lq,M,L,P,2) and grad_attn_weight (B,Lq,M,L,P), both fully written.  Same validation as the
+ * forward (batch % min(batch, im2col_step) == 0, ms_deform_attn_cuda.cu:117-119). */
+int rba_msda_backward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                      const float* sampling_loc, const float* attn_weight, const float* grad_output, int B, int S, int M,
+                      int D, int Lq, int L, int P, int im2col_step, float* grad_value, float* grad_sampling_loc,
+                      float* grad_attn_weight, void* stream);
 
 /* ---- per-kernel entry points (device pointers) ---- */
 /* fp32 [rows,cols] (row pitch ld floats) -> bf16 planes hi, lo [rows,cols] (pitch ldp elements). */

@@ -254,6 +254,57 @@ def msda_bilinear_gather(value, spatial_shapes, sampling_locations, attention_we
     return out.view(N, Lq, M * D)
 
 
+def msda_bilinear_backward(value, spatial_shapes, sampling_locations, attention_weights, grad_output):
+    """Explicit restatement of the reference CUDA backward's arithmetic
+    (ops/src/cuda/ms_deform_im2col_cuda.cuh:92-163 `ms_deform_attn_col2im_bilinear`, driven by the kernels at :306-925):
+      top_grad_value = grad_out * attn_weight;  grad_value[tap] += w_tap * top_grad_value  (atomicAdd, :127-155)
+      grad_attn_weight = sum_d grad_out * val                                              (:158)
+      grad_sampling_loc.x = W * sum_d grad_w_weight * top_grad_value, .y = H * sum_d grad_h_weight * top_grad_value
+                                                                                           (:159-160)
+    with grad_w_weight = -hh v1 + hh v2 - lh v3 + lh v4 and grad_h_weight = -hw v1 - lw v2 + hw v3 + lw v4, taps outside
+    the map reading 0 and samples outside (-1,H)x(-1,W) skipped.  Returns (grad_value, grad_sampling_loc, grad_attn_weight)."""
+    N, S, M, D = value.shape
+    _, Lq, _, L, P, _ = sampling_locations.shape
+    go = grad_output.view(N, Lq, M, 1, D)
+    g_value = torch.zeros_like(value)
+    g_loc = torch.zeros_like(sampling_locations)
+    g_aw = torch.zeros_like(attention_weights)
+    start = 0
+    for lid, (H, W) in enumerate([(int(h), int(w)) for h, w in spatial_shapes]):
+        v = value[:, start:start + H * W].reshape(N, H, W, M, D)
+        gv = torch.zeros_like(v)
+        loc = sampling_locations[:, :, :, lid]
+        w_im = loc[..., 0] * W - 0.5
+        h_im = loc[..., 1] * H - 0.5
+        valid = (h_im > -1) & (w_im > -1) & (h_im < H) & (w_im < W)
+        h_low, w_low = torch.floor(h_im), torch.floor(w_im)
+        lh, lw = h_im - h_low, w_im - w_low
+        hh, hw = 1 - lh, 1 - lw
+        h_low, w_low = h_low.long(), w_low.long()
+        aw = attention_weights[:, :, :, lid]
+        n_idx = torch.arange(N).view(N, 1, 1, 1).expand(N, Lq, M, P)
+        m_idx = torch.arange(M).view(1, 1, M, 1).expand(N, Lq, M, P)
+        top = go * aw.unsqueeze(-1)                                         # N,Lq,M,P,D
+        taps = []
+        for dy, dx, wt in ((0, 0, hh * hw), (0, 1, hh * lw), (1, 0, lh * hw), (1, 1, lh * lw)):
+            yy, xx = h_low + dy, w_low + dx
+            ok = (valid & (yy >= 0) & (yy <= H - 1) & (xx >= 0) & (xx <= W - 1)).to(value.dtype).unsqueeze(-1)
+            yc, xc = yy.clamp(0, H - 1), xx.clamp(0, W - 1)
+            taps.append(v[n_idx, yc, xc, m_idx] * ok)
+            gv.index_put_((n_idx, yc, xc, m_idx), top * wt.unsqueeze(-1) * ok, accumulate=True)
+        v1, v2, v3, v4 = taps
+        e = lambda t: t.unsqueeze(-1)  # noqa: E731
+        val = e(hh * hw) * v1 + e(hh * lw) * v2 + e(lh * hw) * v3 + e(lh * lw) * v4
+        gw_w = -e(hh) * v1 + e(hh) * v2 - e(lh) * v3 + e(lh) * v4
+        gh_w = -e(hw) * v1 - e(lw) * v2 + e(hw) * v3 + e(lw) * v4
+        g_aw[:, :, :, lid] = (go * val).sum(-1)
+        g_loc[:, :, :, lid, :, 0] = W * (gw_w * top).sum(-1)
+        g_loc[:, :, :, lid, :, 1] = H * (gh_w * top).sum(-1)
+        g_value[:, start:start + H * W] = gv.reshape(N, H * W, M, D)
+        start += H * W
+    return g_value, g_loc, g_aw
+
+
 def msda_core_grid_sample(value, spatial_shapes, sampling_locations, attention_weights):
     """ops/functions/ms_deform_attn_func.py:52-72 (the reference's CPU statement); used for
     full-size runs because it is much faster than msda_bilinear_gather."""

@@ -143,6 +143,98 @@ int msda_fused(const float* value, const int* Hs, const int* Ws, const float* oa
   return RBA_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Backward of the sampling step: drop-in for `MultiScaleDeformableAttention.ms_deform_attn_backward`
+// (ops/src/vision.cpp:20, ops/src/cuda/ms_deform_attn_cuda.cu:87-153, kernels
+// ops/src/cuda/ms_deform_im2col_cuda.cuh:92-239 col2im_bilinear + :306-925 reduction variants).
+//   grad_value[b, tap, m, d]      += w_tap * attn_w * grad_out[b,q,m,d]                       (atomic: taps collide)
+//   grad_attn_weight[b,q,m,l,p]    = sum_d grad_out[b,q,m,d] * bilinear(value)[d]
+//   grad_sampling_loc[...,0 / 1]   = W_l / H_l * sum_d attn_w * grad_out[d] * d bilinear / d w_im / d h_im
+// The reference picks one of seven kernels by channel count to reduce over d in shared memory; here ONE warp owns one
+// (b, q, m) row: lanes stride over d (a tap is a coalesced D*4-byte gather / red.global.add), the three per-sample sums are
+// reduced with xor-shuffles and written once -- no atomics except the unavoidable grad_value scatter, any D.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+msda_backward_kernel(const float* __restrict__ value, MsdaLevels lv, const float* __restrict__ loc,
+                     const float* __restrict__ attw, const float* __restrict__ grad_out, int64_t rows, int S, int M, int D,
+                     int Lq, int L, int P, float* __restrict__ grad_value, float* __restrict__ grad_loc,
+                     float* __restrict__ grad_attw) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // (b*Lq + q)*M + m
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int m = (int)(row % M);
+  const int64_t t = row / M;
+  const int64_t b = t / Lq;
+  const int64_t vstride = (int64_t)M * D;
+  const int64_t vbase = (b * S) * vstride + (int64_t)m * D;
+  const float* lp = loc + row * (int64_t)L * P * 2;
+  const float* wp = attw + row * (int64_t)L * P;
+  const float* go = grad_out + row * (int64_t)D;
+  for (int l = 0; l < L; ++l) {
+    const int H = lv.H[l], W = lv.W[l];
+    const int64_t lbase = vbase + (int64_t)lv.start[l] * vstride;
+    for (int p = 0; p < P; ++p) {
+      const float x = lp[(l * P + p) * 2 + 0];
+      const float y = lp[(l * P + p) * 2 + 1];
+      const float wgt = wp[l * P + p];
+      const float h_im = y * H - 0.5f;
+      const float w_im = x * W - 0.5f;
+      float gx = 0.f, gy = 0.f, gw = 0.f;
+      if (h_im > -1.f && w_im > -1.f && h_im < H && w_im < W) {
+        const int h0 = (int)floorf(h_im), w0 = (int)floorf(w_im);
+        const float lh = h_im - h0, lw = w_im - w0;
+        const float hh = 1.f - lh, hw = 1.f - lw;
+        const int h1 = h0 + 1, w1 = w0 + 1;
+        const bool ok00 = h0 >= 0 && w0 >= 0, ok01 = h0 >= 0 && w1 <= W - 1;
+        const bool ok10 = h1 <= H - 1 && w0 >= 0, ok11 = h1 <= H - 1 && w1 <= W - 1;
+        const int64_t o00 = lbase + ((int64_t)h0 * W + w0) * vstride, o01 = o00 + vstride;
+        const int64_t o10 = o00 + (int64_t)W * vstride, o11 = o10 + vstride;
+        for (int d = lane; d < D; d += 32) {
+          const float g = go[d];
+          const float top = g * wgt;
+          float v00 = 0.f, v01 = 0.f, v10 = 0.f, v11 = 0.f;
+          if (ok00) { v00 = __ldg(value + o00 + d); atomicAdd(grad_value + o00 + d, hh * hw * top); }
+          if (ok01) { v01 = __ldg(value + o01 + d); atomicAdd(grad_value + o01 + d, hh * lw * top); }
+          if (ok10) { v10 = __ldg(value + o10 + d); atomicAdd(grad_value + o10 + d, lh * hw * top); }
+          if (ok11) { v11 = __ldg(value + o11 + d); atomicAdd(grad_value + o11 + d, lh * lw * top); }
+          gw = fmaf(g, hh * hw * v00 + hh * lw * v01 + lh * hw * v10 + lh * lw * v11, gw);
+          gx = fmaf(top, hh * (v01 - v00) + lh * (v11 - v10), gx);
+          gy = fmaf(top, hw * (v10 - v00) + lw * (v11 - v01), gy);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        gx += __shfl_xor_sync(0xffffffffu, gx, o);
+        gy += __shfl_xor_sync(0xffffffffu, gy, o);
+        gw += __shfl_xor_sync(0xffffffffu, gw, o);
+      }
+      if (lane == 0) {
+        const int64_t i = row * (int64_t)L * P + l * P + p;
+        grad_loc[2 * i] = gx * (float)W;
+        grad_loc[2 * i + 1] = gy * (float)H;
+        grad_attw[i] = gw;
+      }
+    }
+  }
+}
+
+static int msda_levels(const char* who, const int64_t* spatial_shapes, const int64_t* level_start_index, int L, int S,
+                       MsdaLevels* lv) {
+  RBA_CHECK(L > 0 && L <= MSDA_MAX_LEVELS, "%s: L=%d outside 1..%d levels", who, L, MSDA_MAX_LEVELS);
+  int64_t total_s = 0;
+  for (int l = 0; l < L; ++l) {
+    lv->H[l] = (int)spatial_shapes[2 * l];
+    lv->W[l] = (int)spatial_shapes[2 * l + 1];
+    lv->start[l] = (int)level_start_index[l];
+    RBA_CHECK(lv->H[l] > 0 && lv->W[l] > 0, "%s: empty level %d", who, l);
+    RBA_CHECK(lv->start[l] >= 0 && (int64_t)lv->start[l] + (int64_t)lv->H[l] * lv->W[l] <= S,
+              "%s: level %d exceeds value length", who, l);
+    total_s += (int64_t)lv->H[l] * lv->W[l];
+  }
+  RBA_CHECK(total_s == S, "%s: sum(H*W)=%lld != S=%d", who, (long long)total_s, S);
+  return RBA_OK;
+}
+
 }  // namespace rba
 
 extern "C" int rba_msda_forward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
@@ -175,6 +267,33 @@ extern "C" int rba_msda_forward(const float* value, const int64_t* spatial_shape
   const int64_t total = (int64_t)B * Lq * M * D;
   msda_forward_kernel<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
       value, lv, sampling_loc, attn_weight, total, S, M, D, Lq, L, P, out);
+  RBA_LAUNCHED();
+  return RBA_OK;
+}
+
+// grad_value (B,S,M,D) is zeroed here (the reference allocates it with at::zeros_like, ms_deform_attn_cuda.cu:123);
+// grad_sampling_loc (B,Lq,M,L,P,2) and grad_attn_weight (B,Lq,M,L,P) are fully written.
+extern "C" int rba_msda_backward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                 const float* sampling_loc, const float* attn_weight, const float* grad_output, int B, int S,
+                                 int M, int D, int Lq, int L, int P, int im2col_step, float* grad_value,
+                                 float* grad_sampling_loc, float* grad_attn_weight, void* stream) {
+  using namespace rba;
+  RBA_CHECK(value && spatial_shapes && level_start_index && sampling_loc && attn_weight && grad_output && grad_value &&
+                grad_sampling_loc && grad_attn_weight,
+            "rba_msda_backward: null pointer");
+  RBA_CHECK(B >= 0 && S > 0 && M > 0 && D > 0 && Lq > 0 && L > 0 && P > 0, "rba_msda_backward: bad shape");
+  if (B == 0) return RBA_OK;
+  RBA_CHECK(im2col_step > 0, "rba_msda_backward: im2col_step must be positive");
+  const int step = B < im2col_step ? B : im2col_step;
+  RBA_CHECK(B % step == 0, "batch(%d) must divide im2col_step(%d)", B, step);       // ms_deform_attn_cuda.cu:117-119
+  MsdaLevels lv;
+  RBA_TRY_(msda_levels("rba_msda_backward", spatial_shapes, level_start_index, L, S, &lv));
+  cudaStream_t st = (cudaStream_t)stream;
+  RBA_CUDA(cudaMemsetAsync(grad_value, 0, (size_t)B * S * M * D * sizeof(float), st));
+  const int64_t rows = (int64_t)B * Lq * M;
+  RBA_CHECK(cdiv(rows, 8) < (1LL << 31), "rba_msda_backward: grid too large");
+  msda_backward_kernel<<<(unsigned)cdiv(rows, 8), 256, 0, st>>>(value, lv, sampling_loc, attn_weight, grad_output, rows, S, M, D,
+                                                               Lq, L, P, grad_value, grad_sampling_loc, grad_attn_weight);
   RBA_LAUNCHED();
   return RBA_OK;
 }

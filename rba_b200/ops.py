@@ -94,8 +94,48 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     return out
 
 
-def ms_deform_attn_backward(*args, **kwargs):
-    raise RbaError("ms_deform_attn_backward: training is out of scope of the inference hot path (SURVEY §2 row 8)")
+def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_locations, attention_weights, grad_output,
+                            im2col_step):
+    """Same signature and result as the reference pybind op (ops/src/vision.cpp:20, called from
+    ops/functions/ms_deform_attn_func.py:43-47): returns (grad_value, grad_sampling_loc, grad_attn_weight)."""
+    _chk_cuda(value, sampling_locations, attention_weights, grad_output)
+    if value.dtype != torch.float32 or grad_output.dtype != torch.float32:
+        raise RbaError("ms_deform_attn_backward: only float32 is built")
+    B, S, M, D = value.shape
+    _, Lq, _, L, P, _ = sampling_locations.shape
+    if tuple(grad_output.shape) != (B, Lq, M * D):
+        raise RbaError(f"ms_deform_attn_backward: grad_output {tuple(grad_output.shape)} != {(B, Lq, M * D)}")
+    ss = spatial_shapes.detach().to("cpu", torch.int64).contiguous()
+    ls = level_start_index.detach().to("cpu", torch.int64).contiguous()
+    g_value = torch.empty_like(value)
+    g_loc = torch.empty_like(sampling_locations)
+    g_aw = torch.empty_like(attention_weights)
+    _lib.check(_lib.lib().rba_msda_backward(
+        _p(value), ctypes.cast(ss.data_ptr(), ctypes.POINTER(ctypes.c_int64)),
+        ctypes.cast(ls.data_ptr(), ctypes.POINTER(ctypes.c_int64)), _p(sampling_locations), _p(attention_weights),
+        _p(grad_output), B, S, M, D, Lq, L, P, int(im2col_step), _p(g_value), _p(g_loc), _p(g_aw), _stream()))
+    return g_value, g_loc, g_aw
+
+
+class MSDeformAttnFunction(torch.autograd.Function):
+    """Autograd wrapper with the reference's name and call contract
+    (ops/functions/ms_deform_attn_func.py:32-49): `MSDeformAttnFunction.apply(value, spatial_shapes, level_start_index,
+    sampling_locations, attention_weights, im2col_step)`."""
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights, im2col_step):
+        ctx.im2col_step = im2col_step
+        out = ms_deform_attn_forward(value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                                     attention_weights, im2col_step)
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_output):
+        value, shapes, lsi, loc, aw = ctx.saved_tensors
+        gv, gl, ga = ms_deform_attn_backward(value, shapes, lsi, loc, aw, grad_output.contiguous(), ctx.im2col_step)
+        return gv, None, None, gl, ga, None
 
 
 def gemm(a, w, bias=None, act=RBA_ACT_NONE, residual=None, out_planes=False, out_f32=True, bias_per_row=False,

@@ -261,6 +261,44 @@ def test_msda_reference_test_shapes(dev):
         ops.ms_deform_attn_forward(v3, f["shapes"], lsi, l3, a3, 2)
 
 
+def _msda_grad_inputs(c):
+    """Same recipe as oracle/make_golden_msda_grad.py::make_inputs (only the reference's gradients are stored)."""
+    shapes = torch.as_tensor(c["shapes"], dtype=torch.long)
+    g = torch.Generator().manual_seed(c["seed"])
+    S = int((shapes[:, 0] * shapes[:, 1]).sum())
+    lo, hi = c.get("loc_range", (0.0, 1.0))
+    value = torch.rand(c["N"], S, c["M"], c["D"], generator=g) * c.get("value_scale", 0.01)
+    loc = torch.rand(c["N"], c["Lq"], c["M"], c["L"], c["P"], 2, generator=g) * (hi - lo) + lo
+    aw = torch.rand(c["N"], c["Lq"], c["M"], c["L"], c["P"], generator=g) + 1e-5
+    aw = aw / aw.sum(-1, keepdim=True).sum(-2, keepdim=True)
+    go = torch.randn(c["N"], c["Lq"], c["M"] * c["D"], generator=g)
+    return shapes, value, loc, aw, go
+
+
+def test_msda_backward_matches_reference_gradients(dev):
+    """ms_deform_attn_backward against float64 autograd gradients of the reference's own ms_deform_attn_core_pytorch
+    (tests/golden/msda_grad.pt) at the shapes / channel counts of the reference's check_gradient_numerical
+    (ops/test.py:66-88), directly and through the MSDeformAttnFunction autograd wrapper."""
+    fix = load_golden("msda_grad.pt")
+    for name, f in fix.items():
+        shapes, value, loc, aw, go = _msda_grad_inputs(f["case"])
+        assert abs(float(value.double().sum() + loc.double().sum() + go.double().sum()) - f["in_checksum"]) < 1e-6 * max(1.0, abs(f["in_checksum"]))
+        lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+        step = 2
+        gv, gl, ga = ops.ms_deform_attn_backward(value.to(dev), shapes, lsi, loc.to(dev), aw.to(dev), go.to(dev), step)
+        for got, want, nm in ((gv, f["grad_value"], "grad_value"), (gl, f["grad_loc"], "grad_loc"), (ga, f["grad_aw"], "grad_aw")):
+            err = (got.cpu() - want).abs().max().item()
+            assert err <= 2e-5 * max(1.0, want.abs().max().item()), (name, nm, err)
+        v, l, a = (t.to(dev).requires_grad_(True) for t in (value, loc, aw))
+        out = ops.MSDeformAttnFunction.apply(v, shapes, lsi, l, a, step)
+        assert (out.detach().cpu() - f["out"]).abs().max() < 1e-5 * max(1.0, f["out"].abs().max().item())
+        out.backward(go.to(dev))
+        assert torch.equal(l.grad, gl) and torch.equal(a.grad, ga)
+        assert (v.grad - gv).abs().max() <= 1e-6 * max(1.0, gv.abs().max().item())     # atomics: order may differ
+    with pytest.raises(ops.RbaError):
+        ops.ms_deform_attn_backward(value.to(dev), shapes, lsi, loc.to(dev), aw.to(dev), go[:, :1].contiguous().to(dev), 2)
+
+
 def test_score_golden_and_edges(dev):
     fix = load_golden("score.pt")
     for nm, f in fix.items():

@@ -42,6 +42,18 @@ def test_oracle_msda_matches_reference_golden():
     assert torch.allclose(outd, fix["out_double"])          # ops/test.py:43 (double, default allclose)
 
 
+def test_oracle_msda_backward_matches_reference_gradients():
+    """The oracle's explicit restatement of the reference CUDA backward (col2im_bilinear) against float64 autograd
+    gradients of the reference's own ms_deform_attn_core_pytorch (oracle/make_golden_msda_grad.py)."""
+    from test_kernels_gpu import _msda_grad_inputs
+    fix = load_golden("msda_grad.pt")
+    for name, f in fix.items():
+        shapes, value, loc, aw, go = _msda_grad_inputs(f["case"])
+        gv, gl, ga = O.msda_bilinear_backward(value.double(), shapes, loc.double(), aw.double(), go.double())
+        for got, want, nm in ((gv, f["grad_value"], "grad_value"), (gl, f["grad_loc"], "grad_loc"), (ga, f["grad_aw"], "grad_aw")):
+            assert (got.float() - want).abs().max() <= 2e-6 * max(1.0, want.abs().max().item()), (name, nm)
+
+
 def test_oracle_score_matches_reference_golden():
     fix = load_golden("score.pt")
     for nm, f in fix.items():
