@@ -94,6 +94,18 @@ int rba_model_reserve(rba_model* m, int batch, int height, int width);
  * pred_masks (B,Q,Hp/4,Wp/4) with Hp,Wp = H,W rounded up to size_divisibility. */
 int rba_forward(rba_model* m, const void* images, int img_dtype, int B, int H, int W, float* rba,
                 float* sem_seg, float* pred_logits, float* pred_masks, void* stream);
+/* Same forward with the full output set.  ood_pred (B,2,H,W): the DenseHybrid head's logits resized to the image size
+ * (`model(..., return_ood_pred=True)`, maskformer_model.py:303-305,350-351); needs the head's weights
+ * (sem_seg_head.predictor.ood_pred.*, present when MODEL.MASK_FORMER.DENSE_HYBRID_LOSS is set) in the state_dict. */
+typedef struct rba_outputs {
+  float* rba;         /* (B,H,W) score selected by the "score_func" option */
+  float* sem_seg;     /* (B,K or K+1,H,W) */
+  float* pred_logits; /* (B,Q,K+1) */
+  float* pred_masks;  /* (B,Q,Hp/4,Wp/4) */
+  float* ood_pred;    /* (B,2,H,W) */
+} rba_outputs;
+int rba_forward_ex(rba_model* m, const void* images, int img_dtype, int B, int H, int W, const rba_outputs* out,
+                   void* stream);
 /* Copies a named stage-boundary tensor of the LAST forward into `dst` (device fp32, `capacity` floats):
  * "res2".."res5" (B,H_l*W_l,C_l token-major), "enc_out", "fpn_res4".. , "mask_feat_in", "dec_out".
  * Returns the element count through *count. Test/debug aid. */
@@ -119,6 +131,9 @@ int rba_score_fused(const float* pred_masks, const float* pred_logits, int B, in
  * sem_seg (B, K or K+1, H, W) may be NULL. */
 #define RBA_SCORE_RBA 0
 #define RBA_SCORE_ENERGY 1
+/* engine option only ("score_func"): -logsumexp_c(sem_seg[c]) + log(softmax(ood_pred)[1] + 1e-9)
+ * (get_densehybrid_score, evaluate_ood.py:161-173); the fused kernel runs RBA_SCORE_ENERGY and the head is added. */
+#define RBA_SCORE_DENSEHYBRID 2
 int rba_einsum_score_fused(const uint16_t* embed_hi, const uint16_t* embed_lo, const float* bias, const uint16_t* feat_hi,
                            const uint16_t* feat_lo, const float* pred_logits, int B, int Q, int K, int D, int h, int w,
                            int H, int W, int score_func, int include_void, float* score, float* sem_seg, void* stream);
@@ -155,6 +170,10 @@ int rba_msda_backward(const float* value, const int64_t* spatial_shapes, const i
                       float* grad_attn_weight, void* stream);
 
 /* ---- per-kernel entry points (device pointers) ---- */
+/* ood_pred logits (B,h,w,2) -> bilinear align_corners=True resize to (H,W): ood_pred (B,2,H,W) and/or
+ * score[b,y,x] += log(softmax(.)[1] + 1e-9) (maskformer_model.py:303-305, evaluate_ood.py:167-171). */
+int rba_k_ood_pred_resize(const float* logits, int B, int h, int w, int H, int W, float* ood_pred, float* score,
+                          void* stream);
 /* fp32 [rows,cols] (row pitch ld floats) -> bf16 planes hi, lo [rows,cols] (pitch ldp elements). */
 int rba_k_split(const float* x, int64_t rows, int cols, int64_t ld, uint16_t* hi, uint16_t* lo, int64_t ldp,
                 void* stream);

@@ -13,6 +13,7 @@ CASES = {
     # name: preset, encoder levels, decoder layers, weight seed / perturbation, image seed and sizes
     "tiny_1dl": dict(preset="tiny", levels=1, dec_layers=1, seed=11, perturb=0.02, img_seed=1, sizes=[(70, 100)]),
     "tiny_3lvl": dict(preset="tiny", levels=3, dec_layers=3, seed=248, perturb=0.02, img_seed=2, sizes=[(64, 96), (64, 96)]),
+    "tiny_ood": dict(preset="tiny", levels=1, dec_layers=1, seed=23, perturb=0.02, img_seed=5, sizes=[(70, 100)], ood_prediction=True),
     "swin_b_1dl": dict(preset="swin_b_1dl", levels=1, dec_layers=1, seed=13, perturb=0.02, img_seed=3, sizes=[(96, 160)]),
     "swin_l_1dl": dict(preset="swin_l_1dl", levels=1, dec_layers=1, seed=17, perturb=0.02, img_seed=4, sizes=[(64, 96)]),
 }
@@ -20,7 +21,7 @@ CASES = {
 
 def case_model_config(case):
     if case["preset"] == "tiny":
-        return rcfg.tiny_test(levels=case["levels"], dec_layers=case["dec_layers"])
+        return rcfg.tiny_test(levels=case["levels"], dec_layers=case["dec_layers"], ood_prediction=case.get("ood_prediction", False))
     if case["preset"] == "swin_b_1dl":
         return rcfg.swin_b_1dl()
     if case["preset"] == "swin_l_1dl":

@@ -33,6 +33,8 @@ def reference_overrides(case):
     if case.get("levels", 1) == 3:
         o["MODEL.SEM_SEG_HEAD.DEFORMABLE_TRANSFORMER_ENCODER_IN_FEATURES"] = ["res3", "res4", "res5"]
     o["MODEL.MASK_FORMER.DEC_LAYERS"] = case.get("dec_layers", 1) + 1
+    if case.get("ood_prediction"):
+        o["MODEL.MASK_FORMER.DENSE_HYBRID_LOSS"] = True
     return o
 
 
@@ -40,7 +42,10 @@ def reference_overrides(case):
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    only = set(sys.argv[1:])            # e.g. `python oracle/make_golden.py tiny_ood`: just that model case
     for name, case in CASES.items():
+        if only and name not in only:
+            continue
         base = "swin_l_1dl" if case["preset"] == "swin_l_1dl" else "swin_b_1dl"
         cfg = ref_loader.load_cfg(base, reference_overrides(case))
         model = ref_loader.build_reference_model(cfg, seed=0)
@@ -54,7 +59,10 @@ def main():
         images = case_images(case)
         caps = {}
         model.sem_seg_head.register_forward_hook(lambda m, i, o: caps.__setitem__("head", o))
-        out = model([{"image": im} for im in images])
+        if case.get("ood_prediction"):
+            out, ood_pred = model([{"image": im} for im in images], return_ood_pred=True)
+        else:
+            out, ood_pred = model([{"image": im} for im in images]), None
         sem = torch.stack([o["sem_seg"] for o in out])
         rba = -sem.tanh().sum(1)                                     # evaluate_ood.py:148-150
         import rba_oracle as O
@@ -65,9 +73,18 @@ def main():
             "rba": rba.clone(), "sem_seg_s4": sem[:, :, ::4, ::4].clone(),
             "torch_version": torch.__version__, "reference": "NazirNayal8/RbA @ /root/reference (unmodified modules under oracle/ref_shims)",
         }
+        if ood_pred is not None:
+            import torch.nn.functional as Fn
+            # evaluate_ood.py:161-173 get_densehybrid_score, verbatim arithmetic
+            p2 = Fn.softmax(ood_pred, dim=1)[:, 1]
+            fix["ood_pred"] = ood_pred.clone()
+            fix["densehybrid"] = (-torch.logsumexp(sem, dim=1)) + (p2 + 1e-9).log()
+            fix["energy"] = -torch.logsumexp(sem, dim=1)
         torch.save(fix, os.path.join(OUT, f"model_{name}.pt"))
         print(name, "pred_masks", tuple(fix["pred_masks"].shape), "rba range", float(rba.min()), float(rba.max()), "am_margin", margin)
 
+    if only:
+        return
     # ---- MSDeformAttn: shapes / seed / value scaling of the reference's own ops/test.py:24-47 (CPU RNG) ----
     core = ref_loader.msda_core_pytorch()
     N, M, D, Lq, L, P = 1, 2, 2, 2, 2, 2

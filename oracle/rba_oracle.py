@@ -520,6 +520,23 @@ def score_from_head_outputs(pred_logits, pred_masks, padded_hw, image_hw):
     return sem, rba_from_sem_seg(sem)
 
 
+def ood_pred_head(sd, mask_features, image_size, p="sem_seg_head.predictor.ood_pred."):
+    """DenseHybrid head: BNReluConv(hidden_dim, 2, k=1, bias=True) on mask_features
+    (mask2former_transformer_decoder.py:216-230,365-366,467-468: BatchNorm2d in eval mode -> ReLU -> 1x1 conv), then
+    F.interpolate(..., size=images.image_sizes[0], mode='bilinear', align_corners=True) (maskformer_model.py:303-305).
+    Returns (B,2,H,W)."""
+    x = F.batch_norm(mask_features, sd[p + "norm.running_mean"], sd[p + "norm.running_var"], sd[p + "norm.weight"],
+                     sd[p + "norm.bias"], training=False, eps=1e-5)
+    x = F.conv2d(F.relu(x), sd[p + "conv.weight"], sd[p + "conv.bias"])
+    return F.interpolate(x, size=tuple(image_size), mode="bilinear", align_corners=True)
+
+
+def densehybrid_from_outputs(sem_seg, ood_pred):
+    """evaluate_ood.py:161-173 get_densehybrid_score for ONE image: sem_seg (K,H,W), ood_pred (2,H,W) -> (H,W)."""
+    p2 = F.softmax(ood_pred, dim=0)[1]
+    return -torch.logsumexp(sem_seg, dim=0) + (p2 + 1e-9).log()
+
+
 def preprocess(images, cfg):
     """maskformer_model.py:255-257: (x - mean)/std per image, zero-pad bottom/right to a multiple of
     SIZE_DIVISIBILITY (detectron2 ImageList.from_tensors, pad_value 0)."""
@@ -555,6 +572,9 @@ def forward(sd, cfg, images, explicit_msda=False, want_taps=False):
         sem_seg.append(s)
         rba.append(r)
     res = {"pred_logits": cls, "pred_masks": masks, "sem_seg": sem_seg, "rba": rba}
+    if "sem_seg_head.predictor.ood_pred.conv.weight" in sd:
+        res["ood_pred"] = ood_pred_head(sd, mask_features, sizes[0])
+        res["densehybrid"] = [densehybrid_from_outputs(sem_seg[b], res["ood_pred"][b]) for b in range(len(images))]
     if want_taps:
         taps.update(feats)
         taps["mask_features"] = mask_features

@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "librba_b200.so")
 RBA_IMG_U8, RBA_IMG_F32 = 0, 1
 RBA_ACT_NONE, RBA_ACT_RELU, RBA_ACT_GELU = 0, 1, 2
 RBA_GEMM_FFMA, RBA_GEMM_TC = 0, 1
-RBA_SCORE_RBA, RBA_SCORE_ENERGY = 0, 1
+RBA_SCORE_RBA, RBA_SCORE_ENERGY, RBA_SCORE_DENSEHYBRID = 0, 1, 2
 
 
 class RbaError(RuntimeError):
@@ -25,6 +25,11 @@ class RbaConfig(Structure):
         ("enc_points", c_int32), ("enc_ffn", c_int32), ("num_enc_levels", c_int32), ("size_divisibility", c_int32),
         ("pixel_mean", c_float * 3), ("pixel_std", c_float * 3),
     ]
+
+
+class RbaOutputs(Structure):
+    _fields_ = [("rba", c_void_p), ("sem_seg", c_void_p), ("pred_logits", c_void_p), ("pred_masks", c_void_p),
+                ("ood_pred", c_void_p)]
 
 
 class RbaGemmArgs(Structure):
@@ -54,6 +59,7 @@ PROTOTYPES = {
     "rba_model_set_option": (c_int, [c_void_p, c_char_p, c_int]),
     "rba_model_reserve": (c_int, [c_void_p, c_int, c_int, c_int]),
     "rba_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rba_forward_ex": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, POINTER(RbaOutputs), c_void_p]),
     "rba_model_get_tap": (c_int, [c_void_p, c_char_p, c_void_p, c_int64, POINTER(c_int64), c_void_p]),
     "rba_score_fused": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "rba_einsum_score_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
@@ -66,6 +72,7 @@ PROTOTYPES = {
                                  c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "rba_msda_backward": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64), c_void_p, c_void_p, c_void_p, c_int, c_int,
                                   c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rba_k_ood_pred_resize": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "rba_k_split": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_int64, c_void_p]),
     "rba_k_gemm": (c_int, [POINTER(RbaGemmArgs), c_void_p]),
     "rba_k_conv3x3": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),

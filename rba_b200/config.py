@@ -34,6 +34,7 @@ class ModelConfig:
     size_divisibility: int = 32
     pixel_mean: List[float] = field(default_factory=lambda: [123.675, 116.28, 103.53])
     pixel_std: List[float] = field(default_factory=lambda: [58.395, 57.12, 57.375])
+    ood_prediction: bool = False   # MODEL.MASK_FORMER.DENSE_HYBRID_LOSS: predictor.ood_pred head (mask2former_transformer_decoder.py:365-366,394)
 
     @property
     def num_enc_levels(self):
@@ -74,6 +75,13 @@ def _get(node, dotted):
     return node
 
 
+def _get_default(node, dotted, default):
+    try:
+        return _get(node, dotted)
+    except (KeyError, AttributeError):
+        return default
+
+
 def model_config_from_cfg(cfg):
     """cfg: a yacs-like CfgNode / nested dict with the reference's key names (e.g. yaml.safe_load of
     ckpts/<name>/config.yaml).  Raises on architectures outside the built hot path."""
@@ -100,6 +108,7 @@ def model_config_from_cfg(cfg):
         dim_feedforward=g("MASK_FORMER.DIM_FEEDFORWARD"), dec_layers=g("MASK_FORMER.DEC_LAYERS") - 1,
         num_queries=g("MASK_FORMER.NUM_OBJECT_QUERIES"), size_divisibility=g("MASK_FORMER.SIZE_DIVISIBILITY"),
         pixel_mean=list(g("PIXEL_MEAN")), pixel_std=list(g("PIXEL_STD")),
+        ood_prediction=bool(_get_default(M, "MASK_FORMER.DENSE_HYBRID_LOSS", False)),
     )
     return mc.validate()
 
@@ -124,8 +133,8 @@ def swin_b_full(dec_layers=9):
     return ModelConfig(transformer_in_features=["res3", "res4", "res5"], dec_layers=dec_layers).validate()
 
 
-def tiny_test(depths=(2, 2, 2, 2), levels=1, dec_layers=1):
+def tiny_test(depths=(2, 2, 2, 2), levels=1, dec_layers=1, ood_prediction=False):
     """Small Swin (embed 32) for fast parity tests; same code paths as Swin-B."""
     tin = ["res5"] if levels == 1 else ["res3", "res4", "res5"]
     return ModelConfig(embed_dim=32, depths=list(depths), num_heads=[1, 2, 4, 8], transformer_in_features=tin,
-                       dec_layers=dec_layers, enc_layers=2).validate()
+                       dec_layers=dec_layers, enc_layers=2, ood_prediction=ood_prediction).validate()

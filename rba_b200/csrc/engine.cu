@@ -79,6 +79,20 @@ __global__ void transpose_kernel(const float* __restrict__ w, int R, int Cc, flo
   }
 }
 
+// DenseHybrid head: BatchNorm2d (eval) of mask_features folded into the mask_features 1x1 conv:
+//   relu(bn(Wmf y + bmf)) = relu((s . Wmf) y + s (bmf - mean) + beta),  s = gamma / sqrt(var + eps)
+__global__ void bn_fold_kernel(const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ var,
+                               float eps, int O, int I, float* __restrict__ w_out, float* __restrict__ b_out) {
+  int64_t total = (int64_t)O * I;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int o = (int)(i / I);
+    const float sc = gamma[o] / sqrtf(var[o] + eps);
+    w_out[i] = sc * w[i];
+    if (i % I == 0) b_out[o] = sc * (b[o] - mean[o]) + beta[o];
+  }
+}
+
 }  // namespace rba
 
 using namespace rba;
@@ -93,6 +107,7 @@ struct rba_model {
   int fused_score = 1;              // 1: last mask einsum + score in one kernel (score_fused.cu) when pred_masks is not asked for
   int score_func = RBA_SCORE_RBA;   // per-pixel reduction written to the score output (evaluate_ood.py:143-159)
   int include_void = 0;             // 1: semantic_inference_with_void (maskformer_model.py:388-392): K+1 sem_seg planes
+  bool has_ood_pred = false;        // DenseHybrid head weights present (predictor.ood_pred.*)
   std::unordered_map<std::string, DevTensor> w;
   std::unordered_map<std::string, Planes> wp;      // split planes of GEMM weights, by key
   std::vector<void*> owned;                         // cudaMalloc'ed blocks (weights, derived)
@@ -207,7 +222,7 @@ extern "C" int rba_model_set_option(rba_model* m, const char* name, int value) {
     m->attn_backend = value;
     m->rB = m->rH = m->rW = 0;
   } else if (n == "score_func") {
-    RBA_CHECK(value == RBA_SCORE_RBA || value == RBA_SCORE_ENERGY, "bad score_func %d", value);
+    RBA_CHECK(value == RBA_SCORE_RBA || value == RBA_SCORE_ENERGY || value == RBA_SCORE_DENSEHYBRID, "bad score_func %d", value);
     m->score_func = value;
   } else if (n == "include_void") {
     RBA_CHECK(value == 0 || value == 1, "bad include_void %d", value);
@@ -348,6 +363,30 @@ extern "C" int rba_model_finalize(rba_model* m) {
   }
   // ---- transformer decoder ----
   const std::string pr = "sem_seg_head.predictor.";
+  if (m->get(pr + "ood_pred.conv.weight")) {
+    // DenseHybrid head BNReluConv(hidden_dim, 2, k=1) on mask_features (mask2former_transformer_decoder.py:216-230,365-366)
+    RBA_CHECK(c.mask_dim == D, "ood_pred head needs MASK_DIM == HIDDEN_DIM");
+    const DevTensor *mw, *mb, *g, *be, *mu, *va;
+    RBA_TRY(need(m, pd + "mask_features.weight", {c.mask_dim, D, 1, 1}, &mw));
+    RBA_TRY(need(m, pd + "mask_features.bias", {c.mask_dim}, &mb));
+    RBA_TRY(need(m, pr + "ood_pred.norm.weight", {D}, &g));
+    RBA_TRY(need(m, pr + "ood_pred.norm.bias", {D}, &be));
+    RBA_TRY(need(m, pr + "ood_pred.norm.running_mean", {D}, &mu));
+    RBA_TRY(need(m, pr + "ood_pred.norm.running_var", {D}, &va));
+    float *fw, *fb;
+    RBA_TRY(m->dmalloc(&fw, (size_t)c.mask_dim * D));
+    RBA_TRY(m->dmalloc(&fb, (size_t)c.mask_dim));
+    bn_fold_kernel<<<256, 256>>>(mw->d, mb->d, g->d, be->d, mu->d, va->d, 1e-5f, c.mask_dim, D, fw, fb);
+    RBA_TRY(make_planes(m, pr + "ood_pred.fold.weight", fw, c.mask_dim, D));
+    DevTensor fbt = *mb;
+    fbt.d = fb;
+    m->w[pr + "ood_pred.fold.bias"] = fbt;
+    const DevTensor* cw;
+    RBA_TRY(need(m, pr + "ood_pred.conv.weight", {2, c.mask_dim, 1, 1}, &cw));
+    RBA_TRY(make_planes(m, pr + "ood_pred.conv.weight", cw->d, 2, c.mask_dim));
+    RBA_TRY(need(m, pr + "ood_pred.conv.bias", {2}));
+    m->has_ood_pred = true;
+  }
   RBA_CHECK(m->get(pr + "input_proj.0.weight") == nullptr, "predictor.input_proj (CONVS_DIM != HIDDEN_DIM) is not supported");
   for (int i = 0; i < c.dec_layers; ++i) {
     std::string ca = pr + "transformer_cross_attention_layers." + std::to_string(i) + ".";
@@ -463,7 +502,8 @@ struct Fwd {
 }  // namespace
 
 static int forward_impl(rba_model* m, const void* images, int img_dtype, int B, int H, int W, float* rba_out,
-                        float* sem_seg, float* pred_logits_out, float* pred_masks_out, cudaStream_t st, bool dry) {
+                        float* sem_seg, float* pred_logits_out, float* pred_masks_out, float* ood_pred_out, cudaStream_t st,
+                        bool dry) {
   const rba_config& c = m->cfg;
   Arena& A = m->arena;
   A.off = 0;
@@ -800,10 +840,25 @@ static int forward_impl(rba_model* m, const void* images, int img_dtype, int B, 
     float* ro = rba_out;
     if (!ro) ro = A.f32((int64_t)B * H * W);
     if (fuse_last)
-      RBA_RUN(einsum_score_launch(ef.hi, ef.lo, bq, ypl.hi, ypl.lo, cls, B, Q, c.num_classes, D, mH, mW, H, W, m->score_func,
-                                  m->include_void, ro, sem_seg, st));
+      RBA_RUN(einsum_score_launch(ef.hi, ef.lo, bq, ypl.hi, ypl.lo, cls, B, Q, c.num_classes, D, mH, mW, H, W,
+                                  m->score_func == RBA_SCORE_DENSEHYBRID ? RBA_SCORE_ENERGY : m->score_func, m->include_void,
+                                  ro, sem_seg, st));
     else
       RBA_RUN(rba_score_fused(masks, cls, B, Q, c.num_classes, mH, mW, H, W, ro, sem_seg, (void*)st));
+  }
+  // ---- DenseHybrid head: ood_pred = conv1x1(relu(bn(mask_features))), resized with align_corners=True ----
+  const bool dh_score = m->score_func == RBA_SCORE_DENSEHYBRID && rba_out;
+  if (dry ? m->has_ood_pred : (ood_pred_out || dh_score)) {
+    RBA_CHECK(m->has_ood_pred, "return_ood_pred / densehybrid score need the ood_pred head (state_dict has no "
+                               "sem_seg_head.predictor.ood_pred.*; MODEL.MASK_FORMER.DENSE_HYBRID_LOSS)");
+    const int64_t T = (int64_t)B * HWm;
+    Planes t1 = A.planes(T * c.mask_dim);
+    RBA_TRY(F.lin(ypl, D, T, D, F.P(pr + "ood_pred.fold.weight"), c.mask_dim, F.W(pr + "ood_pred.fold.bias"), RBA_ACT_RELU, nullptr,
+                  nullptr, 0, t1, c.mask_dim));
+    float* ol = A.f32(T * 2);
+    RBA_TRY(F.lin(t1, c.mask_dim, T, c.mask_dim, F.P(pr + "ood_pred.conv.weight"), 2, F.W(pr + "ood_pred.conv.bias"), RBA_ACT_NONE,
+                  nullptr, ol, 2));
+    RBA_RUN(ood_pred_resize(ol, B, mH, mW, H, W, ood_pred_out, dh_score ? rba_out : nullptr, st));
   }
   if (!dry && A.overflow) return fail(RBA_ERR_STATE, "workspace overflow (reserved %zu, needed %zu)", A.cap, A.peak);
   return RBA_OK;
@@ -811,7 +866,7 @@ static int forward_impl(rba_model* m, const void* images, int img_dtype, int B, 
 
 static int ensure_workspace(rba_model* m, int B, int H, int W, cudaStream_t st) {
   if (B == m->rB && H == m->rH && W == m->rW && m->arena.base) return RBA_OK;   // validated shape
-  int rc = forward_impl(m, nullptr, RBA_IMG_U8, B, H, W, nullptr, nullptr, nullptr, nullptr, nullptr, true);
+  int rc = forward_impl(m, nullptr, RBA_IMG_U8, B, H, W, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, true);
   if (rc != RBA_OK) return rc;
   // + room for the optional internal rba buffer (sem_seg-only calls) and slack
   const size_t need_bytes = m->arena.peak + (size_t)B * H * W * 4 + (1 << 20);
@@ -840,15 +895,23 @@ extern "C" int rba_model_reserve(rba_model* m, int batch, int height, int width)
   return ensure_workspace(m, batch, height, width, nullptr);
 }
 
-extern "C" int rba_forward(rba_model* m, const void* images, int img_dtype, int B, int H, int W, float* rba_out,
-                           float* sem_seg, float* pred_logits, float* pred_masks, void* stream) {
+extern "C" int rba_forward_ex(rba_model* m, const void* images, int img_dtype, int B, int H, int W, const rba_outputs* out,
+                              void* stream) {
   RBA_CHECK(m && m->finalized, "rba_forward: model not finalized");
-  RBA_CHECK(images, "rba_forward: null images");
+  RBA_CHECK(images && out, "rba_forward: null pointer");
   RBA_CHECK(B > 0 && H > 0 && W > 0, "rba_forward: bad shape B=%d H=%d W=%d", B, H, W);
   RBA_CHECK(img_dtype == RBA_IMG_U8 || img_dtype == RBA_IMG_F32, "rba_forward: bad image dtype");
   RBA_CUDA(cudaSetDevice(m->device));
   RBA_TRY(ensure_workspace(m, B, H, W, (cudaStream_t)stream));
-  return forward_impl(m, images, img_dtype, B, H, W, rba_out, sem_seg, pred_logits, pred_masks, (cudaStream_t)stream, false);
+  return forward_impl(m, images, img_dtype, B, H, W, out->rba, out->sem_seg, out->pred_logits, out->pred_masks, out->ood_pred,
+                      (cudaStream_t)stream, false);
+}
+
+extern "C" int rba_forward(rba_model* m, const void* images, int img_dtype, int B, int H, int W, float* rba_out,
+                           float* sem_seg, float* pred_logits, float* pred_masks, void* stream) {
+  rba_outputs o;
+  o.rba = rba_out; o.sem_seg = sem_seg; o.pred_logits = pred_logits; o.pred_masks = pred_masks; o.ood_pred = nullptr;
+  return rba_forward_ex(m, images, img_dtype, B, H, W, &o, stream);
 }
 
 extern "C" int rba_model_get_tap(rba_model* m, const char* name, float* dst, int64_t capacity, int64_t* count, void* stream) {

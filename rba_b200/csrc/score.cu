@@ -440,3 +440,58 @@ extern "C" int rba_score_fused(const float* pred_masks, const float* pred_logits
     default: return fail(RBA_ERR_INVALID, "rba_score_fused: K=%d not instantiated (19, 13, 3)", K);
   }
 }
+
+// ------------------------------------------------------------------------------------------------
+// DenseHybrid head: `ood_pred` logits (B, h, w, 2) from the BN-ReLU-1x1 head
+// (mask2former_transformer_decoder.py:216-230,365-366,467-468) are resized to the image size with bilinear
+// align_corners=TRUE (maskformer_model.py:303-305) and, optionally, folded into the score
+//   score += log(softmax(ood_pred)[1] + 1e-9)        (evaluate_ood.py:161-173, score holds -logsumexp(sem_seg))
+// ------------------------------------------------------------------------------------------------
+namespace rba {
+__global__ void __launch_bounds__(256)
+ood_pred_resize_kernel(const float* __restrict__ logits, int B, int h, int w, int H, int W, float sy, float sx,
+                       float* __restrict__ ood_pred, float* __restrict__ score) {
+  const int64_t total = (int64_t)B * H * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int X = (int)(i % W);
+    const int Y = (int)((i / W) % H);
+    const int64_t b = i / ((int64_t)W * H);
+    const float fy = sy * (float)Y, fx = sx * (float)X;                 // align_corners=True: src = dst * (in-1)/(out-1)
+    int y0 = (int)fy, x0 = (int)fx;
+    y0 = y0 > h - 1 ? h - 1 : y0;
+    x0 = x0 > w - 1 ? w - 1 : x0;
+    const int y1 = y0 + (y0 < h - 1), x1 = x0 + (x0 < w - 1);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    const float2* base = reinterpret_cast<const float2*>(logits) + b * (int64_t)h * w;
+    const float2 v00 = base[(int64_t)y0 * w + x0], v01 = base[(int64_t)y0 * w + x1];
+    const float2 v10 = base[(int64_t)y1 * w + x0], v11 = base[(int64_t)y1 * w + x1];
+    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+    const float l0 = w00 * v00.x + w01 * v01.x + w10 * v10.x + w11 * v11.x;
+    const float l1 = w00 * v00.y + w01 * v01.y + w10 * v10.y + w11 * v11.y;
+    if (ood_pred) {
+      ood_pred[(b * 2 + 0) * (int64_t)H * W + (int64_t)Y * W + X] = l0;
+      ood_pred[(b * 2 + 1) * (int64_t)H * W + (int64_t)Y * W + X] = l1;
+    }
+    if (score) {
+      const float p2 = 1.0f / (1.0f + expf(l0 - l1));                   // softmax over the two planes, plane 1
+      score[i] += logf(p2 + 1e-9f);
+    }
+  }
+}
+
+int ood_pred_resize(const float* logits, int B, int h, int w, int H, int W, float* ood_pred, float* score, cudaStream_t st) {
+  RBA_CHECK(logits && (ood_pred || score), "ood_pred_resize: null pointer");
+  RBA_CHECK(B > 0 && h > 0 && w > 0 && H > 0 && W > 0, "ood_pred_resize: bad shape");
+  const float sy = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, sx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
+  const int64_t total = (int64_t)B * H * W;
+  const unsigned grid = (unsigned)std::min<int64_t>(cdiv(total, 256), (int64_t)148 * 16);   // grid-stride, 16 CTAs per SM
+  ood_pred_resize_kernel<<<grid, 256, 0, st>>>(logits, B, h, w, H, W, sy, sx, ood_pred, score);
+  RBA_LAUNCHED();
+  return RBA_OK;
+}
+}  // namespace rba
+
+extern "C" int rba_k_ood_pred_resize(const float* logits, int B, int h, int w, int H, int W, float* ood_pred, float* score,
+                                     void* stream) {
+  return rba::ood_pred_resize(logits, B, h, w, H, W, ood_pred, score, (cudaStream_t)stream);
+}

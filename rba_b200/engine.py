@@ -56,7 +56,8 @@ class Engine:
         self._graphs.clear()
 
     def set_score(self, func="rba", include_void=False):
-        """Per-pixel reduction of the score output: "rba" (evaluate_ood.get_RbA) or "energy"/"pebal" (get_energy);
+        """Per-pixel reduction of the score output: "rba" (evaluate_ood.get_RbA), "energy"/"pebal" (get_energy) or
+        "densehybrid" (get_densehybrid_score; needs the ood_pred head's weights);
         include_void keeps the void column (semantic_inference_with_void): sem_seg gets K+1 planes."""
         from .ops import SCORE_FUNCS
         if func not in SCORE_FUNCS:
@@ -79,7 +80,7 @@ class Engine:
         s = self.mc.size_divisibility
         return (H + s - 1) // s * s, (W + s - 1) // s * s
 
-    def alloc_outputs(self, B, H, W, rba=True, sem_seg=False, logits=False, masks=False):
+    def alloc_outputs(self, B, H, W, rba=True, sem_seg=False, logits=False, masks=False, ood_pred=False):
         Hp, Wp = self.padded_hw(H, W)
         dev, K, Q = self.device, self.mc.num_classes, self.mc.num_queries
         out = {}
@@ -91,6 +92,8 @@ class Engine:
             out["pred_logits"] = torch.empty((B, Q, K + 1), dtype=torch.float32, device=dev)
         if masks:
             out["pred_masks"] = torch.empty((B, Q, Hp // 4, Wp // 4), dtype=torch.float32, device=dev)
+        if ood_pred:
+            out["ood_pred"] = torch.empty((B, 2, H, W), dtype=torch.float32, device=dev)
         return out
 
     def forward_into(self, images, out):
@@ -109,15 +112,15 @@ class Engine:
         B, C, H, W = images.shape
         if C != 3:
             raise RbaError("Engine.forward: images must be (B,3,H,W)")
-        p = lambda k: ctypes.c_void_p(out[k].data_ptr()) if k in out else None  # noqa: E731
+        p = lambda k: out[k].data_ptr() if k in out else None  # noqa: E731
         st = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        _lib.check(_lib.lib().rba_forward(self._h, ctypes.c_void_p(images.data_ptr()), dt, B, H, W, p("rba"), p("sem_seg"),
-                                          p("pred_logits"), p("pred_masks"), st))
+        o = _lib.RbaOutputs(p("rba"), p("sem_seg"), p("pred_logits"), p("pred_masks"), p("ood_pred"))
+        _lib.check(_lib.lib().rba_forward_ex(self._h, ctypes.c_void_p(images.data_ptr()), dt, B, H, W, ctypes.byref(o), st))
         return out
 
-    def forward(self, images, rba=True, sem_seg=False, logits=False, masks=False):
+    def forward(self, images, rba=True, sem_seg=False, logits=False, masks=False, ood_pred=False):
         B, _, H, W = images.shape
-        return self.forward_into(images, self.alloc_outputs(B, H, W, rba, sem_seg, logits, masks))
+        return self.forward_into(images, self.alloc_outputs(B, H, W, rba, sem_seg, logits, masks, ood_pred))
 
     def tap(self, name):
         """Stage-boundary tensor of the last forward (needs set_option('taps', 1) before that forward)."""

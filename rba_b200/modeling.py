@@ -120,13 +120,16 @@ class MaskFormer(nn.Module):
     def forward(self, batched_inputs, include_void=False, return_separately=False, return_aux=False,
                 return_ood_pred=False, **kwargs):
         """maskformer_model.py:227-356, eval + SEMANTIC_ON branch."""
-        if return_aux or return_ood_pred or kwargs.get("return_panoptic_ood"):
-            raise RbaError("return_aux / return_ood_pred (DenseHybrid head) / panoptic outputs are not built (SURVEY §8f-3)")
+        if return_aux or kwargs.get("return_panoptic_ood"):
+            raise RbaError("return_aux / panoptic outputs are not built (SURVEY §8f-3)")
+        if return_ood_pred and not self.mc.ood_prediction:
+            raise RbaError("return_ood_pred needs the DenseHybrid head (MODEL.MASK_FORMER.DENSE_HYBRID_LOSS: True)")
         images = self._batch(batched_inputs)
         B, _, H, W = images.shape
         eng = self.engine()
         eng.set_score("rba", include_void=include_void)     # semantic_inference_with_void (maskformer_model.py:388-392)
-        out = eng.forward(images, rba=False, sem_seg=True, logits=return_separately, masks=return_separately)
+        out = eng.forward(images, rba=False, sem_seg=True, logits=return_separately, masks=return_separately,
+                          ood_pred=return_ood_pred)
         results = []
         for b, inp in enumerate(batched_inputs):
             r = out["sem_seg"][b]
@@ -138,6 +141,8 @@ class MaskFormer(nn.Module):
             Hp, Wp = self.engine().padded_hw(H, W)
             up = F.interpolate(out["pred_masks"][-1:], size=(Hp, Wp), mode="bilinear", align_corners=False)[0]
             return results, out["pred_logits"][-1], up
+        if return_ood_pred:                                  # maskformer_model.py:303-305,350-351
+            return results, out["ood_pred"]
         return results
 
     @torch.no_grad()
@@ -148,8 +153,9 @@ class MaskFormer(nn.Module):
 
     @torch.no_grad()
     def score(self, batched_inputs, score_func="rba"):
-        """Fused anomaly score of evaluate_ood.py --score_func: "rba" (get_RbA, :143-150) or "pebal"/"energy"
-        (get_energy, :152-159: -logsumexp over the class planes).  sem_seg is never materialised."""
+        """Fused anomaly score of evaluate_ood.py --score_func: "rba" (get_RbA, :143-150), "pebal"/"energy"
+        (get_energy, :152-159: -logsumexp over the class planes) or "dense_hybrid" (get_densehybrid_score, :161-173:
+        energy + log p(outlier) from the ood_pred head).  sem_seg is never materialised."""
         images = self._batch(batched_inputs)
         eng = self.engine()
         eng.set_score(score_func, include_void=False)

@@ -52,7 +52,9 @@ def score_fused(pred_masks, pred_logits, out_hw, want_sem_seg=False):
     return (rba, sem) if want_sem_seg else rba
 
 
-SCORE_FUNCS = {"rba": _lib.RBA_SCORE_RBA, "energy": _lib.RBA_SCORE_ENERGY, "pebal": _lib.RBA_SCORE_ENERGY}
+SCORE_FUNCS = {"rba": _lib.RBA_SCORE_RBA, "energy": _lib.RBA_SCORE_ENERGY, "pebal": _lib.RBA_SCORE_ENERGY,
+               "densehybrid": _lib.RBA_SCORE_DENSEHYBRID, "dense_hybrid": _lib.RBA_SCORE_DENSEHYBRID}
+KERNEL_SCORE_FUNCS = ("rba", "energy", "pebal")     # what the fused kernel itself implements
 
 
 def einsum_score_fused(mask_embed, features, pred_logits, out_hw, bias=None, want_sem_seg=False, score_func="rba",

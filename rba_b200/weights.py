@@ -122,6 +122,14 @@ def param_specs(mc):
     for i in range(3):
         S[f"{pr}mask_embed.layers.{i}.weight"] = ((mc.mask_dim if i == 2 else D, D), "linear")
         S[f"{pr}mask_embed.layers.{i}.bias"] = ((mc.mask_dim if i == 2 else D,), f"linear_bias:{D}")
+    if getattr(mc, "ood_prediction", False):   # BNReluConv(hidden_dim, 2, k=1, bias=True), mask2former_transformer_decoder.py:216-230,365-366
+        S[pr + "ood_pred.norm.weight"] = ((D,), "ones")
+        S[pr + "ood_pred.norm.bias"] = ((D,), "zeros")
+        S[pr + "ood_pred.norm.running_mean"] = ((D,), "zeros")
+        S[pr + "ood_pred.norm.running_var"] = ((D,), "bn_var")
+        S[pr + "ood_pred.norm.num_batches_tracked"] = ((), "counter")
+        S[pr + "ood_pred.conv.weight"] = ((2, D, 1, 1), "conv")
+        S[pr + "ood_pred.conv.bias"] = ((2,), f"conv_bias:{D}")
     S["criterion.empty_weight"] = ((mc.num_classes + 1,), "ones")  # training buffer kept for key parity
     return S
 
@@ -151,6 +159,13 @@ def init_state_dict(mc, seed=0, perturb=0.0):
             t = torch.zeros(shape)
         elif kind == "rel_index":
             sd[name] = relative_position_index(mc.window_size)
+            continue
+        elif kind == "counter":
+            sd[name] = torch.zeros((), dtype=torch.int64)
+            continue
+        elif kind == "bn_var":                                   # positive: 1 + |N(0, 10 perturb)|
+            t = torch.ones(shape) + (10.0 * perturb * torch.randn(shape, generator=g)).abs()
+            sd[name] = t.float().contiguous()
             continue
         elif kind == "trunc02":
             t = torch.nn.init.trunc_normal_(torch.empty(shape), std=0.02, generator=g)

@@ -282,3 +282,39 @@ def test_score_stream_overlapped_pipeline(dev):
         stream.submit(torch.zeros((B, 3, H + 32, W), dtype=torch.uint8).pin_memory())
     with pytest.raises(rba_b200.RbaError):
         stream.collect()
+
+
+def test_densehybrid_head_matches_reference_golden(dev):
+    """DenseHybrid: `model(x, return_ood_pred=True)` (maskformer_model.py:303-305,350-351) and the fused
+    `--score_func dense_hybrid` score (evaluate_ood.py:161-173) against the unmodified reference with
+    MODEL.MASK_FORMER.DENSE_HYBRID_LOSS: True (tests/golden/model_tiny_ood.pt)."""
+    fix = load_golden("model_tiny_ood.pt")
+    case = fix["case"]
+    mc = case_model_config(case)
+    assert mc.ood_prediction
+    sd = weights.init_state_dict(mc, seed=case["seed"], perturb=case["perturb"])
+    assert abs(state_checksum(sd) - fix["state_checksum"]) <= 1e-6 * fix["state_checksum"]
+    imgs = case_images(case)
+    model = rba_b200.MaskFormer(mc)
+    model.load_state_dict(sd)
+    model.to(dev).eval()
+    res, ood_pred = model([{"image": im.to(dev)} for im in imgs], return_ood_pred=True)
+    assert tuple(ood_pred.shape) == tuple(fix["ood_pred"].shape)
+    assert (ood_pred.cpu() - fix["ood_pred"]).abs().max() < TOL
+    sem = torch.stack([r["sem_seg"] for r in res])
+    # the reference caller's own arithmetic on our outputs (evaluate_ood.py:165-172)
+    p2 = torch.softmax(ood_pred, dim=1)[:, 1]
+    dh_ref_style = -torch.logsumexp(sem, dim=1) + (p2 + 1e-9).log()
+    assert (dh_ref_style.cpu() - fix["densehybrid"]).abs().max() < TOL
+    # fused: energy from the einsum+score kernel, head added in place
+    dh = model.score([{"image": im.to(dev)} for im in imgs], "dense_hybrid")
+    assert (dh.cpu() - fix["densehybrid"]).abs().max() < TOL
+    en = model.score([{"image": im.to(dev)} for im in imgs], "energy")
+    assert (en.cpu() - fix["energy"]).abs().max() < TOL
+    # a model without the head refuses loudly
+    plain = rba_b200.MaskFormer(case_model_config(CASES["tiny_1dl"]))
+    plain.to(dev)
+    with pytest.raises(rba_b200.RbaError):
+        plain([{"image": imgs[0].to(dev)}], return_ood_pred=True)
+    with pytest.raises(rba_b200.RbaError):
+        plain.score([{"image": imgs[0].to(dev)}], "dense_hybrid")

@@ -28,6 +28,11 @@ def test_oracle_matches_reference_golden(name):
     rba = torch.stack(out["rba"])
     assert (sem[:, :, ::4, ::4] - fix["sem_seg_s4"]).abs().max() < ORACLE_TOL
     assert (rba - fix["rba"]).abs().max() < ORACLE_TOL
+    if case.get("ood_prediction"):      # DenseHybrid head: model(..., return_ood_pred=True) + get_densehybrid_score
+        assert (out["ood_pred"] - fix["ood_pred"]).abs().max() < ORACLE_TOL
+        assert (torch.stack(out["densehybrid"]) - fix["densehybrid"]).abs().max() < ORACLE_TOL
+    else:
+        assert "ood_pred" not in out
 
 
 def test_oracle_msda_matches_reference_golden():
