@@ -9,6 +9,6 @@ from .config import ModelConfig, model_config_from_cfg, model_config_from_yaml  
 from .engine import Engine  # noqa: F401
 from .metrics import OODEvaluator, StreamingOODMetrics, evaluate_ood  # noqa: F401
 from .modeling import MaskFormer, build_model  # noqa: F401
-from .pipeline import ScoreStream  # noqa: F401
+from .pipeline import PinnedBatcher, ScoreStream  # noqa: F401
 
 __version__ = "0.1.0"

@@ -88,3 +88,39 @@ class OODEvaluator:
             metrics.update(score, y.to(dev, non_blocking=True))
         r = metrics.compute()
         return {k: r[k] for k in ("auroc", "aupr", "fpr95")}
+
+    @torch.no_grad()
+    def evaluate_dataset(self, dataset, batch=8, workers=8, upper_limit=None, metrics=None, use_graph=True):
+        """The same evaluation over an indexable dataset of (image, label) pairs (the reference's dataset classes), fully
+        pipelined: threaded decode into pinned batches (PinnedBatcher), H2D of batch i+1 overlapping the forward of batch i
+        (ScoreStream with d2h=False), scores and labels accumulated on the device.  One 40-byte D2H at the end."""
+        from .pipeline import PinnedBatcher, ScoreStream
+        dev = self.model.device
+        metrics = metrics or StreamingOODMetrics(dev)
+        n = len(dataset) if upper_limit is None else min(len(dataset), int(upper_limit))
+        eng = self.model.engine()
+        eng.set_score(self.score_func, include_void=False)
+        stream, ybuf, ev_lab = None, None, None
+        comp = torch.cuda.current_stream(dev)
+        for it, (images, labels, n_valid) in enumerate(PinnedBatcher(dataset, batch, indices=range(n), workers=workers)):
+            if stream is None:
+                stream = ScoreStream(eng, images.shape[0], images.shape[2], images.shape[3], use_graph=use_graph, d2h=False)
+                ybuf = [torch.empty(labels.shape, dtype=torch.uint8, device=dev) for _ in range(2)]
+                ev_lab = [torch.cuda.Event(), torch.cuda.Event()]
+                ev_used = [torch.cuda.Event(), torch.cuda.Event()]
+            k = it & 1
+            with torch.cuda.stream(stream.s_in):              # labels ride the copy-in stream next to the images
+                if it >= 2:
+                    stream.s_in.wait_event(ev_used[k])
+                ybuf[k].copy_(labels, non_blocking=True)
+                ev_lab[k].record(stream.s_in)
+            score = stream.step(images)                       # device tensor of this batch (stream-ordered)
+            comp.wait_event(ev_lab[k])
+            metrics.update(score, ybuf[k])
+            ev_used[k].record(comp)
+            # host: wait only for the two H2D copies (about a millisecond) so the pinned buffers can go back to the
+            # ring; the forward keeps running while the next batch is fetched
+            stream.ev_in_ready[k].synchronize()
+            ev_lab[k].synchronize()
+        r = metrics.compute()
+        return {k: r[k] for k in ("auroc", "aupr", "fpr95")}

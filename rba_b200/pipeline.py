@@ -11,6 +11,11 @@ The reference's evaluation loop is batch-1 and synchronous: per image a blocking
 so at steady state a step costs max(forward, H2D, D2H) instead of their sum.  Results come back in order, one step
 late; `close()`/exhausting the iterator drains the pipeline.  torch is only the carrier of buffers, streams and events.
 """
+import queue
+import threading
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
 import torch
 
 from ._lib import RbaError
@@ -19,11 +24,12 @@ from ._lib import RbaError
 class ScoreStream:
     """eng: rba_b200.Engine with weights loaded.  B, H, W: fixed batch shape (the forward is captured once)."""
 
-    def __init__(self, eng, B, H, W, use_graph=True, post_forward=None):
+    def __init__(self, eng, B, H, W, use_graph=True, post_forward=None, d2h=True):
         if not torch.cuda.is_available():
             raise RbaError("ScoreStream needs a CUDA device: the product path has no CPU fallback")
         self.eng, self.B, self.H, self.W = eng, B, H, W
         self.post_forward = post_forward      # callable(static_out) launched on the compute stream after each forward
+        self.d2h = d2h                        # False: scores stay on the device (step() returns this step's device tensor)
         dev = eng.device
         self.dev = dev
         proto = torch.empty((B, 3, H, W), dtype=torch.uint8, device=dev)
@@ -73,6 +79,10 @@ class ScoreStream:
             self.eng.forward_into(self.static_in, self.static_out)
         if self.post_forward is not None:
             self.post_forward(self.static_out)
+        self.n_submitted += 1
+        if not self.d2h:
+            self.n_collected = self.n_submitted
+            return
         if i >= 2:
             comp.wait_event(self.ev_out_done[k])          # the D2H that last read stage_out[k]
         self.stage_out[k].copy_(self.static_out["rba"], non_blocking=True)
@@ -81,7 +91,6 @@ class ScoreStream:
             self.s_out.wait_event(self.ev_c_done[k])
             self.host_out[k].copy_(self.stage_out[k], non_blocking=True)
             self.ev_out_done[k].record(self.s_out)
-        self.n_submitted += 1
 
     def collect(self):
         """Blocks until the oldest un-collected batch's scores are in host memory; returns the (B,H,W) pinned tensor
@@ -94,7 +103,11 @@ class ScoreStream:
         return self.host_out[k]
 
     def step(self, host_images):
-        """Submit batch i; return the scores of batch i-1 (None on the first call)."""
+        """Submit batch i; return the scores of batch i-1 (None on the first call).  With d2h=False: returns the DEVICE
+        score tensor of batch i itself (stream-ordered; valid until the next submit)."""
+        if not self.d2h:
+            self.submit(host_images)
+            return self.static_out["rba"]
         prev = None
         if self.n_submitted - self.n_collected >= 2:
             raise RbaError("ScoreStream.step: collect() the previous result first")
@@ -117,3 +130,104 @@ class ScoreStream:
                 yield r
         for r in self.drain():
             yield r
+
+
+class PinnedBatcher:
+    """Host side of the input pipeline.  The reference decodes one image at a time on the main thread
+    (`DataLoader(batch_size=1)` + albumentations `ToTensorV2`, support.py:73-81,353-372) and its scorers read only `x[0]`
+    (evaluate_ood.py:146).  Here `dataset[i]` (any indexable returning `(image, label)` with image CHW/HWC uint8 and label
+    HW, tensors or ndarrays -- e.g. the reference's dataset classes) is called from `workers` threads, and consecutive
+    samples are packed into fixed-shape batches of `batch` images in PINNED buffers (a ring of `depth` buffer sets) ready
+    for `ScoreStream.submit`.  A short last batch is padded by repeating its first image with label 255 (ignored by
+    the metrics, support.py:275-279).  Iterating yields `(images (B,3,H,W) uint8, labels (B,H,W) uint8, n_valid)`."""
+
+    def __init__(self, dataset, batch, indices=None, workers=8, depth=3, pin=None):
+        self.ds, self.B = dataset, int(batch)
+        self.idx = list(range(len(dataset))) if indices is None else list(indices)
+        self.workers, self.depth = max(1, int(workers)), max(2, int(depth))
+        self.pin = torch.cuda.is_available() if pin is None else bool(pin)
+        self._bufs = None
+
+    def __len__(self):
+        return -(-len(self.idx) // self.B)
+
+    @staticmethod
+    def _chw_u8(img):
+        t = torch.as_tensor(np.ascontiguousarray(img)) if not torch.is_tensor(img) else img
+        if t.dim() != 3:
+            raise RbaError(f"PinnedBatcher: image must have 3 dims, got {tuple(t.shape)}")
+        if t.shape[0] != 3 and t.shape[-1] == 3:
+            t = t.permute(2, 0, 1)                        # HWC -> CHW (what ToTensorV2 does)
+        if t.dtype != torch.uint8:
+            raise RbaError(f"PinnedBatcher: uint8 images expected (raw pixel values), got {t.dtype}")
+        return t
+
+    def _alloc(self, H, W):
+        mk = (lambda *s: torch.empty(s, dtype=torch.uint8).pin_memory()) if self.pin else (lambda *s: torch.empty(s, dtype=torch.uint8))
+        self._bufs = [(mk(self.B, 3, H, W), mk(self.B, H, W)) for _ in range(self.depth)]
+        self._free = queue.Queue()
+        for b in self._bufs:
+            self._free.put(b)
+
+    def release(self, images):
+        """Hand a yielded buffer set back to the ring (the default iteration does it when the next batch is requested)."""
+        for b in self._bufs:
+            if b[0] is images:
+                self._free.put(b)
+                return
+
+    def __iter__(self):
+        out = queue.Queue(maxsize=self.depth)
+        stop = threading.Event()
+
+        def load(i):
+            img, lab = self.ds[i]
+            lab = torch.as_tensor(np.ascontiguousarray(lab)) if not torch.is_tensor(lab) else lab
+            return self._chw_u8(img), lab.to(torch.uint8)
+
+        def producer():
+            try:
+                with ThreadPoolExecutor(self.workers) as ex:
+                    for s in range(0, len(self.idx), self.B):
+                        if stop.is_set():
+                            return
+                        chunk = self.idx[s:s + self.B]
+                        samples = list(ex.map(load, chunk))
+                        H, W = samples[0][0].shape[-2:]
+                        if self._bufs is None:
+                            self._alloc(H, W)
+                        for im, lab in samples:
+                            if tuple(im.shape[-2:]) != (H, W) or tuple(lab.shape[-2:]) != (H, W) or \
+                                    tuple(self._bufs[0][0].shape[-2:]) != (H, W):
+                                raise RbaError("PinnedBatcher: all images of a run must share one size "
+                                               f"(got {tuple(im.shape[-2:])} vs {(H, W)}); resize in the dataset transform")
+                        ib, lb = self._free.get()
+                        for j, (im, lab) in enumerate(samples):
+                            ib[j].copy_(im)
+                            lb[j].copy_(lab.reshape(H, W))
+                        for j in range(len(samples), self.B):   # pad: repeated image, ignored labels
+                            ib[j].copy_(ib[0])
+                            lb[j].fill_(255)
+                        out.put((ib, lb, len(samples)))
+                out.put(None)
+            except BaseException as e:   # surface loader errors in the consumer
+                out.put(e)
+
+        t = threading.Thread(target=producer, daemon=True)
+        t.start()
+        prev = None
+        try:
+            while True:
+                item = out.get()
+                if item is None:
+                    break
+                if isinstance(item, BaseException):
+                    raise item
+                if prev is not None:
+                    self.release(prev)
+                prev = item[0]
+                yield item
+        finally:
+            stop.set()
+            if prev is not None and self._bufs is not None:
+                self.release(prev)

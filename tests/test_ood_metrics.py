@@ -102,3 +102,42 @@ def test_gpu_ood_evaluator_loop(dev):
     exact = MO.evaluate_ood(MO.quantize_like_kernel(maps), torch.cat(ys[:2]).numpy())
     for k in KEYS:
         assert abs(res[k] - exact[k]) < 1e-9
+
+
+@pytest.mark.gpu
+def test_gpu_ood_evaluator_pipelined_dataset(dev):
+    """OODEvaluator.evaluate_dataset (PinnedBatcher threads -> pinned batches -> ScoreStream(d2h=False) -> device
+    histogram) gives the same metrics as the synchronous per-image loop, including a padded last batch and HWC input."""
+    import rba_b200
+    from golden_cases import CASES, case_model_config
+    from rba_b200 import weights
+    case = CASES["tiny_1dl"]
+    mc = case_model_config(case)
+    model = rba_b200.MaskFormer(mc)
+    model.load_state_dict(weights.init_state_dict(mc, seed=case["seed"], perturb=case["perturb"]))
+    model.to(dev).eval()
+
+    class DS:
+        def __len__(self):
+            return 7
+
+        def __getitem__(self, i):
+            g = torch.Generator().manual_seed(100 + i)
+            img = torch.randint(0, 256, (64, 96, 3), dtype=torch.uint8, generator=g).numpy()     # HWC like cv2
+            lab = torch.randint(0, 3, (64, 96), generator=g)
+            lab[lab == 2] = 255                                                                  # ignored region
+            return img, lab.numpy()
+
+    ds = DS()
+    ev = rba_b200.OODEvaluator(model)
+    loop = ev.evaluate([(torch.as_tensor(ds[i][0]).permute(2, 0, 1)[None], torch.as_tensor(ds[i][1])[None]) for i in range(7)],
+                       upper_limit=7)
+    for use_graph in (True, False):
+        piped = ev.evaluate_dataset(ds, batch=3, workers=4, use_graph=use_graph)
+        for k in KEYS:
+            assert abs(piped[k] - loop[k]) < 1e-12, (k, piped[k], loop[k])
+    part = ev.evaluate_dataset(ds, batch=2, workers=2, upper_limit=4)
+    loop4 = ev.evaluate([(torch.as_tensor(ds[i][0]).permute(2, 0, 1)[None], torch.as_tensor(ds[i][1])[None]) for i in range(4)],
+                        upper_limit=4)
+    for k in KEYS:
+        assert abs(part[k] - loop4[k]) < 1e-12
