@@ -20,6 +20,7 @@
  *                                (modeling/backbone/swin.py:686), MSDeformAttnPixelDecoder
  *                                (modeling/pixel_decoder/msdeformattn.py:173), MultiScaleMaskedTransformerDecoder
  *                                (modeling/transformer_decoder/mask2former_transformer_decoder.py:232)
+ *   rba_outlier_loss          <- SetCriterion.outlier_loss (mask2former/modeling/criterion.py:435-553), fwd + bwd
  *   rba_k_*                   per-kernel entry points (same kernels the engine launches), exported so the
  *                                parity tests can pin every stage against the oracle.
  *
@@ -168,6 +169,22 @@ int rba_msda_backward(const float* value, const int64_t* spatial_shapes, const i
                       const float* sampling_loc, const float* attn_weight, const float* grad_output, int B, int S, int M,
                       int D, int Lq, int L, int P, int im2col_step, float* grad_value, float* grad_sampling_loc,
                       float* grad_attn_weight, void* stream);
+
+/* ---- training-side RbA outlier loss, forward + backward in one call (SetCriterion.outlier_loss,
+ * mask2former/modeling/criterion.py:435-553; OUTLIER_LOSS_FUNC squared_hinge) ----
+ * pred_masks (B,Q,h,w), pred_logits (B,Q,K+1) fp32; outlier_masks (B,H,W) uint8 or int64 (1 = outlier, 0 = inlier,
+ * anything else ignored); score_mode: 0..2 = OUTLIER_LOSS_TARGET "nls" with SCORE_NORM none / tanh / sigmoid, 3 = "energy".
+ * loss: 1 float (device).  d_pred_masks (B,Q,h,w) and d_pred_logits (B,Q,K+1) receive d loss / d input (both or neither).
+ * workspace: rba_outlier_loss_workspace_floats(...) floats, 16-byte aligned.  K <= 32. */
+#define RBA_OL_NLS_NONE 0
+#define RBA_OL_NLS_TANH 1
+#define RBA_OL_NLS_SIGMOID 2
+#define RBA_OL_ENERGY 3
+int64_t rba_outlier_loss_workspace_floats(int B, int Q, int K, int h, int w);
+int rba_outlier_loss(const float* pred_masks, const float* pred_logits, const void* outlier_masks, int label_dtype_bytes, int B,
+                     int Q, int K, int h, int w, int H, int W, int score_mode, float inlier_upper_threshold,
+                     float outlier_lower_threshold, float* loss, float* d_pred_masks, float* d_pred_logits, float* workspace,
+                     void* stream);
 
 /* ---- per-kernel entry points (device pointers) ---- */
 /* ood_pred logits (B,h,w,2) -> bilinear align_corners=True resize to (H,W): ood_pred (B,2,H,W) and/or

@@ -537,6 +537,28 @@ def densehybrid_from_outputs(sem_seg, ood_pred):
     return -torch.logsumexp(sem_seg, dim=0) + (p2 + 1e-9).log()
 
 
+def outlier_loss(pred_masks, pred_logits, outlier_masks, target="nls", score_norm="tanh", t_in=-1.0, t_out=-0.1):
+    """SetCriterion.outlier_loss, squared-hinge branch (mask2former/modeling/criterion.py:435-487):
+    class softmax without void x mask sigmoid contracted over queries (:448-453), score = -sum_c f(.) or -logsumexp
+    (:455-466), bilinear align_corners=True resize to the label size (:474-475), squared hinge on the inlier / outlier
+    pixels with the 0.5 only when outliers exist (:480-487).  Differentiable torch statement (autograd = the reference's
+    backward)."""
+    ood, ind = outlier_masks == 1, outlier_masks == 0
+    logits = torch.einsum("bqc,bqhw->bchw", F.softmax(pred_logits, dim=-1)[..., :-1], pred_masks.sigmoid())
+    if target == "nls":
+        f = {"tanh": torch.tanh, "sigmoid": torch.sigmoid}.get(score_norm, lambda t: t)
+        score = -f(logits).sum(dim=1)
+    elif target == "energy":
+        score = -torch.logsumexp(logits, dim=1)
+    else:
+        raise ValueError(target)
+    score = F.interpolate(score.unsqueeze(1), size=outlier_masks.shape[-2:], mode="bilinear", align_corners=True).squeeze(1)
+    loss = F.relu(score[ind] - t_in).pow(2).mean()
+    if ood.sum() > 0:
+        loss = 0.5 * (loss + F.relu(t_out - score[ood]).pow(2).mean())
+    return loss
+
+
 def preprocess(images, cfg):
     """maskformer_model.py:255-257: (x - mean)/std per image, zero-pad bottom/right to a multiple of
     SIZE_DIVISIBILITY (detectron2 ImageList.from_tensors, pad_value 0)."""

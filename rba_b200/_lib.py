@@ -73,6 +73,9 @@ PROTOTYPES = {
     "rba_msda_backward": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64), c_void_p, c_void_p, c_void_p, c_int, c_int,
                                   c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rba_k_ood_pred_resize": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "rba_outlier_loss_workspace_floats": (c_int64, [c_int, c_int, c_int, c_int, c_int]),
+    "rba_outlier_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                 c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rba_k_split": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_int64, c_void_p]),
     "rba_k_gemm": (c_int, [POINTER(RbaGemmArgs), c_void_p]),
     "rba_k_conv3x3": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),

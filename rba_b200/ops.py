@@ -140,6 +140,60 @@ class MSDeformAttnFunction(torch.autograd.Function):
         return gv, None, None, gl, ga, None
 
 
+OUTLIER_SCORE_MODES = {("nls", "none"): 0, ("nls", "tanh"): 1, ("nls", "sigmoid"): 2, ("energy", None): 3}
+
+
+class _OutlierLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred_masks, pred_logits, outlier_masks, mode, t_in, t_out):
+        B, Q, h, w = pred_masks.shape
+        K = pred_logits.shape[-1] - 1
+        H, W = outlier_masks.shape[-2:]
+        need_grad = pred_masks.requires_grad or pred_logits.requires_grad
+        dev = pred_masks.device
+        ws = torch.empty(int(_lib.lib().rba_outlier_loss_workspace_floats(B, Q, K, h, w)), dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        d_masks = torch.empty_like(pred_masks) if need_grad else None
+        d_logits = torch.empty_like(pred_logits) if need_grad else None
+        _lib.check(_lib.lib().rba_outlier_loss(_p(pred_masks), _p(pred_logits), _p(outlier_masks), outlier_masks.element_size(),
+                                               B, Q, K, h, w, H, W, mode, float(t_in), float(t_out), _p(loss), _p(d_masks),
+                                               _p(d_logits), _p(ws), _stream()))
+        if need_grad:
+            ctx.save_for_backward(d_masks, d_logits)
+        return loss
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        d_masks, d_logits = ctx.saved_tensors
+        return d_masks * grad_out, d_logits * grad_out, None, None, None, None
+
+
+def outlier_loss(pred_masks, pred_logits, outlier_masks, outlier_loss_target="nls", score_norm="tanh",
+                 outlier_loss_func="squared_hinge", inlier_upper_threshold=-1.0, outlier_lower_threshold=-0.1):
+    """SetCriterion.outlier_loss (mask2former/modeling/criterion.py:435-553) as one fused forward + backward launch
+    sequence; differentiable w.r.t. pred_masks (B,Q,h,w) and pred_logits (B,Q,K+1).  outlier_masks: (B,H,W) uint8/int64
+    (1 outlier, 0 inlier, other values ignored).  Argument names and defaults are the reference's config keys
+    (MODEL.MASK_FORMER.OUTLIER_LOSS_TARGET / SCORE_NORM / OUTLIER_LOSS_FUNC / INLIER_UPPER_THRESHOLD / OUTLIER_LOWER_THRESHOLD,
+    mask2former/config.py:188-227).  Returns the scalar loss tensor."""
+    _chk_cuda(pred_masks, pred_logits, outlier_masks)
+    if outlier_loss_func != "squared_hinge":
+        raise RbaError(f"outlier_loss: OUTLIER_LOSS_FUNC {outlier_loss_func!r} is not built (squared_hinge only)")
+    key = (outlier_loss_target, None if outlier_loss_target == "energy" else (score_norm or "none"))
+    if key not in OUTLIER_SCORE_MODES:
+        raise RbaError(f"outlier_loss: target {outlier_loss_target!r} / score_norm {score_norm!r} is not built "
+                       "(nls with none|tanh|sigmoid, or energy)")
+    if pred_masks.dtype != torch.float32 or pred_logits.dtype != torch.float32:
+        raise RbaError("outlier_loss: float32 inputs expected")
+    if outlier_masks.dtype not in (torch.uint8, torch.int64):
+        outlier_masks = outlier_masks.to(torch.int64)
+    if pred_masks.dim() != 4 or pred_logits.dim() != 3 or outlier_masks.dim() != 3 or \
+            pred_masks.shape[:2] != pred_logits.shape[:2] or outlier_masks.shape[0] != pred_masks.shape[0]:
+        raise RbaError(f"outlier_loss: shapes {tuple(pred_masks.shape)}, {tuple(pred_logits.shape)}, {tuple(outlier_masks.shape)}")
+    return _OutlierLoss.apply(pred_masks, pred_logits, outlier_masks.contiguous(), OUTLIER_SCORE_MODES[key],
+                              inlier_upper_threshold, outlier_lower_threshold)
+
+
 def gemm(a, w, bias=None, act=RBA_ACT_NONE, residual=None, out_planes=False, out_f32=True, bias_per_row=False,
          swin=None, backend=RBA_GEMM_FFMA, out=None):
     """C = act(A W^T + bias) (+ residual).  a: (hi, lo) planes [M,K] or [batch,M,K]; w: planes [N,K] or [batch,N,K].

@@ -299,6 +299,49 @@ def test_msda_backward_matches_reference_gradients(dev):
         ops.ms_deform_attn_backward(value.to(dev), shapes, lsi, loc.to(dev), aw.to(dev), go[:, :1].contiguous().to(dev), 2)
 
 
+def _outlier_inputs(c):
+    """Same recipe as oracle/make_golden_outlier_loss.py::make_inputs (only loss + gradients are stored)."""
+    g = torch.Generator().manual_seed(c["seed"])
+    masks = torch.randn(c["B"], c["Q"], c["h"], c["w"], generator=g) * 0.99 - 0.54
+    logits = torch.randn(c["B"], c["Q"], c["K"] + 1, generator=g)
+    r = torch.rand(c["B"], c["H"], c["W"], generator=g)
+    labels = torch.full((c["B"], c["H"], c["W"]), 255, dtype=torch.int64)
+    labels[r < 0.6] = 0
+    labels[r > 1.0 - c["p_ood"]] = 1
+    return masks, logits, labels
+
+
+def test_outlier_loss_matches_reference_criterion(dev):
+    """ops.outlier_loss (fused forward + backward) against the loss value and float64 autograd gradients of the
+    reference's own SetCriterion.outlier_loss (tests/golden/outlier_loss.pt): every shipped configuration, int64 and
+    uint8 labels, ignored pixels, no-outlier batches, non-integer resize ratios."""
+    fix = load_golden("outlier_loss.pt")
+    for name, f in fix.items():
+        c = f["case"]
+        masks, logits, labels = _outlier_inputs(c)
+        assert abs(float(masks.double().sum() + logits.double().sum() + labels.double().sum()) - f["in_checksum"]) < 1e-6 * abs(f["in_checksum"])
+        for lab in (labels, labels.to(torch.uint8)):
+            m, l = masks.to(dev).requires_grad_(True), logits.to(dev).requires_grad_(True)
+            loss = ops.outlier_loss(m, l, lab.to(dev), outlier_loss_target=c["target"], score_norm=c["norm"],
+                                    inlier_upper_threshold=c["t_in"], outlier_lower_threshold=c["t_out"])
+            assert abs(loss.item() - f["loss"]) <= 2e-5 * max(1.0, abs(f["loss"])), (name, loss.item(), f["loss"])
+            (3.0 * loss).backward()                                   # upstream gradient is applied
+            for got, want, nm in ((m.grad, f["d_masks"], "d_masks"), (l.grad, f["d_logits"], "d_logits")):
+                err = (got.cpu() / 3.0 - want).abs().max().item()
+                assert err <= 2e-5 * max(want.abs().max().item(), 1e-3), (name, nm, err, want.abs().max().item())
+    # no gradient requested: loss only
+    with torch.no_grad():
+        loss2 = ops.outlier_loss(masks.to(dev), logits.to(dev), labels.to(dev), outlier_loss_target=c["target"], score_norm=c["norm"],
+                                 inlier_upper_threshold=c["t_in"], outlier_lower_threshold=c["t_out"])
+    assert abs(loss2.item() - f["loss"]) <= 2e-5 * max(1.0, abs(f["loss"]))
+    # no in-distribution pixel at all: mean of an empty set is NaN, as in the reference
+    nan_loss = ops.outlier_loss(masks.to(dev), logits.to(dev), torch.full_like(labels, 255).to(dev))
+    assert torch.isnan(nan_loss)
+    for bad in (dict(outlier_loss_func="mse"), dict(outlier_loss_target="softmax_entropy"), dict(score_norm="softplus")):
+        with pytest.raises(ops.RbaError):
+            ops.outlier_loss(masks.to(dev), logits.to(dev), labels.to(dev), **bad)
+
+
 def test_score_golden_and_edges(dev):
     fix = load_golden("score.pt")
     for nm, f in fix.items():

@@ -59,6 +59,20 @@ def test_oracle_msda_backward_matches_reference_gradients():
             assert (got.float() - want).abs().max() <= 2e-6 * max(1.0, want.abs().max().item()), (name, nm)
 
 
+def test_oracle_outlier_loss_matches_reference_criterion():
+    """The oracle's restatement of SetCriterion.outlier_loss against the reference's loss value and float64 gradients."""
+    from test_kernels_gpu import _outlier_inputs
+    fix = load_golden("outlier_loss.pt")
+    for name, f in fix.items():
+        c = f["case"]
+        masks, logits, labels = _outlier_inputs(c)
+        m, l = masks.double().requires_grad_(True), logits.double().requires_grad_(True)
+        loss = O.outlier_loss(m, l, labels, c["target"], c["norm"], c["t_in"], c["t_out"])
+        loss.backward()
+        assert abs(float(loss) - f["loss"]) < 1e-9 * max(1.0, abs(f["loss"])), name
+        assert (m.grad.float() - f["d_masks"]).abs().max() < 1e-9 and (l.grad.float() - f["d_logits"]).abs().max() < 1e-9, name
+
+
 def test_oracle_score_matches_reference_golden():
     fix = load_golden("score.pt")
     for nm, f in fix.items():
