@@ -206,8 +206,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // m / l: running row max (log2 domain) and row sum for rows g and g+8; oacc: unnormalised output accumulators.
 template <int NB0, int NBN, bool MASK>
 __device__ __forceinline__ void wm_chunk(const uint16_t* sKh, const uint16_t* sKl, const uint16_t* sVh, const uint16_t* sVl,
-                                         const float* sB, const int* sCol, const uint32_t (&qh)[2][4],
-                                         const uint32_t (&ql)[2][4], int lane, int g, int tq, const int (&rterm)[2],
+                                         const char* const (&sBrow)[2], const int* sCol, const int* sReg,
+                                         const uint32_t (&qh)[2][4], const uint32_t (&ql)[2][4], int lane, int g, int tq,
                                          const int (&rid)[2], float scale2, float (&m)[2], float (&l)[2],
                                          float (&oacc)[4][4]) {
   static_assert(NBN % 2 == 0, "chunks are whole k16 steps");
@@ -234,9 +234,11 @@ __device__ __forceinline__ void wm_chunk(const uint16_t* sKh, const uint16_t* sK
     for (int nb = 0; nb < NBN; ++nb)
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const int cinfo = sCol[(NB0 + nb) * 8 + tq * 2 + j];
-        float sv = fmaf(sacc[nb][hrow * 2 + j], scale2, sB[rterm[hrow] - (cinfo & 0xffff)]);
-        if (MASK && rid[hrow] != (cinfo >> 16)) sv += -100.0f * 1.4426950408889634f;
+        // relative position bias: table entry (ri - ci + 11) * 23 + (rj - cj + 11) = this row's base minus the column's
+        // byte offset (one LDS of the offset shared by both rows, one subtract, one LDS of the bias)
+        const int col = (NB0 + nb) * 8 + tq * 2 + j;
+        float sv = fmaf(sacc[nb][hrow * 2 + j], scale2, *reinterpret_cast<const float*>(sBrow[hrow] - sCol[col]));
+        if (MASK && rid[hrow] != sReg[col]) sv += -100.0f * 1.4426950408889634f;
         sacc[nb][hrow * 2 + j] = sv;
         mx = fmaxf(mx, sv);
       }
@@ -293,7 +295,8 @@ window_attn_mma_kernel(const uint16_t* __restrict__ qkv_hi, const uint16_t* __re
   // planes: 0 q_hi, 1 q_lo, 2 k_hi, 3 k_lo, 4 v_hi, 5 v_lo
   uint16_t* sOp = reinterpret_cast<uint16_t*>(wm_smem);
   float* sB = reinterpret_cast<float*>(wm_smem + 6 * WM_PLANE * 2);     // [529] relative position bias * log2(e)
-  int* sCol = reinterpret_cast<int*>(sB + 532);                          // [144] (ci*23 + cj) | region << 16
+  int* sCol = reinterpret_cast<int*>(sB + 532);                          // [144] byte offset 4 * (ci*23 + cj) into the bias table
+  int* sReg = sCol + WA_N;                                               // [144] shift-mask region id of the column
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // heads fastest: the CTAs of one window run together, so the 128-byte lines that hold two heads' 64-byte q/k/v
   // segments are fetched from HBM once
@@ -323,7 +326,8 @@ window_attn_mma_kernel(const uint16_t* __restrict__ qkv_hi, const uint16_t* __re
     const int hs = wh * WA_WS + ci, wsx = ww * WA_WS + cj;
     const int rh = hs < Hp - WA_WS ? 0 : (hs < Hp - shift ? 1 : 2);
     const int rw = wsx < Wp - WA_WS ? 0 : (wsx < Wp - shift ? 1 : 2);
-    sCol[c] = (ci * 23 + cj) | ((rh * 3 + rw) << 16);
+    sCol[c] = 4 * (ci * 23 + cj);
+    sReg[c] = rh * 3 + rw;
   }
   asm volatile("cp.async.wait_group 0;" ::);
   __syncthreads();
@@ -344,12 +348,13 @@ window_attn_mma_kernel(const uint16_t* __restrict__ qkv_hi, const uint16_t* __re
       ldsm_x4(ql[ks][0], ql[ks][1], ql[ks][2], ql[ks][3], sQl + row * WM_PITCH + ks * 16 + col);
     }
   }
-  int rterm[2], rid[2];
+  int rid[2];
+  const char* sBrow[2];
 #pragma unroll
   for (int hrow = 0; hrow < 2; ++hrow) {
     const int r = r0 + g + hrow * 8;
     const int ri = r / WA_WS, rj = r - ri * WA_WS;
-    rterm[hrow] = ri * 23 + rj + (WA_WS - 1) * 23 + (WA_WS - 1);
+    sBrow[hrow] = reinterpret_cast<const char*>(sB + (ri * 23 + rj + (WA_WS - 1) * 23 + (WA_WS - 1)));
     const int hs = wh * WA_WS + ri, wsx = ww * WA_WS + rj;
     rid[hrow] = (hs < Hp - WA_WS ? 0 : (hs < Hp - shift ? 1 : 2)) * 3 + (wsx < Wp - WA_WS ? 0 : (wsx < Wp - shift ? 1 : 2));
   }
@@ -361,11 +366,11 @@ window_attn_mma_kernel(const uint16_t* __restrict__ qkv_hi, const uint16_t* __re
   // only windows in the last window row / column see more than one shift region (swin.py:416-431)
   const bool need_mask = shift > 0 && (wh == nWh - 1 || ww == nWw - 1);
   if (need_mask) {
-    wm_chunk<0, 10, true>(sKh, sKl, sVh, sVl, sB, sCol, qh, ql, lane, g, tq, rterm, rid, scale2, m, l, oacc);
-    wm_chunk<10, 8, true>(sKh, sKl, sVh, sVl, sB, sCol, qh, ql, lane, g, tq, rterm, rid, scale2, m, l, oacc);
+    wm_chunk<0, 10, true>(sKh, sKl, sVh, sVl, sBrow, sCol, sReg, qh, ql, lane, g, tq, rid, scale2, m, l, oacc);
+    wm_chunk<10, 8, true>(sKh, sKl, sVh, sVl, sBrow, sCol, sReg, qh, ql, lane, g, tq, rid, scale2, m, l, oacc);
   } else {
-    wm_chunk<0, 10, false>(sKh, sKl, sVh, sVl, sB, sCol, qh, ql, lane, g, tq, rterm, rid, scale2, m, l, oacc);
-    wm_chunk<10, 8, false>(sKh, sKl, sVh, sVl, sB, sCol, qh, ql, lane, g, tq, rterm, rid, scale2, m, l, oacc);
+    wm_chunk<0, 10, false>(sKh, sKl, sVh, sVl, sBrow, sCol, sReg, qh, ql, lane, g, tq, rid, scale2, m, l, oacc);
+    wm_chunk<10, 8, false>(sKh, sKl, sVh, sVl, sBrow, sCol, sReg, qh, ql, lane, g, tq, rid, scale2, m, l, oacc);
   }
   // ---- store (attn @ v).transpose(1,2).reshape(B_, N, C) as split planes ----
 #pragma unroll
@@ -393,7 +398,7 @@ int window_attn_planes(const uint16_t* qkv_hi, const uint16_t* qkv_lo, const flo
   const int64_t nwin = (int64_t)B * g.nWh * g.nWw;
   if (nwin == 0) return RBA_OK;
   RBA_CHECK(nwin < (1LL << 31), "window_attn_planes: too many windows");
-  const size_t smem = (size_t)6 * WM_PLANE * 2 + 532 * 4 + WA_N * 4;
+  const size_t smem = (size_t)6 * WM_PLANE * 2 + 532 * 4 + 2 * WA_N * 4;
   RBA_CUDA(cudaFuncSetAttribute(window_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   RBA_CHECK(nwin * heads < (1LL << 31), "window_attn_planes: grid too large");
   dim3 grid((unsigned)(nwin * heads));

@@ -58,11 +58,16 @@ __device__ __forceinline__ float bf16lo(uint32_t packed) { return __uint_as_floa
 __device__ __forceinline__ float bf16hi(uint32_t packed) { return __uint_as_float(packed & 0xffff0000u); }
 
 // Two values -> packed bf16x2 hi word and bf16x2 lo (residual) word, element `a` in the low half.
-// cvt.rn.bf16x2.f32 converts and packs a pair in one instruction.
+// cvt.rn.bf16x2.f32 converts and packs a pair in one instruction; the residual x - float(hi) is ONE sm_100 mixed-precision
+// FMA per element (fma.rn.f32.bf16, SASS FHFMA.BF16, reading a half of the packed register directly) instead of a shift /
+// mask to rebuild float(hi) plus a subtract.  Same bits as the two-step form (both are exact).
 __device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint32_t& lo) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
-  const float ra = a - __uint_as_float(hi << 16);
-  const float rb = b - __uint_as_float(hi & 0xffff0000u);
+  float ra, rb;
+  const uint16_t m1 = 0xBF80;                              // -1.0 (bf16)
+  asm("{.reg .b16 l, h; mov.b32 {l, h}, %2; fma.rn.f32.bf16 %0, l, %3, %4; fma.rn.f32.bf16 %1, h, %3, %5;}"
+      : "=f"(ra), "=f"(rb)
+      : "r"(hi), "h"(m1), "f"(a), "f"(b));
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
 }
 

@@ -49,6 +49,18 @@ def test_layernorm_plain(dev, C):
     assert (unplanes(p) - ref).abs().max() < 2e-4
 
 
+def test_layernorm_narrow_rows_many(dev):
+    """The 4-rows-per-warp kernel used for C <= 128 and >= 256 rows (stage-0 LayerNorms), row count not a multiple of 4."""
+    for C, rows in ((128, 1001), (32, 258), (96, 4099)):
+        g = torch.Generator().manual_seed(C)
+        x = torch.randn(rows, C, generator=g) * 3 + 1
+        gm, bt = torch.randn(C, generator=g), torch.randn(C, generator=g)
+        ref = F.layer_norm(x, (C,), gm, bt)
+        y, p = ops.layernorm(x.to(dev), gm.to(dev), bt.to(dev), mode=0, B=1, H=1, W=rows, want_planes=True)
+        assert (y.cpu() - ref).abs().max() < 2e-5
+        assert (unplanes(p) - ref).abs().max() < 2e-4
+
+
 @pytest.mark.parametrize("H,W,shift", [(24, 36, 0), (30, 41, 6), (7, 50, 6), (12, 12, 0)])
 def test_layernorm_window_gather(dev, H, W, shift):
     """swin.py:247-271: norm1, pad, roll(-shift), window_partition."""
