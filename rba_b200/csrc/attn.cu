@@ -202,23 +202,38 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return r;
 }
 
+__device__ __forceinline__ void ldsm_x4_a(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t_a(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ int lds_i32(uint32_t addr) {
+  int v;
+  asm("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+// Per-lane shared-memory BYTE addresses (32-bit shared space; everything else is a compile-time immediate):
+//   ka  K_hi plane + this lane's ldmatrix row/column; K_lo = + WM_PLANE * 2
+//   va  V_hi plane + this lane's transposed-ldmatrix row/column; V_lo = + WM_PLANE * 2
+//   ca  column table entry of key column 2 tq (bias byte offset); region ids at + WA_N * 4
+struct WmAddr { uint32_t ka, va, ca; };
+
 // One key chunk [NB0*8, (NB0+NBN)*8) of the online-softmax attention for this warp's 16 query rows.
 // m / l: running row max (log2 domain) and row sum for rows g and g+8; oacc: unnormalised output accumulators.
 template <int NB0, int NBN, bool MASK>
-__device__ __forceinline__ void wm_chunk(const uint16_t* sKh, const uint16_t* sKl, const uint16_t* sVh, const uint16_t* sVl,
-                                         const char* const (&sBrow)[2], const int* sCol, const int* sReg,
-                                         const uint32_t (&qh)[2][4], const uint32_t (&ql)[2][4], int lane, int g, int tq,
-                                         const int (&rid)[2], float scale2, float (&m)[2], float (&l)[2],
-                                         float (&oacc)[4][4]) {
+__device__ __forceinline__ void wm_chunk(const WmAddr& ad, const uint32_t (&sBrow)[2], const uint32_t (&qh)[2][4],
+                                         const uint32_t (&ql)[2][4], const int (&rid)[2], float scale2, float (&m)[2],
+                                         float (&l)[2], float (&oacc)[4][4]) {
   static_assert(NBN % 2 == 0, "chunks are whole k16 steps");
   float sacc[NBN][4];
 #pragma unroll
   for (int nb = 0; nb < NBN; ++nb) {
     sacc[nb][0] = sacc[nb][1] = sacc[nb][2] = sacc[nb][3] = 0.f;
     uint32_t kh[4], kl[4];
-    const int krow = (NB0 + nb) * 8 + (lane & 7), kcol = (lane >> 3) * 8;
-    ldsm_x4(kh[0], kh[1], kh[2], kh[3], sKh + krow * WM_PITCH + kcol);
-    ldsm_x4(kl[0], kl[1], kl[2], kl[3], sKl + krow * WM_PITCH + kcol);
+    ldsm_x4_a(kh[0], kh[1], kh[2], kh[3], ad.ka + (NB0 + nb) * 8 * WM_PITCH * 2);
+    ldsm_x4_a(kl[0], kl[1], kl[2], kl[3], ad.ka + (NB0 + nb) * 8 * WM_PITCH * 2 + WM_PLANE * 2);
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
       mma_bf16(sacc[nb], qh[ks], kh[2 * ks], kh[2 * ks + 1]);
@@ -226,22 +241,30 @@ __device__ __forceinline__ void wm_chunk(const uint16_t* sKh, const uint16_t* sK
       mma_bf16(sacc[nb], ql[ks], kh[2 * ks], kh[2 * ks + 1]);
     }
   }
-  // scale + relative position bias (+ shift mask), all in the log2 domain; online softmax update
+  // scale + relative position bias (+ shift mask), all in the log2 domain; online softmax update.
+  // bias: table entry (ri - ci + 11) * 23 + (rj - cj + 11) = this row's base minus the column's byte offset
+#pragma unroll
+  for (int nb = 0; nb < NBN; ++nb)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint32_t centry = ad.ca + ((NB0 + nb) * 8 + j) * 4;
+      const uint32_t coff = (uint32_t)lds_i32(centry);
+      int creg = 0;
+      if (MASK) creg = lds_i32(centry + WA_N * 4);
+#pragma unroll
+      for (int hrow = 0; hrow < 2; ++hrow) {
+        float bias;
+        asm("ld.shared.f32 %0, [%1];" : "=f"(bias) : "r"(sBrow[hrow] - coff));
+        float sv = fmaf(sacc[nb][hrow * 2 + j], scale2, bias);
+        if (MASK && rid[hrow] != creg) sv += -100.0f * 1.4426950408889634f;
+        sacc[nb][hrow * 2 + j] = sv;
+      }
+    }
 #pragma unroll
   for (int hrow = 0; hrow < 2; ++hrow) {
     float mx = m[hrow];
 #pragma unroll
-    for (int nb = 0; nb < NBN; ++nb)
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        // relative position bias: table entry (ri - ci + 11) * 23 + (rj - cj + 11) = this row's base minus the column's
-        // byte offset (one LDS of the offset shared by both rows, one subtract, one LDS of the bias)
-        const int col = (NB0 + nb) * 8 + tq * 2 + j;
-        float sv = fmaf(sacc[nb][hrow * 2 + j], scale2, *reinterpret_cast<const float*>(sBrow[hrow] - sCol[col]));
-        if (MASK && rid[hrow] != sReg[col]) sv += -100.0f * 1.4426950408889634f;
-        sacc[nb][hrow * 2 + j] = sv;
-        mx = fmaxf(mx, sv);
-      }
+    for (int nb = 0; nb < NBN; ++nb) mx = fmaxf(mx, fmaxf(sacc[nb][hrow * 2], sacc[nb][hrow * 2 + 1]));
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
     const float alpha = ex2_approx(m[hrow] - mx);               // 0 on the first chunk (m = -inf)
@@ -269,13 +292,12 @@ __device__ __forceinline__ void wm_chunk(const uint16_t* sKh, const uint16_t* sK
     split_pack2(sacc[2 * kk][2], sacc[2 * kk][3], ph[1], pl[1]);          // row g+8
     split_pack2(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1], ph[2], pl[2]);  // row g,   keys 16kk + 8 + 2t, +1
     split_pack2(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3], ph[3], pl[3]);  // row g+8
-    const int vrow = (NB0 / 2 + kk) * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
 #pragma unroll
     for (int np = 0; np < 2; ++np) {                                     // pairs of 8-wide d blocks
       uint32_t vh[4], vl[4];
-      const int vcol = np * 16 + (lane >> 4) * 8;
-      ldsm_x4_t(vh[0], vh[1], vh[2], vh[3], sVh + vrow * WM_PITCH + vcol);
-      ldsm_x4_t(vl[0], vl[1], vl[2], vl[3], sVl + vrow * WM_PITCH + vcol);
+      const uint32_t voff = ((NB0 / 2 + kk) * 16 * WM_PITCH + np * 16) * 2;
+      ldsm_x4_t_a(vh[0], vh[1], vh[2], vh[3], ad.va + voff);
+      ldsm_x4_t_a(vl[0], vl[1], vl[2], vl[3], ad.va + voff + WM_PLANE * 2);
 #pragma unroll
       for (int q2 = 0; q2 < 2; ++q2) {
         float* o = oacc[np * 2 + q2];
@@ -306,17 +328,21 @@ window_attn_mma_kernel(const uint16_t* __restrict__ qkv_hi, const uint16_t* __re
   const int Hp = nWh * WA_WS, Wp = nWw * WA_WS;
   constexpr float LOG2E = 1.4426950408889634f;
 
-  // ---- stage q/k/v planes: 144 rows x 64 B per operand plane ----
+  // ---- stage q/k/v planes: 144 rows x 64 B per operand plane = 576 16-byte chunks = 2 per thread and plane; the
+  // (row, chunk) of a thread is the same for all six planes, so the address arithmetic is done twice, not 3456 / 288 times ----
   {
-    const int64_t rowbase = win * WA_N;
-    for (int e = tid; e < 6 * WA_N * 4; e += WM_THREADS) {
-      const int chunk = e & 3;                     // 16 B chunk within the 64 B row segment
-      int t = e >> 2;
-      const int r = t % WA_N;
-      const int pl = t / WA_N;                     // 0..5
-      const int part = pl >> 1;                    // q, k, v
-      const uint16_t* src = ((pl & 1) ? qkv_lo : qkv_hi) + (rowbase + r) * (int64_t)(3 * C) + part * C + head * WA_D + chunk * 8;
-      cp_async16(sOp + pl * WM_PLANE + r * WM_PITCH + chunk * 8, src);
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sOp);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int idx = tid + half * WM_THREADS;                 // 0..575
+      const int r = idx >> 2, chunk = idx & 3;
+      const int64_t goff = (win * WA_N + r) * (int64_t)(3 * C) + head * WA_D + chunk * 8;
+      const uint32_t soff = sbase + (r * WM_PITCH + chunk * 8) * 2;
+#pragma unroll
+      for (int part = 0; part < 3; ++part) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(soff + (2 * part) * WM_PLANE * 2), "l"(qkv_hi + goff + part * C));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(soff + (2 * part + 1) * WM_PLANE * 2), "l"(qkv_lo + goff + part * C));
+      }
     }
     asm volatile("cp.async.commit_group;" ::);
   }
@@ -332,8 +358,14 @@ window_attn_mma_kernel(const uint16_t* __restrict__ qkv_hi, const uint16_t* __re
   asm volatile("cp.async.wait_group 0;" ::);
   __syncthreads();
 
-  const uint16_t* sQh = sOp, *sQl = sOp + WM_PLANE, *sKh = sOp + 2 * WM_PLANE, *sKl = sOp + 3 * WM_PLANE;
-  const uint16_t* sVh = sOp + 4 * WM_PLANE, *sVl = sOp + 5 * WM_PLANE;
+  const uint16_t* sQh = sOp, *sQl = sOp + WM_PLANE;
+  WmAddr ad;
+  {
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sOp);
+    ad.ka = sbase + (2 * WM_PLANE + (lane & 7) * WM_PITCH + (lane >> 3) * 8) * 2;
+    ad.va = sbase + (4 * WM_PLANE + ((lane & 7) + ((lane >> 3) & 1) * 8) * WM_PITCH + (lane >> 4) * 8) * 2;
+    ad.ca = (uint32_t)__cvta_generic_to_shared(sCol) + (lane & 3) * 2 * 4;
+  }
   const int g = lane >> 2, tq = lane & 3;
   const int r0 = warp * 16;
 
@@ -349,12 +381,12 @@ window_attn_mma_kernel(const uint16_t* __restrict__ qkv_hi, const uint16_t* __re
     }
   }
   int rid[2];
-  const char* sBrow[2];
+  uint32_t sBrow[2];                                  // shared-space byte address of this row's bias-table base
 #pragma unroll
   for (int hrow = 0; hrow < 2; ++hrow) {
     const int r = r0 + g + hrow * 8;
     const int ri = r / WA_WS, rj = r - ri * WA_WS;
-    sBrow[hrow] = reinterpret_cast<const char*>(sB + (ri * 23 + rj + (WA_WS - 1) * 23 + (WA_WS - 1)));
+    sBrow[hrow] = (uint32_t)__cvta_generic_to_shared(sB + (ri * 23 + rj + (WA_WS - 1) * 23 + (WA_WS - 1)));
     const int hs = wh * WA_WS + ri, wsx = ww * WA_WS + rj;
     rid[hrow] = (hs < Hp - WA_WS ? 0 : (hs < Hp - shift ? 1 : 2)) * 3 + (wsx < Wp - WA_WS ? 0 : (wsx < Wp - shift ? 1 : 2));
   }
@@ -365,12 +397,15 @@ window_attn_mma_kernel(const uint16_t* __restrict__ qkv_hi, const uint16_t* __re
   const float scale2 = scale * LOG2E;
   // only windows in the last window row / column see more than one shift region (swin.py:416-431)
   const bool need_mask = shift > 0 && (wh == nWh - 1 || ww == nWw - 1);
+  // three key chunks of 48 keys (6 n-blocks): 24 score registers per chunk keep the kernel at 96 registers without spills
   if (need_mask) {
-    wm_chunk<0, 10, true>(sKh, sKl, sVh, sVl, sBrow, sCol, sReg, qh, ql, lane, g, tq, rid, scale2, m, l, oacc);
-    wm_chunk<10, 8, true>(sKh, sKl, sVh, sVl, sBrow, sCol, sReg, qh, ql, lane, g, tq, rid, scale2, m, l, oacc);
+    wm_chunk<0, 6, true>(ad, sBrow, qh, ql, rid, scale2, m, l, oacc);
+    wm_chunk<6, 6, true>(ad, sBrow, qh, ql, rid, scale2, m, l, oacc);
+    wm_chunk<12, 6, true>(ad, sBrow, qh, ql, rid, scale2, m, l, oacc);
   } else {
-    wm_chunk<0, 10, false>(sKh, sKl, sVh, sVl, sBrow, sCol, sReg, qh, ql, lane, g, tq, rid, scale2, m, l, oacc);
-    wm_chunk<10, 8, false>(sKh, sKl, sVh, sVl, sBrow, sCol, sReg, qh, ql, lane, g, tq, rid, scale2, m, l, oacc);
+    wm_chunk<0, 6, false>(ad, sBrow, qh, ql, rid, scale2, m, l, oacc);
+    wm_chunk<6, 6, false>(ad, sBrow, qh, ql, rid, scale2, m, l, oacc);
+    wm_chunk<12, 6, false>(ad, sBrow, qh, ql, rid, scale2, m, l, oacc);
   }
   // ---- store (attn @ v).transpose(1,2).reshape(B_, N, C) as split planes ----
 #pragma unroll
