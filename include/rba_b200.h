@@ -245,9 +245,11 @@ int rba_k_window_attn_planes(const uint16_t* qkv_hi, const uint16_t* qkv_lo, con
 
 /* nn.MultiheadAttention core for the decoder (mask2former_transformer_decoder.py:52-53,110-113):
  * q [B,Lq,E], k,v [B,Lk,E] fp32 (already projected, q NOT yet scaled), mask (B,Lq,Lk) uint8 (1 = blocked, shared by
- * all heads) or NULL; out planes [B*Lq, E]. */
+ * all heads) or NULL; out planes [B*Lq, E].
+ * workspace: rba_k_mha_workspace_floats(...) floats (partials of the key splits). */
+int64_t rba_k_mha_workspace_floats(int B, int Lq, int Lk, int heads);
 int rba_k_mha(const float* q, const float* k, const float* v, const uint8_t* mask, int B, int Lq, int Lk, int E, int heads,
-              uint16_t* out_hi, uint16_t* out_lo, void* stream);
+              uint16_t* out_hi, uint16_t* out_lo, float* workspace, void* stream);
 
 /* GroupNorm(32) over token-major x [B, HW, C] (two deterministic passes) fused with what follows it in the pixel
  * decoder: y = GN(x) (+ bilinear_up(prev [B,hp,wp,C]) if prev) (relu if relu); writes fp32 and/or planes. */

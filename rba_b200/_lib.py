@@ -83,7 +83,9 @@ PROTOTYPES = {
                                 c_void_p, c_void_p, c_void_p, c_void_p]),
     "rba_k_window_attn": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "rba_k_window_attn_planes": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
-    "rba_k_mha": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "rba_k_mha_workspace_floats": (c_int64, [c_int, c_int, c_int, c_int]),
+    "rba_k_mha": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                          c_void_p]),
     "rba_k_groupnorm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int,
                                 c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rba_k_groupnorm_ws": (c_int64, [c_int, c_int, c_int, c_int, c_int]),

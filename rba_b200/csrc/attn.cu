@@ -446,73 +446,194 @@ int window_attn_planes(const uint16_t* qkv_hi, const uint16_t* qkv_lo, const flo
 // ------------------------------------------------------------------------------------------------
 // Decoder multi-head attention core (nn.MultiheadAttention, mask2former_transformer_decoder.py:52-53,110-113)
 // ------------------------------------------------------------------------------------------------
-// One warp per (b, head, query); keys are streamed in chunks of 32 (lane <-> key for the scores, lane <-> dim for
-// P.V) with an online softmax, so Lk is unbounded (2048 at 1dl, 32768 for the 3-level decoder).  head_dim = 32.
-__global__ void __launch_bounds__(256)
-mha_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
-           const uint8_t* __restrict__ mask, int B, int Lq, int Lk, int E, int heads, int64_t ldq, int64_t ldk,
-           int64_t ldv, float scale, uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo) {
-  const int lane = threadIdx.x & 31;
-  const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int64_t total = (int64_t)B * heads * Lq;
-  if (wid >= total) return;
-  const int qi = (int)(wid % Lq);
-  const int head = (int)((wid / Lq) % heads);
-  const int b = (int)(wid / ((int64_t)Lq * heads));
-  const float* qp = q + ((int64_t)b * Lq + qi) * ldq + head * 32;
+// Q = 100 queries attend to Lk keys (100 for self-attention, 2048 at 1dl, up to 32768 per image for the 3-level decoder);
+// head_dim = 32.  One CTA per (b, head, key split): a thread owns one query (its q row, running max / sum and the 32 output
+// accumulators live in registers) and the CTA streams its key range in tiles of 32 keys through a double-buffered
+// cp.async ring, so every K / V row is fetched ONCE per (b, head) and broadcast from shared memory to all queries (the
+// first version gave each (b, head, query) its own warp and re-read all keys per query: 100x the L2 traffic, 32 ms per
+// forward at Lk = 32768).  Key splits write un-normalised partials (m, l, acc[32]); a second kernel merges them.
+constexpr int MH_TK = 32;                  // keys per tile
+constexpr int MH_THREADS = 128;            // queries per CTA
+constexpr int MH_PART = 34;                // floats per partial: m, l, acc[32]
+
+__global__ void __launch_bounds__(MH_THREADS)
+mha_split_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                 const uint8_t* __restrict__ mask, int Lq, int Lk, int heads, int64_t ldq, int64_t ldk, int64_t ldv,
+                 float scale, int keys_per_split, int nsplit, float* __restrict__ part) {
+  __shared__ __align__(16) float sK[2][MH_TK * 32];
+  __shared__ __align__(16) float sV[2][MH_TK * 32];
+  const int tid = threadIdx.x;
+  const int split = blockIdx.x % nsplit;
+  const int bh = blockIdx.x / nsplit;
+  const int head = bh % heads, b = bh / heads;
+  const int qi = blockIdx.y * MH_THREADS + tid;
+  const bool qok = qi < Lq;
+  const int j_begin = split * keys_per_split;
+  const int j_end = min(Lk, j_begin + keys_per_split);
+  const int ntiles = (j_end - j_begin + MH_TK - 1) / MH_TK;
+
   float qr[32];
+  {
+    const float* qp = q + ((int64_t)b * Lq + (qok ? qi : 0)) * ldq + head * 32;
 #pragma unroll
-  for (int d4 = 0; d4 < 8; ++d4) {
-    float4 t = *reinterpret_cast<const float4*>(qp + d4 * 4);
-    qr[d4 * 4] = t.x * scale; qr[d4 * 4 + 1] = t.y * scale; qr[d4 * 4 + 2] = t.z * scale; qr[d4 * 4 + 3] = t.w * scale;
+    for (int d4 = 0; d4 < 8; ++d4) {
+      const float4 t = *reinterpret_cast<const float4*>(qp + d4 * 4);
+      qr[d4 * 4] = t.x * scale; qr[d4 * 4 + 1] = t.y * scale; qr[d4 * 4 + 2] = t.z * scale; qr[d4 * 4 + 3] = t.w * scale;
+    }
   }
   const float* kb = k + (int64_t)b * Lk * ldk + head * 32;
   const float* vb = v + (int64_t)b * Lk * ldv + head * 32;
-  const uint8_t* mrow = mask ? mask + ((int64_t)b * Lq + qi) * Lk : nullptr;
-  float m = -INFINITY, l = 0.f, acc = 0.f;
-  for (int j0 = 0; j0 < Lk; j0 += 32) {
-    const int j = j0 + lane;
-    float s = -INFINITY;
-    if (j < Lk && !(mrow && mrow[j])) {
-      const float* kr = kb + (int64_t)j * ldk;
-      float dot = 0.f;
+  const uint8_t* mrow = (mask && qok) ? mask + ((int64_t)b * Lq + qi) * Lk : nullptr;
+
+  // tile loader: 32 keys x 32 floats for K and for V = 2 x 256 16-byte chunks, two of each per thread
+  auto load_tile = [&](int t, int buf) {
+    const int j0 = j_begin + t * MH_TK;
 #pragma unroll
-      for (int d4 = 0; d4 < 8; ++d4) {
-        float4 t = *reinterpret_cast<const float4*>(kr + d4 * 4);
-        dot = fmaf(qr[d4 * 4], t.x, dot);
-        dot = fmaf(qr[d4 * 4 + 1], t.y, dot);
-        dot = fmaf(qr[d4 * 4 + 2], t.z, dot);
-        dot = fmaf(qr[d4 * 4 + 3], t.w, dot);
+    for (int h2 = 0; h2 < 2; ++h2) {
+      const int c = tid + h2 * MH_THREADS;               // 0..255
+      const int r = c >> 3, ch = c & 7;
+      const int j = min(j0 + r, Lk - 1);                 // rows past the end are clamped (their scores are discarded)
+      cp_async16(&sK[buf][r * 32 + ch * 4], kb + (int64_t)j * ldk + ch * 4);
+      cp_async16(&sV[buf][r * 32 + ch * 4], vb + (int64_t)j * ldv + ch * 4);
+    }
+    asm volatile("cp.async.commit_group;" ::);
+  };
+
+  float m = -INFINITY, l = 0.f;
+  float acc[32];
+#pragma unroll
+  for (int d = 0; d < 32; ++d) acc[d] = 0.f;
+  if (ntiles > 0) load_tile(0, 0);
+  for (int t = 0; t < ntiles; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < ntiles) {
+      load_tile(t + 1, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::);
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::);
+    }
+    __syncthreads();
+    const int j0 = j_begin + t * MH_TK;
+    // this query's mask bytes for the tile (two 16-byte loads when aligned, else bytewise)
+    uint32_t blocked = 0;                                // bit i: key j0 + i is masked or out of range
+    {
+      const int nk = min(MH_TK, j_end - j0);
+      if (nk < MH_TK) blocked = 0xffffffffu << nk;
+      if (mrow) {
+        if ((((uintptr_t)(mrow + j0)) & 15) == 0 && nk == MH_TK) {
+          const uint4 m0 = *reinterpret_cast<const uint4*>(mrow + j0), m1 = *reinterpret_cast<const uint4*>(mrow + j0 + 16);
+          const uint32_t w[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int bb = 0; bb < 4; ++bb)
+              if ((w[i] >> (8 * bb)) & 0xffu) blocked |= 1u << (4 * i + bb);
+        } else {
+          for (int i = 0; i < nk; ++i)
+            if (mrow[j0 + i]) blocked |= 1u << i;
+        }
       }
-      s = dot;
     }
-    const float cm = warp_max(s);
-    if (cm == -INFINITY) continue;           // whole chunk masked
-    const float mn = fmaxf(m, cm);
-    const float corr = (m == -INFINITY) ? 0.f : expf(m - mn);
-    const float p = (s == -INFINITY) ? 0.f : expf(s - mn);
-    l = l * corr + warp_sum(p);
-    acc *= corr;
-    const int nk = min(32, Lk - j0);
-    for (int t = 0; t < nk; ++t) {
-      const float pt = __shfl_sync(0xffffffffu, p, t);
-      acc = fmaf(pt, vb[(int64_t)(j0 + t) * ldv + lane], acc);
+    if (blocked != 0xffffffffu) {
+      float sc[MH_TK];
+      float tmax = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < MH_TK; ++i) {
+        const float4* kr = reinterpret_cast<const float4*>(&sK[buf][i * 32]);
+        float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+        for (int d4 = 0; d4 < 8; d4 += 2) {
+          const float4 a4 = kr[d4], b4 = kr[d4 + 1];
+          d0 = fmaf(qr[d4 * 4], a4.x, d0); d0 = fmaf(qr[d4 * 4 + 1], a4.y, d0);
+          d0 = fmaf(qr[d4 * 4 + 2], a4.z, d0); d0 = fmaf(qr[d4 * 4 + 3], a4.w, d0);
+          d1 = fmaf(qr[d4 * 4 + 4], b4.x, d1); d1 = fmaf(qr[d4 * 4 + 5], b4.y, d1);
+          d1 = fmaf(qr[d4 * 4 + 6], b4.z, d1); d1 = fmaf(qr[d4 * 4 + 7], b4.w, d1);
+        }
+        sc[i] = ((blocked >> i) & 1u) ? -INFINITY : d0 + d1;
+        tmax = fmaxf(tmax, sc[i]);
+      }
+      const float mn = fmaxf(m, tmax);
+      const float corr = (m == -INFINITY) ? 0.f : expf(m - mn);
+      l *= corr;
+#pragma unroll
+      for (int d = 0; d < 32; ++d) acc[d] *= corr;
+#pragma unroll
+      for (int i = 0; i < MH_TK; ++i) {
+        const float pv = (sc[i] == -INFINITY) ? 0.f : expf(sc[i] - mn);
+        l += pv;
+        const float4* vr = reinterpret_cast<const float4*>(&sV[buf][i * 32]);
+#pragma unroll
+        for (int d4 = 0; d4 < 8; ++d4) {
+          const float4 t4 = vr[d4];
+          acc[d4 * 4] = fmaf(pv, t4.x, acc[d4 * 4]); acc[d4 * 4 + 1] = fmaf(pv, t4.y, acc[d4 * 4 + 1]);
+          acc[d4 * 4 + 2] = fmaf(pv, t4.z, acc[d4 * 4 + 2]); acc[d4 * 4 + 3] = fmaf(pv, t4.w, acc[d4 * 4 + 3]);
+        }
+      }
+      m = mn;
     }
-    m = mn;
+    __syncthreads();                                     // the other buffer is overwritten by the next iteration's load
+  }
+  if (qok) {
+    float* pp = part + ((((int64_t)b * heads + head) * Lq + qi) * nsplit + split) * MH_PART;
+    pp[0] = m; pp[1] = l;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) pp[2 + d] = acc[d];
+  }
+}
+
+// merge the key splits of one (b, head, query): lane <-> output dim
+__global__ void __launch_bounds__(256)
+mha_combine_kernel(const float* __restrict__ part, int64_t rows /*B*heads*Lq*/, int Lq, int heads, int E, int nsplit,
+                   uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float* pp = part + r * nsplit * MH_PART;
+  float m = -INFINITY;
+  for (int s0 = 0; s0 < nsplit; ++s0) m = fmaxf(m, pp[s0 * MH_PART]);
+  float l = 0.f, acc = 0.f;
+  for (int s0 = 0; s0 < nsplit; ++s0) {
+    const float ms = pp[s0 * MH_PART];
+    if (ms == -INFINITY) continue;
+    const float w = expf(ms - m);
+    l = fmaf(w, pp[s0 * MH_PART + 1], l);
+    acc = fmaf(w, pp[s0 * MH_PART + 2 + lane], acc);
   }
   const float o = (l > 0.f) ? acc / l : 0.f;
-  store_split1(out_hi, out_lo, ((int64_t)b * Lq + qi) * E + head * 32 + lane, o);
+  const int qi = (int)(r % Lq);
+  const int head = (int)((r / Lq) % heads);
+  const int64_t b = r / ((int64_t)Lq * heads);
+  store_split1(out_hi, out_lo, (b * Lq + qi) * E + head * 32 + lane, o);
+}
+
+static int mha_splits(int Lk, int* keys_per_split) {
+  int kps = 512;
+  while ((Lk + kps - 1) / kps > 32) kps *= 2;           // at most 32 splits
+  *keys_per_split = kps;
+  return (Lk + kps - 1) / kps;
+}
+
+int64_t mha_workspace_floats(int B, int Lq, int Lk, int heads) {
+  int kps;
+  const int ns = mha_splits(Lk, &kps);
+  return (int64_t)B * heads * Lq * ns * MH_PART;
 }
 
 int mha(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv, const uint8_t* mask, int B,
-        int Lq, int Lk, int E, int heads, uint16_t* out_hi, uint16_t* out_lo, cudaStream_t st) {
-  RBA_CHECK(q && k && v && out_hi && out_lo, "mha: null pointer");
+        int Lq, int Lk, int E, int heads, uint16_t* out_hi, uint16_t* out_lo, float* workspace, cudaStream_t st) {
+  RBA_CHECK(q && k && v && out_hi && out_lo && workspace, "mha: null pointer");
   RBA_CHECK(heads > 0 && E == heads * 32, "mha: head_dim must be 32 (E=%d heads=%d)", E, heads);
   RBA_CHECK(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0, "mha: pitches must be multiples of 4");
+  RBA_CHECK((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v) & 15) == 0, "mha: q/k/v must be 16-byte aligned");
   const int64_t total = (int64_t)B * heads * Lq;
   if (total == 0 || Lk == 0) return RBA_OK;
-  mha_kernel<<<(unsigned)cdiv(total, 8), 256, 0, st>>>(q, k, v, mask, B, Lq, Lk, E, heads, ldq, ldk, ldv,
-                                                      1.0f / sqrtf(32.0f), out_hi, out_lo);
+  int kps;
+  const int ns = mha_splits(Lk, &kps);
+  RBA_CHECK((int64_t)B * heads * ns < (1LL << 31), "mha: grid too large");
+  const dim3 grid((unsigned)(B * heads * ns), (unsigned)cdiv(Lq, MH_THREADS));
+  mha_split_kernel<<<grid, MH_THREADS, 0, st>>>(q, k, v, mask, Lq, Lk, heads, ldq, ldk, ldv, 1.0f / sqrtf(32.0f), kps, ns, workspace);
+  RBA_LAUNCHED();
+  mha_combine_kernel<<<(unsigned)cdiv(total, 8), 256, 0, st>>>(workspace, total, Lq, heads, E, ns, out_hi, out_lo);
   RBA_LAUNCHED();
   return RBA_OK;
 }
@@ -580,9 +701,11 @@ extern "C" int rba_k_window_attn_planes(const uint16_t* qkv_hi, const uint16_t* 
   return rba::window_attn_planes(qkv_hi, qkv_lo, bias_table, B, H, W, C, heads, ws, shift, out_hi, out_lo, (cudaStream_t)stream);
 }
 
+extern "C" int64_t rba_k_mha_workspace_floats(int B, int Lq, int Lk, int heads) { return rba::mha_workspace_floats(B, Lq, Lk, heads); }
+
 extern "C" int rba_k_mha(const float* q, const float* k, const float* v, const uint8_t* mask, int B, int Lq, int Lk, int E,
-                         int heads, uint16_t* out_hi, uint16_t* out_lo, void* stream) {
-  return rba::mha(q, E, k, E, v, E, mask, B, Lq, Lk, E, heads, out_hi, out_lo, (cudaStream_t)stream);
+                         int heads, uint16_t* out_hi, uint16_t* out_lo, float* workspace, void* stream) {
+  return rba::mha(q, E, k, E, v, E, mask, B, Lq, Lk, E, heads, out_hi, out_lo, workspace, (cudaStream_t)stream);
 }
 
 extern "C" int rba_k_attn_mask(const float* masks, int B, int Q, int h, int w, int th, int tw, uint8_t* out, void* stream) {

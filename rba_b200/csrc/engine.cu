@@ -792,7 +792,8 @@ static int forward_impl(rba_model* m, const void* images, int img_dtype, int B, 
       RBA_TRY(F.lin(kin[l], D, (int64_t)B * Nl, D, w.offset((int64_t)D * D), D, bi + D, RBA_ACT_NONE, nullptr, kp, D));
       RBA_TRY(F.lin(vin[l], D, (int64_t)B * Nl, D, w.offset((int64_t)2 * D * D), D, bi + 2 * D, RBA_ACT_NONE, nullptr, vp, D));
       Planes ao = A.planes(BQ * D);
-      RBA_RUN(mha(qp, D, kp, D, vp, D, am, B, Q, (int)Nl, D, c.nheads, ao.hi, ao.lo, st));
+      float* mws = A.f32(mha_workspace_floats(B, Q, (int)Nl, c.nheads));
+      RBA_RUN(mha(qp, D, kp, D, vp, D, am, B, Q, (int)Nl, D, c.nheads, ao.hi, ao.lo, mws, st));
       float* t = A.f32(BQ * D);
       RBA_TRY(F.lin(ao, D, BQ, D, F.P(ca + "multihead_attn.out_proj.weight"), D, F.W(ca + "multihead_attn.out_proj.bias"),
                     RBA_ACT_NONE, out, t, D));
@@ -810,7 +811,8 @@ static int forward_impl(rba_model* m, const void* images, int img_dtype, int B, 
       float* vp = A.f32(BQ * D);
       RBA_TRY(F.lin(vi, D, BQ, D, w.offset((int64_t)2 * D * D), D, bi + 2 * D, RBA_ACT_NONE, nullptr, vp, D));
       Planes ao = A.planes(BQ * D);
-      RBA_RUN(mha(qkp, 2 * D, qkp + D, 2 * D, vp, D, nullptr, B, Q, Q, D, c.nheads, ao.hi, ao.lo, st));
+      float* mws = A.f32(mha_workspace_floats(B, Q, Q, c.nheads));
+      RBA_RUN(mha(qkp, 2 * D, qkp + D, 2 * D, vp, D, nullptr, B, Q, Q, D, c.nheads, ao.hi, ao.lo, mws, st));
       float* t = A.f32(BQ * D);
       RBA_TRY(F.lin(ao, D, BQ, D, F.P(sa + "self_attn.out_proj.weight"), D, F.W(sa + "self_attn.out_proj.bias"), RBA_ACT_NONE, out,
                     t, D));

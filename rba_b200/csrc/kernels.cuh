@@ -23,7 +23,8 @@ int window_attn(const float* qkv, const float* bias_table, int B, int H, int W, 
 int window_attn_planes(const uint16_t* qkv_hi, const uint16_t* qkv_lo, const float* bias_table, int B, int H, int W, int C,
                        int heads, int ws, int shift, uint16_t* out_hi, uint16_t* out_lo, cudaStream_t st);
 int mha(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv, const uint8_t* mask, int B,
-        int Lq, int Lk, int E, int heads, uint16_t* out_hi, uint16_t* out_lo, cudaStream_t st);
+        int Lq, int Lk, int E, int heads, uint16_t* out_hi, uint16_t* out_lo, float* workspace, cudaStream_t st);
+int64_t mha_workspace_floats(int B, int Lq, int Lk, int heads);
 int attn_mask(const float* masks, int B, int Q, int h, int w, int th, int tw, uint8_t* out, cudaStream_t st);
 int einsum_score_supported(int Q, int K, int D);
 int einsum_score_launch(const uint16_t* e_hi, const uint16_t* e_lo, const float* bias, const uint16_t* y_hi,

@@ -306,7 +306,8 @@ def mha(q, k, v, mask, heads):
     Lk = k.shape[1]
     hi = torch.empty((B * Lq, E), dtype=torch.bfloat16, device=q.device)
     lo = torch.empty((B * Lq, E), dtype=torch.bfloat16, device=q.device)
-    _lib.check(_lib.lib().rba_k_mha(_p(q), _p(k), _p(v), _p(mask), B, Lq, Lk, E, heads, _p(hi), _p(lo), _stream()))
+    ws = torch.empty(max(1, int(_lib.lib().rba_k_mha_workspace_floats(B, Lq, Lk, heads))), dtype=torch.float32, device=q.device)
+    _lib.check(_lib.lib().rba_k_mha(_p(q), _p(k), _p(v), _p(mask), B, Lq, Lk, E, heads, _p(hi), _p(lo), _p(ws), _stream()))
     return hi, lo
 
 

@@ -180,10 +180,11 @@ def test_window_attention(dev, H, W, shift):
     assert (unplanes(out) - ref).abs().max() < 1e-4
 
 
-@pytest.mark.parametrize("Lk,masked", [(100, False), (77, True), (2048, True)])
-def test_mha(dev, Lk, masked):
-    """nn.MultiheadAttention core as used by the decoder (mask2former_transformer_decoder.py:52-53,110-113)."""
-    B, Lq, E, heads = 2, 100, 256, 8
+@pytest.mark.parametrize("Lk,masked,Lq", [(100, False, 100), (77, True, 100), (2048, True, 100), (5000, True, 100), (40000, True, 7), (600, False, 130)])
+def test_mha(dev, Lk, masked, Lq):
+    """nn.MultiheadAttention core as used by the decoder (mask2former_transformer_decoder.py:52-53,110-113): one and many key
+    splits, ragged last tile, unaligned mask rows, more queries than one CTA holds."""
+    B, E, heads = 2, 256, 8
     g = torch.Generator().manual_seed(9)
     q, k, v = torch.randn(B, Lq, E, generator=g), torch.randn(B, Lk, E, generator=g), torch.randn(B, Lk, E, generator=g)
     mask = None

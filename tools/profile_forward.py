@@ -14,9 +14,10 @@ ap.add_argument("--batch", type=int, default=8)
 ap.add_argument("--height", type=int, default=1024)
 ap.add_argument("--width", type=int, default=2048)
 ap.add_argument("--backend", default="tc")
+ap.add_argument("--model", default="swin_b_1dl", choices=["swin_b_1dl", "swin_l_1dl", "swin_b_full"])
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
-mc = rba_b200.config.swin_b_1dl()
+mc = getattr(rba_b200.config, a.model)()
 eng = rba_b200.Engine(mc, 0).load_state_dict(weights.init_state_dict(mc, seed=0))
 eng.set_gemm_backend(a.backend)
 img = torch.randint(0, 256, (a.batch, 3, a.height, a.width), dtype=torch.uint8, device=dev)
