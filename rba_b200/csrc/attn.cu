@@ -176,6 +176,9 @@ int window_attn(const float* qkv, const float* bias_table, int B, int H, int W, 
 constexpr int WM_PITCH = 40;                         // bf16 per smem row (32 used): 80 B pitch, conflict-free ldmatrix
 constexpr int WM_PLANE = WA_N * WM_PITCH;            // one 144 x 32 operand plane
 constexpr int WM_THREADS = 288;
+#ifndef WM_CTAS_PER_SM
+#define WM_CTAS_PER_SM 2
+#endif
 
 __device__ __forceinline__ void ldsm_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const void* p) {
   unsigned a = (unsigned)__cvta_generic_to_shared(p);
@@ -309,7 +312,7 @@ __device__ __forceinline__ void wm_chunk(const WmAddr& ad, const uint32_t (&sBro
   }
 }
 
-__global__ void __launch_bounds__(WM_THREADS, 2)
+__global__ void __launch_bounds__(WM_THREADS, WM_CTAS_PER_SM)
 window_attn_mma_kernel(const uint16_t* __restrict__ qkv_hi, const uint16_t* __restrict__ qkv_lo,
                        const float* __restrict__ bias_table, int C, int heads, int nWh, int nWw, int shift, float scale,
                        uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo) {

@@ -63,6 +63,55 @@ msda_forward_kernel(const float* __restrict__ value, MsdaLevels lv, const float*
   out[idx] = acc;
 }
 
+// Same op, one thread per 4 channels (D % 4 == 0): 16-byte gathers, the location / weight loads shared by D/4 lanes.
+__global__ void __launch_bounds__(256)
+msda_forward_vec4_kernel(const float* __restrict__ value, MsdaLevels lv, const float* __restrict__ loc,
+                         const float* __restrict__ attw, int64_t total, int S, int M, int D, int Lq, int L, int P,
+                         float* __restrict__ out) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;        // over B*Lq*M*(D/4)
+  if (idx >= total) return;
+  const int D4 = D >> 2;
+  const int d = (int)(idx % D4) * 4;
+  int64_t t = idx / D4;
+  const int m = (int)(t % M);
+  t /= M;                                   // t = b*Lq + q
+  const int64_t b = t / Lq;
+  const float* vb = value + (b * S) * (int64_t)M * D + (int64_t)m * D + d;
+  const int64_t vstride = (int64_t)M * D;
+  const float* lp = loc + (t * M + m) * (int64_t)L * P * 2;
+  const float* wp = attw + (t * M + m) * (int64_t)L * P;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int l = 0; l < L; ++l) {
+    const int H = lv.H[l], W = lv.W[l];
+    const float* vl = vb + (int64_t)lv.start[l] * vstride;
+    for (int p = 0; p < P; ++p) {
+      const float x = lp[(l * P + p) * 2 + 0];
+      const float y = lp[(l * P + p) * 2 + 1];
+      const float wgt = wp[l * P + p];
+      const float h_im = y * H - 0.5f;
+      const float w_im = x * W - 0.5f;
+      if (h_im > -1.f && w_im > -1.f && h_im < H && w_im < W) {
+        const int h0 = (int)floorf(h_im), w0 = (int)floorf(w_im);
+        const float lh = h_im - h0, lw = w_im - w0;
+        const float hh = 1.f - lh, hw = 1.f - lw;
+        const int h1 = h0 + 1, w1 = w0 + 1;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 v00 = z, v01 = z, v10 = z, v11 = z;
+        if (h0 >= 0 && w0 >= 0) v00 = __ldg(reinterpret_cast<const float4*>(vl + ((int64_t)h0 * W + w0) * vstride));
+        if (h0 >= 0 && w1 <= W - 1) v01 = __ldg(reinterpret_cast<const float4*>(vl + ((int64_t)h0 * W + w1) * vstride));
+        if (h1 <= H - 1 && w0 >= 0) v10 = __ldg(reinterpret_cast<const float4*>(vl + ((int64_t)h1 * W + w0) * vstride));
+        if (h1 <= H - 1 && w1 <= W - 1) v11 = __ldg(reinterpret_cast<const float4*>(vl + ((int64_t)h1 * W + w1) * vstride));
+        const float w00 = hh * hw, w01 = hh * lw, w10 = lh * hw, w11 = lh * lw;
+        acc.x = fmaf(wgt, w00 * v00.x + w01 * v01.x + w10 * v10.x + w11 * v11.x, acc.x);
+        acc.y = fmaf(wgt, w00 * v00.y + w01 * v01.y + w10 * v10.y + w11 * v11.y, acc.y);
+        acc.z = fmaf(wgt, w00 * v00.z + w01 * v01.z + w10 * v10.z + w11 * v11.z, acc.z);
+        acc.w = fmaf(wgt, w00 * v00.w + w01 * v01.w + w10 * v10.w + w11 * v11.w, acc.w);
+      }
+    }
+  }
+  *reinterpret_cast<float4*>(out + idx * 4) = acc;
+}
+
 // Engine variant (ops/modules/ms_deform_attn.py:102-109 fused in): takes the raw output of the merged
 // sampling_offsets | attention_weights Linear, `oa` [B*Lq, M*L*P*3] = offsets (M,L,P,2) then logits (M,L,P),
 // applies softmax over L*P, builds sampling locations from the encoder reference points of
@@ -275,9 +324,15 @@ extern "C" int rba_msda_forward(const float* value, const int64_t* spatial_shape
     total_s += (int64_t)lv.H[l] * lv.W[l];
   }
   RBA_CHECK(total_s == S, "rba_msda_forward: sum(H*W)=%lld != S=%d", (long long)total_s, S);
-  const int64_t total = (int64_t)B * Lq * M * D;
-  msda_forward_kernel<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      value, lv, sampling_loc, attn_weight, total, S, M, D, Lq, L, P, out);
+  if (D % 4 == 0 && ((((uintptr_t)value) | ((uintptr_t)out)) & 15) == 0) {
+    const int64_t total = (int64_t)B * Lq * M * (D / 4);
+    msda_forward_vec4_kernel<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        value, lv, sampling_loc, attn_weight, total, S, M, D, Lq, L, P, out);
+  } else {
+    const int64_t total = (int64_t)B * Lq * M * D;
+    msda_forward_kernel<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        value, lv, sampling_loc, attn_weight, total, S, M, D, Lq, L, P, out);
+  }
   RBA_LAUNCHED();
   return RBA_OK;
 }
