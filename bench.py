@@ -172,6 +172,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL writes its version banner (NCCL_DEBUG=VERSION/INFO) to stdout by default: keep stdout for the ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     mc = model_config(args.model)
     B, H, W = args.batch, args.height, args.width
