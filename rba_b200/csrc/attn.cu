@@ -176,6 +176,7 @@ int window_attn(const float* qkv, const float* bias_table, int B, int H, int W, 
 constexpr int WM_PITCH = 40;                         // bf16 per smem row (32 used): 80 B pitch, conflict-free ldmatrix
 constexpr int WM_PLANE = WA_N * WM_PITCH;            // one 144 x 32 operand plane
 constexpr int WM_THREADS = 288;
+constexpr int WM_BIAS_PITCH = 532;                   // floats per head in the prepared bias table (529 padded to 16 bytes)
 #ifndef WM_CTAS_PER_SM
 #define WM_CTAS_PER_SM 2
 #endif
@@ -314,8 +315,8 @@ __device__ __forceinline__ void wm_chunk(const WmAddr& ad, const uint32_t (&sBro
 
 __global__ void __launch_bounds__(WM_THREADS, WM_CTAS_PER_SM)
 window_attn_mma_kernel(const uint16_t* __restrict__ qkv_hi, const uint16_t* __restrict__ qkv_lo,
-                       const float* __restrict__ bias_table, int C, int heads, int nWh, int nWw, int shift, float scale,
-                       uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo) {
+                       const float* __restrict__ bias_table, const float* __restrict__ bias_t, int C, int heads, int nWh,
+                       int nWw, int shift, float scale, uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo) {
   extern __shared__ __align__(16) uint8_t wm_smem[];
   // planes: 0 q_hi, 1 q_lo, 2 k_hi, 3 k_lo, 4 v_hi, 5 v_lo
   uint16_t* sOp = reinterpret_cast<uint16_t*>(wm_smem);
@@ -349,7 +350,16 @@ window_attn_mma_kernel(const uint16_t* __restrict__ qkv_hi, const uint16_t* __re
     }
     asm volatile("cp.async.commit_group;" ::);
   }
-  for (int e = tid; e < 23 * 23; e += WM_THREADS) sB[e] = bias_table[(int64_t)e * heads + head] * LOG2E;
+  // relative-position bias of this head, in the log2 domain.  Prepared form (engine): [heads][WM_BIAS_PITCH] already scaled
+  // by log2(e), contiguous per head -> 133 16-byte cp.async in the same group as the operand planes.  Raw form (the
+  // reference's (529, heads) table, per-kernel entry point): strided loads, which stall every CTA for a global round trip
+  // (ncu: 16 % of the kernel's stall samples sat on this loop).
+  if (bias_t) {
+    for (int c = tid; c < WM_BIAS_PITCH / 4; c += WM_THREADS) cp_async16(sB + c * 4, bias_t + (int64_t)head * WM_BIAS_PITCH + c * 4);
+    asm volatile("cp.async.commit_group;" ::);
+  } else {
+    for (int e = tid; e < 23 * 23; e += WM_THREADS) sB[e] = bias_table[(int64_t)e * heads + head] * LOG2E;
+  }
   for (int c = tid; c < WA_N; c += WM_THREADS) {
     const int ci = c / WA_WS, cj = c - ci * WA_WS;
     const int hs = wh * WA_WS + ci, wsx = ww * WA_WS + cj;
@@ -360,6 +370,10 @@ window_attn_mma_kernel(const uint16_t* __restrict__ qkv_hi, const uint16_t* __re
   }
   asm volatile("cp.async.wait_group 0;" ::);
   __syncthreads();
+  if (scale < 0.f) {                                   // RBA_WA_DEBUG=1 (profiling aid): loads + tables only, no attention
+    if (tid == 0) out_hi[win * WA_N * (int64_t)C + head * WA_D] = sOp[0];
+    return;
+  }
 
   const uint16_t* sQh = sOp, *sQl = sOp + WM_PLANE;
   WmAddr ad;
@@ -426,9 +440,25 @@ window_attn_mma_kernel(const uint16_t* __restrict__ qkv_hi, const uint16_t* __re
   }
 }
 
-int window_attn_planes(const uint16_t* qkv_hi, const uint16_t* qkv_lo, const float* bias_table, int B, int H, int W, int C,
-                       int heads, int ws, int shift, uint16_t* out_hi, uint16_t* out_lo, cudaStream_t st) {
-  RBA_CHECK(qkv_hi && qkv_lo && bias_table && out_hi && out_lo, "window_attn_planes: null pointer");
+__global__ void window_attn_prepare_bias_kernel(const float* __restrict__ table, int heads, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= heads * WM_BIAS_PITCH) return;
+  const int h = i / WM_BIAS_PITCH, e = i - h * WM_BIAS_PITCH;
+  out[i] = e < 23 * 23 ? table[(int64_t)e * heads + h] * 1.4426950408889634f : 0.f;
+}
+
+int window_attn_bias_floats(int heads) { return heads * WM_BIAS_PITCH; }
+
+int window_attn_prepare_bias(const float* table, int heads, float* out, cudaStream_t st) {
+  RBA_CHECK(table && out && heads > 0, "window_attn_prepare_bias: bad arguments");
+  window_attn_prepare_bias_kernel<<<(unsigned)cdiv(heads * WM_BIAS_PITCH, 256), 256, 0, st>>>(table, heads, out);
+  return RBA_OK;
+}
+
+int window_attn_planes(const uint16_t* qkv_hi, const uint16_t* qkv_lo, const float* bias_table, const float* bias_prepared,
+                       int B, int H, int W, int C, int heads, int ws, int shift, uint16_t* out_hi, uint16_t* out_lo,
+                       cudaStream_t st) {
+  RBA_CHECK(qkv_hi && qkv_lo && (bias_table || bias_prepared) && out_hi && out_lo, "window_attn_planes: null pointer");
   RBA_CHECK(ws == WA_WS, "window_attn_planes: only window_size 12 is built (got %d)", ws);
   RBA_CHECK(heads > 0 && C == heads * WA_D, "window_attn_planes: head_dim must be 32 (C=%d heads=%d)", C, heads);
   RBA_CHECK(shift >= 0 && shift < ws, "window_attn_planes: bad shift %d", shift);
@@ -440,8 +470,9 @@ int window_attn_planes(const uint16_t* qkv_hi, const uint16_t* qkv_lo, const flo
   RBA_CUDA(cudaFuncSetAttribute(window_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   RBA_CHECK(nwin * heads < (1LL << 31), "window_attn_planes: grid too large");
   dim3 grid((unsigned)(nwin * heads));
-  window_attn_mma_kernel<<<grid, WM_THREADS, smem, st>>>(qkv_hi, qkv_lo, bias_table, C, heads, g.nWh, g.nWw, shift,
-                                                         1.0f / sqrtf((float)WA_D), out_hi, out_lo);
+  static const bool dbg_loads_only = []() { const char* e = getenv("RBA_WA_DEBUG"); return e && e[0] == '1'; }();
+  window_attn_mma_kernel<<<grid, WM_THREADS, smem, st>>>(qkv_hi, qkv_lo, bias_table, bias_prepared, C, heads, g.nWh, g.nWw, shift,
+                                                         (dbg_loads_only ? -1.0f : 1.0f) / sqrtf((float)WA_D), out_hi, out_lo);
   RBA_LAUNCHED();
   return RBA_OK;
 }
@@ -701,7 +732,7 @@ extern "C" int rba_k_window_attn(const float* qkv, const float* bias_table, int 
 extern "C" int rba_k_window_attn_planes(const uint16_t* qkv_hi, const uint16_t* qkv_lo, const float* bias_table, int B, int H,
                                         int W, int C, int heads, int ws, int shift, uint16_t* out_hi, uint16_t* out_lo,
                                         void* stream) {
-  return rba::window_attn_planes(qkv_hi, qkv_lo, bias_table, B, H, W, C, heads, ws, shift, out_hi, out_lo, (cudaStream_t)stream);
+  return rba::window_attn_planes(qkv_hi, qkv_lo, bias_table, nullptr, B, H, W, C, heads, ws, shift, out_hi, out_lo, (cudaStream_t)stream);
 }
 
 extern "C" int64_t rba_k_mha_workspace_floats(int B, int Lq, int Lk, int heads) { return rba::mha_workspace_floats(B, Lq, Lk, heads); }

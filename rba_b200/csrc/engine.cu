@@ -266,7 +266,17 @@ extern "C" int rba_model_finalize(rba_model* m) {
       std::string p = "backbone.layers." + std::to_string(i) + ".blocks." + std::to_string(j) + ".";
       RBA_TRY(need(m, p + "norm1.weight", {C}));
       RBA_TRY(need(m, p + "norm1.bias", {C}));
-      RBA_TRY(need(m, p + "attn.relative_position_bias_table", {23 * 23, c.num_heads[i]}));
+      const DevTensor* rpb;
+      RBA_TRY(need(m, p + "attn.relative_position_bias_table", {23 * 23, c.num_heads[i]}, &rpb));
+      {  // head-major, log2(e)-scaled copy for the tensor-core attention kernel (one contiguous cp.async burst per CTA)
+        float* prep;
+        RBA_TRY(m->dmalloc(&prep, (size_t)window_attn_bias_floats(c.num_heads[i])));
+        RBA_TRY(window_attn_prepare_bias(rpb->d, c.num_heads[i], prep, nullptr));
+        DevTensor pt = *rpb;
+        pt.d = prep;
+        pt.numel = window_attn_bias_floats(c.num_heads[i]);
+        m->w[p + "attn.relative_position_bias_prepared"] = pt;
+      }
       RBA_TRY(linear_planes(m, p + "attn.qkv.weight", 3 * C, C));
       RBA_TRY(need(m, p + "attn.qkv.bias", {3 * C}));
       RBA_TRY(linear_planes(m, p + "attn.proj.weight", C, C));
@@ -543,7 +553,8 @@ static int forward_impl(rba_model* m, const void* images, int img_dtype, int B, 
         Planes qkv = A.planes(RW * 3 * C);
         RBA_TRY(F.lin(a1, C, RW, C, F.P(p + "attn.qkv.weight"), 3 * C, F.W(p + "attn.qkv.bias"), RBA_ACT_NONE, nullptr, nullptr, 0,
                       qkv, 3 * C));
-        RBA_RUN(window_attn_planes(qkv.hi, qkv.lo, F.W(p + "attn.relative_position_bias_table"), B, Hs, Wsz, C, heads, ws, shift,
+        RBA_RUN(window_attn_planes(qkv.hi, qkv.lo, F.W(p + "attn.relative_position_bias_table"),
+                                   F.W(p + "attn.relative_position_bias_prepared"), B, Hs, Wsz, C, heads, ws, shift,
                                    ao.hi, ao.lo, st));
       } else {
         float* qkv = A.f32(RW * 3 * C);
