@@ -318,3 +318,35 @@ def test_densehybrid_head_matches_reference_golden(dev):
         plain([{"image": imgs[0].to(dev)}], return_ood_pred=True)
     with pytest.raises(rba_b200.RbaError):
         plain.score([{"image": imgs[0].to(dev)}], "dense_hybrid")
+
+
+def test_full_size_properties_swin_b_1024x2048(dev):
+    """BASELINE.json's full size (Swin-B 1dl, 1024 x 2048), where the CPU oracle would take minutes per image: size-independent
+    properties instead.  (1) the fused score equals the reference caller's own arithmetic on the materialised sem_seg
+    (evaluate_ood.py:148-150); (2) the two routes to the score (mask einsum fused into the score kernel vs stored pred_masks
+    -> Variant-B score kernel) agree; (3) images are independent units: permuting the batch permutes the result bitwise;
+    (4) the tensor-core and the fp32 CUDA-core backends agree within the parity bar; (5) every score is finite and inside the
+    range of -sum_c tanh (-K, 0]."""
+    mc = rba_b200.config.swin_b_1dl()
+    sd = weights.init_state_dict(mc, seed=0, perturb=0.02)
+    e = _engine(mc, sd, dev)
+    e.set_gemm_backend("tc")
+    g = torch.Generator().manual_seed(21)
+    imgs = torch.randint(0, 256, (2, 3, 1024, 2048), dtype=torch.uint8, generator=g).to(dev)
+    out = e.forward(imgs, rba=True, sem_seg=True)
+    rba, sem = out["rba"], out["sem_seg"]
+    assert torch.isfinite(rba).all() and float(rba.max()) <= 1e-6 and float(rba.min()) > -mc.num_classes - 1e-3
+    assert (rba - (-sem.tanh().sum(1))).abs().max() < 5e-5                      # (1)
+    del sem, out
+    out2 = e.forward(imgs, rba=True, masks=True)                                 # pred_masks requested -> un-fused route
+    assert (out2["rba"] - rba).abs().max() < 2e-4                                # (2)
+    del out2
+    flipped = e.forward(imgs.flip(0).contiguous(), rba=True)["rba"]
+    assert torch.equal(flipped.flip(0), rba)                                     # (3)
+    del flipped
+    e.set_gemm_backend("ffma")
+    ref = e.forward(imgs[:1].contiguous(), rba=True, logits=True)
+    e.set_gemm_backend("tc")
+    tc = e.forward(imgs[:1].contiguous(), rba=True, logits=True)
+    assert (tc["pred_logits"] - ref["pred_logits"]).abs().max() < TOL           # (4)
+    assert (tc["rba"] - ref["rba"]).abs().max() < TOL
