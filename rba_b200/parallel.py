@@ -58,3 +58,51 @@ def score_sharded(score_fn, images, rank=None, world=None, group=None, batch=8):
         ref = images[0]
         local = torch.zeros((0, ref.shape[-2], ref.shape[-1]), dtype=torch.float32, device=ref.device)
     return gather_scores(local, len(images), rank, world, group)
+
+
+class OverlappedGather:
+    """The path's one collective, taken off the critical path: the all-gather of step i's score maps runs on a side stream
+    while step i+1's forward runs on the compute stream.  `submit(local)` snapshots the (n_local, H, W) maps into one of two
+    staging buffers (a 20 us device copy, so the producer may overwrite its output at once) and launches
+    `all_gather_into_tensor` on the side stream; `wait()` makes the current stream wait for everything submitted;
+    `submit` returns the (world * n_local, H, W) result tensor of that submission (valid after `wait()`, until the
+    submission after next reuses it)."""
+
+    def __init__(self, shape, device, dtype=torch.float32, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.stage = [torch.empty(shape, dtype=dtype, device=device) for _ in range(2)]
+        self.out = [torch.empty((self.world * shape[0],) + tuple(shape[1:]), dtype=dtype, device=device) for _ in range(2)]
+        self.stream = torch.cuda.Stream(device) if device.type == "cuda" else None
+        self.ev_ready = [torch.cuda.Event(), torch.cuda.Event()] if self.stream else None
+        self.ev_done = [torch.cuda.Event(), torch.cuda.Event()] if self.stream else None
+        self.n = 0
+
+    def submit(self, local):
+        k = self.n & 1
+        if self.stream is None:                       # CPU tensors (gloo tests): synchronous
+            self.stage[k].copy_(local)
+            if self.world > 1:
+                dist.all_gather_into_tensor(self.out[k], self.stage[k], group=self.group)
+            else:
+                self.out[k].copy_(self.stage[k])
+            self.n += 1
+            return self.out[k]
+        comp = torch.cuda.current_stream(local.device)
+        if self.n >= 2:
+            comp.wait_event(self.ev_done[k])          # the all-gather that last read stage[k]
+        self.stage[k].copy_(local, non_blocking=True)
+        self.ev_ready[k].record(comp)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(self.ev_ready[k])
+            if self.world > 1:
+                dist.all_gather_into_tensor(self.out[k], self.stage[k], group=self.group)
+            else:
+                self.out[k].copy_(self.stage[k], non_blocking=True)
+            self.ev_done[k].record(self.stream)
+        self.n += 1
+        return self.out[k]
+
+    def wait(self):
+        if self.stream is not None:
+            torch.cuda.current_stream(self.stage[0].device).wait_stream(self.stream)

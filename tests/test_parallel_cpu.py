@@ -34,6 +34,38 @@ def _worker(rank, world, port, n_items, q):
     dist.destroy_process_group()
 
 
+def _worker_og(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    og = parallel.OverlappedGather((2, 3, 4), torch.device("cpu"))
+    outs = []
+    for step in range(3):                                # three submissions through the two staging buffers
+        local = torch.full((2, 3, 4), float(10 * step + rank))
+        outs.append(og.submit(local).clone())
+    og.wait()
+    q.put((rank, torch.stack(outs)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_overlapped_gather_gloo():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_worker_og, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank in (0, 1):
+        for step in range(3):
+            want = torch.cat([torch.full((2, 3, 4), float(10 * step + r)) for r in range(world)])
+            assert torch.equal(res[rank][step], want)
+
+
 def _run(n_items):
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
