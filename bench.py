@@ -173,9 +173,20 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL writes its version banner (NCCL_DEBUG=VERSION/INFO) to stdout by default: keep stdout for the ONE JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner to stdout (NCCL_DEBUG=VERSION/WARN in this image): stdout must carry only the ONE
+        # JSON line, so file descriptor 1 points at stderr while the communicator is created and warmed up
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     mc = model_config(args.model)
     B, H, W = args.batch, args.height, args.width
     sd = weights.init_state_dict(mc, seed=0)
@@ -190,7 +201,6 @@ def run_ours(args):
     host_imgs = [torch.randint(0, 256, (B, 3, H, W), dtype=torch.uint8, generator=g).pin_memory() for _ in range(2)]
     dev_imgs = [h.to(dev) for h in host_imgs]
     host_out = torch.empty((B, H, W), dtype=torch.float32).pin_memory()
-    gathered = torch.empty((world * B, H, W), dtype=torch.float32, device=dev) if world > 1 else None
     from rba_b200.parallel import OverlappedGather
     og = OverlappedGather((B, H, W), dev) if world > 1 else None      # the all-gather of step i overlaps the forward of step i+1
 
@@ -224,7 +234,7 @@ def run_ours(args):
 
     # e2e: the public streaming call (rba_b200.ScoreStream): pinned H2D of batch i+1, forward of batch i and D2H of the
     # scores of batch i-1 run on three streams; every step copies its own inputs in and its own results out
-    post = (lambda out: dist.all_gather_into_tensor(gathered, out["rba"])) if world > 1 else None
+    post = (lambda out: og.submit(out["rba"])) if world > 1 else None
     stream = rba_b200.ScoreStream(eng, B, H, W, use_graph=use_graph, post_forward=post)
 
     def timed_e2e(warmup, steps):
@@ -244,6 +254,8 @@ def run_ours(args):
                 chk += float(r[0, 0, 0])                         # the caller reads the scores every step
         for r in stream.drain():                                 # blocks until the last D2H has landed
             chk += float(r[0, 0, 0])
+        if og is not None:
+            og.wait()
         e1.record()
         torch.cuda.synchronize()
         assert chk == chk, "non-finite scores on the host"
