@@ -327,15 +327,22 @@ def run_ours(args):
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     # DRAM traffic of this kernel from the committed `ncu --set full` capture (dram__bytes_read.sum + dram__bytes_write.sum,
     # per image; profiles/r1_fused_score_traffic.json), scaled to this launch's batch
-    traffic = None
+    traffic, issue = None, None
     tp = os.path.join(ROOT, "profiles", "r1_fused_score_traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp))["dram_bytes_per_image"] * B
+        cap = json.load(open(tp))
+        traffic = cap["dram_bytes_per_image"] * B
+        if "warp_instructions_per_image" in cap:
+            # the resource that actually binds this kernel: warp-instruction issue (4 schedulers x 1 instruction / clk / SM)
+            sm_clock_hz = 1e6 * float(peaks.get("sm_max_mhz", 1965.0))
+            floor_ms = cap["warp_instructions_per_image"] * B / (4.0 * 148 * sm_clock_hz) * 1e3
+            issue = {"warp_instructions_per_launch": cap["warp_instructions_per_image"] * B, "floor_ms": floor_ms,
+                     "frac": floor_ms / k_ms, "source": "smsp__inst_executed.sum of the committed ncu capture, at sm_max_mhz"}
     roofline = {"kernel": "rba_einsum_score_kernel (tcgen05 mask einsum -> x4 bilinear on tf32 MMA -> sigmoid -> (Q,K) contraction "
                           "on f16 hi/lo MMA -> tanh -> class sum; one HBM pass)", "bound": "hbm",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst, kernel timed alone)" if peaks else "fallback 6.65 TB/s",
-                "traffic": traffic, "ms_per_launch": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "traffic": traffic, "ms_per_launch": k_ms, "algorithmic_bytes_per_launch": alg_bytes, "issue_bound": issue,
                 "note": "fp32 semantics make this kernel issue/MUFU-bound, not HBM-bound (SURVEY §0.5): per output pixel "
                         "Q sigmoids of individually interpolated logits (2 MUFU each) + 2*K*Q contraction FLOP vs 68 B"}
 
