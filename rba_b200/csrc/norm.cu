@@ -265,15 +265,26 @@ gn_stats_kernel(const float* __restrict__ x, int64_t x_bs, int HW, int C, int gr
 __global__ void __launch_bounds__(256)
 gn_finalize_kernel(const double* __restrict__ part, int nchunks, int groups, int64_t count, float eps,
                    float* __restrict__ mean_rstd) {
-  // grid: B; block: groups threads
-  const int b = blockIdx.x, g = threadIdx.x;
-  if (g >= groups) return;
+  // grid: B; 256 threads = (256 / groups) slices x groups: slice s adds chunks s, s + S, ... in order, then thread g adds the S
+  // slice sums in order -- a fixed summation tree, independent of the batch size (deterministic, batch-invariant)
+  __shared__ double sh[2][256];
+  const int b = blockIdx.x;
+  const int S = 256 / groups;
+  const int g = threadIdx.x % groups, sl = threadIdx.x / groups;
   double s = 0.0, q = 0.0;
-  for (int c = 0; c < nchunks; ++c) {
-    const double* p = part + (((int64_t)b * nchunks + c) * groups + g) * 2;
-    s += p[0];
-    q += p[1];
+  if (sl < S) {
+    for (int c = sl; c < nchunks; c += S) {
+      const double* p = part + (((int64_t)b * nchunks + c) * groups + g) * 2;
+      s += p[0];
+      q += p[1];
+    }
   }
+  sh[0][threadIdx.x] = s;
+  sh[1][threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.x >= groups) return;
+  s = 0.0; q = 0.0;
+  for (int k = 0; k < S; ++k) { s += sh[0][k * groups + g]; q += sh[1][k * groups + g]; }
   double mean = s / (double)count;
   double var = q / (double)count - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -292,51 +303,70 @@ __device__ __forceinline__ void bilin_coeff(int o, int in, int out, int& i0, int
   l1 = src - (float)i0;
 }
 
+// One CTA iteration covers 256 / (C/4) consecutive pixels x all channel quads; the (pixel-in-group, quad) split of a thread,
+// its gamma / beta and all strides are fixed for the kernel, and each thread keeps UNR pixels in flight.  (The first version
+// decomposed a flat 64-bit element index with three divisions per float4 and had one load in flight per thread: 2x off the
+// HBM floor on the 1/4-resolution FPN level.)
+template <bool PREV, int UNR>
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const float* __restrict__ x, int64_t x_bs, const float* __restrict__ gamma,
                 const float* __restrict__ beta, const float* __restrict__ mean_rstd, int B, int H, int W, int C,
                 int groups, const float* __restrict__ prev, int64_t prev_bs, int hp, int wp, int relu,
                 float* __restrict__ y, uint16_t* __restrict__ y_hi, uint16_t* __restrict__ y_lo, int64_t y_bs) {
   const int cq_n = C >> 2;
-  const int64_t total = (int64_t)B * H * W * cq_n;
-  const int cpg = C / groups;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int cq = (int)(i % cq_n);
-    int64_t pix = i / cq_n;
-    const int xw = (int)(pix % W);
-    int64_t t = pix / W;
-    const int yh = (int)(t % H);
-    const int b = (int)(t / H);
-    const int c = 4 * cq;
-    const int g = c / cpg;
-    const float mean = mean_rstd[((int64_t)b * groups + g) * 2], rstd = mean_rstd[((int64_t)b * groups + g) * 2 + 1];
-    const int64_t inb = (int64_t)(yh * W + xw) * C + c;          // offset inside the image
-    float4 v = *reinterpret_cast<const float4*>(x + (int64_t)b * x_bs + inb);
-    float4 gm = *reinterpret_cast<const float4*>(gamma + c);
-    float4 bt = *reinterpret_cast<const float4*>(beta + c);
-    float4 o;
-    o.x = (v.x - mean) * rstd * gm.x + bt.x;
-    o.y = (v.y - mean) * rstd * gm.y + bt.y;
-    o.z = (v.z - mean) * rstd * gm.z + bt.z;
-    o.w = (v.w - mean) * rstd * gm.w + bt.w;
-    if (prev) {
-      int y0, y1, x0, x1; float ly, lx;
-      bilin_coeff(yh, hp, H, y0, y1, ly);
-      bilin_coeff(xw, wp, W, x0, x1, lx);
-      const float* pb = prev + (int64_t)b * prev_bs + c;
-      float4 p00 = *reinterpret_cast<const float4*>(pb + ((int64_t)y0 * wp + x0) * C);
-      float4 p01 = *reinterpret_cast<const float4*>(pb + ((int64_t)y0 * wp + x1) * C);
-      float4 p10 = *reinterpret_cast<const float4*>(pb + ((int64_t)y1 * wp + x0) * C);
-      float4 p11 = *reinterpret_cast<const float4*>(pb + ((int64_t)y1 * wp + x1) * C);
-      const float hy = 1.f - ly, hx = 1.f - lx;
-      o.x += hy * (hx * p00.x + lx * p01.x) + ly * (hx * p10.x + lx * p11.x);
-      o.y += hy * (hx * p00.y + lx * p01.y) + ly * (hx * p10.y + lx * p11.y);
-      o.z += hy * (hx * p00.z + lx * p01.z) + ly * (hx * p10.z + lx * p11.z);
-      o.w += hy * (hx * p00.w + lx * p01.w) + ly * (hx * p10.w + lx * p11.w);
+  const int ppi = 256 / cq_n;                            // pixels per CTA iteration
+  const int cq = threadIdx.x % cq_n, pl = threadIdx.x / cq_n;
+  if (pl >= ppi) return;
+  const int c = 4 * cq;
+  const int g = c / (C / groups);
+  const int HW = H * W;
+  const int npix = B * HW;                               // < 2^31 (checked by the launcher)
+  const float4 gm = *reinterpret_cast<const float4*>(gamma + c);
+  const float4 bt = *reinterpret_cast<const float4*>(beta + c);
+  const int step = gridDim.x * ppi;
+  for (int p0 = blockIdx.x * ppi + pl; p0 < npix; p0 += step * UNR) {
+    float4 v[UNR];
+    int bb[UNR], rem[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int p = p0 + u * step;
+      bb[u] = -1;
+      if (p < npix) {
+        bb[u] = p / HW;
+        rem[u] = p - bb[u] * HW;
+        v[u] = *reinterpret_cast<const float4*>(x + (int64_t)bb[u] * x_bs + (int64_t)rem[u] * C + c);
+      }
     }
-    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-    if (y) *reinterpret_cast<float4*>(y + (int64_t)b * y_bs + inb) = o;
-    if (y_hi) store_split4(y_hi, y_lo, (int64_t)b * y_bs + inb, o.x, o.y, o.z, o.w);
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      if (bb[u] < 0) continue;
+      const float2 mr = *reinterpret_cast<const float2*>(mean_rstd + ((int64_t)bb[u] * groups + g) * 2);
+      float4 o;
+      o.x = (v[u].x - mr.x) * mr.y * gm.x + bt.x;
+      o.y = (v[u].y - mr.x) * mr.y * gm.y + bt.y;
+      o.z = (v[u].z - mr.x) * mr.y * gm.z + bt.z;
+      o.w = (v[u].w - mr.x) * mr.y * gm.w + bt.w;
+      if (PREV) {
+        const int yh = rem[u] / W, xw = rem[u] - yh * W;
+        int y0, y1, x0, x1; float ly, lx;
+        bilin_coeff(yh, hp, H, y0, y1, ly);
+        bilin_coeff(xw, wp, W, x0, x1, lx);
+        const float* pb = prev + (int64_t)bb[u] * prev_bs + c;
+        const float4 p00 = *reinterpret_cast<const float4*>(pb + ((int64_t)y0 * wp + x0) * C);
+        const float4 p01 = *reinterpret_cast<const float4*>(pb + ((int64_t)y0 * wp + x1) * C);
+        const float4 p10 = *reinterpret_cast<const float4*>(pb + ((int64_t)y1 * wp + x0) * C);
+        const float4 p11 = *reinterpret_cast<const float4*>(pb + ((int64_t)y1 * wp + x1) * C);
+        const float hy = 1.f - ly, hx = 1.f - lx;
+        o.x += hy * (hx * p00.x + lx * p01.x) + ly * (hx * p10.x + lx * p11.x);
+        o.y += hy * (hx * p00.y + lx * p01.y) + ly * (hx * p10.y + lx * p11.y);
+        o.z += hy * (hx * p00.z + lx * p01.z) + ly * (hx * p10.z + lx * p11.z);
+        o.w += hy * (hx * p00.w + lx * p01.w) + ly * (hx * p10.w + lx * p11.w);
+      }
+      if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+      const int64_t ob = (int64_t)bb[u] * y_bs + (int64_t)rem[u] * C + c;
+      if (y) *reinterpret_cast<float4*>(y + ob) = o;
+      if (y_hi) store_split4(y_hi, y_lo, ob, o.x, o.y, o.z, o.w);
+    }
   }
 }
 
@@ -362,10 +392,15 @@ int groupnorm(const float* x, int64_t x_bs, const float* gamma, const float* bet
   RBA_LAUNCHED();
   gn_finalize_kernel<<<B, 256, 0, st>>>(part, nchunks, groups, (int64_t)HW * (C / groups), eps, mean_rstd);
   RBA_LAUNCHED();
-  const int64_t total = (int64_t)B * HW * (C / 4);
-  int blocks = (int)std::min<int64_t>(cdiv(total, 256), 148 * 16);
-  gn_apply_kernel<<<blocks, 256, 0, st>>>(x, x_bs, gamma, beta, mean_rstd, B, H, W, C, groups, prev, prev_bs, hp, wp, relu, y,
-                                         y_hi, y_lo, y_bs);
+  RBA_CHECK((int64_t)B * HW < (1LL << 31), "groupnorm: too many pixels");
+  const int ppi = 256 / (C / 4);
+  int blocks = (int)std::min<int64_t>(cdiv((int64_t)B * HW, ppi), 148 * 8);
+  if (prev)
+    gn_apply_kernel<true, 2><<<blocks, 256, 0, st>>>(x, x_bs, gamma, beta, mean_rstd, B, H, W, C, groups, prev, prev_bs, hp, wp,
+                                                    relu, y, y_hi, y_lo, y_bs);
+  else
+    gn_apply_kernel<false, 4><<<blocks, 256, 0, st>>>(x, x_bs, gamma, beta, mean_rstd, B, H, W, C, groups, prev, prev_bs, hp, wp,
+                                                     relu, y, y_hi, y_lo, y_bs);
   RBA_LAUNCHED();
   return RBA_OK;
 }
