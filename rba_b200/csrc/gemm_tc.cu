@@ -438,7 +438,10 @@ static int launch_tc3(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CU
   return RBA_OK;
 }
 
-static const bool g_tc_bn256 = []() { const char* e = getenv("RBA_TC_BN256"); return e && e[0] == '1'; }();
+// 256-wide N tiles halve the A-operand shared-memory reads per MAC.  Under sustained (board-power-capped) load they gain
+// 4-7 % on the K >= 1024 shapes and lose on K = 512 / 128 (profiles/r1e_gemm_power_sustained.txt): RBA_TC_BN256 = 0 never,
+// 1 always (when N % 256 == 0), 2 (default) for K >= 1024.
+static const int g_tc_bn256 = []() { const char* e = getenv("RBA_TC_BN256"); return e ? atoi(e) : 2; }();
 static const int g_tc_stg_maxk = []() { const char* e = getenv("RBA_TC_STG_MAXK"); return e ? atoi(e) : 512; }();
 
 template <int BN, bool CONV, int ACT, bool OUTP>
@@ -491,7 +494,7 @@ int gemm_tc_launch(const rba_gemm_args& a, cudaStream_t st) {
   p.a_batched = a.batch > 1 && a.a_bstride != 0;
   p.w_batched = a.batch > 1 && a.w_bstride != 0;
   int BN = a.N > 64 ? 128 : 64;
-  if (a.N % 256 == 0 && g_tc_bn256) BN = 256;
+  if (a.N % 256 == 0 && (g_tc_bn256 == 1 || (g_tc_bn256 == 2 && a.K >= 1024))) BN = 256;
   CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
   RBA_TRY_(make_map_3d(&ta_hi, a.a_hi, a.K, a.M, a.lda, p.a_batched ? a.batch : 1, a.a_bstride, TC_BM));
   RBA_TRY_(make_map_3d(&ta_lo, a.a_lo, a.K, a.M, a.lda, p.a_batched ? a.batch : 1, a.a_bstride, TC_BM));

@@ -493,7 +493,7 @@ TC_TOL = 2e-4
 
 
 @pytest.mark.parametrize("M,N,K", [(300, 20, 256), (129, 96, 128), (1000, 384, 64), (5, 1, 256), (257, 130, 2304),
-                                   (128, 128, 32), (700, 512, 512)])
+                                   (128, 128, 32), (700, 512, 512), (300, 512, 1024), (129, 256, 2048)])   # last two: 256-wide N tiles
 @pytest.mark.parametrize("act", [ops.RBA_ACT_NONE, ops.RBA_ACT_GELU])
 def test_gemm_tc(dev, M, N, K, act):
     g = torch.Generator().manual_seed(M + N + K + 1)
