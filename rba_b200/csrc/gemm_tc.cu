@@ -524,7 +524,7 @@ int conv3x3_tc_launch(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t
   CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
   RBA_TRY_(make_map_nhwc(&ta_hi, x_hi, B, H, W, Cin));
   RBA_TRY_(make_map_nhwc(&ta_lo, x_lo, B, H, W, Cin));
-  const int BN = Cout > 64 ? 128 : 64;
+  const int BN = (Cout % 256 == 0 && g_tc_bn256 != 0) ? 256 : (Cout > 64 ? 128 : 64);   // K = 9 Cin >= 576: long-K shape
   RBA_TRY_(make_map_3d(&tw_hi, w_hi, 9 * Cin, Cout, 9 * Cin, 1, 0, BN));
   RBA_TRY_(make_map_3d(&tw_lo, w_lo, 9 * Cin, Cout, 9 * Cin, 1, 0, BN));
   p.tilesM = 1; p.tilesN = (int)cdiv(Cout, BN);
@@ -532,6 +532,7 @@ int conv3x3_tc_launch(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t
   RBA_CHECK(nt < (1LL << 31), "conv3x3(tc): too many tiles");
   p.ntiles = (int)nt;
   dim3 grid((unsigned)std::min<int64_t>(nt, num_sms()));
+  if (BN == 256) return launch_tc<256, true>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
   if (BN == 128) return launch_tc<128, true>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
   return launch_tc<64, true>(ta_hi, ta_lo, tw_hi, tw_lo, p, grid, st);
 }

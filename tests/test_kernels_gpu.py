@@ -540,9 +540,9 @@ def test_gemm_tc_batched_and_swin(dev):
     assert (c.cpu() - ref).abs().max() < TC_TOL * max(1.0, float(ref.abs().max()))
 
 
-@pytest.mark.parametrize("H,W", [(16, 32), (9, 13)])
-def test_conv3x3_tc(dev, H, W):
-    B, Cin, Cout = 2, 64, 128
+@pytest.mark.parametrize("H,W,Cout", [(16, 32, 128), (9, 13, 128), (17, 20, 256)])    # Cout 256: the 256-wide N tile
+def test_conv3x3_tc(dev, H, W, Cout):
+    B, Cin = 2, 64
     g = torch.Generator().manual_seed(22)
     x = torch.randn(B, H, W, Cin, generator=g)
     w = torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(9 * Cin)
