@@ -494,7 +494,7 @@ int gemm_tc_launch(const rba_gemm_args& a, cudaStream_t st) {
   p.a_batched = a.batch > 1 && a.a_bstride != 0;
   p.w_batched = a.batch > 1 && a.w_bstride != 0;
   int BN = a.N > 64 ? 128 : 64;
-  if (a.N % 256 == 0 && (g_tc_bn256 == 1 || (g_tc_bn256 == 2 && a.K >= 1024))) BN = 256;
+  if (a.N % 256 == 0 && (g_tc_bn256 == 1 || (g_tc_bn256 == 2 && a.K >= 1024))) BN = 256;   // K = 512, N >= 2048 measured slower
   CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
   RBA_TRY_(make_map_3d(&ta_hi, a.a_hi, a.K, a.M, a.lda, p.a_batched ? a.batch : 1, a.a_bstride, TC_BM));
   RBA_TRY_(make_map_3d(&ta_lo, a.a_lo, a.K, a.M, a.lda, p.a_batched ? a.batch : 1, a.a_bstride, TC_BM));
