@@ -270,6 +270,7 @@ rba_einsum_score_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid
     const int dyA = g >> 2, dx = g & 3;
     const float lyA = 0.125f + 0.25f * (float)dyA, lyB = lyA + 0.5f, lxx = 0.125f + 0.25f * (float)dx;
     const float wyA_in = tr ? lyA : 1.f - lyA, wyB_in = tr ? lyB : 1.f - lyB, wx_in = tcn ? lxx : 1.f - lxx;
+    const uint32_t a0_in = __float_as_uint(wyA_in * wx_in), a1_in = __float_as_uint(wyB_in * wx_in);
     const uint4* const bp = sP + (size_t)g * FS_KS * 4 + tq;
     int cur_b = -1;
     uint32_t lt = 0;
@@ -295,8 +296,11 @@ rba_einsum_score_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid
           const int ks = q >> 4, r = q & 15;
           const int hoff = (r >> 3) * 2 + (r & 1);         // half index inside the 16-byte entry (hi); lo = +4
           __half* base = reinterpret_cast<__half*>(sP) + ((size_t)ks * 4 + ((r & 7) >> 1)) * 8 + hoff;
+          // RbA-only launches fold the 2 log2(e) of tanh(s) = 1 - 2 / (1 + 2^(2 log2(e) s)) into the probabilities, so the
+          // epilogue feeds the class sums straight into ex2 (one FMUL less per class and pixel)
+          const float pscale = (!WRITE_SEM && p.score_func == RBA_SCORE_RBA) ? 2.8853900817779268f : 1.0f;
           for (int c = 0; c < p.Kc; ++c) {
-            const float pv = expf(lg[c] - m) * inv;
+            const float pv = expf(lg[c] - m) * inv * pscale;
             const __half hh = __float2half_rn(pv);
             __half* d = base + (size_t)c * FS_KS * 4 * 8;
             d[0] = hh;
@@ -351,22 +355,30 @@ rba_einsum_score_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid
 
       // ---- score phase: one 4x4 output cell per warp iteration; cell index advances by 16 = one row + one column ----
       float* const rba_b = p.rba + (size_t)b * p.H * p.W;
+      // interior tile (89 % of them at 1024 x 2048): every cell has four in-range taps and sixteen in-range output pixels,
+      // so the per-cell range checks, border weights and store predicates are skipped (CTA-uniform branch)
+      const bool interior = r0 >= 0 && c0 >= 0 && r0 + FS_BR <= p.h - 1 && c0 + FS_BC <= p.w - 1 &&
+                            4 * (r0 + FS_BR - 1) + 5 < p.H && 4 * (c0 + FS_BC - 1) + 5 < p.W;
       int br = cw / FS_BC, bc = cw - br * FS_BC;
       for (int blk = cw; blk < FS_NBLK; blk += FS_CW, br += FS_CW / FS_BC, bc += FS_CW % FS_BC) {
         if (bc >= FS_BC) { bc -= FS_BC; ++br; }
         if (dbg & 16) continue;
         const int i = r0 + br, j = c0 + bc;                // low-res coordinates of the cell's top-left tap
-        if (i > p.h - 1 || j > p.w - 1) continue;
         const int y0 = 4 * i + 2, x0 = 4 * j + 2;          // the cell's 4x4 output pixels
-        if (y0 >= p.H || x0 >= p.W) continue;
-        // tap weights: interior cells use the phase weights; at the image border the clamped source index puts
-        // all the weight on the in-range tap (the out-of-range tap was zero-filled by TMA)
-        float wyA = wyA_in, wyB = wyB_in, wx = wx_in;
-        if (i < 0) wyA = wyB = tr ? 1.f : 0.f;
-        if (i == p.h - 1) wyA = wyB = tr ? 0.f : 1.f;
-        if (j < 0) wx = tcn ? 1.f : 0.f;
-        if (j == p.w - 1) wx = tcn ? 0.f : 1.f;
-        const uint32_t a0 = __float_as_uint(wyA * wx), a1 = __float_as_uint(wyB * wx);
+        uint32_t a0 = a0_in, a1 = a1_in;
+        if (!interior) {
+          if (i > p.h - 1 || j > p.w - 1) continue;
+          if (y0 >= p.H || x0 >= p.W) continue;
+          // tap weights: interior cells use the phase weights; at the image border the clamped source index puts
+          // all the weight on the in-range tap (the out-of-range tap was zero-filled by TMA)
+          float wyA = wyA_in, wyB = wyB_in, wx = wx_in;
+          if (i < 0) wyA = wyB = tr ? 1.f : 0.f;
+          if (i == p.h - 1) wyA = wyB = tr ? 0.f : 1.f;
+          if (j < 0) wx = tcn ? 1.f : 0.f;
+          if (j == p.w - 1) wx = tcn ? 0.f : 1.f;
+          a0 = __float_as_uint(wyA * wx);
+          a1 = __float_as_uint(wyB * wx);
+        }
         const float* tp = sPatch + (br + tr) * FS_ROWSTRIDE + (bc + tcn) * FS_QP + g;
 
         float acc[FS_NT][4];
@@ -431,8 +443,8 @@ rba_einsum_score_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid
         // ---- epilogue: acc[nt][e] = sem_seg[class 8nt+2tq+e] of pixel A (row g), acc[nt][2+e] of pixel B (row g+8).
         // sum_c tanh(s_c) = n - 2 sum_c 1/(1 + e^(2 s_c)); padded classes hold exactly 0 and contribute tanh(0) = 0 ----
         const int yA = y0 + dyA, yB = yA + 2, x = x0 + dx;
-        const bool okx = x >= 0 && x < p.W;
-        const bool okA = okx && yA >= 0 && yA < p.H, okB = okx && yB >= 0 && yB < p.H;
+        const bool okx = interior || (x >= 0 && x < p.W);
+        const bool okA = interior || (okx && yA >= 0 && yA < p.H), okB = interior || (okx && yB >= 0 && yB < p.H);
         if (WRITE_SEM) {
 #pragma unroll
           for (int nt = 0; nt < FS_NT; ++nt)
@@ -476,8 +488,13 @@ rba_einsum_score_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               if (ABL & 8) { ra += acc[nt][e]; rb += acc[nt][2 + e]; continue; }
-              ra += fs_rcp(1.0f + fs_ex2(2.8853900817779268f * acc[nt][e]));
-              rb += fs_rcp(1.0f + fs_ex2(2.8853900817779268f * acc[nt][2 + e]));
+              if (WRITE_SEM) {
+                ra += fs_rcp(1.0f + fs_ex2(2.8853900817779268f * acc[nt][e]));
+                rb += fs_rcp(1.0f + fs_ex2(2.8853900817779268f * acc[nt][2 + e]));
+              } else {                                       // class sums arrive pre-scaled by 2 log2(e)
+                ra += fs_rcp(1.0f + fs_ex2(acc[nt][e]));
+                rb += fs_rcp(1.0f + fs_ex2(acc[nt][2 + e]));
+              }
             }
           ra += __shfl_xor_sync(0xffffffffu, ra, 1);
           ra += __shfl_xor_sync(0xffffffffu, ra, 2);

@@ -434,7 +434,8 @@ def test_einsum_score_fused(dev, B, Q, K, D, h, w, crop):
     assert (sem.cpu() - sem_ref).abs().max() < 5e-5, float((sem.cpu() - sem_ref).abs().max())
     assert (rba.cpu() - rba_ref).abs().max() < 5e-5
     rba2 = ops.einsum_score_fused(e_pl, f_pl, logits.to(dev), (H, W), bias=bias.to(dev))
-    assert torch.equal(rba2, rba)
+    assert (rba2 - rba).abs().max() < 5e-6      # score-only launches pre-scale the class probabilities: same value, other rounding
+    assert (rba2.cpu() - rba_ref).abs().max() < 5e-5
     # same answer as the two-kernel path (GEMM -> pred_masks -> rba_score_fused)
     rba3 = ops.score_fused(masks.to(dev), logits.to(dev), (H, W))
     assert (rba3 - rba).abs().max() < 5e-5

@@ -341,9 +341,11 @@ def test_full_size_properties_swin_b_1024x2048(dev):
     out2 = e.forward(imgs, rba=True, masks=True)                                 # pred_masks requested -> un-fused route
     assert (out2["rba"] - rba).abs().max() < 2e-4                                # (2)
     del out2
+    rba_only = e.forward(imgs, rba=True)["rba"]                                  # the score-only launch (pre-scaled probabilities)
+    assert (rba_only - rba).abs().max() < 1e-5
     flipped = e.forward(imgs.flip(0).contiguous(), rba=True)["rba"]
-    assert torch.equal(flipped.flip(0), rba)                                     # (3)
-    del flipped
+    assert torch.equal(flipped.flip(0), rba_only)                                # (3)
+    del flipped, rba_only
     e.set_gemm_backend("ffma")
     ref = e.forward(imgs[:1].contiguous(), rba=True, logits=True)
     e.set_gemm_backend("tc")
