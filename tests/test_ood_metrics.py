@@ -87,7 +87,7 @@ def test_gpu_ood_evaluator_loop(dev):
     """rba_b200.OODEvaluator: the reference's compute_anomaly_scores + evaluate_ood flow (support.py:353-399, 270-303)
     with scores kept on the device, against the oracle metrics of the model's own score maps."""
     import rba_b200
-    from golden_cases import CASES, case_images, case_model_config
+    from golden_cases import CASES, case_model_config
     from rba_b200 import weights
     case = CASES["tiny_1dl"]
     mc = case_model_config(case)

@@ -1,5 +1,4 @@
 """CPU: host side of the input pipeline (rba_b200.PinnedBatcher): order, padding, layout conversion, error surfacing."""
-import numpy as np
 import pytest
 import torch
 
