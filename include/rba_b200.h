@@ -88,6 +88,21 @@ int rba_model_set_option(rba_model* m, const char* name, int value);
 /* Max batch / padded image size the workspace is sized for; (re)allocates device workspace. */
 int rba_model_reserve(rba_model* m, int batch, int height, int width);
 
+/* The workspace arena is re-allocated when a larger (batch, height, width) is seen.  The generation counter increments
+ * on every re-allocation: a caller that captured rba_forward into a CUDA graph must re-capture when it changes (the
+ * new forward runs in the new arena).  An arena that a capture ran in is NOT freed when outgrown (the old graph stays
+ * replayable); rba_model_release_retired() frees such arenas after the caller has dropped the graphs (it
+ * synchronises the device). */
+int64_t rba_model_arena_generation(rba_model* m);
+int rba_model_release_retired(rba_model* m);
+/* Parity aid for the boolean attention masks of forward_prediction_heads (mask2former_transformer_decoder.py:483-486,
+ * :433).  For prediction head `head` (0 = the head on the raw query features, i = after decoder layer i; only heads
+ * < dec_layers feed a cross-attention): `dump` (device, B*Q*S_l uint8, or NULL) receives this engine's decisions
+ * (1 = blocked, after the all-blocked-row reset) during the next forwards; `force` (device, same layout, or NULL) is
+ * copied over them before the cross-attention reads them.  Lets a test run on the reference's own decisions and so
+ * separate arithmetic parity from near-threshold decision flips.  Pointers are borrowed. */
+int rba_model_debug_attn_mask(rba_model* m, int head, const uint8_t* force, uint8_t* dump);
+
 #define RBA_IMG_U8 0   /* uint8 CHW, as produced by the reference's datasets (ToTensorV2) */
 #define RBA_IMG_F32 1  /* float32 CHW */
 /* MaskFormer.forward (eval) + get_RbA for a batch of B equally sized images (B,3,H,W), DEVICE pointers.

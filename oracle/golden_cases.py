@@ -26,6 +26,8 @@ def case_model_config(case):
         return rcfg.swin_b_1dl()
     if case["preset"] == "swin_l_1dl":
         return rcfg.swin_l_1dl()
+    if case["preset"] == "swin_b_full":
+        return rcfg.swin_b_full(dec_layers=case["dec_layers"])
     raise KeyError(case["preset"])
 
 
@@ -41,3 +43,13 @@ def state_checksum(sd):
         if v.is_floating_point():
             s += float(v.double().abs().sum())
     return s
+
+
+# Cases at the metric's shape (oracle/make_golden_fullsize.py -> tests/golden/model_full_*.pt).  No seed search here: with
+# 100 x 2048 decisions per image a near-threshold one is expected; the fixture records every decision within 1e-3 of its
+# threshold and the reference's own decisions, and the GPU test separates arithmetic parity from decision flips.
+FULL_CASES = {
+    "swin_b_1dl_1024x2048": dict(preset="swin_b_1dl", levels=1, dec_layers=1, seed=13, perturb=0.02, img_seed=31, sizes=[(1024, 2048)], sub=8),
+    "swin_l_1dl_256x512": dict(preset="swin_l_1dl", levels=1, dec_layers=1, seed=17, perturb=0.02, img_seed=32, sizes=[(256, 512)], sub=4),
+    "swin_b_3lvl_256x512": dict(preset="swin_b_full", levels=3, dec_layers=3, seed=19, perturb=0.02, img_seed=33, sizes=[(256, 512)], sub=4),
+}

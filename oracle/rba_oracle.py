@@ -450,6 +450,8 @@ def prediction_heads(sd, p, output, mask_features, target_size, nheads, taps=Non
     am = F.interpolate(masks, size=target_size, mode="bilinear", align_corners=False)
     if taps is not None:   # distance of the closest boolean decision (sigmoid(x) < 0.5 <=> x < 0) from its threshold
         taps["am_margin"] = min(taps.get("am_margin", float("inf")), float(am.abs().min()))
+        taps.setdefault("head_masks", []).append(masks)            # every head whose decisions feed a cross-attention
+        taps.setdefault("head_sizes", []).append(tuple(target_size))
     am = (am.sigmoid().flatten(2).unsqueeze(1).repeat(1, nheads, 1, 1).flatten(0, 1) < 0.5).bool()
     return cls, masks, am
 

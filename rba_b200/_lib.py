@@ -58,6 +58,9 @@ PROTOTYPES = {
     "rba_model_finalize": (c_int, [c_void_p]),
     "rba_model_set_option": (c_int, [c_void_p, c_char_p, c_int]),
     "rba_model_reserve": (c_int, [c_void_p, c_int, c_int, c_int]),
+    "rba_model_arena_generation": (c_int64, [c_void_p]),
+    "rba_model_release_retired": (c_int, [c_void_p]),
+    "rba_model_debug_attn_mask": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "rba_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rba_forward_ex": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, POINTER(RbaOutputs), c_void_p]),
     "rba_model_get_tap": (c_int, [c_void_p, c_char_p, c_void_p, c_int64, POINTER(c_int64), c_void_p]),

@@ -47,6 +47,17 @@ extern std::atomic<int64_t> g_launches;
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Once-per-DEVICE guard for cudaFuncSetAttribute (function attributes are per device; a process-wide `static bool`
+// leaves the second GPU of a multi-GPU process without its > 48 KB dynamic shared memory opt-in).  Usage:
+//   static PerDeviceOnce once; if (once.needed()) { RBA_CUDA(cudaFuncSetAttribute(...)); once.done(); }
+// Two racing threads may both set the attribute (harmless); neither launches before it is set.
+struct PerDeviceOnce {
+  std::atomic<uint64_t> mask{0};
+  static uint64_t bit() { int d = 0; cudaGetDevice(&d); return 1ull << (d & 63); }
+  bool needed() const { return !(mask.load(std::memory_order_acquire) & bit()); }
+  void done() { mask.fetch_or(bit(), std::memory_order_release); }
+};
+
 // ---- bf16 split planes ----
 // x ~= hi + lo with hi = bf16_rn(x), lo = bf16_rn(x - hi): |x - hi - lo| <= 2^-18 |x|.
 __device__ __forceinline__ void split2(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {

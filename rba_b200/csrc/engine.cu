@@ -113,12 +113,18 @@ struct rba_model {
   std::vector<void*> owned;                         // cudaMalloc'ed blocks (weights, derived)
   std::map<std::pair<int, int>, float*> pos_cache;  // sine position embeddings per (h, w), token-major (h*w, D)
   Arena arena;
+  std::vector<void*> retired_arenas;                // outgrown arenas that a captured CUDA graph may still reference
+  bool arena_captured = false;                      // a forward into the current arena ran under stream capture
+  int64_t arena_generation = 0;                     // bumped whenever the arena is re-allocated
+  std::map<int, const uint8_t*> am_force;           // parity aid: per prediction head, decisions to use instead of our own
+  std::map<int, uint8_t*> am_dump;                  // parity aid: per prediction head, where to copy our own decisions
   int rB = 0, rH = 0, rW = 0;
   struct Tap { const float* p; int64_t n; };
   std::map<std::string, Tap> taps;
 
   ~rba_model() {
     for (void* p : owned) cudaFree(p);
+    for (void* p : retired_arenas) cudaFree(p);
     if (arena.base) cudaFree(arena.base);
   }
   template <typename T>
@@ -748,8 +754,10 @@ static int forward_impl(rba_model* m, const void* images, int img_dtype, int B, 
   Planes ef = A.planes(BQ * D);                 // E' = mask_embed . Wmf (kept for the fused kernel)
   float* bq = A.f32(BQ);                        // b' = mask_embed . bmf
 
+  int head_idx = 0;
   auto heads = [&](int target_level, bool last) -> int {   // forward_prediction_heads (:472-489)
     const size_t mk = A.mark();
+    const int hd = head_idx++;
     Planes dn = A.planes(BQ * D);
     RBA_RUN(layernorm(out, F.W(pr + "decoder_norm.weight"), F.W(pr + "decoder_norm.bias"), 0, 1, 1, (int)BQ, D, 0, 0, eps,
                       nullptr, dn.hi, dn.lo, st));
@@ -775,7 +783,16 @@ static int forward_impl(rba_model* m, const void* images, int img_dtype, int B, 
       ga.c = masks; ga.ldc = HWm; ga.c_bstride = (int64_t)Q * HWm;
       ga.backend = F.backend;
       RBA_RUN(gemm(ga, st));
-      if (!last) RBA_RUN(attn_mask(masks, B, Q, mH, mW, lv.H[target_level], lv.W[target_level], am, st));
+      if (!last) {
+        RBA_RUN(attn_mask(masks, B, Q, mH, mW, lv.H[target_level], lv.W[target_level], am, st));
+        if (!dry) {   // parity aids (rba_model_debug_attn_mask): export our decisions / run on the reference's
+          const size_t nb = (size_t)BQ * lv.H[target_level] * lv.W[target_level];
+          auto du = m->am_dump.find(hd);
+          if (du != m->am_dump.end() && du->second) RBA_CUDA(cudaMemcpyAsync(du->second, am, nb, cudaMemcpyDeviceToDevice, st));
+          auto fo = m->am_force.find(hd);
+          if (fo != m->am_force.end() && fo->second) RBA_CUDA(cudaMemcpyAsync(am, fo->second, nb, cudaMemcpyDeviceToDevice, st));
+        }
+      }
     }
     A.release(mk);
     return RBA_OK;
@@ -889,7 +906,14 @@ static int ensure_workspace(rba_model* m, int B, int H, int W, cudaStream_t st) 
     RBA_CHECK(cs == cudaStreamCaptureStatusNone,
               "workspace too small during stream capture; call rba_model_reserve(batch, height, width) first");
     RBA_CUDA(cudaDeviceSynchronize());
-    if (m->arena.base) RBA_CUDA(cudaFree(m->arena.base));
+    // A CUDA graph captured on the old arena has its pointers baked in: keep that arena alive (retired) instead of
+    // freeing it under the graph; rba_model_release_retired() frees retired arenas once the caller dropped its graphs.
+    if (m->arena.base) {
+      if (m->arena_captured) m->retired_arenas.push_back(m->arena.base);
+      else RBA_CUDA(cudaFree(m->arena.base));
+    }
+    m->arena_captured = false;
+    m->arena_generation++;
     m->arena.base = nullptr;
     m->arena.cap = 0;
     void* p = nullptr;
@@ -916,6 +940,11 @@ extern "C" int rba_forward_ex(rba_model* m, const void* images, int img_dtype, i
   RBA_CHECK(img_dtype == RBA_IMG_U8 || img_dtype == RBA_IMG_F32, "rba_forward: bad image dtype");
   RBA_CUDA(cudaSetDevice(m->device));
   RBA_TRY(ensure_workspace(m, B, H, W, (cudaStream_t)stream));
+  if (stream) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing((cudaStream_t)stream, &cs);
+    if (cs != cudaStreamCaptureStatusNone) m->arena_captured = true;
+  }
   return forward_impl(m, images, img_dtype, B, H, W, out->rba, out->sem_seg, out->pred_logits, out->pred_masks, out->ood_pred,
                       (cudaStream_t)stream, false);
 }
@@ -925,6 +954,25 @@ extern "C" int rba_forward(rba_model* m, const void* images, int img_dtype, int 
   rba_outputs o;
   o.rba = rba_out; o.sem_seg = sem_seg; o.pred_logits = pred_logits; o.pred_masks = pred_masks; o.ood_pred = nullptr;
   return rba_forward_ex(m, images, img_dtype, B, H, W, &o, stream);
+}
+
+extern "C" int64_t rba_model_arena_generation(rba_model* m) { return m ? m->arena_generation : -1; }
+
+extern "C" int rba_model_release_retired(rba_model* m) {
+  RBA_CHECK(m, "rba_model_release_retired: null model");
+  RBA_CUDA(cudaSetDevice(m->device));
+  RBA_CUDA(cudaDeviceSynchronize());
+  for (void* p : m->retired_arenas) cudaFree(p);
+  m->retired_arenas.clear();
+  return RBA_OK;
+}
+
+extern "C" int rba_model_debug_attn_mask(rba_model* m, int head, const uint8_t* force, uint8_t* dump) {
+  RBA_CHECK(m, "rba_model_debug_attn_mask: null model");
+  RBA_CHECK(head >= 0 && head < m->cfg.dec_layers, "rba_model_debug_attn_mask: head %d outside [0, %d)", head, m->cfg.dec_layers);
+  m->am_force[head] = force;
+  m->am_dump[head] = dump;
+  return RBA_OK;
 }
 
 extern "C" int rba_model_get_tap(rba_model* m, const char* name, float* dst, int64_t capacity, int64_t* count, void* stream) {

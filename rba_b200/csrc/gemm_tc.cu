@@ -428,10 +428,10 @@ template <int BN, bool CONV, int ACT, bool OUTP, bool STG>
 static int launch_tc3(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
                       const TcParams& p, dim3 grid, cudaStream_t st) {
   constexpr int smem = TcSmem<BN, STG>::TOTAL;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce once;
+  if (once.needed()) {
     RBA_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CONV, ACT, OUTP, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_done = true;
+    once.done();
   }
   gemm_tc_kernel<BN, CONV, ACT, OUTP, STG><<<grid, TC_THREADS2, smem, st>>>(a_hi, a_lo, w_hi, w_lo, p);
   RBA_LAUNCHED();

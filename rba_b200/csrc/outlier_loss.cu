@@ -281,11 +281,11 @@ static int ol_run(const float* masks, const float* logits, const void* labels, i
   const size_t sm_f = (size_t)Q * KP * 4;
   const size_t sm_b = sm_f + (size_t)Q * OL_TP * 4 + (size_t)KP * (OL_TP + 1) * 4;
   RBA_CHECK(sm_b <= 200 * 1024, "outlier_loss: Q=%d too large for the shared-memory tile", Q);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce once;
+  if (once.needed()) {
     RBA_CUDA(cudaFuncSetAttribute(ol_backward_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     RBA_CUDA(cudaFuncSetAttribute(ol_score_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr_done = true;
+    once.done();
   }
   RBA_CHECK(sm_f <= 64 * 1024, "outlier_loss: Q=%d too large", Q);
   ol_score_kernel<KP><<<grid, OL_TP, sm_f, st>>>(masks, logits, Q, K, hw, mode, score);

@@ -545,16 +545,16 @@ int einsum_score_launch(const uint16_t* e_hi, const uint16_t* e_lo, const float*
   RBA_TRY_(make_map_3d(&te_lo, e_lo, D, Q, D, B, (int64_t)Q * D, FS_NQ));
   dim3 grid((unsigned)std::min<int64_t>(nt, num_sms()));
   if (sem) {
-    static bool done = false;
-    if (!done) { RBA_CUDA(cudaFuncSetAttribute(rba_einsum_score_kernel<true, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM)); done = true; }
+    static PerDeviceOnce once;
+    if (once.needed()) { RBA_CUDA(cudaFuncSetAttribute(rba_einsum_score_kernel<true, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM)); once.done(); }
     rba_einsum_score_kernel<true, 0, 1><<<grid, FS_THREADS, FS_SMEM, st>>>(ty_hi, ty_lo, te_hi, te_lo, p);
   } else {
     static const int abl = []() { const char* e = getenv("RBA_FS_ABL"); return e ? atoi(e) : 0; }();
     static const int rcpm = []() { const char* e = getenv("RBA_FS_RCP"); return e ? atoi(e) : 1; }();
 #define RBA_FS_LAUNCH(A, R)                                                                                                  \
   do {                                                                                                                     \
-    static bool done = false;                                                                                              \
-    if (!done) { RBA_CUDA(cudaFuncSetAttribute(rba_einsum_score_kernel<false, A, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM)); done = true; } \
+    static PerDeviceOnce once;                                                                                             \
+    if (once.needed()) { RBA_CUDA(cudaFuncSetAttribute(rba_einsum_score_kernel<false, A, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM)); once.done(); } \
     rba_einsum_score_kernel<false, A, R><<<grid, FS_THREADS, FS_SMEM, st>>>(ty_hi, ty_lo, te_hi, te_lo, p);                \
   } while (0)
     switch (abl * 4 + (abl ? 0 : rcpm)) {

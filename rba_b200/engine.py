@@ -75,6 +75,26 @@ class Engine:
     def reserve(self, B, H, W):
         _lib.check(_lib.lib().rba_model_reserve(self._h, B, H, W))
 
+    def arena_generation(self):
+        """Increments whenever the workspace arena was re-allocated (a larger shape was seen): graphs captured before
+        that must be re-captured.  `graphed()` checks it; holders of a graph (ScoreStream) compare it themselves."""
+        return int(_lib.lib().rba_model_arena_generation(self._h))
+
+    def release_retired(self):
+        """Frees outgrown arenas that earlier graph captures ran in.  Call only after dropping every graph captured
+        before the last growth (this engine's own cache is dropped here)."""
+        self._graphs.clear()
+        _lib.check(_lib.lib().rba_model_release_retired(self._h))
+
+    def debug_attn_mask(self, head, force=None, dump=None):
+        """Parity aid (rba_model_debug_attn_mask): uint8 CUDA tensors (B,Q,S_l); keeps them alive on the engine."""
+        self._dbg = getattr(self, "_dbg", {})
+        self._dbg[head] = (force, dump)
+        _lib.check(_lib.lib().rba_model_debug_attn_mask(
+            self._h, head, ctypes.c_void_p(force.data_ptr()) if force is not None else None,
+            ctypes.c_void_p(dump.data_ptr()) if dump is not None else None))
+        self._graphs.clear()
+
     # ---- forward ----
     def padded_hw(self, H, W):
         s = self.mc.size_divisibility
@@ -136,9 +156,11 @@ class Engine:
     def graphed(self, images, rba=True, sem_seg=False, logits=False, masks=False):
         """Captures rba_forward for this (shape, dtype, outputs) once and returns (static_images, static_out, replay)."""
         key = (tuple(images.shape), images.dtype, rba, sem_seg, logits, masks)
+        B, _, H, W = images.shape
+        self.reserve(B, H, W)
+        if key in self._graphs and self._graphs[key][3] != self.arena_generation():
+            del self._graphs[key]                       # captured in an arena that has since been outgrown
         if key not in self._graphs:
-            B, _, H, W = images.shape
-            self.reserve(B, H, W)
             static_in = torch.empty_like(images)
             static_in.copy_(images)
             out = self.alloc_outputs(B, H, W, rba, sem_seg, logits, masks)
@@ -151,5 +173,5 @@ class Engine:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self.forward_into(static_in, out)
-            self._graphs[key] = (static_in, out, g)
-        return self._graphs[key]
+            self._graphs[key] = (static_in, out, g, self.arena_generation())
+        return self._graphs[key][:3]

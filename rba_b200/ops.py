@@ -8,8 +8,12 @@ from . import _lib
 from ._lib import RBA_ACT_GELU, RBA_ACT_NONE, RBA_ACT_RELU, RBA_GEMM_FFMA, RBA_GEMM_TC, RbaError, RbaGemmArgs  # noqa: F401
 
 
+_last_dev = [None]
+
+
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """Current stream of the device the last checked tensors live on (not of the thread's current device)."""
+    return ctypes.c_void_p(torch.cuda.current_stream(_last_dev[0]).cuda_stream)
 
 
 def _p(t):
@@ -23,6 +27,7 @@ def _chk_cuda(*ts):
                 raise RbaError("rba_b200 ops need CUDA tensors (no CPU path)")
             if not t.is_contiguous():
                 raise RbaError("rba_b200 ops need contiguous tensors")
+            _last_dev[0] = t.device
 
 
 def split_planes(x):

@@ -36,6 +36,7 @@ class ScoreStream:
         self.use_graph = use_graph
         if use_graph:
             self.static_in, self.static_out, self.graph = eng.graphed(proto, rba=True)
+            self._gen = eng.arena_generation()
         else:
             eng.reserve(B, H, W)
             self.static_in = proto
@@ -71,6 +72,11 @@ class ScoreStream:
             self.stage_in[k].copy_(host_images, non_blocking=True)
             self.ev_in_ready[k].record(self.s_in)
         comp.wait_event(self.ev_in_ready[k])
+        if self.graph is not None and self.eng.arena_generation() != self._gen:
+            # the engine's arena was outgrown by a larger forward elsewhere: re-capture in the new arena (the old graph
+            # stays valid -- its arena is retired, not freed -- but would pin that memory)
+            self.static_in, self.static_out, self.graph = self.eng.graphed(self.static_in, rba=True)
+            self._gen = self.eng.arena_generation()
         self.static_in.copy_(self.stage_in[k], non_blocking=True)
         self.ev_in_free[k].record(comp)
         if self.graph is not None:
@@ -183,7 +189,18 @@ class PinnedBatcher:
         def load(i):
             img, lab = self.ds[i]
             lab = torch.as_tensor(np.ascontiguousarray(lab)) if not torch.is_tensor(lab) else lab
-            return self._chw_u8(img), lab.to(torch.uint8)
+            # only 0 (in-distribution) and 1 (OoD) count (support.py:275-279); anything else -- including int64 values
+            # that would wrap to 0/1 in a uint8 cast -- becomes the ignore value 255
+            lab = torch.where((lab == 0) | (lab == 1), lab, torch.full_like(lab, 255)).to(torch.uint8)
+            return self._chw_u8(img), lab
+
+        def put(item):                            # polls `stop`: a consumer that left cannot strand the producer
+            while not stop.is_set():
+                try:
+                    out.put(item, timeout=0.2)
+                    return
+                except queue.Full:
+                    pass
 
         def producer():
             try:
@@ -201,17 +218,23 @@ class PinnedBatcher:
                                     tuple(self._bufs[0][0].shape[-2:]) != (H, W):
                                 raise RbaError("PinnedBatcher: all images of a run must share one size "
                                                f"(got {tuple(im.shape[-2:])} vs {(H, W)}); resize in the dataset transform")
-                        ib, lb = self._free.get()
+                        while True:               # polls `stop` so an abandoned iteration cannot strand this thread
+                            try:
+                                ib, lb = self._free.get(timeout=0.2)
+                                break
+                            except queue.Empty:
+                                if stop.is_set():
+                                    return
                         for j, (im, lab) in enumerate(samples):
                             ib[j].copy_(im)
                             lb[j].copy_(lab.reshape(H, W))
                         for j in range(len(samples), self.B):   # pad: repeated image, ignored labels
                             ib[j].copy_(ib[0])
                             lb[j].fill_(255)
-                        out.put((ib, lb, len(samples)))
-                out.put(None)
+                        put((ib, lb, len(samples)))
+                put(None)
             except BaseException as e:   # surface loader errors in the consumer
-                out.put(e)
+                put(e)
 
         t = threading.Thread(target=producer, daemon=True)
         t.start()

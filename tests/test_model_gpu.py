@@ -352,3 +352,160 @@ def test_full_size_properties_swin_b_1024x2048(dev):
     tc = e.forward(imgs[:1].contiguous(), rba=True, logits=True)
     assert (tc["pred_logits"] - ref["pred_logits"]).abs().max() < TOL           # (4)
     assert (tc["rba"] - ref["rba"]).abs().max() < TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Parity at the metric's shape against the UNMODIFIED reference (tests/golden/model_full_*.pt, oracle/make_golden_fullsize.py)
+# ---------------------------------------------------------------------------------------------------------------------
+def _unpack_ref_decisions(fix, hd):
+    """The reference's boolean decisions of prediction head `hd` (pre-reset, bit-packed) -> uint8 (B,Q,S) with the
+    all-blocked-row reset of mask2former_transformer_decoder.py:433 applied (that is what the cross-attention reads)."""
+    import numpy as np
+    shp = fix["attn_mask_shapes"][hd]
+    n = int(np.prod(shp))
+    bits = np.unpackbits(fix["attn_masks"][hd].numpy())[:n].reshape(shp)
+    am = torch.from_numpy(bits.astype("bool"))
+    am = am.clone()
+    am[am.all(-1)] = False
+    return am.to(torch.uint8)
+
+
+def _full_errs(out, fix):
+    s = fix["sub"]
+    return {
+        "pred_logits": (out["pred_logits"].cpu() - fix["pred_logits"]).abs().max().item(),
+        "pred_masks": (out["pred_masks"].cpu()[:, :, ::s, ::s] - fix["pred_masks_sub"]).abs().max().item(),
+        "sem_seg": (out["sem_seg"].cpu()[:, :, ::s, ::s] - fix["sem_seg_sub"]).abs().max().item(),
+        "rba": (out["rba"].cpu()[:, ::s, ::s] - fix["rba_sub"]).abs().max().item(),
+    }
+
+
+FULL_RESULTS = {}
+
+
+@pytest.mark.parametrize("name", ["swin_b_1dl_1024x2048", "swin_l_1dl_256x512", "swin_b_3lvl_256x512"])
+@pytest.mark.parametrize("backend", ["tc", "ffma"])
+def test_full_size_matches_reference_golden(dev, name, backend):
+    """North star: "outputs match the reference's own forward on identical random-init weights and synthetic 1024x2048
+    inputs within 1e-3 fp32".  The fixture is the unmodified reference run at the metric's shape.  With 100 x 2048 boolean
+    attention-mask decisions per image (mask2former_transformer_decoder.py:483-486) some sit within ~1e-6 of their
+    threshold (fixture `am_margin`), where ANY implementation whose mask logits differ by round-off may decide
+    differently, and a flipped decision changes the outputs by more than round-off.  So parity is checked in two parts:
+      (a) arithmetic: stage tensors before any decision (res2..res5 against the oracle's, which equals the reference
+          bitwise at this size -- fixture `oracle_vs_reference`), and ALL outputs with the cross-attention reading the
+          reference's own decisions: < 1e-3 max-abs;
+      (b) decisions: every decision where this engine differs from the reference is within 1e-3 of its threshold (in
+          the fixture's near list); the free-running outputs are reported, and must also meet 1e-3 when no decision flipped.
+    """
+    if backend == "ffma" and name == "swin_b_1dl_1024x2048":
+        pytest.skip("the fp32 CUDA-core backend is the cross-check at the smaller cases; 1024x2048 runs on tcgen05")
+    fix = load_golden(f"model_full_{name}.pt")
+    case = fix["case"]
+    mc = case_model_config(case)
+    sd = weights.init_state_dict(mc, seed=case["seed"], perturb=case["perturb"])
+    assert abs(state_checksum(sd) - fix["state_checksum"]) <= 1e-6 * fix["state_checksum"]
+    assert max(fix["oracle_vs_reference"].values()) == 0.0
+    imgs = torch.stack(case_images(case)).to(dev)
+    B = imgs.shape[0]
+    e = _engine(mc, sd, dev, taps=True)
+    e.set_gemm_backend(backend)
+    L = mc.dec_layers
+    ref_dec = [_unpack_ref_decisions(fix, hd).to(dev) for hd in range(L)]
+    dumps = [torch.zeros_like(r) for r in ref_dec]
+    for hd in range(L):
+        e.debug_attn_mask(hd, dump=dumps[hd])
+    free = e.forward(imgs, rba=True, sem_seg=True, logits=True, masks=True)
+    torch.cuda.synchronize()
+    # (a1) backbone stage tensors, before any decision
+    t = fix["taps"]
+    stage_err = {}
+    for k, (cs, ss) in {"res2": (8, 8), "res3": (8, 4), "res4": (8, 2), "res5": (8, 1)}.items():
+        r = t[f"{k}_sub"]
+        Cc = r.shape[1] * cs if cs > 1 else r.shape[1]
+        g = e.tap(k).cpu().view(B, -1, Cc)
+        hw = g.shape[1]
+        # token-major (B, H*W, C) -> NCHW
+        Hs = {"res2": 4, "res3": 8, "res4": 16, "res5": 32}[k]
+        Hh, Ww = e.padded_hw(*imgs.shape[-2:])
+        g = g.view(B, Hh // Hs, Ww // Hs, Cc).permute(0, 3, 1, 2)[:, ::cs, ::ss, ::ss]
+        stage_err[k] = (g - r).abs().max().item()
+        assert hw == (Hh // Hs) * (Ww // Hs)
+    print(name, backend, "stage max-abs vs reference", stage_err)
+    for k, v in stage_err.items():
+        assert v < 5e-4, (k, v)
+    # (b) decisions
+    near = {(hd, b, q, p) for hd, b, q, p, _ in fix["am_near"]}
+    flips = []
+    for hd in range(L):
+        d = (dumps[hd] != ref_dec[hd]).nonzero().cpu().tolist()
+        flips += [(hd, b, q, p) for b, q, p in d]
+    # a whole row may differ through the all-blocked reset when one decision in it flipped; only count rows' own flips
+    bad = [f for f in flips if f not in near]
+    rows_near = {(hd, b, q) for hd, b, q, p in near}
+    bad = [f for f in bad if (f[0], f[1], f[2]) not in rows_near]
+    n_dec = sum(int(r.numel()) for r in ref_dec)
+    free_errs = _full_errs(free, fix)
+    print(name, backend, f"decisions differing from the reference: {len(flips)} of {n_dec} (near-threshold list: {len(near)}, "
+          f"closest margin {fix['am_margin']:.2e}); free-running max-abs {free_errs}")
+    assert not bad, f"decisions differ away from the threshold: {bad[:5]}"
+    if not flips:
+        for k, v in free_errs.items():
+            assert v < TOL, ("free-running", k, v)
+    # (a2) arithmetic parity of everything downstream, on the reference's decisions
+    for hd in range(L):
+        e.debug_attn_mask(hd, force=ref_dec[hd])
+    forced = e.forward(imgs, rba=True, sem_seg=True, logits=True, masks=True)
+    torch.cuda.synchronize()
+    forced_errs = _full_errs(forced, fix)
+    print(name, backend, "max-abs on the reference's decisions", forced_errs)
+    for k, v in forced_errs.items():
+        assert v < TOL, ("forced", k, v)
+    # the fused route (pred_masks never materialised) on the same decisions
+    fused = e.forward(imgs, rba=True, sem_seg=True)
+    s = fix["sub"]
+    assert (fused["rba"].cpu()[:, ::s, ::s] - fix["rba_sub"]).abs().max() < TOL
+    assert (fused["sem_seg"].cpu()[:, :, ::s, ::s] - fix["sem_seg_sub"]).abs().max() < TOL
+    # fraction of score pixels within the bar when free-running (what a user sees)
+    frac = ((free["rba"].cpu()[:, ::s, ::s] - fix["rba_sub"]).abs() < TOL).float().mean().item()
+    FULL_RESULTS[(name, backend)] = dict(stage=stage_err, flips=len(flips), decisions=n_dec, free=free_errs, forced=forced_errs,
+                                         free_rba_frac_within_tol=frac)
+    print(name, backend, f"free-running: {100 * frac:.3f}% of score pixels within {TOL}")
+    import json
+    import os
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/full_size_parity.json", "w") as f:
+        json.dump({f"{k[0]}/{k[1]}": v for k, v in FULL_RESULTS.items()}, f, indent=1)
+
+
+def test_arena_growth_keeps_captured_graphs_valid(dev):
+    """growing the arena must not leave a captured graph replaying into freed memory.  A graph captured at a
+    small shape stays replayable (its arena is retired, not freed) after a larger forward re-allocated the arena, the
+    generation counter tells holders to re-capture, and ScoreStream does."""
+    case = CASES["tiny_1dl"]
+    mc = case_model_config(case)
+    sd = weights.init_state_dict(mc, seed=case["seed"], perturb=case["perturb"])
+    e = _engine(mc, sd, dev)
+    g = torch.Generator().manual_seed(3)
+    small = torch.randint(0, 256, (1, 3, 64, 96), dtype=torch.uint8, generator=g).to(dev)
+    big = torch.randint(0, 256, (2, 3, 128, 192), dtype=torch.uint8, generator=g).to(dev)
+    want = e.forward(small, rba=True)["rba"].clone()
+    static_in, static_out, graph = e.graphed(small, rba=True)
+    gen0 = e.arena_generation()
+    stream = rba_b200.ScoreStream(e, 1, 64, 96)
+    e.forward(big, rba=True)                                    # outgrows the arena
+    assert e.arena_generation() > gen0
+    filler = torch.full((64 << 20,), 1.0, device=dev)           # would land in the freed arena if it had been freed
+    static_in.copy_(small)
+    graph.replay()                                              # the OLD graph: still valid
+    torch.cuda.synchronize()
+    assert torch.equal(static_out["rba"], want)
+    got = list(stream.run([small.cpu().pin_memory()]))          # ScoreStream re-captures by itself
+    assert torch.equal(got[0], want.cpu())
+    s2, o2, g2 = e.graphed(small, rba=True)                     # the engine's cache re-captures in the new arena
+    assert g2 is not graph
+    s2.copy_(small)
+    g2.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(o2["rba"], want)
+    del filler
+    e.release_retired()
