@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--backend", default=os.environ.get("RBA_GEMM_BACKEND", "auto"), choices=["auto", "ffma", "tc"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-images", type=int, default=1)
     return ap.parse_args()
 
@@ -135,23 +136,147 @@ def cpu_port_images_per_s(mc, H, W, n_images, warmup, steps, budget_s=240.0):
     return n_images * len(times) / total, len(times), total / len(times), threads
 
 
+# ------------------------------------------------------------------------------------------------
+# the UNMODIFIED reference modules (baseline/_ref, installed by tools/make_baseline_ref.py; travels to the GPU box)
+# ------------------------------------------------------------------------------------------------
+REF_CKPT = {"swin_b_1dl": "swin_b_1dl", "swin_l_1dl": "swin_l_1dl", "swin_b_full": "swin_b_1dl"}
+
+
+def reference_available(model_name):
+    return model_name in REF_CKPT and os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "mask2former"))
+
+
+def build_reference(model_name, mc, device, native_msda):
+    """MaskFormer(cfg) of the reference itself (its own swin.py / msdeformattn.py / decoder / maskformer_model.py under
+    the detectron2 / fvcore / timm stand-ins of oracle/ref_shims), with the SAME seeded weights this repo's arm uses."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    os.environ.setdefault("RBA_REFERENCE_ROOT", os.path.join(ROOT, "baseline", "_ref"))
+    import ref_loader
+    from rba_b200 import weights
+    if native_msda:
+        ref_loader.use_native_msda()
+    over = {}
+    if model_name == "swin_b_full":
+        over = {"MODEL.SEM_SEG_HEAD.DEFORMABLE_TRANSFORMER_ENCODER_IN_FEATURES": ["res3", "res4", "res5"],
+                "MODEL.MASK_FORMER.DEC_LAYERS": mc.dec_layers + 1}
+    cfg = ref_loader.load_cfg(REF_CKPT[model_name], over)
+    model = ref_loader.build_reference_model(cfg, seed=0)
+    ref_loader.load_state_dict_into(model, weights.init_state_dict(mc, seed=0))
+    return model.to(device).eval()
+
+
+def reference_cpu_images_per_s(model_name, mc, H, W, n_images, warmup, steps, budget_s=240.0):
+    """The reference's own CPU path: model([{"image": x}, ...]) + get_RbA (evaluate_ood.py:143-150), all host threads."""
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    model = build_reference(model_name, mc, torch.device("cpu"), native_msda=False)
+    g = torch.Generator().manual_seed(1)
+    imgs = [torch.randint(0, 256, (3, H, W), dtype=torch.uint8, generator=g) for _ in range(n_images)]
+
+    def one():
+        with torch.no_grad():
+            out = model([{"image": x} for x in imgs])
+            return [-o["sem_seg"].tanh().sum(dim=0) for o in out]
+
+    t_start = time.perf_counter()
+    for _ in range(warmup):
+        one()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        r = one()
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s:
+            break
+    assert torch.isfinite(r[0]).all()
+    total = sum(times)
+    return n_images * len(times) / total, len(times), total / len(times), threads
+
+
+def reference_gpu_baseline(model_name, mc, B, H, W, dev, warmup=2, steps=5, ours_rba=None, ours_img=None):
+    """SURVEY §8d "Reference GPU path (the >=4x denominator)": the reference modules on the same B200, fp32, default
+    torch flags (matmul TF32 off, cuDNN conv TF32 on: what a user gets), eval + no_grad, the batch as a list of B dicts,
+    MSDeformAttn through the reference's own CUDA extension; CUDA-event timing.  `value` has the images resident on the
+    device; `e2e` copies each image from pinned host memory and brings every score map back (evaluate_ood.py:143-150)."""
+    model = build_reference(model_name, mc, dev, native_msda=True)
+    g = torch.Generator().manual_seed(1)
+    host = torch.randint(0, 256, (B, 3, H, W), dtype=torch.uint8, generator=g).pin_memory()
+    imgs = host.to(dev)
+
+    def fwd(batch):
+        with torch.no_grad():
+            out = model([{"image": x} for x in batch])
+            return [-o["sem_seg"].tanh().sum(dim=0) for o in out]
+
+    def timed(fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    for _ in range(warmup):
+        fwd(imgs)
+    clocks = ClockSampler(dev.index or 0)
+    clocks.start()
+    ms = timed(lambda: fwd(imgs), steps)
+
+    def e2e_step():
+        r = fwd([host[b].to(dev, non_blocking=True) for b in range(B)])
+        return [x.cpu() for x in r]
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, max(2, steps // 2))
+    clk = clocks.stop()
+    res = {"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "batch": B, "steps": steps, "warmup": warmup,
+           "e2e": {"value": B / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * 3 * H * W, "d2h_bytes_per_step": B * H * W * 4},
+           "kind": "reference", "clocks": clk, "torch": torch.__version__,
+           "flags": {"matmul_allow_tf32": torch.backends.cuda.matmul.allow_tf32, "cudnn_allow_tf32": torch.backends.cudnn.allow_tf32},
+           "how": "unmodified reference modules (baseline/_ref) under oracle/ref_shims on cuda, MSDeformAttn through the reference's "
+                  "own CUDA extension rebuilt for sm_100a, batch as a list of B dicts, eval + no_grad, CUDA events"}
+    if ours_rba is not None and ours_img is not None:
+        # live cross-check on this box: the reference with TF32 off against this repo's scores of the same image
+        tf = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        r = fwd([ours_img])[0]
+        torch.backends.cudnn.allow_tf32 = tf
+        d = (r - ours_rba).abs()
+        res["live_check"] = {"rba_max_abs_vs_ours": float(d.max()), "rba_frac_within_1e-3": float((d < 1e-3).float().mean()),
+                             "note": "free-running (near-threshold attention-mask decisions may differ; tests/test_reference_gpu.py "
+                                     "separates them)"}
+    del model
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     mc = model_config(args.model)
     warm = min(args.warmup, 1)
-    ips, steps, sec_per_step, threads = cpu_port_images_per_s(mc, args.height, args.width, args.cpu_sample_images, warm, args.steps)
+    kind = "reference" if reference_available(args.model) else "port"
+    if kind == "reference":
+        ips, steps, sec_per_step, threads = reference_cpu_images_per_s(args.model, mc, args.height, args.width,
+                                                                       args.cpu_sample_images, warm, args.steps)
+    else:
+        ips, steps, sec_per_step, threads = cpu_port_images_per_s(mc, args.height, args.width, args.cpu_sample_images, warm, args.steps)
     line = {
         "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.model} Mask2Former forward + RbA score, {args.height}x{args.width}, "
                                f"{args.cpu_sample_images} image/step (bounded sample of the 8-image batch)"},
-        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
+        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": threads, "kind": kind,
                          "sample": f"{steps} step(s) x {args.cpu_sample_images} image(s) at {args.height}x{args.width}; "
-                                   "oracle/rba_oracle.py = PyTorch-CPU fp32 restatement of the reference modules "
-                                   "(the reference itself cannot travel to the GPU box)"},
+                                   + ("the reference's own modules (baseline/_ref: mask2former/*.py unmodified, under the detectron2 / "
+                                      "fvcore / timm stand-ins of oracle/ref_shims; MSDeformAttn through its own PyTorch statement "
+                                      "ms_deform_attn_core_pytorch, as on any CPU run of the reference)" if kind == "reference" else
+                                      "oracle/rba_oracle.py = PyTorch-CPU fp32 restatement of the reference modules "
+                                      "(baseline/_ref is absent)")},
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -363,12 +488,28 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    gpu_baseline = None
+    if world == 1 and not args.no_gpu_baseline and reference_available(args.model):
+        try:
+            ours_img = dev_imgs[0][0].contiguous()
+            ours_rba = eng.forward(ours_img[None], rba=True)["rba"][0].clone()
+            gpu_baseline = reference_gpu_baseline(args.model, mc, B, H, W, dev, ours_rba=ours_rba, ours_img=ours_img)
+            gpu_baseline["speedup_value"] = value / gpu_baseline["value"]
+            gpu_baseline["speedup_e2e"] = e2e / gpu_baseline["e2e"]["value"]
+        except Exception as ex:          # the baseline leg must never take the product's line down
+            gpu_baseline = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        ips, steps, sps, threads = cpu_port_images_per_s(mc, H, W, args.cpu_sample_images, 0, 1)
-        cpu_baseline = {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": f"{steps} step x {args.cpu_sample_images} image at {H}x{W} ({sps:.1f} s); oracle/rba_oracle.py, "
-                                  "PyTorch-CPU fp32 restatement of the reference modules"}
+        if reference_available(args.model):
+            ips, steps, sps, threads = reference_cpu_images_per_s(args.model, mc, H, W, args.cpu_sample_images, 0, 1)
+            cpu_baseline = {"value": ips, "unit": UNIT, "cores": threads, "kind": "reference",
+                            "sample": f"{steps} step x {args.cpu_sample_images} image at {H}x{W} ({sps:.1f} s); the reference's own "
+                                      "modules from baseline/_ref on the host cores"}
+        else:
+            ips, steps, sps, threads = cpu_port_images_per_s(mc, H, W, args.cpu_sample_images, 0, 1)
+            cpu_baseline = {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
+                            "sample": f"{steps} step x {args.cpu_sample_images} image at {H}x{W} ({sps:.1f} s); oracle/rba_oracle.py, "
+                                      "PyTorch-CPU fp32 restatement of the reference modules"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -386,6 +527,8 @@ def run_ours(args):
     }
     if cpu_baseline:
         line["cpu_baseline"] = cpu_baseline
+    if gpu_baseline:
+        line["gpu_baseline"] = gpu_baseline
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -175,6 +175,13 @@ int rba_msda_forward(const float* value, const int64_t* spatial_shapes, const in
                      const float* sampling_loc, const float* attn_weight, int B, int S, int M, int D, int Lq, int L,
                      int P, int im2col_step, float* out, void* stream);
 
+/* Same op with spatial_shapes / level_start_index as DEVICE int64 arrays -- exactly the tensors the reference FFI
+ * receives and its kernel reads on the device (ms_deform_im2col_cuda.cuh:242-250): no host copy, no synchronisation,
+ * CUDA-graph capturable.  (The host-array variant above additionally validates sum(H*W) == S.) */
+int rba_msda_forward_dev(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                         const float* sampling_loc, const float* attn_weight, int B, int S, int M, int D, int Lq, int L,
+                         int P, int im2col_step, float* out, void* stream);
+
 /* ---- MSDeformAttn backward: `ms_deform_attn_backward` of the same FFI (ops/src/vision.cpp:20,
  * ops/src/ms_deform_attn.h:44-66, ops/src/cuda/ms_deform_attn_cuda.cu:87-153) ----
  * grad_output (B,Lq,M*D) fp32.  Outputs (device): grad_value (B,S,M,D) -- zeroed inside, then accumulated with atomics --
@@ -184,6 +191,11 @@ int rba_msda_backward(const float* value, const int64_t* spatial_shapes, const i
                       const float* sampling_loc, const float* attn_weight, const float* grad_output, int B, int S, int M,
                       int D, int Lq, int L, int P, int im2col_step, float* grad_value, float* grad_sampling_loc,
                       float* grad_attn_weight, void* stream);
+
+int rba_msda_backward_dev(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                          const float* sampling_loc, const float* attn_weight, const float* grad_output, int B, int S, int M,
+                          int D, int Lq, int L, int P, int im2col_step, float* grad_value, float* grad_sampling_loc,
+                          float* grad_attn_weight, void* stream);
 
 /* ---- training-side RbA outlier loss, forward + backward in one call (SetCriterion.outlier_loss,
  * mask2former/modeling/criterion.py:435-553; OUTLIER_LOSS_FUNC squared_hinge) ----

@@ -22,12 +22,29 @@ import types
 import torch
 import yaml
 
-REF_ROOT = os.environ.get("RBA_REFERENCE_ROOT", "/root/reference")
-_SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_shims")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_BASELINE_REF = os.path.join(os.path.dirname(_HERE), "baseline", "_ref")      # tools/make_baseline_ref.py (travels to the GPU box)
+REF_ROOT = os.environ.get("RBA_REFERENCE_ROOT") or ("/root/reference" if os.path.isdir("/root/reference/mask2former") else _BASELINE_REF)
+_SHIMS = os.path.join(_HERE, "ref_shims")
+NATIVE_MSDA = False      # set by use_native_msda(): the reference's own CUDA extension instead of the raising stub
 
 
 def available():
     return os.path.isdir(os.path.join(REF_ROOT, "mask2former"))
+
+
+def native_msda_available():
+    import glob
+    return bool(glob.glob(os.path.join(_BASELINE_REF, "MultiScaleDeformableAttention*.so")))
+
+
+def use_native_msda():
+    """Bind the reference's own MultiScaleDeformableAttention extension (built unmodified-kernels for sm_100a by
+    tools/make_baseline_ref.py) instead of the stub.  Must be called before the first build/load."""
+    global NATIVE_MSDA
+    assert "mask2former.maskformer_model" not in sys.modules, "use_native_msda() must precede the first import"
+    assert native_msda_available(), "baseline/_ref has no MultiScaleDeformableAttention*.so (run tools/make_baseline_ref.py)"
+    NATIVE_MSDA = True
 
 
 def _install():
@@ -35,14 +52,19 @@ def _install():
         return
     if _SHIMS not in sys.path:
         sys.path.insert(0, _SHIMS)
-    msda = types.ModuleType("MultiScaleDeformableAttention")
+    if NATIVE_MSDA:
+        if _BASELINE_REF not in sys.path:
+            sys.path.insert(0, _BASELINE_REF)
+        import MultiScaleDeformableAttention  # noqa: F401  (the real extension; registers itself in sys.modules)
+    else:
+        msda = types.ModuleType("MultiScaleDeformableAttention")
 
-    def _no_native(*a, **k):
-        raise RuntimeError("reference CUDA op not built; reference falls back to its PyTorch statement")
+        def _no_native(*a, **k):
+            raise RuntimeError("reference CUDA op not built; reference falls back to its PyTorch statement")
 
-    msda.ms_deform_attn_forward = _no_native
-    msda.ms_deform_attn_backward = _no_native
-    sys.modules["MultiScaleDeformableAttention"] = msda
+        msda.ms_deform_attn_forward = _no_native
+        msda.ms_deform_attn_backward = _no_native
+        sys.modules["MultiScaleDeformableAttention"] = msda
     for name, rel in [
         ("mask2former", "mask2former"),
         ("mask2former.modeling", "mask2former/modeling"),
@@ -109,6 +131,35 @@ def build_reference_model(cfg, seed=0):
     model = MaskFormer(cfg)
     model.eval()
     return model
+
+
+def load_state_dict_into(model, sd):
+    """Loads a reference-layout state_dict keeping the module versions (no legacy-key upgrade fires)."""
+    ref_sd = model.state_dict()
+    assert list(ref_sd.keys()) == list(sd.keys()), "state_dict keys differ from the reference"
+    sd_meta = type(ref_sd)(sd)
+    sd_meta._metadata = ref_sd._metadata
+    model.load_state_dict(sd_meta)
+    return model
+
+
+def spy_attention_decisions(model):
+    """Wraps the reference's forward_prediction_heads (mask2former_transformer_decoder.py:472-489) and returns the list
+    its boolean attention masks are appended to, one (B,Q,S_l) bool tensor per head (head 0 of the nheads copies,
+    BEFORE the all-blocked-row reset of :433)."""
+    pred = model.sem_seg_head.predictor
+    orig = pred.forward_prediction_heads
+    am_list = []
+
+    def spy(output, mask_features, attn_mask_target_size):
+        r = orig(output, mask_features, attn_mask_target_size)
+        am = r[2]
+        B = mask_features.shape[0]
+        am_list.append(am.view(B, -1, am.shape[1], am.shape[2])[:, 0].clone())
+        return r
+
+    pred.forward_prediction_heads = spy
+    return am_list
 
 
 def msda_core_pytorch():

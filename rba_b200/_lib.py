@@ -75,6 +75,10 @@ PROTOTYPES = {
                                  c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "rba_msda_backward": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64), c_void_p, c_void_p, c_void_p, c_int, c_int,
                                   c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rba_msda_forward_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                     c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "rba_msda_backward_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                      c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rba_k_ood_pred_resize": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "rba_outlier_loss_workspace_floats": (c_int64, [c_int, c_int, c_int, c_int, c_int]),
     "rba_outlier_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,

@@ -11,6 +11,8 @@
 // makes every tap a D*4-byte coalesced gather (128 B for D=32) and the location/weight loads warp-uniform
 // broadcasts.  The op is gather/latency bound (16 taps x 128 B per (q,head) at 1 level x 4 points): the grid is
 // sized to cover all B*Lq*M*D elements at 256 threads/CTA, no shared memory, no reuse to exploit.
+#include <cstring>
+
 #include "common.cuh"
 
 namespace rba {
@@ -20,12 +22,27 @@ struct MsdaLevels {
   int H[MSDA_MAX_LEVELS], W[MSDA_MAX_LEVELS], start[MSDA_MAX_LEVELS];
 };
 
+// The *_dev entry points keep spatial_shapes / level_start_index on the DEVICE, where the reference's own kernel reads
+// them (ms_deform_im2col_cuda.cuh:242-250): no host copy, no synchronisation, graph-capturable.  The level table is
+// then filled from global memory (L*3 uniform, L1-resident loads) instead of the kernel parameter.
+__device__ __forceinline__ void load_device_levels(MsdaLevels& lv, const int64_t* __restrict__ dshapes,
+                                                   const int64_t* __restrict__ dstart, int L) {
+  if (dshapes == nullptr) return;
+  for (int l = 0; l < L; ++l) {
+    lv.H[l] = (int)__ldg(dshapes + 2 * l);
+    lv.W[l] = (int)__ldg(dshapes + 2 * l + 1);
+    lv.start[l] = (int)__ldg(dstart + l);
+  }
+}
+
 __global__ void __launch_bounds__(256)
-msda_forward_kernel(const float* __restrict__ value, MsdaLevels lv, const float* __restrict__ loc,
+msda_forward_kernel(const float* __restrict__ value, MsdaLevels lv, const int64_t* __restrict__ dshapes,
+                    const int64_t* __restrict__ dstart, const float* __restrict__ loc,
                     const float* __restrict__ attw, int64_t total, int S, int M, int D, int Lq, int L, int P,
                     float* __restrict__ out) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
+  load_device_levels(lv, dshapes, dstart, L);
   const int d = (int)(idx % D);
   int64_t t = idx / D;
   const int m = (int)(t % M);
@@ -65,11 +82,13 @@ msda_forward_kernel(const float* __restrict__ value, MsdaLevels lv, const float*
 
 // Same op, one thread per 4 channels (D % 4 == 0): 16-byte gathers, the location / weight loads shared by D/4 lanes.
 __global__ void __launch_bounds__(256)
-msda_forward_vec4_kernel(const float* __restrict__ value, MsdaLevels lv, const float* __restrict__ loc,
+msda_forward_vec4_kernel(const float* __restrict__ value, MsdaLevels lv, const int64_t* __restrict__ dshapes,
+                         const int64_t* __restrict__ dstart, const float* __restrict__ loc,
                          const float* __restrict__ attw, int64_t total, int S, int M, int D, int Lq, int L, int P,
                          float* __restrict__ out) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;        // over B*Lq*M*(D/4)
   if (idx >= total) return;
+  load_device_levels(lv, dshapes, dstart, L);
   const int D4 = D >> 2;
   const int d = (int)(idx % D4) * 4;
   int64_t t = idx / D4;
@@ -215,12 +234,14 @@ int msda_fused(const float* value, const int* Hs, const int* Ws, const float* oa
 // reduced with xor-shuffles and written once -- no atomics except the unavoidable grad_value scatter, any D.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-msda_backward_kernel(const float* __restrict__ value, MsdaLevels lv, const float* __restrict__ loc,
+msda_backward_kernel(const float* __restrict__ value, MsdaLevels lv, const int64_t* __restrict__ dshapes,
+                     const int64_t* __restrict__ dstart, const float* __restrict__ loc,
                      const float* __restrict__ attw, const float* __restrict__ grad_out, int64_t rows, int S, int M, int D,
                      int Lq, int L, int P, float* __restrict__ grad_value, float* __restrict__ grad_loc,
                      float* __restrict__ grad_attw) {
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // (b*Lq + q)*M + m
   if (row >= rows) return;
+  load_device_levels(lv, dshapes, dstart, L);
   const int lane = threadIdx.x & 31;
   const int m = (int)(row % M);
   const int64_t t = row / M;
@@ -297,42 +318,76 @@ static int msda_levels(const char* who, const int64_t* spatial_shapes, const int
 
 }  // namespace rba
 
-extern "C" int rba_msda_forward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
-                                const float* sampling_loc, const float* attn_weight, int B, int S, int M, int D, int Lq,
-                                int L, int P, int im2col_step, float* out, void* stream) {
+static int msda_forward_impl(const char* who, const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                             bool shapes_on_device, const float* sampling_loc, const float* attn_weight, int B, int S, int M,
+                             int D, int Lq, int L, int P, int im2col_step, float* out, void* stream) {
   using namespace rba;
-  RBA_CHECK(value && spatial_shapes && level_start_index && sampling_loc && attn_weight && out,
-            "rba_msda_forward: null pointer");
-  RBA_CHECK(B >= 0 && S > 0 && M > 0 && D > 0 && Lq > 0 && L > 0 && P > 0, "rba_msda_forward: bad shape");
-  RBA_CHECK(L <= MSDA_MAX_LEVELS, "rba_msda_forward: L=%d > %d levels", L, MSDA_MAX_LEVELS);
+  RBA_CHECK(value && spatial_shapes && level_start_index && sampling_loc && attn_weight && out, "%s: null pointer", who);
+  RBA_CHECK(B >= 0 && S > 0 && M > 0 && D > 0 && Lq > 0 && L > 0 && P > 0, "%s: bad shape", who);
+  RBA_CHECK(L <= MSDA_MAX_LEVELS, "%s: L=%d > %d levels", who, L, MSDA_MAX_LEVELS);
   if (B == 0) return RBA_OK;
   // same precondition as the reference host function (ms_deform_attn_cuda.cu:55-57)
-  RBA_CHECK(im2col_step > 0, "rba_msda_forward: im2col_step must be positive");
+  RBA_CHECK(im2col_step > 0, "%s: im2col_step must be positive", who);
   const int step = B < im2col_step ? B : im2col_step;
   RBA_CHECK(B % step == 0, "batch(%d) must divide im2col_step(%d)", B, step);
-  // spatial_shapes / level_start_index are HOST int64 arrays here (the Python shim passes .cpu() copies;
-  // they are L*3 integers and shape metadata, not data).
   MsdaLevels lv;
-  int64_t total_s = 0;
-  for (int l = 0; l < L; ++l) {
-    lv.H[l] = (int)spatial_shapes[2 * l];
-    lv.W[l] = (int)spatial_shapes[2 * l + 1];
-    lv.start[l] = (int)level_start_index[l];
-    RBA_CHECK(lv.H[l] > 0 && lv.W[l] > 0, "rba_msda_forward: empty level %d", l);
-    RBA_CHECK(lv.start[l] >= 0 && (int64_t)lv.start[l] + (int64_t)lv.H[l] * lv.W[l] <= S,
-              "rba_msda_forward: level %d exceeds value length", l);
-    total_s += (int64_t)lv.H[l] * lv.W[l];
-  }
-  RBA_CHECK(total_s == S, "rba_msda_forward: sum(H*W)=%lld != S=%d", (long long)total_s, S);
+  memset(&lv, 0, sizeof(lv));
+  const int64_t *dsh = nullptr, *dst = nullptr;
+  if (shapes_on_device) { dsh = spatial_shapes; dst = level_start_index; }
+  else RBA_TRY_(msda_levels(who, spatial_shapes, level_start_index, L, S, &lv));
   if (D % 4 == 0 && ((((uintptr_t)value) | ((uintptr_t)out)) & 15) == 0) {
     const int64_t total = (int64_t)B * Lq * M * (D / 4);
     msda_forward_vec4_kernel<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        value, lv, sampling_loc, attn_weight, total, S, M, D, Lq, L, P, out);
+        value, lv, dsh, dst, sampling_loc, attn_weight, total, S, M, D, Lq, L, P, out);
   } else {
     const int64_t total = (int64_t)B * Lq * M * D;
     msda_forward_kernel<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        value, lv, sampling_loc, attn_weight, total, S, M, D, Lq, L, P, out);
+        value, lv, dsh, dst, sampling_loc, attn_weight, total, S, M, D, Lq, L, P, out);
   }
+  RBA_LAUNCHED();
+  return RBA_OK;
+}
+
+// spatial_shapes / level_start_index are HOST int64 arrays here (validated: sum(H*W) == S)
+extern "C" int rba_msda_forward(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                const float* sampling_loc, const float* attn_weight, int B, int S, int M, int D, int Lq,
+                                int L, int P, int im2col_step, float* out, void* stream) {
+  return msda_forward_impl("rba_msda_forward", value, spatial_shapes, level_start_index, false, sampling_loc, attn_weight, B, S,
+                           M, D, Lq, L, P, im2col_step, out, stream);
+}
+// ... and DEVICE int64 arrays here, exactly the tensors the reference FFI receives (no host copy, no sync)
+extern "C" int rba_msda_forward_dev(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                    const float* sampling_loc, const float* attn_weight, int B, int S, int M, int D, int Lq,
+                                    int L, int P, int im2col_step, float* out, void* stream) {
+  return msda_forward_impl("rba_msda_forward_dev", value, spatial_shapes, level_start_index, true, sampling_loc, attn_weight, B,
+                           S, M, D, Lq, L, P, im2col_step, out, stream);
+}
+
+static int msda_backward_impl(const char* who, const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                              bool shapes_on_device, const float* sampling_loc, const float* attn_weight, const float* grad_output,
+                              int B, int S, int M, int D, int Lq, int L, int P, int im2col_step, float* grad_value,
+                              float* grad_sampling_loc, float* grad_attn_weight, void* stream) {
+  using namespace rba;
+  RBA_CHECK(value && spatial_shapes && level_start_index && sampling_loc && attn_weight && grad_output && grad_value &&
+                grad_sampling_loc && grad_attn_weight,
+            "%s: null pointer", who);
+  RBA_CHECK(B >= 0 && S > 0 && M > 0 && D > 0 && Lq > 0 && L > 0 && P > 0, "%s: bad shape", who);
+  RBA_CHECK(L <= MSDA_MAX_LEVELS, "%s: L=%d > %d levels", who, L, MSDA_MAX_LEVELS);
+  if (B == 0) return RBA_OK;
+  RBA_CHECK(im2col_step > 0, "%s: im2col_step must be positive", who);
+  const int step = B < im2col_step ? B : im2col_step;
+  RBA_CHECK(B % step == 0, "batch(%d) must divide im2col_step(%d)", B, step);       // ms_deform_attn_cuda.cu:117-119
+  MsdaLevels lv;
+  memset(&lv, 0, sizeof(lv));
+  const int64_t *dsh = nullptr, *dst = nullptr;
+  if (shapes_on_device) { dsh = spatial_shapes; dst = level_start_index; }
+  else RBA_TRY_(msda_levels(who, spatial_shapes, level_start_index, L, S, &lv));
+  cudaStream_t st = (cudaStream_t)stream;
+  RBA_CUDA(cudaMemsetAsync(grad_value, 0, (size_t)B * S * M * D * sizeof(float), st));
+  const int64_t rows = (int64_t)B * Lq * M;
+  RBA_CHECK(cdiv(rows, 8) < (1LL << 31), "%s: grid too large", who);
+  msda_backward_kernel<<<(unsigned)cdiv(rows, 8), 256, 0, st>>>(value, lv, dsh, dst, sampling_loc, attn_weight, grad_output, rows,
+                                                               S, M, D, Lq, L, P, grad_value, grad_sampling_loc, grad_attn_weight);
   RBA_LAUNCHED();
   return RBA_OK;
 }
@@ -343,23 +398,13 @@ extern "C" int rba_msda_backward(const float* value, const int64_t* spatial_shap
                                  const float* sampling_loc, const float* attn_weight, const float* grad_output, int B, int S,
                                  int M, int D, int Lq, int L, int P, int im2col_step, float* grad_value,
                                  float* grad_sampling_loc, float* grad_attn_weight, void* stream) {
-  using namespace rba;
-  RBA_CHECK(value && spatial_shapes && level_start_index && sampling_loc && attn_weight && grad_output && grad_value &&
-                grad_sampling_loc && grad_attn_weight,
-            "rba_msda_backward: null pointer");
-  RBA_CHECK(B >= 0 && S > 0 && M > 0 && D > 0 && Lq > 0 && L > 0 && P > 0, "rba_msda_backward: bad shape");
-  if (B == 0) return RBA_OK;
-  RBA_CHECK(im2col_step > 0, "rba_msda_backward: im2col_step must be positive");
-  const int step = B < im2col_step ? B : im2col_step;
-  RBA_CHECK(B % step == 0, "batch(%d) must divide im2col_step(%d)", B, step);       // ms_deform_attn_cuda.cu:117-119
-  MsdaLevels lv;
-  RBA_TRY_(msda_levels("rba_msda_backward", spatial_shapes, level_start_index, L, S, &lv));
-  cudaStream_t st = (cudaStream_t)stream;
-  RBA_CUDA(cudaMemsetAsync(grad_value, 0, (size_t)B * S * M * D * sizeof(float), st));
-  const int64_t rows = (int64_t)B * Lq * M;
-  RBA_CHECK(cdiv(rows, 8) < (1LL << 31), "rba_msda_backward: grid too large");
-  msda_backward_kernel<<<(unsigned)cdiv(rows, 8), 256, 0, st>>>(value, lv, sampling_loc, attn_weight, grad_output, rows, S, M, D,
-                                                               Lq, L, P, grad_value, grad_sampling_loc, grad_attn_weight);
-  RBA_LAUNCHED();
-  return RBA_OK;
+  return msda_backward_impl("rba_msda_backward", value, spatial_shapes, level_start_index, false, sampling_loc, attn_weight,
+                            grad_output, B, S, M, D, Lq, L, P, im2col_step, grad_value, grad_sampling_loc, grad_attn_weight, stream);
+}
+extern "C" int rba_msda_backward_dev(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                     const float* sampling_loc, const float* attn_weight, const float* grad_output, int B, int S,
+                                     int M, int D, int Lq, int L, int P, int im2col_step, float* grad_value,
+                                     float* grad_sampling_loc, float* grad_attn_weight, void* stream) {
+  return msda_backward_impl("rba_msda_backward_dev", value, spatial_shapes, level_start_index, true, sampling_loc, attn_weight,
+                            grad_output, B, S, M, D, Lq, L, P, im2col_step, grad_value, grad_sampling_loc, grad_attn_weight, stream);
 }

@@ -84,6 +84,10 @@ def einsum_score_fused(mask_embed, features, pred_logits, out_hw, bias=None, wan
     return (rba, sem) if want_sem_seg else rba
 
 
+def _dev_i64(t, like):
+    return t.is_cuda and t.device == like.device and t.dtype == torch.int64 and t.is_contiguous()
+
+
 def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_locations, attention_weights, im2col_step):
     """Same signature and result as the reference pybind op (ops/src/vision.cpp:18-21)."""
     _chk_cuda(value, sampling_locations, attention_weights)
@@ -91,9 +95,15 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
         raise RbaError("ms_deform_attn_forward: only float32 is built (the pixel decoder forces fp32, msdeformattn.py:323,329)")
     B, S, M, D = value.shape
     _, Lq, _, L, P, _ = sampling_locations.shape
+    out = torch.empty((B, Lq, M * D), dtype=torch.float32, device=value.device)
+    if _dev_i64(spatial_shapes, value) and _dev_i64(level_start_index, value):
+        # the reference passes CUDA int64 tensors: hand them through (no host copy, no sync, graph-capturable)
+        _lib.check(_lib.lib().rba_msda_forward_dev(
+            _p(value), _p(spatial_shapes), _p(level_start_index), _p(sampling_locations), _p(attention_weights),
+            B, S, M, D, Lq, L, P, int(im2col_step), _p(out), _stream()))
+        return out
     ss = spatial_shapes.detach().to("cpu", torch.int64).contiguous()
     ls = level_start_index.detach().to("cpu", torch.int64).contiguous()
-    out = torch.empty((B, Lq, M * D), dtype=torch.float32, device=value.device)
     _lib.check(_lib.lib().rba_msda_forward(
         _p(value), ctypes.cast(ss.data_ptr(), ctypes.POINTER(ctypes.c_int64)),
         ctypes.cast(ls.data_ptr(), ctypes.POINTER(ctypes.c_int64)), _p(sampling_locations), _p(attention_weights),
@@ -112,11 +122,16 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     _, Lq, _, L, P, _ = sampling_locations.shape
     if tuple(grad_output.shape) != (B, Lq, M * D):
         raise RbaError(f"ms_deform_attn_backward: grad_output {tuple(grad_output.shape)} != {(B, Lq, M * D)}")
-    ss = spatial_shapes.detach().to("cpu", torch.int64).contiguous()
-    ls = level_start_index.detach().to("cpu", torch.int64).contiguous()
     g_value = torch.empty_like(value)
     g_loc = torch.empty_like(sampling_locations)
     g_aw = torch.empty_like(attention_weights)
+    if _dev_i64(spatial_shapes, value) and _dev_i64(level_start_index, value):
+        _lib.check(_lib.lib().rba_msda_backward_dev(
+            _p(value), _p(spatial_shapes), _p(level_start_index), _p(sampling_locations), _p(attention_weights),
+            _p(grad_output), B, S, M, D, Lq, L, P, int(im2col_step), _p(g_value), _p(g_loc), _p(g_aw), _stream()))
+        return g_value, g_loc, g_aw
+    ss = spatial_shapes.detach().to("cpu", torch.int64).contiguous()
+    ls = level_start_index.detach().to("cpu", torch.int64).contiguous()
     _lib.check(_lib.lib().rba_msda_backward(
         _p(value), ctypes.cast(ss.data_ptr(), ctypes.POINTER(ctypes.c_int64)),
         ctypes.cast(ls.data_ptr(), ctypes.POINTER(ctypes.c_int64)), _p(sampling_locations), _p(attention_weights),

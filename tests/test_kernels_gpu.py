@@ -302,6 +302,12 @@ def test_msda_backward_matches_reference_gradients(dev):
         for got, want, nm in ((gv, f["grad_value"], "grad_value"), (gl, f["grad_loc"], "grad_loc"), (ga, f["grad_aw"], "grad_aw")):
             err = (got.cpu() - want).abs().max().item()
             assert err <= 2e-5 * max(1.0, want.abs().max().item()), (name, nm, err)
+        # shapes as DEVICE int64 tensors (what the reference's caller passes): the sync-free *_dev entry points
+        gv2, gl2, ga2 = ops.ms_deform_attn_backward(value.to(dev), shapes.to(dev), lsi.to(dev), loc.to(dev), aw.to(dev), go.to(dev), step)
+        assert torch.equal(gl2, gl) and torch.equal(ga2, ga) and (gv2 - gv).abs().max() <= 1e-6 * max(1.0, gv.abs().max().item())
+        o_host = ops.ms_deform_attn_forward(value.to(dev), shapes, lsi, loc.to(dev), aw.to(dev), step)
+        o_dev = ops.ms_deform_attn_forward(value.to(dev), shapes.to(dev), lsi.to(dev), loc.to(dev), aw.to(dev), step)
+        assert torch.equal(o_host, o_dev)
         v, l, a = (t.to(dev).requires_grad_(True) for t in (value, loc, aw))
         out = ops.MSDeformAttnFunction.apply(v, shapes, lsi, l, a, step)
         assert (out.detach().cpu() - f["out"]).abs().max() < 1e-5 * max(1.0, f["out"].abs().max().item())
