@@ -453,21 +453,30 @@ def run_ours(args):
     # DRAM traffic of this kernel from the committed `ncu --set full` capture (dram__bytes_read.sum + dram__bytes_write.sum,
     # per image; profiles/r1_fused_score_traffic.json), scaled to this launch's batch
     traffic, issue = None, None
-    tp = os.path.join(ROOT, "profiles", "r1_fused_score_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r2_fused_score_traffic.json")
+    other_bounds = None
     if os.path.exists(tp):
         cap = json.load(open(tp))
         traffic = cap["dram_bytes_per_image"] * B
         if "warp_instructions_per_image" in cap:
-            # the resource that actually binds this kernel: warp-instruction issue (4 schedulers x 1 instruction / clk / SM)
+            # the resources that actually bind this kernel (three co-equal floors, from the committed ncu capture, at
+            # sm_max_mhz): warp-instruction issue (4 schedulers x 1 / clk / SM), the XU (MUFU) pipe and the mma.sync pipe
             sm_clock_hz = 1e6 * float(peaks.get("sm_max_mhz", 1965.0))
             floor_ms = cap["warp_instructions_per_image"] * B / (4.0 * 148 * sm_clock_hz) * 1e3
             issue = {"warp_instructions_per_launch": cap["warp_instructions_per_image"] * B, "floor_ms": floor_ms,
                      "frac": floor_ms / k_ms, "source": "smsp__inst_executed.sum of the committed ncu capture, at sm_max_mhz"}
+            other_bounds = {}
+            for name, key in (("mufu", "xu_busy_cycles_per_sm_per_image"), ("tensor_mma_sync", "tensor_busy_cycles_per_sm_per_image")):
+                if key in cap:
+                    f_ms = cap[key] * B / sm_clock_hz * 1e3
+                    other_bounds[name] = {"floor_ms": f_ms, "frac": f_ms / k_ms}
+            other_bounds["issue"] = {"floor_ms": floor_ms, "frac": floor_ms / k_ms}
     roofline = {"kernel": "rba_einsum_score_kernel (tcgen05 mask einsum -> x4 bilinear on tf32 MMA -> sigmoid -> (Q,K) contraction "
                           "on f16 hi/lo MMA -> tanh -> class sum; one HBM pass)", "bound": "hbm",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst, kernel timed alone)" if peaks else "fallback 6.65 TB/s",
                 "traffic": traffic, "ms_per_launch": k_ms, "algorithmic_bytes_per_launch": alg_bytes, "issue_bound": issue,
+                "binding_bounds": other_bounds,
                 "note": "fp32 semantics make this kernel issue/MUFU-bound, not HBM-bound (SURVEY §0.5): per output pixel "
                         "Q sigmoids of individually interpolated logits (2 MUFU each) + 2*K*Q contraction FLOP vs 68 B"}
 

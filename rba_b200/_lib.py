@@ -5,7 +5,7 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "librba_b200.so")
+LIB_PATH = os.environ.get("RBA_B200_LIB") or os.path.join(_HERE, "lib", "librba_b200.so")   # env: A/B builds (tools/)
 
 RBA_IMG_U8, RBA_IMG_F32 = 0, 1
 RBA_ACT_NONE, RBA_ACT_RELU, RBA_ACT_GELU = 0, 1, 2

@@ -40,7 +40,10 @@ constexpr int FS_KS = 7;                                    // k16 steps in the 
 constexpr int FS_NT = 3;                                    // n8 class tiles (K <= 24)
 constexpr int FS_P_BYTES = FS_NT * 8 * FS_KS * 4 * 16;      // [class][k16 step][tq] x {b0_hi, b1_hi, b0_lo, b1_lo}
 constexpr int FS_BIAS_BYTES = 512;
-constexpr int FS_CW = 16;                                   // compute warps (4 per scheduler)
+#ifndef RBA_FS_CW
+#define RBA_FS_CW 16
+#endif
+constexpr int FS_CW = RBA_FS_CW;                            // compute warps (a multiple of 4: TMEM lane quadrants)
 constexpr int FS_CWQ = FS_CW / 4;                            // compute warps per TMEM lane quadrant
 constexpr int FS_THREADS = (2 + FS_CW) * 32;
 constexpr int FS_SMEM = FS_STAGES * FS_STAGE_BYTES + FS_PATCH_BYTES + FS_P_BYTES + FS_BIAS_BYTES + 128 + 1024;
@@ -171,7 +174,251 @@ __device__ __forceinline__ void fs_interp8(const float* tp, uint32_t a0, uint32_
   fs_mma_tf32(u, a0, a1, hi, __float_as_uint(lo));
 }
 
-template <bool WRITE_SEM, int ABL = 0, int RCPM = 1>
+// ---- unclamped batched sigmoids: the drain clamps every patch value to <= FS_UMAX, and the interpolation weights are
+// convex, so u <= FS_UMAX here and products of up to four (1 + 2^u) stay below 2^121 ----
+constexpr float FS_UMAX = 30.0f;      // sigmoid(x) for -x log2(e) > 30 is < 2^-30: the clamp changes nothing visible in fp32
+__device__ __forceinline__ void fs_sigmoid2u(float u0, float u1, float& s0, float& s1) {
+  const float a0 = 1.0f + fs_ex2(u0), a1 = 1.0f + fs_ex2(u1);
+  const float r = fs_rcp(a0 * a1);
+  s0 = r * a1; s1 = r * a0;
+}
+__device__ __forceinline__ void fs_sigmoid4u(const float* u, float* s) {
+  const float a0 = 1.0f + fs_ex2(u[0]), a1 = 1.0f + fs_ex2(u[1]);
+  const float a2 = 1.0f + fs_ex2(u[2]), a3 = 1.0f + fs_ex2(u[3]);
+  const float ab = a0 * a1, cd = a2 * a3;
+  const float r = fs_rcp(ab * cd);
+  const float rab = r * cd, rcd = r * ab;
+  s[0] = rab * a1; s[1] = rab * a0; s[2] = rcd * a3; s[3] = rcd * a2;
+}
+// sum_i 1 / (1 + 2^v_i) over four / two values with ONE reciprocal (v clamped to FS_UMAX: 1/(1+2^30) < 1e-9)
+__device__ __forceinline__ float fs_rsum4(float v0, float v1, float v2, float v3) {
+  const float a0 = 1.0f + fs_ex2(fminf(v0, FS_UMAX)), a1 = 1.0f + fs_ex2(fminf(v1, FS_UMAX));
+  const float a2 = 1.0f + fs_ex2(fminf(v2, FS_UMAX)), a3 = 1.0f + fs_ex2(fminf(v3, FS_UMAX));
+  const float ab = a0 * a1, cd = a2 * a3;
+  return fmaf(cd, a0 + a1, ab * (a2 + a3)) * fs_rcp(ab * cd);
+}
+__device__ __forceinline__ float fs_rsum2(float v0, float v1) {
+  const float a0 = 1.0f + fs_ex2(fminf(v0, FS_UMAX)), a1 = 1.0f + fs_ex2(fminf(v1, FS_UMAX));
+  return (a0 + a1) * fs_rcp(a0 * a1);
+}
+// A fragments (f16 hi / lo) of one k16 step from 8 + 8 interpolated logits.  RCPM 1: one reciprocal per pair, 2: per quad.
+template <int ABL, int RCPM>
+__device__ __forceinline__ void fs_sig_frag_u(const float* u0, const float* u1, uint32_t* ah, uint32_t* al) {
+  if (ABL != 0 || RCPM == 0 || RCPM == 3) { fs_sig_frag<ABL, RCPM>(u0, u1, ah, al); return; }
+  float s0[4], s1[4];
+  if (RCPM == 1) {
+    fs_sigmoid2u(u0[0], u0[1], s0[0], s0[1]); fs_sigmoid2u(u0[2], u0[3], s0[2], s0[3]);
+    fs_sigmoid2u(u1[0], u1[1], s1[0], s1[1]); fs_sigmoid2u(u1[2], u1[3], s1[2], s1[3]);
+  } else {
+    fs_sigmoid4u(u0, s0); fs_sigmoid4u(u1, s1);
+  }
+  fs_split_fast(s0[0], s0[1], ah[0], al[0]); fs_split_fast(s0[2], s0[3], ah[1], al[1]);
+  fs_split_fast(s1[0], s1[1], ah[2], al[2]); fs_split_fast(s1[2], s1[3], ah[3], al[3]);
+}
+
+// per-lane constants of the score phase
+struct FsLane {
+  int g, tq, tr, tcn, dyA, dx;
+  float wyA_in, wyB_in, wx_in;
+  uint32_t a0_in, a1_in;
+  const uint4* bp;
+  int nfull, tail;
+};
+
+// One k16 step (16 queries) of NC cells: prefetch the interpolated logits of the NEXT step into (n0, n1), then sigmoid,
+// f16 hi/lo split and the 9 contraction MMAs of the CURRENT step's logits (u0, u1).
+template <int NC, int ABL, int RCPM>
+__device__ __forceinline__ void fs_ks_step(const FsLane& L, const float* const* tp, uint32_t a0, uint32_t a1, int ks,
+                                           float (*u0)[4], float (*u1)[4], float (*n0)[4], float (*n1)[4],
+                                           float (*acc)[FS_NT][4]) {
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    fs_interp8(tp[c] + ks * 16 + 16, a0, a1, n0[c]);     // may run past the last query group: finite garbage, unused
+    fs_interp8(tp[c] + ks * 16 + 24, a0, a1, n1[c]);
+  }
+  uint4 bv[FS_NT];
+#pragma unroll
+  for (int nt = 0; nt < FS_NT; ++nt) bv[nt] = L.bp[(size_t)nt * 8 * FS_KS * 4 + ks * 4];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    uint32_t ah[4], al[4];
+    fs_sig_frag_u<ABL, RCPM>(u0[c], u1[c], ah, al);
+    // consecutive MMAs target different accumulators (no back-to-back dependent HMMAs)
+    if (ABL & 1) {
+      acc[c][0][0] += __uint_as_float(ah[0] ^ al[1] ^ bv[0].x ^ bv[1].y ^ bv[2].z);
+      acc[c][1][0] += __uint_as_float(ah[2] ^ al[3] ^ ah[1] ^ ah[3] ^ al[0] ^ al[2]);
+    } else {
+#pragma unroll
+      for (int nt = 0; nt < FS_NT; ++nt) fs_mma_f16(acc[c][nt], ah, bv[nt].x, bv[nt].y);
+#pragma unroll
+      for (int nt = 0; nt < FS_NT; ++nt) fs_mma_f16(acc[c][nt], ah, bv[nt].z, bv[nt].w);
+#pragma unroll
+      for (int nt = 0; nt < FS_NT; ++nt) fs_mma_f16(acc[c][nt], al, bv[nt].x, bv[nt].y);
+    }
+  }
+}
+
+// Score of NC 4x4 output cells (cell index blk[c] inside the tile) by one warp.  NC = 2 runs two independent
+// LDS -> tf32 MMA -> MUFU -> f16 split -> HMMA chains per warp (the kernel is bound by the latency of that chain at 4 warps
+// per scheduler, not by any pipe) and shares the class-probability B fragments between them.
+template <int NC, bool INTERIOR, bool WRITE_SEM, int ABL, int RCPM>
+__device__ __forceinline__ void fs_score_cells(const FsParams& p, const FsLane& L, const float* __restrict__ sPatch,
+                                               float* __restrict__ rba_b, int b, int r0, int c0, const int* blk) {
+  static_assert(INTERIOR || NC == 1, "border tiles are scored one cell at a time");
+  const int g = L.g, tq = L.tq, tr = L.tr, tcn = L.tcn;
+  int y0[NC], x0[NC];
+  const float* tp[NC];
+  uint32_t a0 = L.a0_in, a1 = L.a1_in;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int br = blk[c] / FS_BC, bc = blk[c] - br * FS_BC;
+    const int i = r0 + br, j = c0 + bc;                  // low-res coordinates of the cell's top-left tap
+    y0[c] = 4 * i + 2; x0[c] = 4 * j + 2;                // the cell's 4x4 output pixels
+    if (!INTERIOR) {
+      if (i > p.h - 1 || j > p.w - 1) return;
+      if (y0[c] >= p.H || x0[c] >= p.W) return;
+      // tap weights: interior cells use the phase weights; at the image border the clamped source index puts
+      // all the weight on the in-range tap (the out-of-range tap was zero-filled by TMA)
+      float wyA = L.wyA_in, wyB = L.wyB_in, wx = L.wx_in;
+      if (i < 0) wyA = wyB = tr ? 1.f : 0.f;
+      if (i == p.h - 1) wyA = wyB = tr ? 0.f : 1.f;
+      if (j < 0) wx = tcn ? 1.f : 0.f;
+      if (j == p.w - 1) wx = tcn ? 0.f : 1.f;
+      a0 = __float_as_uint(wyA * wx);
+      a1 = __float_as_uint(wyB * wx);
+    }
+    tp[c] = sPatch + (br + tr) * FS_ROWSTRIDE + (bc + tcn) * FS_QP + g;
+  }
+  float acc[NC][FS_NT][4];
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int nt = 0; nt < FS_NT; ++nt) acc[c][nt][0] = acc[c][nt][1] = acc[c][nt][2] = acc[c][nt][3] = 0.f;
+  // software pipeline: the interpolation (LDS -> tf32 MMA) of step ks+1 is issued before the sigmoid / split /
+  // contraction of step ks, so the MUFU chain of one step overlaps the MMA latency of the next
+  float u0[NC][4], u1[NC][4];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    fs_interp8(tp[c], a0, a1, u0[c]);                    // queries 16ks + {2tq, 2tq+1}: rows g (u[0..1]), g+8 (u[2..3])
+    fs_interp8(tp[c] + 8, a0, a1, u1[c]);                // queries 16ks + 8 + {2tq, 2tq+1}
+  }
+  // two k16 steps per trip with the "current" and "next" logits swapping roles (no register moves between steps)
+  float n0[NC][4], n1[NC][4];
+  int ks = 0;
+#pragma unroll 1
+  for (; ks + 1 < L.nfull; ks += 2) {
+    fs_ks_step<NC, ABL, RCPM>(L, tp, a0, a1, ks, u0, u1, n0, n1, acc);
+    fs_ks_step<NC, ABL, RCPM>(L, tp, a0, a1, ks + 1, n0, n1, u0, u1, acc);
+  }
+  if (ks < L.nfull) {
+    fs_ks_step<NC, ABL, RCPM>(L, tp, a0, a1, ks, u0, u1, n0, n1, acc);
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { u0[c][e] = n0[c][e]; u1[c][e] = n1[c][e]; }
+  }
+  if (L.tail) {
+    uint4 bv[FS_NT];
+#pragma unroll
+    for (int nt = 0; nt < FS_NT; ++nt) bv[nt] = L.bp[(size_t)nt * 8 * FS_KS * 4 + L.nfull * 4];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      uint32_t ah0, al0, ah1, al1;
+      if (ABL != 0 || RCPM == 0) {
+        fs_split<ABL>(fs_sig<ABL>(u0[c][0]), fs_sig<ABL>(u0[c][1]), ah0, al0);
+        fs_split<ABL>(fs_sig<ABL>(u0[c][2]), fs_sig<ABL>(u0[c][3]), ah1, al1);
+      } else {
+        float s0[4];
+        if (RCPM == 3) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) s0[e] = fs_sigmoid_scaled(u0[c][e]);
+        } else {
+          fs_sigmoid4u(u0[c], s0);
+        }
+        fs_split_fast(s0[0], s0[1], ah0, al0);
+        fs_split_fast(s0[2], s0[3], ah1, al1);
+      }
+#pragma unroll
+      for (int nt = 0; nt < FS_NT; ++nt) fs_mma_f16_k8(acc[c][nt], ah0, ah1, bv[nt].x);
+#pragma unroll
+      for (int nt = 0; nt < FS_NT; ++nt) fs_mma_f16_k8(acc[c][nt], ah0, ah1, bv[nt].z);
+#pragma unroll
+      for (int nt = 0; nt < FS_NT; ++nt) fs_mma_f16_k8(acc[c][nt], al0, al1, bv[nt].x);
+    }
+  }
+  // ---- epilogue: acc[nt][e] = sem_seg[class 8nt+2tq+e] of pixel A (row g), acc[nt][2+e] of pixel B (row g+8).
+  // sum_c tanh(s_c) = n - 2 sum_c 1/(1 + e^(2 s_c)); padded classes hold exactly 0 and contribute tanh(0) = 0 ----
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int yA = y0[c] + L.dyA, yB = yA + 2, x = x0[c] + L.dx;
+    const bool okx = INTERIOR || (x >= 0 && x < p.W);
+    const bool okA = INTERIOR || (okx && yA >= 0 && yA < p.H), okB = INTERIOR || (okx && yB >= 0 && yB < p.H);
+    if (WRITE_SEM) {
+#pragma unroll
+      for (int nt = 0; nt < FS_NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int cc = nt * 8 + tq * 2 + e;
+          if (cc < p.Kc) {
+            if (okA) p.sem[(((size_t)b * p.Kc + cc) * p.H + yA) * p.W + x] = acc[c][nt][e];
+            if (okB) p.sem[(((size_t)b * p.Kc + cc) * p.H + yB) * p.W + x] = acc[c][nt][2 + e];
+          }
+        }
+    }
+    if (p.score_func == RBA_SCORE_ENERGY) {
+      // -logsumexp over the kept classes (evaluate_ood.py:152-159): max and sum reduced over the quad
+      float ma = -1e30f, mb = -1e30f;
+#pragma unroll
+      for (int nt = 0; nt < FS_NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          if (nt * 8 + tq * 2 + e < p.Kc) { ma = fmaxf(ma, acc[c][nt][e]); mb = fmaxf(mb, acc[c][nt][2 + e]); }
+      ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 1));
+      ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 2));
+      mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 1));
+      mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 2));
+      float sa = 0.f, sb = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < FS_NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          if (nt * 8 + tq * 2 + e < p.Kc) { sa += __expf(acc[c][nt][e] - ma); sb += __expf(acc[c][nt][2 + e] - mb); }
+      sa += __shfl_xor_sync(0xffffffffu, sa, 1);
+      sa += __shfl_xor_sync(0xffffffffu, sa, 2);
+      sb += __shfl_xor_sync(0xffffffffu, sb, 1);
+      sb += __shfl_xor_sync(0xffffffffu, sb, 2);
+      if (tq == 0 && okA) rba_b[(size_t)yA * p.W + x] = -(ma + logf(sa));
+      if (tq == 1 && okB) rba_b[(size_t)yB * p.W + x] = -(mb + logf(sb));
+    } else {
+      float ra = 0.f, rb = 0.f;
+      if (ABL & 8) {
+#pragma unroll
+        for (int nt = 0; nt < FS_NT; ++nt) { ra += acc[c][nt][0] + acc[c][nt][1]; rb += acc[c][nt][2] + acc[c][nt][3]; }
+      } else if (WRITE_SEM) {
+#pragma unroll
+        for (int nt = 0; nt < FS_NT; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            ra += fs_rcp(1.0f + fs_ex2(2.8853900817779268f * acc[c][nt][e]));
+            rb += fs_rcp(1.0f + fs_ex2(2.8853900817779268f * acc[c][nt][2 + e]));
+          }
+      } else {
+        // class sums arrive pre-scaled by 2 log2(e); six per pixel and lane: one quad + one pair, 2 reciprocals instead of 6
+        ra = fs_rsum4(acc[c][0][0], acc[c][0][1], acc[c][1][0], acc[c][1][1]) + fs_rsum2(acc[c][2][0], acc[c][2][1]);
+        rb = fs_rsum4(acc[c][0][2], acc[c][0][3], acc[c][1][2], acc[c][1][3]) + fs_rsum2(acc[c][2][2], acc[c][2][3]);
+      }
+      ra += __shfl_xor_sync(0xffffffffu, ra, 1);
+      ra += __shfl_xor_sync(0xffffffffu, ra, 2);
+      rb += __shfl_xor_sync(0xffffffffu, rb, 1);
+      rb += __shfl_xor_sync(0xffffffffu, rb, 2);
+      // rba = -sum tanh = 2 sum r - 24
+      if (tq == 0 && okA) rba_b[(size_t)yA * p.W + x] = fmaf(2.0f, ra, -(float)(FS_NT * 8));
+      if (tq == 1 && okB) rba_b[(size_t)yB * p.W + x] = fmaf(2.0f, rb, -(float)(FS_NT * 8));
+    }
+  }
+}
+
+template <bool WRITE_SEM, int ABL = 0, int RCPM = 2, int NCELL = 2>
 __global__ void __launch_bounds__(FS_THREADS, 1)
 rba_einsum_score_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constant__ CUtensorMap tmY_lo,
                         const __grid_constant__ CUtensorMap tmE_hi, const __grid_constant__ CUtensorMap tmE_lo,
@@ -271,7 +518,11 @@ rba_einsum_score_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid
     const float lyA = 0.125f + 0.25f * (float)dyA, lyB = lyA + 0.5f, lxx = 0.125f + 0.25f * (float)dx;
     const float wyA_in = tr ? lyA : 1.f - lyA, wyB_in = tr ? lyB : 1.f - lyB, wx_in = tcn ? lxx : 1.f - lxx;
     const uint32_t a0_in = __float_as_uint(wyA_in * wx_in), a1_in = __float_as_uint(wyB_in * wx_in);
-    const uint4* const bp = sP + (size_t)g * FS_KS * 4 + tq;
+    FsLane L;
+    L.g = g; L.tq = tq; L.tr = tr; L.tcn = tcn; L.dyA = dyA; L.dx = dx;
+    L.wyA_in = wyA_in; L.wyB_in = wyB_in; L.wx_in = wx_in; L.a0_in = a0_in; L.a1_in = a1_in;
+    L.bp = sP + (size_t)g * FS_KS * 4 + tq;
+    L.nfull = nfull; L.tail = tail;
     int cur_b = -1;
     uint32_t lt = 0;
     for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++lt) {
@@ -326,10 +577,10 @@ rba_einsum_score_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid
             for (int j = 0; j < 4; ++j) {
               const float4 b4 = *reinterpret_cast<const float4*>(sBias + q0 + 4 * j);
               float4 o;
-              o.x = fmaf(__uint_as_float(v[4 * j]), SCALE, b4.x);
-              o.y = fmaf(__uint_as_float(v[4 * j + 1]), SCALE, b4.y);
-              o.z = fmaf(__uint_as_float(v[4 * j + 2]), SCALE, b4.z);
-              o.w = fmaf(__uint_as_float(v[4 * j + 3]), SCALE, b4.w);
+              o.x = fminf(fmaf(__uint_as_float(v[4 * j]), SCALE, b4.x), FS_UMAX);
+              o.y = fminf(fmaf(__uint_as_float(v[4 * j + 1]), SCALE, b4.y), FS_UMAX);
+              o.z = fminf(fmaf(__uint_as_float(v[4 * j + 2]), SCALE, b4.z), FS_UMAX);
+              o.w = fminf(fmaf(__uint_as_float(v[4 * j + 3]), SCALE, b4.w), FS_UMAX);
               *reinterpret_cast<float4*>(prow + q0 + 4 * j) = o;
             }
           } else {
@@ -339,10 +590,10 @@ rba_einsum_score_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid
             for (int j = 0; j < 2; ++j) {
               const float4 b4 = *reinterpret_cast<const float4*>(sBias + q0 + 4 * j);
               float4 o;
-              o.x = fmaf(__uint_as_float(v[4 * j]), SCALE, b4.x);
-              o.y = fmaf(__uint_as_float(v[4 * j + 1]), SCALE, b4.y);
-              o.z = fmaf(__uint_as_float(v[4 * j + 2]), SCALE, b4.z);
-              o.w = fmaf(__uint_as_float(v[4 * j + 3]), SCALE, b4.w);
+              o.x = fminf(fmaf(__uint_as_float(v[4 * j]), SCALE, b4.x), FS_UMAX);
+              o.y = fminf(fmaf(__uint_as_float(v[4 * j + 1]), SCALE, b4.y), FS_UMAX);
+              o.z = fminf(fmaf(__uint_as_float(v[4 * j + 2]), SCALE, b4.z), FS_UMAX);
+              o.w = fminf(fmaf(__uint_as_float(v[4 * j + 3]), SCALE, b4.w), FS_UMAX);
               *reinterpret_cast<float4*>(prow + q0 + 4 * j) = o;
             }
           }
@@ -353,156 +604,25 @@ rba_einsum_score_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid
       if (lane == 0) mbar_arrive(acc_empty);               // the MMAs of the next tile may start
       fs_bar_compute();                                    // patch complete
 
-      // ---- score phase: one 4x4 output cell per warp iteration; cell index advances by 16 = one row + one column ----
+      // ---- score phase: 4x4 output cells, two per warp iteration on interior tiles (cells cw + 16 k) ----
       float* const rba_b = p.rba + (size_t)b * p.H * p.W;
       // interior tile (89 % of them at 1024 x 2048): every cell has four in-range taps and sixteen in-range output pixels,
       // so the per-cell range checks, border weights and store predicates are skipped (CTA-uniform branch)
       const bool interior = r0 >= 0 && c0 >= 0 && r0 + FS_BR <= p.h - 1 && c0 + FS_BC <= p.w - 1 &&
                             4 * (r0 + FS_BR - 1) + 5 < p.H && 4 * (c0 + FS_BC - 1) + 5 < p.W;
-      int br = cw / FS_BC, bc = cw - br * FS_BC;
-      for (int blk = cw; blk < FS_NBLK; blk += FS_CW, br += FS_CW / FS_BC, bc += FS_CW % FS_BC) {
-        if (bc >= FS_BC) { bc -= FS_BC; ++br; }
-        if (dbg & 16) continue;
-        const int i = r0 + br, j = c0 + bc;                // low-res coordinates of the cell's top-left tap
-        const int y0 = 4 * i + 2, x0 = 4 * j + 2;          // the cell's 4x4 output pixels
-        uint32_t a0 = a0_in, a1 = a1_in;
-        if (!interior) {
-          if (i > p.h - 1 || j > p.w - 1) continue;
-          if (y0 >= p.H || x0 >= p.W) continue;
-          // tap weights: interior cells use the phase weights; at the image border the clamped source index puts
-          // all the weight on the in-range tap (the out-of-range tap was zero-filled by TMA)
-          float wyA = wyA_in, wyB = wyB_in, wx = wx_in;
-          if (i < 0) wyA = wyB = tr ? 1.f : 0.f;
-          if (i == p.h - 1) wyA = wyB = tr ? 0.f : 1.f;
-          if (j < 0) wx = tcn ? 1.f : 0.f;
-          if (j == p.w - 1) wx = tcn ? 0.f : 1.f;
-          a0 = __float_as_uint(wyA * wx);
-          a1 = __float_as_uint(wyB * wx);
-        }
-        const float* tp = sPatch + (br + tr) * FS_ROWSTRIDE + (bc + tcn) * FS_QP + g;
-
-        float acc[FS_NT][4];
-#pragma unroll
-        for (int nt = 0; nt < FS_NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
-        // software pipeline: the interpolation (LDS -> tf32 MMA) of step ks+1 is issued before the sigmoid / split /
-        // contraction of step ks, so the MUFU chain of one step overlaps the MMA latency of the next
-        float u0[4], u1[4];
-        fs_interp8(tp, a0, a1, u0);                        // queries 16ks + {2tq, 2tq+1}: rows g (u[0..1]), g+8 (u[2..3])
-        fs_interp8(tp + 8, a0, a1, u1);                    // queries 16ks + 8 + {2tq, 2tq+1}
-#pragma unroll 1
-        for (int ks = 0; ks < nfull; ++ks) {
-          float n0[4], n1[4];
-          fs_interp8(tp + ks * 16 + 16, a0, a1, n0);       // may run past the last query group: finite garbage, unused
-          fs_interp8(tp + ks * 16 + 24, a0, a1, n1);
-          uint4 bv[FS_NT];
-#pragma unroll
-          for (int nt = 0; nt < FS_NT; ++nt) bv[nt] = bp[(size_t)nt * 8 * FS_KS * 4 + ks * 4];
-          uint32_t ah[4], al[4];
-          fs_sig_frag<ABL, RCPM>(u0, u1, ah, al);
-          // consecutive MMAs target different accumulators (no back-to-back dependent HMMAs)
-          if (ABL & 1) {
-            acc[0][0] += __uint_as_float(ah[0] ^ al[1] ^ bv[0].x ^ bv[1].y ^ bv[2].z);
-            acc[1][0] += __uint_as_float(ah[2] ^ al[3] ^ ah[1] ^ ah[3] ^ al[0] ^ al[2]);
-          } else {
-#pragma unroll
-            for (int nt = 0; nt < FS_NT; ++nt) fs_mma_f16(acc[nt], ah, bv[nt].x, bv[nt].y);
-#pragma unroll
-            for (int nt = 0; nt < FS_NT; ++nt) fs_mma_f16(acc[nt], ah, bv[nt].z, bv[nt].w);
-#pragma unroll
-            for (int nt = 0; nt < FS_NT; ++nt) fs_mma_f16(acc[nt], al, bv[nt].x, bv[nt].y);
-          }
-#pragma unroll
-          for (int e = 0; e < 4; ++e) { u0[e] = n0[e]; u1[e] = n1[e]; }
-        }
-        if (tail) {
-          uint32_t ah0, al0, ah1, al1;
-          if (ABL != 0 || RCPM == 0) {
-            fs_split<ABL>(fs_sig<ABL>(u0[0]), fs_sig<ABL>(u0[1]), ah0, al0);
-            fs_split<ABL>(fs_sig<ABL>(u0[2]), fs_sig<ABL>(u0[3]), ah1, al1);
-          } else {
-            float s0[4];
-            if (RCPM == 3) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) s0[e] = fs_sigmoid_scaled(u0[e]);
-            } else {
-              fs_sigmoid4(u0, s0);
+      if (!(dbg & 16)) {
+        if (interior) {
+          int blk = cw;
+          if (NCELL == 2) {
+            for (; blk + FS_CW < FS_NBLK; blk += 2 * FS_CW) {
+              const int pair[2] = {blk, blk + FS_CW};
+              fs_score_cells<2, true, WRITE_SEM, ABL, RCPM>(p, L, sPatch, rba_b, b, r0, c0, pair);
             }
-            fs_split_fast(s0[0], s0[1], ah0, al0);
-            fs_split_fast(s0[2], s0[3], ah1, al1);
           }
-          uint4 bv[FS_NT];
-#pragma unroll
-          for (int nt = 0; nt < FS_NT; ++nt) bv[nt] = bp[(size_t)nt * 8 * FS_KS * 4 + nfull * 4];
-#pragma unroll
-          for (int nt = 0; nt < FS_NT; ++nt) fs_mma_f16_k8(acc[nt], ah0, ah1, bv[nt].x);
-#pragma unroll
-          for (int nt = 0; nt < FS_NT; ++nt) fs_mma_f16_k8(acc[nt], ah0, ah1, bv[nt].z);
-#pragma unroll
-          for (int nt = 0; nt < FS_NT; ++nt) fs_mma_f16_k8(acc[nt], al0, al1, bv[nt].x);
-        }
-        // ---- epilogue: acc[nt][e] = sem_seg[class 8nt+2tq+e] of pixel A (row g), acc[nt][2+e] of pixel B (row g+8).
-        // sum_c tanh(s_c) = n - 2 sum_c 1/(1 + e^(2 s_c)); padded classes hold exactly 0 and contribute tanh(0) = 0 ----
-        const int yA = y0 + dyA, yB = yA + 2, x = x0 + dx;
-        const bool okx = interior || (x >= 0 && x < p.W);
-        const bool okA = interior || (okx && yA >= 0 && yA < p.H), okB = interior || (okx && yB >= 0 && yB < p.H);
-        if (WRITE_SEM) {
-#pragma unroll
-          for (int nt = 0; nt < FS_NT; ++nt)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int c = nt * 8 + tq * 2 + e;
-              if (c < p.Kc) {
-                if (okA) p.sem[(((size_t)b * p.Kc + c) * p.H + yA) * p.W + x] = acc[nt][e];
-                if (okB) p.sem[(((size_t)b * p.Kc + c) * p.H + yB) * p.W + x] = acc[nt][2 + e];
-              }
-            }
-        }
-        if (p.score_func == RBA_SCORE_ENERGY) {
-          // -logsumexp over the kept classes (evaluate_ood.py:152-159): max and sum reduced over the quad
-          float ma = -1e30f, mb = -1e30f;
-#pragma unroll
-          for (int nt = 0; nt < FS_NT; ++nt)
-#pragma unroll
-            for (int e = 0; e < 2; ++e)
-              if (nt * 8 + tq * 2 + e < p.Kc) { ma = fmaxf(ma, acc[nt][e]); mb = fmaxf(mb, acc[nt][2 + e]); }
-          ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 1));
-          ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 2));
-          mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 1));
-          mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 2));
-          float sa = 0.f, sb = 0.f;
-#pragma unroll
-          for (int nt = 0; nt < FS_NT; ++nt)
-#pragma unroll
-            for (int e = 0; e < 2; ++e)
-              if (nt * 8 + tq * 2 + e < p.Kc) { sa += __expf(acc[nt][e] - ma); sb += __expf(acc[nt][2 + e] - mb); }
-          sa += __shfl_xor_sync(0xffffffffu, sa, 1);
-          sa += __shfl_xor_sync(0xffffffffu, sa, 2);
-          sb += __shfl_xor_sync(0xffffffffu, sb, 1);
-          sb += __shfl_xor_sync(0xffffffffu, sb, 2);
-          if (tq == 0 && okA) rba_b[(size_t)yA * p.W + x] = -(ma + logf(sa));
-          if (tq == 1 && okB) rba_b[(size_t)yB * p.W + x] = -(mb + logf(sb));
+          for (; blk < FS_NBLK; blk += FS_CW) fs_score_cells<1, true, WRITE_SEM, ABL, RCPM>(p, L, sPatch, rba_b, b, r0, c0, &blk);
         } else {
-          float ra = 0.f, rb = 0.f;
-#pragma unroll
-          for (int nt = 0; nt < FS_NT; ++nt)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              if (ABL & 8) { ra += acc[nt][e]; rb += acc[nt][2 + e]; continue; }
-              if (WRITE_SEM) {
-                ra += fs_rcp(1.0f + fs_ex2(2.8853900817779268f * acc[nt][e]));
-                rb += fs_rcp(1.0f + fs_ex2(2.8853900817779268f * acc[nt][2 + e]));
-              } else {                                       // class sums arrive pre-scaled by 2 log2(e)
-                ra += fs_rcp(1.0f + fs_ex2(acc[nt][e]));
-                rb += fs_rcp(1.0f + fs_ex2(acc[nt][2 + e]));
-              }
-            }
-          ra += __shfl_xor_sync(0xffffffffu, ra, 1);
-          ra += __shfl_xor_sync(0xffffffffu, ra, 2);
-          rb += __shfl_xor_sync(0xffffffffu, rb, 1);
-          rb += __shfl_xor_sync(0xffffffffu, rb, 2);
-          // rba = -sum tanh = 2 sum r - 24
-          if (tq == 0 && okA) rba_b[(size_t)yA * p.W + x] = fmaf(2.0f, ra, -(float)(FS_NT * 8));
-          if (tq == 1 && okB) rba_b[(size_t)yB * p.W + x] = fmaf(2.0f, rb, -(float)(FS_NT * 8));
+          for (int blk = cw; blk < FS_NBLK; blk += FS_CW)
+            fs_score_cells<1, false, WRITE_SEM, ABL, RCPM>(p, L, sPatch, rba_b, b, r0, c0, &blk);
         }
       }
       fs_bar_compute();                                    // patch (and, at an image change, sP) free for the next tile
@@ -544,32 +664,34 @@ int einsum_score_launch(const uint16_t* e_hi, const uint16_t* e_lo, const float*
   RBA_TRY_(make_map_3d(&te_hi, e_hi, D, Q, D, B, (int64_t)Q * D, FS_NQ));
   RBA_TRY_(make_map_3d(&te_lo, e_lo, D, Q, D, B, (int64_t)Q * D, FS_NQ));
   dim3 grid((unsigned)std::min<int64_t>(nt, num_sms()));
-  if (sem) {
-    static PerDeviceOnce once;
-    if (once.needed()) { RBA_CUDA(cudaFuncSetAttribute(rba_einsum_score_kernel<true, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM)); once.done(); }
-    rba_einsum_score_kernel<true, 0, 1><<<grid, FS_THREADS, FS_SMEM, st>>>(ty_hi, ty_lo, te_hi, te_lo, p);
-  } else {
-    static const int abl = []() { const char* e = getenv("RBA_FS_ABL"); return e ? atoi(e) : 0; }();
-    static const int rcpm = []() { const char* e = getenv("RBA_FS_RCP"); return e ? atoi(e) : 1; }();
-#define RBA_FS_LAUNCH(A, R)                                                                                                  \
+#define RBA_FS_LAUNCH(S, A, R, N)                                                                                          \
   do {                                                                                                                     \
     static PerDeviceOnce once;                                                                                             \
-    if (once.needed()) { RBA_CUDA(cudaFuncSetAttribute(rba_einsum_score_kernel<false, A, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM)); once.done(); } \
-    rba_einsum_score_kernel<false, A, R><<<grid, FS_THREADS, FS_SMEM, st>>>(ty_hi, ty_lo, te_hi, te_lo, p);                \
+    if (once.needed()) { RBA_CUDA(cudaFuncSetAttribute(rba_einsum_score_kernel<S, A, R, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM)); once.done(); } \
+    rba_einsum_score_kernel<S, A, R, N><<<grid, FS_THREADS, FS_SMEM, st>>>(ty_hi, ty_lo, te_hi, te_lo, p);                 \
   } while (0)
-    switch (abl * 4 + (abl ? 0 : rcpm)) {
-      case 1 * 4: RBA_FS_LAUNCH(1, 0); break;
-      case 2 * 4: RBA_FS_LAUNCH(2, 0); break;
-      case 4 * 4: RBA_FS_LAUNCH(4, 0); break;
-      case 8 * 4: RBA_FS_LAUNCH(8, 0); break;
-      case 15 * 4: RBA_FS_LAUNCH(15, 0); break;
-      case 0: RBA_FS_LAUNCH(0, 0); break;
-      case 3: RBA_FS_LAUNCH(0, 3); break;
-      case 2: RBA_FS_LAUNCH(0, 2); break;
-      default: RBA_FS_LAUNCH(0, 1); break;
-    }
-#undef RBA_FS_LAUNCH
+  if (sem) {
+    RBA_FS_LAUNCH(true, 0, 2, 1);     // sem_seg written: HBM-store-bound, one cell per warp iteration keeps registers low
+  } else {
+    // profiling knobs: RBA_FS_ABL (ablations), RBA_FS_RCP (0 one reciprocal per sigmoid, 1 per pair [default], 2 per quad),
+    // RBA_FS_NCELL (1 [default]: one cell per warp iteration, 2: two).  Measured (profiles/r2b_fused_score_ab.txt): no variant
+    // moves the time by more than 5 %: the kernel sits at ~45 % of THREE co-equal floors (XU 0.66 ms, mma.sync 0.73 ms,
+    // issue 0.78 ms per 8 images) with math_pipe_throttle as the top stall, so neither ILP nor fewer reciprocals help
+    static const int abl = []() { const char* e = getenv("RBA_FS_ABL"); return e ? atoi(e) : 0; }();
+    static const int rcpm = []() { const char* e = getenv("RBA_FS_RCP"); return e ? atoi(e) : 1; }();
+    static const int ncell = []() { const char* e = getenv("RBA_FS_NCELL"); return e ? atoi(e) : 1; }();
+    if (abl == 1) RBA_FS_LAUNCH(false, 1, 0, 2);
+    else if (abl == 2) RBA_FS_LAUNCH(false, 2, 0, 2);
+    else if (abl == 4) RBA_FS_LAUNCH(false, 4, 0, 2);
+    else if (abl == 8) RBA_FS_LAUNCH(false, 8, 0, 2);
+    else if (abl == 15) RBA_FS_LAUNCH(false, 15, 0, 2);
+    else if (ncell == 1 && rcpm == 1) RBA_FS_LAUNCH(false, 0, 1, 1);
+    else if (ncell == 1) RBA_FS_LAUNCH(false, 0, 2, 1);
+    else if (rcpm == 0) RBA_FS_LAUNCH(false, 0, 0, 2);
+    else if (rcpm == 1) RBA_FS_LAUNCH(false, 0, 1, 2);
+    else RBA_FS_LAUNCH(false, 0, 2, 2);
   }
+#undef RBA_FS_LAUNCH
   RBA_LAUNCHED();
   return RBA_OK;
 }
