@@ -82,8 +82,8 @@ int rba_model_load_tensor(rba_model* m, const char* key, const float* data, cons
  * buffers (bf16 split planes of the weights, re-laid-out conv filters, fused projection matrices). */
 int rba_model_finalize(rba_model* m);
 /* Options: "taps" (0/1: keep stage-boundary tensors of the next forwards for rba_model_get_tap),
- * "gemm_backend" (RBA_GEMM_FFMA / RBA_GEMM_TC, see below), "attn_backend" (1 = tensor-core window attention,
- * 0 = fp32 CUDA-core kernel). */
+ * "gemm_backend" (RBA_GEMM_FFMA / RBA_GEMM_TC, see below), "attn_backend" (2 = tcgen05 + TMA window attention
+ * [default], 1 = mma.sync tensor-core kernel, 0 = fp32 CUDA-core kernel). */
 int rba_model_set_option(rba_model* m, const char* name, int value);
 /* Max batch / padded image size the workspace is sized for; (re)allocates device workspace. */
 int rba_model_reserve(rba_model* m, int batch, int height, int width);
@@ -269,6 +269,16 @@ int rba_k_window_attn(const float* qkv, const float* bias_table, int B, int H, i
 /* Tensor-core variant (mma.sync m16n8k16, bf16x3): qkv given as split planes [rows, 3C] (what the QKV GEMM writes). */
 int rba_k_window_attn_planes(const uint16_t* qkv_hi, const uint16_t* qkv_lo, const float* bias_table, int B, int H, int W,
                              int C, int heads, int ws, int shift, uint16_t* out_hi, uint16_t* out_lo, void* stream);
+
+/* tcgen05 + TMA variant (the engine's default): S = q k^T and O = P v as tcgen05.mma (bf16x3) with fp32 accumulators in
+ * tensor memory, q / k / v tiles fetched by TMA straight from the planes, P handed to the second MMA through tensor memory.
+ * `bias_prepared` is the per-head, log2(e)-scaled copy of relative_position_bias_table that
+ * rba_k_window_attn_prepare_bias writes (rba_k_window_attn_bias_floats(heads) floats, once per block at load time).
+ * shift must be 0 or ws / 2. */
+int64_t rba_k_window_attn_bias_floats(int heads);
+int rba_k_window_attn_prepare_bias(const float* bias_table, int heads, float* prepared, void* stream);
+int rba_k_window_attn_tc(const uint16_t* qkv_hi, const uint16_t* qkv_lo, const float* bias_prepared, int B, int H, int W, int C,
+                         int heads, int ws, int shift, uint16_t* out_hi, uint16_t* out_lo, void* stream);
 
 /* nn.MultiheadAttention core for the decoder (mask2former_transformer_decoder.py:52-53,110-113):
  * q [B,Lq,E], k,v [B,Lk,E] fp32 (already projected, q NOT yet scaled), mask (B,Lq,Lk) uint8 (1 = blocked, shared by

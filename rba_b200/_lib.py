@@ -90,6 +90,9 @@ PROTOTYPES = {
                                 c_void_p, c_void_p, c_void_p, c_void_p]),
     "rba_k_window_attn": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "rba_k_window_attn_planes": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "rba_k_window_attn_bias_floats": (c_int64, [c_int]),
+    "rba_k_window_attn_prepare_bias": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    "rba_k_window_attn_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "rba_k_mha_workspace_floats": (c_int64, [c_int, c_int, c_int, c_int]),
     "rba_k_mha": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                           c_void_p]),

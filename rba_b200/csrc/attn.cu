@@ -735,6 +735,10 @@ extern "C" int rba_k_window_attn_planes(const uint16_t* qkv_hi, const uint16_t* 
   return rba::window_attn_planes(qkv_hi, qkv_lo, bias_table, nullptr, B, H, W, C, heads, ws, shift, out_hi, out_lo, (cudaStream_t)stream);
 }
 
+extern "C" int64_t rba_k_window_attn_bias_floats(int heads) { return rba::window_attn_bias_floats(heads); }
+extern "C" int rba_k_window_attn_prepare_bias(const float* bias_table, int heads, float* prepared, void* stream) {
+  return rba::window_attn_prepare_bias(bias_table, heads, prepared, (cudaStream_t)stream);
+}
 extern "C" int64_t rba_k_mha_workspace_floats(int B, int Lq, int Lk, int heads) { return rba::mha_workspace_floats(B, Lq, Lk, heads); }
 
 extern "C" int rba_k_mha(const float* q, const float* k, const float* v, const uint8_t* mask, int B, int Lq, int Lk, int E,

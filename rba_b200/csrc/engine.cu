@@ -102,7 +102,7 @@ struct rba_model {
   int device = 0;
   bool finalized = false;
   bool taps_enabled = false;
-  int attn_backend = 1;             // 1: tensor-core window attention (mma.sync bf16x3), 0: fp32 CUDA-core kernel
+  int attn_backend = 2;             // 2: tcgen05 + TMA window attention (bf16x3), 1: mma.sync bf16x3 kernel, 0: fp32 CUDA-core kernel
   int gemm_backend = RBA_GEMM_TC;   // tcgen05 bf16x3; RBA_GEMM_BACKEND=ffma selects the exact fp32 FMA kernels
   int fused_score = 1;              // 1: last mask einsum + score in one kernel (score_fused.cu) when pred_masks is not asked for
   int score_func = RBA_SCORE_RBA;   // per-pixel reduction written to the score output (evaluate_ood.py:143-159)
@@ -224,7 +224,7 @@ extern "C" int rba_model_set_option(rba_model* m, const char* name, int value) {
     RBA_CHECK(value == RBA_GEMM_FFMA || value == RBA_GEMM_TC, "bad gemm backend %d", value);
     m->gemm_backend = value;
   } else if (n == "attn_backend") {
-    RBA_CHECK(value == 0 || value == 1, "bad attn backend %d", value);
+    RBA_CHECK(value >= 0 && value <= 2, "bad attn backend %d", value);
     m->attn_backend = value;
     m->rB = m->rH = m->rW = 0;
   } else if (n == "score_func") {
@@ -555,7 +555,13 @@ static int forward_impl(rba_model* m, const void* images, int img_dtype, int B, 
       RBA_RUN(layernorm(x, F.W(p + "norm1.weight"), F.W(p + "norm1.bias"), 1, B, Hs, Wsz, C, ws, shift, eps, nullptr, a1.hi,
                         a1.lo, st));
       Planes ao = A.planes(RW * C);
-      if (m->attn_backend == 1) {
+      if (m->attn_backend == 2) {
+        Planes qkv = A.planes(RW * 3 * C);
+        RBA_TRY(F.lin(a1, C, RW, C, F.P(p + "attn.qkv.weight"), 3 * C, F.W(p + "attn.qkv.bias"), RBA_ACT_NONE, nullptr, nullptr, 0,
+                      qkv, 3 * C));
+        RBA_RUN(window_attn_tc(qkv.hi, qkv.lo, F.W(p + "attn.relative_position_bias_prepared"), B, Hs, Wsz, C, heads, ws, shift,
+                               ao.hi, ao.lo, st));
+      } else if (m->attn_backend == 1) {
         Planes qkv = A.planes(RW * 3 * C);
         RBA_TRY(F.lin(a1, C, RW, C, F.P(p + "attn.qkv.weight"), 3 * C, F.W(p + "attn.qkv.bias"), RBA_ACT_NONE, nullptr, nullptr, 0,
                       qkv, 3 * C));

@@ -1,0 +1,543 @@
+// Swin window attention core on tcgen05 + TMA (swin.py:145-168).
+//
+//   S = (q k^T) * scale + relative_position_bias (+ shift mask);  P = softmax(S);  O = P v        per (window, head)
+//
+// q, k, v arrive as bf16 split planes [rows = B*nW*144, 3C] (what the QKV GEMM epilogue writes), O leaves as split planes
+// [rows, C] (what the proj GEMM reads through TMA).  Both contractions run on the 5th-generation tensor cores in bf16x3
+// split precision (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM), everything else in fp32.
+//
+// One persistent CTA per SM walks (window, head) items.  Per item:
+//   TMA        six 144 x 32 bf16 boxes (q, k, v  x  hi, lo; 64-byte rows, SWIZZLE_64B) + the head's 529-entry bias table
+//              (bulk copy) into one of three shared-memory stages                                     55.3 KB in flight / stage
+//   S          tcgen05.mma M=128 N=144 K=32: query rows 0..127 -> TMEM buffer S1[item & 1]; query rows 128..143 (+112 rows
+//              that are never read) -> S2.  A = q (K-major), B = k (K-major), 6 MMAs each.
+//   softmax    thread per (row, half of the 144 keys): tcgen05.ld its 72 logits, bias (+ mask), max / sum exchanged with
+//              the thread that owns the other half, exp2, bf16 hi/lo split of the UN-normalised probabilities written
+//              back over S with tcgen05.st (P aliases S: 144 fp32 columns = 72 + 72 packed bf16x2 columns).
+//   O          tcgen05.mma M=128 N=32 K=144 with A = P read from TENSOR MEMORY and B = v straight from the TMA tile
+//              (MN-major descriptor: no transpose anywhere), 27 MMAs per tile.
+//   epilogue   O rows * 1 / row sum -> bf16 hi/lo -> global planes.
+// The MMAs of item i+1 (S) run under the softmax of item i; TMA runs two items ahead.  Warps: 0 and 12 = softmax of the
+// 16-row tile (TMEM lane quadrant 0), 1 = TMA producer, 2 = MMA issuer of the 128-row tile + TMEM owner, 3 = MMA issuer of
+// the 16-row tile (two issuers: 66 small MMAs per item are issue-bound from one thread, and the two tiles' chains stay
+// independent), 4..11 = softmax of the 128-row tile (quadrant w % 4, key half (w - 4) / 4).
+// TMEM columns: S1[0] 0..143 | S1[1] 144..287 | S2 288..431 | O1 432..463 | O2 464..495 (496 of 512: S2 cannot be double
+// buffered; an M=64 variant that would have packed two items' 16-row tiles into one block at lane offsets 0 / 16 gave
+// wrong results at offset 16 on this hardware / toolchain and was dropped).
+// Measured (profiles/r2c_*): the softmax warps bound the kernel (10 warp-passes of 72 elements per item at ~8 instructions
+// and one MUFU.EX2 per element; the SM sub-partition that owns the 16-row tile's lanes carries 4 of them), not the tensor
+// pipe (66 MMAs, ~1.7k clk) nor HBM (74 KB per item).  RBA_WT_DEBUG bits 1/2/4/8/16 and RBA_WT_TIMELINE are the ablation /
+// in-kernel clock aids those measurements came from.
+#include <type_traits>
+
+#include "tcgen05.cuh"
+
+namespace rba {
+
+constexpr int WT_N = 144, WT_D = 32, WT_WS = 12;
+constexpr int WT_TILE_BYTES = WT_N * WT_D * 2;            // 9216 = 9 * 1024: one plane of q, k or v of one item
+constexpr int WT_BIAS_FLOATS = 532;                       // == WM_BIAS_PITCH of attn.cu (prepared, log2(e)-scaled table)
+constexpr int WT_BIAS_BYTES = WT_BIAS_FLOATS * 4;         // 2128 (multiple of 16: bulk-copy granularity)
+constexpr int WT_STAGE_BYTES = 6 * WT_TILE_BYTES + 3072;  // 58368 = 57 * 1024
+constexpr int WT_STAGES = 3;
+constexpr int WT_THREADS = 13 * 32;
+constexpr uint32_t WT_TMEM_COLS = 512;
+constexpr int WT_COL_S1 = 0, WT_COL_S2 = 288, WT_COL_O1 = 432, WT_COL_O2 = 464;
+constexpr int WT_EXCH_FLOATS = 2 /*parity*/ * 2 /*half*/ * 160 /*rows (144, padded)*/;
+constexpr int WT_SMEM = WT_STAGES * WT_STAGE_BYTES + 2 * WT_EXCH_FLOATS * 4 + 256 + 1024;
+
+struct WtParams {
+  const float* bias;        // [heads][532] prepared table
+  uint16_t* out_hi;
+  uint16_t* out_lo;
+  int C, heads, nWh, nWw, shift;
+  int64_t nitems;           // B * nWh * nWw * heads
+  float scale_log2e;        // head_dim^-0.5 * log2(e)
+  int debug;
+  long long* tl;            // profiling aid (RBA_WT_TIMELINE): clock64 stamps of CTA 0, [item < 32][16 events]
+};
+#define WT_STAMP(item, ev)                                                                   \
+  do {                                                                                       \
+    if (p.tl && blockIdx.x == 0 && (item) < 32) p.tl[(item) * 16 + (ev)] = clock64();        \
+  } while (0)
+
+__device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem, const void* gptr, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem)), "l"(gptr), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// SWIZZLE_64B shared-memory matrix descriptor: 64-byte rows, 8-row groups 512 B apart.  The same encoding serves the
+// K-major operands (q, k: ((8,n),2):((4,SBO),1) in 16-byte units) and the MN-major operand (v: ((4,n),(8,k)):((1,LBO),(4,SBO))).
+__device__ __forceinline__ uint64_t make_sdesc64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(512 >> 4) << 16;                   // leading byte offset (one 64-byte column block; unused: N = 32)
+  d |= (uint64_t)(512 >> 4) << 32;                   // stride byte offset: 8 rows x 64 B
+  d |= (uint64_t)1 << 46;                            // version 1 (Blackwell)
+  d |= (uint64_t)4 << 61;                            // SWIZZLE_64B
+  return d;
+}
+// kind::f16 instruction descriptor: D fp32, A / B bf16, A K-major, B K-major or MN-major (bit 16)
+__host__ __device__ constexpr uint32_t wt_idesc(int M, int N, bool b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// tcgen05.wait::ld that also names the destination registers, so that the compiler cannot schedule their first use above it
+// when independent work is interleaved between a tcgen05.ld and its wait
+template <int N>
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t* v) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < N; ++i) asm volatile("" : "+r"(v[i]));
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),
+      "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),
+      "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float wt_ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void wt_pair_bar(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+// 16 consecutive output values * inv -> bf16 hi / lo planes, two 16-byte stores each (g is a multiple of 16 elements)
+__device__ __forceinline__ void wt_store16(uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo, int64_t g, const uint32_t* o, float inv) {
+  uint32_t h[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) split_pack2(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv, h[i], l[i]);
+  uint4* ph = reinterpret_cast<uint4*>(out_hi + g);
+  uint4* pl = reinterpret_cast<uint4*>(out_lo + g);
+  ph[0] = make_uint4(h[0], h[1], h[2], h[3]);
+  ph[1] = make_uint4(h[4], h[5], h[6], h[7]);
+  pl[0] = make_uint4(l[0], l[1], l[2], l[3]);
+  pl[1] = make_uint4(l[4], l[5], l[6], l[7]);
+}
+
+// barriers (shared memory, 8 bytes each)
+struct WtBars {
+  uint64_t full[WT_STAGES], empty[WT_STAGES];
+  uint64_t s1_full[2], p1_ready[2];
+  uint64_t o1_full, o1_empty;
+  uint64_t s2_full, p2_ready, o2_full, o2_empty;
+  uint32_t tmem_slot, pad;
+};
+
+// item -> (window index in [0, B*nWh*nWw), head); heads fastest so that consecutive items share the window's rows in L2
+__device__ __forceinline__ void wt_item(const WtParams& p, int64_t it, int64_t& win, int& head) {
+  win = it / p.heads;
+  head = (int)(it - win * p.heads);
+}
+
+// The softmax + epilogue role.  TILE2 = false: one of the eight warps of the 128-row tile; true: one of the two warps that own
+// query rows 128..143 (lanes 0..15; lanes 16..31 run along on rows that are never stored).
+template <bool TILE2>
+__device__ __forceinline__ void wt_softmax_role(const WtParams& p, uint8_t* smem, WtBars* bars, float* exch_max, float* exch_sum,
+                                                uint32_t tmem_base, int quadrant, int half, int lane) {
+  const int row = TILE2 ? 128 + lane : quadrant * 32 + lane;      // query index inside the window (garbage rows: >= 144)
+  const int rowc = row < WT_N ? row : WT_N - 1;                    // clamped for address arithmetic only
+  const int iy = rowc / WT_WS, ix = rowc - iy * WT_WS;
+  // bias index of (query i, key j) = (iy - jy + 11) * 23 + (ix - jx + 11) = base - (jy * 23 + jx)
+  const int bias_base = (iy + WT_WS - 1) * (2 * WT_WS - 1) + ix + WT_WS - 1 - half * 6 * (2 * WT_WS - 1);
+  const uint32_t lane_addr = (uint32_t)(quadrant * 32) << 16;
+  const int pair_bar = TILE2 ? 5 : 1 + quadrant;
+  // slot of this thread's row in the max / sum exchange arrays (160 per half: rows 0..127 of the big tile, 144..159 = rows
+  // 128..143 of the small tile, 128..143 = scratch for the small tile's lanes 16..31, whose rows do not exist)
+  const int er = TILE2 ? (lane < 16 ? 144 + lane : 128 + (lane - 16)) : row;
+  const bool rf = iy >= WT_WS - p.shift, cf = ix >= WT_WS - p.shift;   // region flags of this query in a boundary window
+  const float NEG = -100.0f * 1.4426950408889634f;
+  uint32_t lt = 0;
+  int64_t prev_row0 = 0;
+  int prev_head = 0;
+  const uint32_t nitems = (uint32_t)p.nitems, uheads = (uint32_t)p.heads;       // < 2^31 (checked on the host): 32-bit divides
+  for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x, ++lt) {
+    const int s = lt % WT_STAGES, b = lt & 1;
+    const uint32_t win = it / uheads;
+    const int head = (int)(it - win * uheads);
+    const uint32_t wrow = win / (uint32_t)p.nWw;
+    const int wx = (int)(win - wrow * (uint32_t)p.nWw), wy = (int)(wrow % (uint32_t)p.nWh);
+    const bool lastrow = p.shift > 0 && wy == p.nWh - 1, lastcol = p.shift > 0 && wx == p.nWw - 1;
+    uint8_t* st = smem + s * WT_STAGE_BYTES;
+    const float* sBias = reinterpret_cast<const float*>(st + 6 * WT_TILE_BYTES) + bias_base;
+    // ---- logits of this thread: 72 keys of one query ----
+    mbar_wait(&bars->full[s], (lt / WT_STAGES) & 1);                 // the bias table of this stage has landed
+    if (TILE2) mbar_wait(&bars->s2_full, lt & 1); else mbar_wait(&bars->s1_full[b], (lt >> 1) & 1);
+    tc_fence_after();
+    const bool stamp = !TILE2 && quadrant == 0 && half == 0 && lane == 0;
+    if (stamp) WT_STAMP(lt, 6);
+    const uint32_t scol = TILE2 ? WT_COL_S2 : WT_COL_S1 + b * WT_N;
+    const uint32_t saddr = tmem_base + lane_addr + scol;
+    float x[72];
+    uint32_t* xv = reinterpret_cast<uint32_t*>(x);
+    // shift mask (swin.py:416-440): -100 where query and key lie in different regions of a boundary window.  Keys of this
+    // half all have jy >= 6 iff half == 1; jx >= 6 is a compile-time property of the unrolled index.
+    const bool masked = lastrow || lastcol;
+    const bool rowdiff = lastrow && ((half == 1) != rf);
+    const float mlo = (rowdiff || (lastcol && cf)) ? NEG : 0.f, mhi = (rowdiff || (lastcol && !cf)) ? NEG : 0.f;
+    float mm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};        // four independent max chains
+    // x = S * scale * log2(e) + bias (+ mask) for keys [J0, J1), software-pipelined against the TMEM loads of the next chunk
+    auto logits = [&](auto j0c, auto j1c) {
+      constexpr int J0 = decltype(j0c)::value, J1 = decltype(j1c)::value;
+      if (p.debug & 1) return;
+      if (masked) {
+#pragma unroll
+        for (int jj = J0; jj < J1; ++jj) {
+          const int off = (jj / WT_WS) * (2 * WT_WS - 1) + (jj % WT_WS);
+          x[jj] = fmaf(x[jj], p.scale_log2e, sBias[-off]) + ((jj % WT_WS) < WT_WS / 2 ? mlo : mhi);
+          mm[jj & 3] = fmaxf(mm[jj & 3], x[jj]);
+        }
+      } else {
+#pragma unroll
+        for (int jj = J0; jj < J1; ++jj) {
+          const int off = (jj / WT_WS) * (2 * WT_WS - 1) + (jj % WT_WS);
+          x[jj] = fmaf(x[jj], p.scale_log2e, sBias[-off]);
+          mm[jj & 3] = fmaxf(mm[jj & 3], x[jj]);
+        }
+      }
+    };
+    tmem_ld32(saddr + half * 72, xv);
+    tmem_ld_wait_dep<32>(xv);
+    tmem_ld32(saddr + half * 72 + 32, xv + 32);                       // in flight under the first chunk's arithmetic
+    logits(std::integral_constant<int, 0>{}, std::integral_constant<int, 32>{});
+    tmem_ld_wait_dep<32>(xv + 32);
+    tmem_ld8(saddr + half * 72 + 64, xv + 64);
+    logits(std::integral_constant<int, 32>{}, std::integral_constant<int, 64>{});
+    tmem_ld_wait_dep<8>(xv + 64);
+    logits(std::integral_constant<int, 64>{}, std::integral_constant<int, 72>{});
+    if (stamp) WT_STAMP(lt, 7);
+    float m = (p.debug & 1) ? 0.f : fmaxf(fmaxf(mm[0], mm[1]), fmaxf(mm[2], mm[3]));
+    // ---- row max across the two halves (every S column of this row has been read once both threads are here) ----
+    float* emax = exch_max + (b * 2) * 160;
+    emax[half * 160 + er] = m;
+    wt_pair_bar(pair_bar);
+    m = fmaxf(m, emax[(half ^ 1) * 160 + er]);
+    if (stamp) WT_STAMP(lt, 8);
+    // ---- un-normalised probabilities, bf16 hi / lo, written back over S: hi -> columns [0,72), lo -> [72,144) ----
+    float sum = 0.f;
+    uint32_t ph[36], pl[36];
+    if (p.debug & 2) {                       // ablation: no exp / split
+#pragma unroll
+      for (int jj = 0; jj < 36; ++jj) { ph[jj] = __float_as_uint(x[jj]); pl[jj] = __float_as_uint(x[jj + 36]); }
+      sum = 1.f;
+    } else {
+      float ss[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int jj = 0; jj < 72; jj += 2) {
+        const float e0 = wt_ex2(x[jj] - m), e1 = wt_ex2(x[jj + 1] - m);
+        ss[(jj >> 1) & 3] += e0 + e1;
+        split_pack2(e0, e1, ph[jj >> 1], pl[jj >> 1]);
+      }
+      sum = (ss[0] + ss[1]) + (ss[2] + ss[3]);
+    }
+    tmem_st32(saddr + half * 36, ph);
+    tmem_st4(saddr + half * 36 + 32, ph + 32);
+    tmem_st32(saddr + 72 + half * 36, pl);
+    tmem_st4(saddr + 72 + half * 36 + 32, pl + 32);
+    if (stamp) WT_STAMP(lt, 9);
+    tmem_st_wait();
+    tc_fence_before();
+    if (stamp) WT_STAMP(lt, 10);
+    float* esum = exch_sum + (b * 2) * 160;
+    esum[half * 160 + er] = sum;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(TILE2 ? &bars->p2_ready : &bars->p1_ready[b]);
+    // ---- epilogue of the PREVIOUS item (its P.v has had a whole softmax to finish) ----
+    if (lt > 0) {
+      const uint32_t pl_ = lt - 1;
+      if (stamp) WT_STAMP(lt, 11);
+      mbar_wait(TILE2 ? &bars->o2_full : &bars->o1_full, pl_ & 1);
+      tc_fence_after();
+      if (stamp) WT_STAMP(lt, 12);
+      const float* ps = exch_sum + ((pl_ & 1) * 2) * 160;
+      const float inv = 1.0f / (ps[er] + ps[160 + er]);
+      uint32_t o[16];
+      tmem_ld16(tmem_base + lane_addr + (TILE2 ? WT_COL_O2 : WT_COL_O1) + half * 16, o);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(TILE2 ? &bars->o2_empty : &bars->o1_empty);
+      if (stamp) WT_STAMP(lt, 13);
+      if (!TILE2 || lane < 16) {
+        const int64_t g = (prev_row0 + row) * p.C + prev_head * WT_D + half * 16;
+wt_store16(p.out_hi, p.out_lo, g, o, inv);
+      }
+    }
+    if (stamp) WT_STAMP(lt, 14);
+    prev_row0 = (int64_t)win * WT_N;
+    prev_head = head;
+  }
+  if (lt > 0) {                                   // epilogue of the last item
+    const uint32_t pl_ = lt - 1;
+    mbar_wait(TILE2 ? &bars->o2_full : &bars->o1_full, pl_ & 1);
+    tc_fence_after();
+    wt_pair_bar(pair_bar);                        // the partner's sum of the last item is in shared memory
+    const float* ps = exch_sum + ((pl_ & 1) * 2) * 160;
+    const float inv = 1.0f / (ps[er] + ps[160 + er]);
+    uint32_t o[16];
+    tmem_ld16(tmem_base + lane_addr + (TILE2 ? WT_COL_O2 : WT_COL_O1) + half * 16, o);
+    tmem_ld_wait();
+    tc_fence_before();
+    if (!TILE2 || lane < 16) {
+      const int64_t g = (prev_row0 + row) * p.C + prev_head * WT_D + half * 16;
+wt_store16(p.out_hi, p.out_lo, g, o, inv);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(WT_THREADS, 1)
+window_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const WtParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* exch_max = reinterpret_cast<float*>(smem + WT_STAGES * WT_STAGE_BYTES);
+  float* exch_sum = exch_max + WT_EXCH_FLOATS;
+  WtBars* bars = reinterpret_cast<WtBars*>(smem + WT_STAGES * WT_STAGE_BYTES + 2 * WT_EXCH_FLOATS * 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tm_hi); prefetch_tmap(&tm_lo);
+    for (int s = 0; s < WT_STAGES; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 2); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&bars->s1_full[b], 1); mbar_init(&bars->p1_ready[b], 8); }
+    mbar_init(&bars->o1_full, 1); mbar_init(&bars->o1_empty, 8);
+    mbar_init(&bars->s2_full, 1); mbar_init(&bars->p2_ready, 2);
+    mbar_init(&bars->o2_full, 1); mbar_init(&bars->o2_empty, 2);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_slot)), "r"(WT_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_slot;
+
+  if (warp == 1) {
+    // ===================== TMA producer (whole warp, one elected lane issues) =====================
+    const uint32_t n = (uint32_t)((p.nitems - (int64_t)blockIdx.x + (int64_t)gridDim.x - 1) / (int64_t)gridDim.x);
+    uint32_t s = 0, ph = 1;                               // fresh "empty" barriers pass a wait on parity 1
+    int64_t it = blockIdx.x;
+    for (uint32_t lt = 0; lt < n; ++lt, it += gridDim.x) {
+      int64_t win;
+      int head;
+      wt_item(p, it, win, head);
+      mbar_wait_sleep(&bars->empty[s], ph);
+      WT_STAMP(lt, 0);
+      if (elect_one()) {
+        uint8_t* st = smem + s * WT_STAGE_BYTES;
+        mbar_expect_tx(&bars->full[s], 6 * WT_TILE_BYTES + WT_BIAS_BYTES);
+        const int r0 = (int)(win * WT_N);
+#pragma unroll
+        for (int part = 0; part < 3; ++part) {              // q, k, v column blocks of this head
+          const int c0 = part * p.C + head * WT_D;
+          tma_load_2d(st + (2 * part) * WT_TILE_BYTES, &tm_hi, &bars->full[s], c0, r0);
+          tma_load_2d(st + (2 * part + 1) * WT_TILE_BYTES, &tm_lo, &bars->full[s], c0, r0);
+        }
+        bulk_load(st + 6 * WT_TILE_BYTES, p.bias + (size_t)head * WT_BIAS_FLOATS, WT_BIAS_BYTES, &bars->full[s]);
+      }
+      __syncwarp();
+      if (++s == WT_STAGES) { s = 0; ph ^= 1; }
+    }
+  } else if (warp == 2 || warp == 3) {
+    // ===================== MMA issuers: warp 2 = 128-row tile, warp 3 = 16-row tile =====================
+    // The WHOLE warp walks the loop (uniform control flow, 32-bit uniform counters) and one elected lane issues: descriptors
+    // then live in uniform registers.  (Under `if (lane == 0)` ptxas wraps every tcgen05.mma in an ELECT / R2UR.BROADCAST /
+    // BRA.U.ANY loop -- measured ~70 clk per MMA, which made 66 small MMAs per item the bottleneck of the whole kernel.)
+    constexpr uint32_t idS = wt_idesc(128, WT_N, false), idO = wt_idesc(128, WT_D, true);
+    const bool t2 = warp == 3;
+    uint32_t n = (uint32_t)((p.nitems - (int64_t)blockIdx.x + (int64_t)gridDim.x - 1) / (int64_t)gridDim.x);
+    if (t2 && (p.debug & 4)) n = 0;
+    const uint32_t smem0 = smem_u32(smem);
+    const uint32_t q_off = t2 ? 128u * WT_D * 2u : 0u;       // first q row of this issuer's tile, in bytes
+    uint32_t s_i = 0, ph_i = 0;                              // stage / phase of item i   (S issue)
+    uint32_t s_j = 0;                                        // stage of item j = i - 1   (P v issue)
+    const bool run = !(t2 && (p.debug & 4));
+    for (uint32_t i = 0; run && i <= n; ++i) {
+      const uint32_t j = i - 1;
+      // ---- tile 2 frees its single S buffer first: O2(j) = P2 v ----
+      if (t2 && i >= 1) {
+        mbar_wait(&bars->p2_ready, j & 1);
+        mbar_wait(&bars->o2_empty, (j & 1) ^ 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sb = smem0 + s_j * WT_STAGE_BYTES;
+          const uint64_t vh = make_sdesc64(sb + 4 * WT_TILE_BYTES), vl = make_sdesc64(sb + 5 * WT_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < ((p.debug & 8) ? 0 : WT_N / 16); ++k) {
+            const uint64_t adv = (uint64_t)(k * 16 * 64 >> 4);     // 16 keys = 16 rows of 64 B
+            umma_bf16_ts(tmem_base + WT_COL_O2, tmem_base + WT_COL_S2 + k * 8, vh + adv, idO, k != 0);
+            umma_bf16_ts(tmem_base + WT_COL_O2, tmem_base + WT_COL_S2 + k * 8, vl + adv, idO, 1);
+            umma_bf16_ts(tmem_base + WT_COL_O2, tmem_base + WT_COL_S2 + 72 + k * 8, vh + adv, idO, 1);
+          }
+          umma_commit(&bars->o2_full);
+          umma_commit(&bars->empty[s_j]);
+        }
+        __syncwarp();
+        s_j = s_j + 1 == WT_STAGES ? 0 : s_j + 1;
+      }
+      // ---- S(i) = q k^T ----
+      if (i < n) {
+        mbar_wait(&bars->full[s_i], ph_i);
+        tc_fence_after();
+        if (!t2) WT_STAMP(i, 1);
+        if (elect_one()) {
+          const uint32_t sb = smem0 + s_i * WT_STAGE_BYTES;
+          const uint32_t dcol = tmem_base + (t2 ? (uint32_t)WT_COL_S2 : (uint32_t)WT_COL_S1 + (i & 1) * WT_N);
+          const uint64_t qh = make_sdesc64(sb + q_off), ql = make_sdesc64(sb + WT_TILE_BYTES + q_off);
+          const uint64_t kh = make_sdesc64(sb + 2 * WT_TILE_BYTES), kl = make_sdesc64(sb + 3 * WT_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < ((p.debug & 16) ? 0 : WT_D / 16); ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+            umma_bf16(dcol, qh + adv, kh + adv, idS, k != 0);
+            umma_bf16(dcol, qh + adv, kl + adv, idS, 1);
+            umma_bf16(dcol, ql + adv, kh + adv, idS, 1);
+          }
+          umma_commit(t2 ? &bars->s2_full : &bars->s1_full[i & 1]);
+        }
+        __syncwarp();
+        if (!t2) WT_STAMP(i, 2);
+        if (++s_i == WT_STAGES) { s_i = 0; ph_i ^= 1; }
+      }
+      // ---- tile 1: O1(j) = P1 v ----
+      if (!t2 && i >= 1) {
+        mbar_wait(&bars->p1_ready[j & 1], (j >> 1) & 1);
+        WT_STAMP(j, 3);
+        mbar_wait(&bars->o1_empty, (j & 1) ^ 1);
+        tc_fence_after();
+        WT_STAMP(j, 4);
+        if (elect_one()) {
+          const uint32_t sb = smem0 + s_j * WT_STAGE_BYTES;
+          const uint32_t pcol = tmem_base + WT_COL_S1 + (j & 1) * WT_N;
+          const uint64_t vh = make_sdesc64(sb + 4 * WT_TILE_BYTES), vl = make_sdesc64(sb + 5 * WT_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < ((p.debug & 8) ? 0 : WT_N / 16); ++k) {
+            const uint64_t adv = (uint64_t)(k * 16 * 64 >> 4);
+            umma_bf16_ts(tmem_base + WT_COL_O1, pcol + k * 8, vh + adv, idO, k != 0);
+            umma_bf16_ts(tmem_base + WT_COL_O1, pcol + k * 8, vl + adv, idO, 1);
+            umma_bf16_ts(tmem_base + WT_COL_O1, pcol + 72 + k * 8, vh + adv, idO, 1);
+          }
+          umma_commit(&bars->o1_full);
+          umma_commit(&bars->empty[s_j]);
+          if (p.debug & 4) umma_commit(&bars->empty[s_j]);
+        }
+        __syncwarp();
+        WT_STAMP(j, 5);
+        s_j = s_j + 1 == WT_STAGES ? 0 : s_j + 1;
+      }
+    }
+  } else if (warp >= 4 && warp < 12) {
+    wt_softmax_role<false>(p, smem, bars, exch_max, exch_sum, tmem_base, warp & 3, (warp - 4) >> 2, lane);
+  } else if ((warp == 0 || warp == 12) && !(p.debug & 4)) {
+    wt_softmax_role<true>(p, smem, bars, exch_max, exch_sum, tmem_base, 0, warp == 12 ? 1 : 0, lane);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(WT_TMEM_COLS) : "memory");
+  }
+}
+
+// bf16 [rows][cols] row-major -> 2-D map, box = (32 columns, 144 rows), SWIZZLE_64B
+static int make_map_wattn(CUtensorMap* m, const uint16_t* ptr, int64_t rows, int64_t cols) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(RBA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)WT_D, (cuuint32_t)WT_N};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(RBA_ERR_CUDA, "cuTensorMapEncodeTiled(window attention) failed with %d", (int)r);
+  return RBA_OK;
+}
+
+int window_attn_tc(const uint16_t* qkv_hi, const uint16_t* qkv_lo, const float* bias_prepared, int B, int H, int W, int C,
+                   int heads, int ws, int shift, uint16_t* out_hi, uint16_t* out_lo, cudaStream_t st) {
+  RBA_CHECK(qkv_hi && qkv_lo && bias_prepared && out_hi && out_lo, "window_attn_tc: null pointer");
+  RBA_CHECK(ws == WT_WS, "window_attn_tc: only window_size 12 is built (got %d)", ws);
+  RBA_CHECK(heads > 0 && C == heads * WT_D, "window_attn_tc: head_dim must be 32 (C=%d heads=%d)", C, heads);
+  RBA_CHECK(shift == 0 || shift == ws / 2, "window_attn_tc: shift must be 0 or window_size / 2 (got %d)", shift);
+  RBA_CHECK((((uintptr_t)qkv_hi | (uintptr_t)qkv_lo | (uintptr_t)out_hi | (uintptr_t)out_lo | (uintptr_t)bias_prepared) & 15) == 0,
+            "window_attn_tc: pointers must be 16-byte aligned");
+  SwinGeom g = make_swin_geom(H, W, ws, shift);
+  const int64_t nwin = (int64_t)B * g.nWh * g.nWw;
+  if (nwin == 0) return RBA_OK;
+  RBA_CHECK(nwin * WT_N < (1LL << 31), "window_attn_tc: too many rows");
+  CUtensorMap tm_hi, tm_lo;
+  RBA_TRY_(make_map_wattn(&tm_hi, qkv_hi, nwin * WT_N, 3 * (int64_t)C));
+  RBA_TRY_(make_map_wattn(&tm_lo, qkv_lo, nwin * WT_N, 3 * (int64_t)C));
+  WtParams p;
+  memset(&p, 0, sizeof(p));
+  p.bias = bias_prepared; p.out_hi = out_hi; p.out_lo = out_lo;
+  p.C = C; p.heads = heads; p.nWh = g.nWh; p.nWw = g.nWw; p.shift = shift;
+  p.nitems = nwin * heads;
+  p.scale_log2e = 1.4426950408889634f / sqrtf((float)WT_D);
+  { static const int dbg = []() { const char* e = getenv("RBA_WT_DEBUG"); return e ? atoi(e) : 0; }(); p.debug = dbg; }   // profiling ablations
+  static PerDeviceOnce once;
+  if (once.needed()) {
+    RBA_CUDA(cudaFuncSetAttribute(window_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM));
+    once.done();
+  }
+  const unsigned grid = (unsigned)std::min<int64_t>(p.nitems, num_sms());
+  static const bool timeline = getenv("RBA_WT_TIMELINE") != nullptr;       // profiling aid: prints CTA 0's clock stamps
+  static long long* tl_dev = nullptr;
+  if (timeline) {
+    if (!tl_dev) RBA_CUDA(cudaMalloc(&tl_dev, 32 * 16 * sizeof(long long)));
+    RBA_CUDA(cudaMemsetAsync(tl_dev, 0, 32 * 16 * sizeof(long long), st));
+    p.tl = tl_dev;
+  }
+  window_attn_tc_kernel<<<grid, WT_THREADS, WT_SMEM, st>>>(tm_hi, tm_lo, p);
+  RBA_LAUNCHED();
+  if (timeline) {
+    long long h[32 * 16];
+    RBA_CUDA(cudaStreamSynchronize(st));
+    RBA_CUDA(cudaMemcpy(h, tl_dev, sizeof(h), cudaMemcpyDeviceToHost));
+    const long long t0 = h[0];
+    fprintf(stderr, "[wattn_tc timeline, CTA 0, clocks since first TMA issue]\n item  tma  full s1iss  p1rdy o1emp pviss | s1full  ld   bar   st   stw | epi: start o1full ldarr | end\n");
+    for (int i = 0; i < 12; ++i) {
+      fprintf(stderr, "%5d", i);
+      for (int e = 0; e < 15; ++e) fprintf(stderr, " %6lld", h[i * 16 + e] ? h[i * 16 + e] - t0 : -1);
+      fprintf(stderr, "\n");
+    }
+  }
+  return RBA_OK;
+}
+
+}  // namespace rba
+
+extern "C" int rba_k_window_attn_tc(const uint16_t* qkv_hi, const uint16_t* qkv_lo, const float* bias_prepared, int B, int H, int W,
+                                    int C, int heads, int ws, int shift, uint16_t* out_hi, uint16_t* out_lo, void* stream) {
+  return rba::window_attn_tc(qkv_hi, qkv_lo, bias_prepared, B, H, W, C, heads, ws, shift, out_hi, out_lo, (cudaStream_t)stream);
+}
+

@@ -68,9 +68,9 @@ class Engine:
             self.set_option("include_void", int(bool(include_void)))
 
     def set_gemm_backend(self, name):
-        """'tc': tcgen05 GEMMs + tensor-core window attention; 'ffma': exact fp32 CUDA-core kernels everywhere."""
+        """'tc': tcgen05 GEMMs + tcgen05 window attention; 'ffma': exact fp32 CUDA-core kernels everywhere."""
         self.set_option("gemm_backend", {"ffma": RBA_GEMM_FFMA, "tc": RBA_GEMM_TC}[name])
-        self.set_option("attn_backend", 1 if name == "tc" else 0)
+        self.set_option("attn_backend", 2 if name == "tc" else 0)
 
     def reserve(self, B, H, W):
         _lib.check(_lib.lib().rba_model_reserve(self._h, B, H, W))

@@ -319,6 +319,21 @@ def window_attn_planes(qkv, bias_table, B, H, W, C, heads, ws, shift):
     return hi, lo
 
 
+def window_attn_tc(qkv, bias_table, B, H, W, C, heads, ws, shift):
+    """tcgen05 + TMA window attention; qkv = (hi, lo) planes [rows, 3C]; bias_table is the reference's
+    relative_position_bias_table [(2ws-1)^2, heads] (prepared per call here; the engine prepares it once at load)."""
+    q_hi, q_lo = qkv
+    _chk_cuda(q_hi, q_lo, bias_table)
+    rows = q_hi.shape[0]
+    L = _lib.lib()
+    prep = torch.empty(int(L.rba_k_window_attn_bias_floats(heads)), dtype=torch.float32, device=q_hi.device)
+    _lib.check(L.rba_k_window_attn_prepare_bias(_p(bias_table), heads, _p(prep), _stream()))
+    hi = torch.empty((rows, C), dtype=torch.bfloat16, device=q_hi.device)
+    lo = torch.empty((rows, C), dtype=torch.bfloat16, device=q_hi.device)
+    _lib.check(L.rba_k_window_attn_tc(_p(q_hi), _p(q_lo), _p(prep), B, H, W, C, heads, ws, shift, _p(hi), _p(lo), _stream()))
+    return hi, lo
+
+
 def mha(q, k, v, mask, heads):
     """q (B,Lq,E), k/v (B,Lk,E) fp32 projected; mask (B,Lq,Lk) uint8 (1 = blocked) or None -> planes (B*Lq, E)."""
     _chk_cuda(q, k, v, mask)

@@ -562,10 +562,14 @@ def test_conv3x3_tc(dev, H, W, Cout):
     assert (y.cpu() - ref).abs().max() < TC_TOL * max(1.0, float(ref.abs().max()))
 
 
-@pytest.mark.parametrize("H,W,shift", [(24, 24, 0), (30, 41, 6), (12, 12, 6)])
-def test_window_attention_tensor_core(dev, H, W, shift):
-    """swin.py:145-168 with q/k/v as split planes, both contractions on mma.sync (bf16x3)."""
-    B, heads, ws = 2, 2, 12
+@pytest.mark.parametrize("kernel", ["tcgen05", "mma_sync"])
+@pytest.mark.parametrize("H,W,shift,B,heads", [(24, 24, 0, 2, 2), (30, 41, 6, 2, 2), (12, 12, 6, 2, 2), (12, 12, 0, 1, 1),
+                                               (96, 180, 6, 3, 4), (40, 40, 6, 1, 16)])
+def test_window_attention_tensor_core(dev, H, W, shift, B, heads, kernel):
+    """swin.py:145-168 with q/k/v as split planes, both contractions on tensor cores (bf16x3): the tcgen05 + TMA kernel the
+    engine runs (wattn_tc.cu: more items than SMs in the big case, so the persistent pipeline wraps its TMEM / stage rings)
+    and the mma.sync kernel kept as its cross-check."""
+    ws = 12
     C = heads * 32
     nWh, nWw = -(-H // ws), -(-W // ws)
     nW = nWh * nWw
@@ -582,5 +586,7 @@ def test_window_attention_tensor_core(dev, H, W, shift):
         mask = O.shift_attn_mask(H, W, ws, shift)
         attn = (attn.view(B, nW, heads, ws * ws, ws * ws) + mask.unsqueeze(1).unsqueeze(0)).view(-1, heads, ws * ws, ws * ws)
     ref = (attn.softmax(-1) @ v).transpose(1, 2).reshape(B * nW * ws * ws, C)
-    out = ops.window_attn_planes(qp, table.to(dev), B, H, W, C, heads, ws, shift)
-    assert (unplanes(out) - ref).abs().max() < 3e-4
+    fn = ops.window_attn_tc if kernel == "tcgen05" else ops.window_attn_planes
+    out = fn(qp, table.to(dev), B, H, W, C, heads, ws, shift)
+    err = (unplanes(out) - ref).abs()
+    assert err.max() < 3e-4, (float(err.max()), int(err.argmax()) // C, int(err.argmax()) % C)
