@@ -70,6 +70,9 @@ typedef struct rba_config {
   int32_t size_divisibility;/* MODEL.MASK_FORMER.SIZE_DIVISIBILITY */
   float pixel_mean[3];      /* MODEL.PIXEL_MEAN */
   float pixel_std[3];       /* MODEL.PIXEL_STD */
+  int32_t backbone_type;    /* MODEL.BACKBONE.NAME: 0 = D2SwinTransformer, 1 = build_resnet_backbone (detectron2 bottleneck ResNet,
+                               RESNETS.STRIDE_IN_1X1 false; the SWIN fields are then ignored) */
+  int32_t resnet_depth;     /* MODEL.RESNETS.DEPTH: 50 or 101 */
 } rba_config;
 
 /* ---- engine ---- */
@@ -299,6 +302,20 @@ int64_t rba_k_groupnorm_ws(int B, int H, int W, int C, int groups);
 int rba_k_patch_embed(const void* images, int img_dtype, int B, int H, int W, int Hp, int Wp, const float* mean,
                       const float* stdv, const float* conv_w /* [C,3,4,4] */, const float* conv_b, const float* gamma,
                       const float* beta, int C, float* tokens /* [B,(Hp/4)*(Wp/4),C] */, void* stream);
+
+/* ---- ResNet backbone pieces (detectron2 build_resnet_backbone; the 1x1 / 3x3 bottleneck convolutions run on rba_k_gemm /
+ * rba_k_conv3x3 with the batch norm folded into weights + bias) ----
+ * stem: normalise + zero-pad to (Hp,Wp) (maskformer_model.py:255-257), 7x7 / stride 2 / pad 3 convolution with folded BN
+ * (w [64][3*7*7], bias [64]) and ReLU -> out (B,Hp/2,Wp/2,64) NHWC fp32. */
+int rba_k_stem_conv(const void* images, int img_dtype, int B, int H, int W, int Hp, int Wp, const float* mean,
+                    const float* stdv, const float* w, const float* bias, float* out, void* stream);
+/* 3x3 / stride 2 / pad 1 max-pool, NHWC fp32 in -> (B,H/2,W/2,C) fp32 and / or split planes (either may be NULL). */
+int rba_k_maxpool3x3s2(const float* x, int B, int H, int W, int C, float* y, uint16_t* y_hi, uint16_t* y_lo, void* stream);
+/* y[b,oy,ox,:] = [relu](x[b,oy*stride,ox*stride,:] + bias): epilogue of the 3x3 convolutions (stride-2 ones are computed
+ * at stride 1 and sub-sampled here), the ReLU after the residual add, the stride-2 gather of the projection shortcuts.
+ * bias may be NULL; y (fp32) may alias x when stride == 1. */
+int rba_k_bias_act_sub(const float* x, const float* bias, int B, int H, int W, int C, int stride, int relu, float* y,
+                       uint16_t* y_hi, uint16_t* y_lo, void* stream);
 
 /* Attention-mask of forward_prediction_heads (mask2former_transformer_decoder.py:483-486): bilinear resize of
  * mask logits (B,Q,h,w) to (th,tw), sigmoid < 0.5 -> 1, then rows that are entirely 1 are reset to 0 (:433).

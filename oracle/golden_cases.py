@@ -28,6 +28,10 @@ def case_model_config(case):
         return rcfg.swin_l_1dl()
     if case["preset"] == "swin_b_full":
         return rcfg.swin_b_full(dec_layers=case["dec_layers"])
+    if case["preset"] == "r50_1dl":
+        return rcfg.r50_1dl()
+    if case["preset"] == "r50_full":
+        return rcfg.r50_full(dec_layers=case["dec_layers"])
     raise KeyError(case["preset"])
 
 
@@ -52,4 +56,9 @@ FULL_CASES = {
     "swin_b_1dl_1024x2048": dict(preset="swin_b_1dl", levels=1, dec_layers=1, seed=13, perturb=0.02, img_seed=31, sizes=[(1024, 2048)], sub=8),
     "swin_l_1dl_256x512": dict(preset="swin_l_1dl", levels=1, dec_layers=1, seed=17, perturb=0.02, img_seed=32, sizes=[(256, 512)], sub=4),
     "swin_b_3lvl_256x512": dict(preset="swin_b_full", levels=3, dec_layers=3, seed=19, perturb=0.02, img_seed=33, sizes=[(256, 512)], sub=4),
+    # BASELINE.json configs[0]: ResNet-50 1dl at 1 x 512 x 1024.  The reference's own modules around the stand-in backbone of
+    # oracle/ref_shims/detectron2/modeling/backbone/resnet.py (detectron2 is not vendored: backbone parity unpinned, pinned on
+    # torchvision instead, tests/test_resnet_oracle.py); plus the 3-level / 3-layer variant at a smaller size
+    "r50_1dl_512x1024": dict(preset="r50_1dl", levels=1, dec_layers=1, seed=37, perturb=0.02, img_seed=34, sizes=[(512, 1024)], sub=4),
+    "r50_3lvl_192x320": dict(preset="r50_full", levels=3, dec_layers=3, seed=41, perturb=0.02, img_seed=35, sizes=[(192, 320), (192, 320)], sub=4),
 }

@@ -41,7 +41,10 @@ OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 @torch.no_grad()
 def run_case(name, case):
     base = "swin_l_1dl" if case["preset"] == "swin_l_1dl" else "swin_b_1dl"
-    cfg = ref_loader.load_cfg(base, reference_overrides(case))
+    over = reference_overrides(case)
+    if case["preset"].startswith("r50"):
+        over.update(ref_loader.r50_overrides(dec_layers=case["dec_layers"], levels=case["levels"]))
+    cfg = ref_loader.load_cfg(base, over)
     model = ref_loader.build_reference_model(cfg, seed=0)
     mc = case_model_config(case)
     sd = weights.init_state_dict(mc, seed=case["seed"], perturb=case["perturb"])

@@ -37,11 +37,13 @@ def config_from_yaml_dict(y):
     Keys follow mask2former/config.py:74-90 (SWIN), :40-64 (MASK_FORMER), :67,170-172."""
     M = y["MODEL"]
     mf, sh, sw = M["MASK_FORMER"], M["SEM_SEG_HEAD"], M["SWIN"]
-    assert M["BACKBONE"]["NAME"] == "D2SwinTransformer"
+    assert M["BACKBONE"]["NAME"] in ("D2SwinTransformer", "build_resnet_backbone")
     assert sh["PIXEL_DECODER_NAME"] == "MSDeformAttnPixelDecoder"
     assert mf["TRANSFORMER_DECODER_NAME"] == "MultiScaleMaskedTransformerDecoder"
     assert not mf["PRE_NORM"] and not sw["APE"]
     return SimpleNamespace(
+        backbone="resnet" if M["BACKBONE"]["NAME"] == "build_resnet_backbone" else "swin",
+        resnet_depth=int(M.get("RESNETS", {}).get("DEPTH", 50)),
         embed_dim=sw["EMBED_DIM"], depths=list(sw["DEPTHS"]), num_heads=list(sw["NUM_HEADS"]),
         window_size=sw["WINDOW_SIZE"], mlp_ratio=sw["MLP_RATIO"], patch_size=sw["PATCH_SIZE"],
         conv_dim=sh["CONVS_DIM"], mask_dim=sh["MASK_DIM"], num_classes=sh["NUM_CLASSES"],
@@ -193,6 +195,43 @@ def swin_forward(sd, cfg, x, p="backbone."):
         if i < len(cfg.depths) - 1:
             x = patch_merging(sd, f"{p}layers.{i}.downsample.", x, Wh, Ww)
             Wh, Ww = (Wh + 1) // 2, (Ww + 1) // 2
+    return outs
+
+
+# --------------------------------------------------------------------------------------
+# ResNet backbone  (detectron2 `build_resnet_backbone`, selected by configs/cityscapes/semantic-segmentation/
+# Base-Cityscapes-SemanticSegmentation.yaml:4,8-15; call site maskformer_model.py:109)
+# --------------------------------------------------------------------------------------
+# PARITY UNPINNED: detectron2 is neither vendored by the reference nor pinned (INSTALL.md:13-19).  This restates the published
+# architecture -- BasicStem (7x7/2 conv, norm, ReLU, 3x3/2 max-pool), bottleneck blocks with the stride in the 3x3 conv
+# (RESNETS.STRIDE_IN_1X1: False), eval-mode batch norm -- over detectron2's state_dict names, which are the names
+# tools/convert-torchvision-to-d2.py:33-44 maps torchvision's to.  tests/test_resnet_oracle.py pins it on torchvision's
+# resnet50 / resnet101 under that mapping.
+
+RESNET_BLOCKS = {50: [3, 4, 6, 3], 101: [3, 4, 23, 3]}
+
+
+def _conv_bn(sd, p, x, stride=1, padding=0, eps=1e-5):
+    x = F.conv2d(x, sd[p + "weight"], None, stride=stride, padding=padding)
+    return F.batch_norm(x, sd[p + "norm.running_mean"], sd[p + "norm.running_var"], sd[p + "norm.weight"], sd[p + "norm.bias"],
+                        training=False, eps=eps)
+
+
+def resnet_forward(sd, cfg, x, p="backbone."):
+    """x: normalised (B,3,H,W) fp32.  Returns {"res2".."res5"} NCHW with 256 / 512 / 1024 / 2048 channels."""
+    x = F.relu(_conv_bn(sd, p + "stem.conv1.", x, stride=2, padding=3))
+    x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+    outs = {}
+    for i, n in enumerate(RESNET_BLOCKS[getattr(cfg, "resnet_depth", 50)]):
+        for j in range(n):
+            q = f"{p}res{i + 2}.{j}."
+            stride = 2 if (j == 0 and i > 0) else 1
+            out = F.relu(_conv_bn(sd, q + "conv1.", x))
+            out = F.relu(_conv_bn(sd, q + "conv2.", out, stride=stride, padding=1))
+            out = _conv_bn(sd, q + "conv3.", out)
+            sc = _conv_bn(sd, q + "shortcut.", x, stride=stride) if (q + "shortcut.weight") in sd else x
+            x = F.relu(out + sc)
+        outs[f"res{i + 2}"] = x
     return outs
 
 
@@ -587,7 +626,7 @@ def forward(sd, cfg, images, explicit_msda=False, want_taps=False):
     `sem_seg`, `rba`, plus batched `pred_logits`, `pred_masks` and (optionally) taps."""
     taps = {} if want_taps else None
     x, sizes = preprocess(images, cfg)
-    feats = swin_forward(sd, cfg, x)
+    feats = resnet_forward(sd, cfg, x) if getattr(cfg, "backbone", "swin") == "resnet" else swin_forward(sd, cfg, x)
     mask_features, multi_scale = pixel_decoder_forward(sd, cfg, feats, explicit_msda=explicit_msda, taps=taps)
     cls, masks = transformer_decoder_forward(sd, cfg, multi_scale, mask_features, taps=taps)
     sem_seg, rba = [], []

@@ -77,6 +77,16 @@ def _install():
         m = types.ModuleType(name)
         m.__path__ = [os.path.join(REF_ROOT, rel)]
         sys.modules[name] = m
+    # register the build_resnet_backbone stand-in in whichever detectron2 stand-in is active (oracle/ref_shims, or the
+    # product's rba_b200.compat stand-ins when a test plugged those in first)
+    from detectron2.modeling import BACKBONE_REGISTRY
+    try:
+        BACKBONE_REGISTRY.get("build_resnet_backbone")
+    except KeyError:
+        spec = importlib.util.spec_from_file_location(
+            "_ref_shim_resnet", os.path.join(_SHIMS, "detectron2", "modeling", "backbone", "resnet.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
     for mod in [
         "mask2former.modeling.backbone.swin",
         "mask2former.modeling.pixel_decoder.msdeformattn",
@@ -120,6 +130,17 @@ def load_cfg(name_or_path="swin_b_1dl", overrides=None):
         node[keys[-1]] = v
     cfg.MODEL.DEVICE = "cpu"
     return cfg
+
+
+def r50_overrides(dec_layers=1, levels=1, depth=50):
+    """The R50 variants have no dumped ckpt YAML: derive them from the swin_b_1dl dump (every detectron2 default key is
+    spelled out there, MODEL.RESNETS included) by switching the backbone, as configs/cityscapes/semantic-segmentation/
+    maskformer2_R50_bs16_90k.yaml + Base-Cityscapes-SemanticSegmentation.yaml:4-15 do."""
+    o = {"MODEL.BACKBONE.NAME": "build_resnet_backbone", "MODEL.RESNETS.DEPTH": depth, "MODEL.RESNETS.STRIDE_IN_1X1": False,
+         "MODEL.RESNETS.OUT_FEATURES": ["res2", "res3", "res4", "res5"], "MODEL.MASK_FORMER.DEC_LAYERS": dec_layers + 1}
+    if levels == 3:
+        o["MODEL.SEM_SEG_HEAD.DEFORMABLE_TRANSFORMER_ENCODER_IN_FEATURES"] = ["res3", "res4", "res5"]
+    return o
 
 
 def build_reference_model(cfg, seed=0):

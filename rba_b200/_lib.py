@@ -24,6 +24,7 @@ class RbaConfig(Structure):
         ("nheads", c_int32), ("dim_feedforward", c_int32), ("dec_layers", c_int32), ("enc_layers", c_int32),
         ("enc_points", c_int32), ("enc_ffn", c_int32), ("num_enc_levels", c_int32), ("size_divisibility", c_int32),
         ("pixel_mean", c_float * 3), ("pixel_std", c_float * 3),
+        ("backbone_type", c_int32), ("resnet_depth", c_int32),
     ]
 
 
@@ -101,6 +102,10 @@ PROTOTYPES = {
     "rba_k_groupnorm_ws": (c_int64, [c_int, c_int, c_int, c_int, c_int]),
     "rba_k_patch_embed": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float),
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "rba_k_stem_conv": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float),
+                                c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rba_k_maxpool3x3s2": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rba_k_bias_act_sub": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rba_k_attn_mask": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
 }
 

@@ -34,13 +34,26 @@ class ModelConfig:
     size_divisibility: int = 32
     pixel_mean: List[float] = field(default_factory=lambda: [123.675, 116.28, 103.53])
     pixel_std: List[float] = field(default_factory=lambda: [58.395, 57.12, 57.375])
+    backbone: str = "swin"         # "swin" (D2SwinTransformer) or "resnet" (detectron2 build_resnet_backbone, bottleneck R50 / R101)
+    resnet_depth: int = 50         # MODEL.RESNETS.DEPTH
     ood_prediction: bool = False   # MODEL.MASK_FORMER.DENSE_HYBRID_LOSS: predictor.ood_pred head (mask2former_transformer_decoder.py:365-366,394)
 
     @property
     def num_enc_levels(self):
         return len(self.transformer_in_features)
 
+    @property
+    def feature_channels(self):
+        """Channels of res2..res5 as the pixel decoder sees them."""
+        if self.backbone == "resnet":
+            return [256, 512, 1024, 2048]
+        return [self.embed_dim << i for i in range(4)]
+
     def validate(self):
+        if self.backbone not in ("swin", "resnet"):
+            raise ValueError(f"unknown backbone {self.backbone!r}")
+        if self.backbone == "resnet" and self.resnet_depth not in (50, 101):
+            raise ValueError("only bottleneck ResNet-50 / ResNet-101 are built")
         if self.mlp_ratio != 4.0 or self.patch_size != 4:
             raise ValueError("only MLP_RATIO 4.0 / PATCH_SIZE 4 are supported")
         if self.hidden_dim != self.conv_dim:
@@ -63,6 +76,8 @@ class ModelConfig:
         c.dec_layers, c.enc_layers, c.enc_points, c.enc_ffn = self.dec_layers, self.enc_layers, self.enc_points, self.enc_ffn
         c.num_enc_levels = self.num_enc_levels
         c.size_divisibility = self.size_divisibility
+        c.backbone_type = 1 if self.backbone == "resnet" else 0
+        c.resnet_depth = self.resnet_depth
         for i in range(3):
             c.pixel_mean[i] = self.pixel_mean[i]
             c.pixel_std[i] = self.pixel_std[i]
@@ -87,19 +102,26 @@ def model_config_from_cfg(cfg):
     ckpts/<name>/config.yaml).  Raises on architectures outside the built hot path."""
     M = cfg["MODEL"] if isinstance(cfg, dict) else cfg.MODEL
     g = lambda k: _get(M, k)  # noqa: E731
-    if g("BACKBONE.NAME") != "D2SwinTransformer":
-        raise ValueError(f"backbone {g('BACKBONE.NAME')} is not built (Swin only)")
+    if g("BACKBONE.NAME") not in ("D2SwinTransformer", "build_resnet_backbone"):
+        raise ValueError(f"backbone {g('BACKBONE.NAME')} is not built (D2SwinTransformer and build_resnet_backbone are)")
+    resnet = g("BACKBONE.NAME") == "build_resnet_backbone"
+    if resnet:
+        if _get_default(M, "RESNETS.STRIDE_IN_1X1", False) or _get_default(M, "RESNETS.NUM_GROUPS", 1) != 1 or \
+                any(_get_default(M, "RESNETS.DEFORM_ON_PER_STAGE", [False])):
+            raise ValueError("only plain bottleneck ResNets with STRIDE_IN_1X1: False are built")
     if g("SEM_SEG_HEAD.PIXEL_DECODER_NAME") != "MSDeformAttnPixelDecoder":
         raise ValueError("only MSDeformAttnPixelDecoder is built")
     if g("MASK_FORMER.TRANSFORMER_DECODER_NAME") != "MultiScaleMaskedTransformerDecoder":
         raise ValueError("only MultiScaleMaskedTransformerDecoder is built")
-    if g("MASK_FORMER.PRE_NORM") or g("SWIN.APE") or not g("SWIN.QKV_BIAS") or not g("SWIN.PATCH_NORM"):
+    if g("MASK_FORMER.PRE_NORM") or (not resnet and (g("SWIN.APE") or not g("SWIN.QKV_BIAS") or not g("SWIN.PATCH_NORM"))):
         raise ValueError("PRE_NORM / APE / no QKV_BIAS / no PATCH_NORM variants are not built")
     if g("SEM_SEG_HEAD.NORM") != "GN":
         raise ValueError("SEM_SEG_HEAD.NORM must be GN")
-    mc = ModelConfig(
+    sw = {} if resnet else dict(
         embed_dim=g("SWIN.EMBED_DIM"), depths=list(g("SWIN.DEPTHS")), num_heads=list(g("SWIN.NUM_HEADS")),
-        window_size=g("SWIN.WINDOW_SIZE"), mlp_ratio=float(g("SWIN.MLP_RATIO")), patch_size=g("SWIN.PATCH_SIZE"),
+        window_size=g("SWIN.WINDOW_SIZE"), mlp_ratio=float(g("SWIN.MLP_RATIO")), patch_size=g("SWIN.PATCH_SIZE"))
+    mc = ModelConfig(
+        backbone="resnet" if resnet else "swin", resnet_depth=int(_get_default(M, "RESNETS.DEPTH", 50)), **sw,
         conv_dim=g("SEM_SEG_HEAD.CONVS_DIM"), mask_dim=g("SEM_SEG_HEAD.MASK_DIM"), num_classes=g("SEM_SEG_HEAD.NUM_CLASSES"),
         in_features=list(g("SEM_SEG_HEAD.IN_FEATURES")),
         transformer_in_features=list(g("SEM_SEG_HEAD.DEFORMABLE_TRANSFORMER_ENCODER_IN_FEATURES")),
@@ -131,6 +153,18 @@ def swin_l_1dl():
 def swin_b_full(dec_layers=9):
     """3-level / full-decoder variant (configs/.../maskformer2_R50_bs16_90k.yaml:15,35 inherited by the swin_base yaml)."""
     return ModelConfig(transformer_in_features=["res3", "res4", "res5"], dec_layers=dec_layers).validate()
+
+
+def r50_1dl(depth=50):
+    """ResNet-50 single-decoder-layer variant (BASELINE.json configs[0]): maskformer2_R50_bs16_90k.yaml with the two overrides
+    of maskformer2_R101_bs16_90k_1dl.yaml:13-15 (DEC_LAYERS 2, encoder on res5 only); depth=101 is that R101 file itself."""
+    return ModelConfig(backbone="resnet", resnet_depth=depth).validate()
+
+
+def r50_full(dec_layers=9, depth=50):
+    """maskformer2_R50_bs16_90k.yaml as is: 3 encoder levels, DEC_LAYERS 10."""
+    return ModelConfig(backbone="resnet", resnet_depth=depth, transformer_in_features=["res3", "res4", "res5"],
+                       dec_layers=dec_layers).validate()
 
 
 def tiny_test(depths=(2, 2, 2, 2), levels=1, dec_layers=1, ood_prediction=False):

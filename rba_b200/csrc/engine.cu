@@ -175,6 +175,13 @@ int linear_planes(rba_model* m, const std::string& key, int64_t N, int64_t K) {
   return make_planes(m, key, t->d, N, (int)K);
 }
 
+// channels of res2..res5 as the pixel decoder sees them
+int feat_channels(const rba_config& c, int i) { return c.backbone_type == 1 ? (256 << i) : (c.embed_dim << i); }
+int resnet_blocks(const rba_config& c, int stage) {
+  static const int r50[4] = {3, 4, 6, 3}, r101[4] = {3, 4, 23, 3};
+  return (c.resnet_depth == 101 ? r101 : r50)[stage];
+}
+
 struct Levels {
   int n;
   int H[4], W[4], start[4];
@@ -193,10 +200,16 @@ extern "C" int rba_model_create(const rba_config* cfg, int device, rba_model** o
   if (e != cudaSuccess || ndev == 0)
     return fail(RBA_ERR_CUDA, "rba_model_create: no CUDA device (%s); this library has no CPU path", cudaGetErrorString(e));
   RBA_CHECK(device >= 0 && device < ndev, "rba_model_create: bad device %d", device);
-  RBA_CHECK(cfg->window_size == 12, "only MODEL.SWIN.WINDOW_SIZE 12 is built (got %d)", cfg->window_size);
-  RBA_CHECK(cfg->embed_dim % 32 == 0 && cfg->embed_dim <= 256, "unsupported EMBED_DIM %d", cfg->embed_dim);
-  for (int i = 0; i < 4; ++i)
-    RBA_CHECK(cfg->num_heads[i] * 32 == (cfg->embed_dim << i), "stage %d: head_dim must be 32", i);
+  RBA_CHECK(cfg->backbone_type == 0 || cfg->backbone_type == 1, "unknown backbone type %d", cfg->backbone_type);
+  if (cfg->backbone_type == 0) {
+    RBA_CHECK(cfg->window_size == 12, "only MODEL.SWIN.WINDOW_SIZE 12 is built (got %d)", cfg->window_size);
+    RBA_CHECK(cfg->embed_dim % 32 == 0 && cfg->embed_dim <= 256, "unsupported EMBED_DIM %d", cfg->embed_dim);
+    for (int i = 0; i < 4; ++i)
+      RBA_CHECK(cfg->num_heads[i] * 32 == (cfg->embed_dim << i), "stage %d: head_dim must be 32", i);
+  } else {
+    RBA_CHECK(cfg->resnet_depth == 50 || cfg->resnet_depth == 101, "only bottleneck ResNet-50 / -101 are built (got depth %d)",
+              cfg->resnet_depth);
+  }
   RBA_CHECK(cfg->conv_dim == 256 && cfg->mask_dim == 256 && cfg->nheads == 8, "CONVS_DIM/MASK_DIM 256 and NHEADS 8 expected");
   RBA_CHECK(cfg->num_enc_levels == 1 || cfg->num_enc_levels == 3, "1 or 3 encoder levels supported");
   RBA_CHECK(cfg->size_divisibility > 0 && cfg->size_divisibility % 32 == 0, "SIZE_DIVISIBILITY must be a multiple of 32");
@@ -255,6 +268,54 @@ extern "C" int rba_model_load_tensor(rba_model* m, const char* key, const float*
   return RBA_OK;
 }
 
+// conv (bias-free) + eval-mode batch norm -> folded fp32 weight [O][I] (3x3: re-laid out to [O][tap][Cin]) + bias; planes under
+// `key + "weight"` when `as_planes`
+static int fold_conv_bn(rba_model* m, const std::string& key, int O, int Cin, int k, bool as_planes) {
+  const DevTensor *w, *g, *be, *mu, *va;
+  RBA_TRY(need(m, key + "weight", {O, Cin, k, k}, &w));
+  RBA_TRY(need(m, key + "norm.weight", {O}, &g));
+  RBA_TRY(need(m, key + "norm.bias", {O}, &be));
+  RBA_TRY(need(m, key + "norm.running_mean", {O}, &mu));
+  RBA_TRY(need(m, key + "norm.running_var", {O}, &va));
+  const int64_t I = (int64_t)Cin * k * k;
+  const float* src = w->d;
+  if (k == 3) {
+    float* perm;
+    RBA_TRY(m->dmalloc(&perm, (size_t)O * I));
+    permute_conv3x3_kernel<<<256, 256>>>(w->d, O, Cin, perm);
+    src = perm;
+  }
+  float *fw, *fb;
+  RBA_TRY(m->dmalloc(&fw, (size_t)O * I));
+  RBA_TRY(m->dmalloc(&fb, (size_t)O));
+  RBA_TRY(bn_fold_conv(src, g->d, be->d, mu->d, va->d, 1e-5f, O, I, fw, fb, nullptr));
+  DevTensor wt; wt.d = fw; wt.numel = (int64_t)O * I; wt.shape = {O, I};
+  DevTensor bt; bt.d = fb; bt.numel = O; bt.shape = {O};
+  m->w[key + "folded.weight"] = wt;
+  m->w[key + "folded.bias"] = bt;
+  if (as_planes) RBA_TRY(make_planes(m, key + "folded.weight", fw, O, (int)I));
+  return RBA_OK;
+}
+
+static int finalize_resnet(rba_model* m) {
+  const rba_config& c = m->cfg;
+  RBA_TRY(fold_conv_bn(m, "backbone.stem.conv1.", 64, 3, 7, false));
+  int cin = 64, width = 64;
+  for (int i = 0; i < 4; ++i) {
+    const int cout = width * 4;
+    for (int j = 0; j < resnet_blocks(c, i); ++j) {
+      const std::string p = "backbone.res" + std::to_string(i + 2) + "." + std::to_string(j) + ".";
+      if (cin != cout) RBA_TRY(fold_conv_bn(m, p + "shortcut.", cout, cin, 1, true));
+      RBA_TRY(fold_conv_bn(m, p + "conv1.", width, cin, 1, true));
+      RBA_TRY(fold_conv_bn(m, p + "conv2.", width, width, 3, true));
+      RBA_TRY(fold_conv_bn(m, p + "conv3.", cout, width, 1, true));
+      cin = cout;
+    }
+    width *= 2;
+  }
+  return RBA_OK;
+}
+
 extern "C" int rba_model_finalize(rba_model* m) {
   RBA_CHECK(m, "rba_model_finalize: null model");
   if (m->finalized) return RBA_OK;
@@ -262,53 +323,57 @@ extern "C" int rba_model_finalize(rba_model* m) {
   const rba_config& c = m->cfg;
   const int D = c.conv_dim;
   // ---- backbone ----
+  if (c.backbone_type == 1) {
+    RBA_TRY(finalize_resnet(m));
+  } else {
   RBA_TRY(need(m, "backbone.patch_embed.proj.weight", {c.embed_dim, 3, 4, 4}));
-  RBA_TRY(need(m, "backbone.patch_embed.proj.bias", {c.embed_dim}));
-  RBA_TRY(need(m, "backbone.patch_embed.norm.weight", {c.embed_dim}));
-  RBA_TRY(need(m, "backbone.patch_embed.norm.bias", {c.embed_dim}));
-  for (int i = 0; i < 4; ++i) {
-    const int64_t C = (int64_t)c.embed_dim << i;
-    for (int j = 0; j < c.depths[i]; ++j) {
-      std::string p = "backbone.layers." + std::to_string(i) + ".blocks." + std::to_string(j) + ".";
-      RBA_TRY(need(m, p + "norm1.weight", {C}));
-      RBA_TRY(need(m, p + "norm1.bias", {C}));
-      const DevTensor* rpb;
-      RBA_TRY(need(m, p + "attn.relative_position_bias_table", {23 * 23, c.num_heads[i]}, &rpb));
-      {  // head-major, log2(e)-scaled copy for the tensor-core attention kernel (one contiguous cp.async burst per CTA)
-        float* prep;
-        RBA_TRY(m->dmalloc(&prep, (size_t)window_attn_bias_floats(c.num_heads[i])));
-        RBA_TRY(window_attn_prepare_bias(rpb->d, c.num_heads[i], prep, nullptr));
-        DevTensor pt = *rpb;
-        pt.d = prep;
-        pt.numel = window_attn_bias_floats(c.num_heads[i]);
-        m->w[p + "attn.relative_position_bias_prepared"] = pt;
+    RBA_TRY(need(m, "backbone.patch_embed.proj.bias", {c.embed_dim}));
+    RBA_TRY(need(m, "backbone.patch_embed.norm.weight", {c.embed_dim}));
+    RBA_TRY(need(m, "backbone.patch_embed.norm.bias", {c.embed_dim}));
+    for (int i = 0; i < 4; ++i) {
+      const int64_t C = (int64_t)c.embed_dim << i;
+      for (int j = 0; j < c.depths[i]; ++j) {
+        std::string p = "backbone.layers." + std::to_string(i) + ".blocks." + std::to_string(j) + ".";
+        RBA_TRY(need(m, p + "norm1.weight", {C}));
+        RBA_TRY(need(m, p + "norm1.bias", {C}));
+        const DevTensor* rpb;
+        RBA_TRY(need(m, p + "attn.relative_position_bias_table", {23 * 23, c.num_heads[i]}, &rpb));
+        {  // head-major, log2(e)-scaled copy for the tensor-core attention kernel (one contiguous cp.async burst per CTA)
+          float* prep;
+          RBA_TRY(m->dmalloc(&prep, (size_t)window_attn_bias_floats(c.num_heads[i])));
+          RBA_TRY(window_attn_prepare_bias(rpb->d, c.num_heads[i], prep, nullptr));
+          DevTensor pt = *rpb;
+          pt.d = prep;
+          pt.numel = window_attn_bias_floats(c.num_heads[i]);
+          m->w[p + "attn.relative_position_bias_prepared"] = pt;
+        }
+        RBA_TRY(linear_planes(m, p + "attn.qkv.weight", 3 * C, C));
+        RBA_TRY(need(m, p + "attn.qkv.bias", {3 * C}));
+        RBA_TRY(linear_planes(m, p + "attn.proj.weight", C, C));
+        RBA_TRY(need(m, p + "attn.proj.bias", {C}));
+        RBA_TRY(need(m, p + "norm2.weight", {C}));
+        RBA_TRY(need(m, p + "norm2.bias", {C}));
+        RBA_TRY(linear_planes(m, p + "mlp.fc1.weight", 4 * C, C));
+        RBA_TRY(need(m, p + "mlp.fc1.bias", {4 * C}));
+        RBA_TRY(linear_planes(m, p + "mlp.fc2.weight", C, 4 * C));
+        RBA_TRY(need(m, p + "mlp.fc2.bias", {C}));
       }
-      RBA_TRY(linear_planes(m, p + "attn.qkv.weight", 3 * C, C));
-      RBA_TRY(need(m, p + "attn.qkv.bias", {3 * C}));
-      RBA_TRY(linear_planes(m, p + "attn.proj.weight", C, C));
-      RBA_TRY(need(m, p + "attn.proj.bias", {C}));
-      RBA_TRY(need(m, p + "norm2.weight", {C}));
-      RBA_TRY(need(m, p + "norm2.bias", {C}));
-      RBA_TRY(linear_planes(m, p + "mlp.fc1.weight", 4 * C, C));
-      RBA_TRY(need(m, p + "mlp.fc1.bias", {4 * C}));
-      RBA_TRY(linear_planes(m, p + "mlp.fc2.weight", C, 4 * C));
-      RBA_TRY(need(m, p + "mlp.fc2.bias", {C}));
-    }
-    std::string n = "backbone.norm" + std::to_string(i) + ".";
-    RBA_TRY(need(m, n + "weight", {C}));
-    RBA_TRY(need(m, n + "bias", {C}));
-    if (i < 3) {
-      std::string p = "backbone.layers." + std::to_string(i) + ".downsample.";
-      RBA_TRY(need(m, p + "norm.weight", {4 * C}));
-      RBA_TRY(need(m, p + "norm.bias", {4 * C}));
-      RBA_TRY(linear_planes(m, p + "reduction.weight", 2 * C, 4 * C));
+      std::string n = "backbone.norm" + std::to_string(i) + ".";
+      RBA_TRY(need(m, n + "weight", {C}));
+      RBA_TRY(need(m, n + "bias", {C}));
+      if (i < 3) {
+        std::string p = "backbone.layers." + std::to_string(i) + ".downsample.";
+        RBA_TRY(need(m, p + "norm.weight", {4 * C}));
+        RBA_TRY(need(m, p + "norm.bias", {4 * C}));
+        RBA_TRY(linear_planes(m, p + "reduction.weight", 2 * C, 4 * C));
+      }
     }
   }
   // ---- pixel decoder ----
   const std::string pd = "sem_seg_head.pixel_decoder.";
   const int L = c.num_enc_levels;
   for (int idx = 0; idx < L; ++idx) {       // input_proj[idx]: low-res first (res5, res4, res3), msdeformattn.py:221-235
-    const int64_t Cin = (int64_t)c.embed_dim << (3 - idx);
+    const int64_t Cin = feat_channels(c, 3 - idx);
     std::string p = pd + "input_proj." + std::to_string(idx) + ".";
     RBA_TRY(linear_planes(m, p + "0.weight", D, Cin));
     RBA_TRY(need(m, p + "0.bias", {D}));
@@ -351,7 +416,7 @@ extern "C" int rba_model_finalize(rba_model* m) {
   }
   const int num_fpn = (L == 1) ? 3 : 1;     // log2(min transformer stride) - log2(4), msdeformattn.py:267-268
   for (int k = 1; k <= num_fpn; ++k) {      // adapter_k / layer_k act on res(k+1)
-    const int64_t Cin = (int64_t)c.embed_dim << (k - 1);
+    const int64_t Cin = feat_channels(c, k - 1);
     std::string a = pd + "adapter_" + std::to_string(k) + ".", l = pd + "layer_" + std::to_string(k) + ".";
     RBA_TRY(linear_planes(m, a + "weight", D, Cin));
     RBA_TRY(need(m, a + "norm.weight", {D}));
@@ -533,6 +598,65 @@ static int forward_impl(rba_model* m, const void* images, int img_dtype, int B, 
   const int D = c.conv_dim, Q = c.num_queries, K1 = c.num_classes + 1, ws = c.window_size;
   const float eps = 1e-5f;
 
+  Planes resp[4];
+  int resH[4], resW[4], resC[4];
+  if (c.backbone_type == 1) {
+    // ================= ResNet backbone (detectron2 build_resnet_backbone; bottleneck blocks, stride in the 3x3) =================
+    const int H2 = Hp / 2, W2 = Wp / 2;
+    int Hs = Hp / 4, Wsz = Wp / 4;
+    float* x = A.f32((int64_t)B * Hs * Wsz * 64);
+    Planes xp = A.planes((int64_t)B * Hs * Wsz * 64);
+    {
+      const size_t mk = A.mark();
+      float* t0 = A.f32((int64_t)B * H2 * W2 * 64);
+      RBA_RUN(stem_conv(images, img_dtype, B, H, W, Hp, Wp, c.pixel_mean, c.pixel_std, F.W("backbone.stem.conv1.folded.weight"),
+                        F.W("backbone.stem.conv1.folded.bias"), t0, st));
+      RBA_RUN(maxpool3x3s2(t0, B, H2, W2, 64, x, xp.hi, xp.lo, st));
+      A.release(mk);
+    }
+    int cin = 64, width = 64;
+    for (int i = 0; i < 4; ++i) {
+      const int cout = width * 4;
+      for (int j = 0; j < resnet_blocks(c, i); ++j) {
+        const std::string p = "backbone.res" + std::to_string(i + 2) + "." + std::to_string(j) + ".";
+        const int stride = (j == 0 && i > 0) ? 2 : 1;
+        const int Ho = Hs / stride, Wo = Wsz / stride;
+        const int64_t T = (int64_t)B * Hs * Wsz, To = (int64_t)B * Ho * Wo;
+        // outputs of the block live below the mark; temporaries above it
+        float* xo = A.f32(To * cout);
+        Planes xop = A.planes(To * cout);
+        const size_t mk = A.mark();
+        Planes t1 = A.planes(T * width);
+        RBA_TRY(F.lin(xp, cin, T, cin, F.P(p + "conv1.folded.weight"), width, F.W(p + "conv1.folded.bias"), RBA_ACT_RELU, nullptr,
+                      nullptr, 0, t1, width));
+        float* y2 = A.f32(T * width);
+        Planes w2 = F.P(p + "conv2.folded.weight");
+        RBA_RUN(conv3x3(t1.hi, t1.lo, w2.hi, w2.lo, B, Hs, Wsz, width, width, y2, F.backend, st));
+        Planes t2 = A.planes(To * width);
+        RBA_RUN(bias_act_sub(y2, F.W(p + "conv2.folded.bias"), B, Hs, Wsz, width, stride, 1, nullptr, t2.hi, t2.lo, st));
+        const float* sc = x;
+        if (cin != cout) {
+          Planes xs = xp;
+          if (stride == 2) {
+            xs = A.planes(To * cin);
+            RBA_RUN(bias_act_sub(x, nullptr, B, Hs, Wsz, cin, 2, 0, nullptr, xs.hi, xs.lo, st));
+          }
+          float* scf = A.f32(To * cout);
+          RBA_TRY(F.lin(xs, cin, To, cin, F.P(p + "shortcut.folded.weight"), cout, F.W(p + "shortcut.folded.bias"), RBA_ACT_NONE,
+                        nullptr, scf, cout));
+          sc = scf;
+        }
+        RBA_TRY(F.lin(t2, width, To, width, F.P(p + "conv3.folded.weight"), cout, F.W(p + "conv3.folded.bias"), RBA_ACT_NONE, sc, xo,
+                      cout));
+        RBA_RUN(bias_act_sub(xo, nullptr, B, Ho, Wo, cout, 1, 1, xo, xop.hi, xop.lo, st));   // ReLU after the residual add
+        A.release(mk);
+        x = xo; xp = xop; cin = cout; Hs = Ho; Wsz = Wo;
+      }
+      resp[i] = xp; resH[i] = Hs; resW[i] = Wsz; resC[i] = cout;
+      F.tap(("res" + std::to_string(i + 2)).c_str(), x, (int64_t)B * Hs * Wsz * cout);
+      width *= 2;
+    }
+  } else {
   // ================= backbone (swin.py:651-678) =================
   int Hs = Hp / 4, Wsz = Wp / 4;
   int C = c.embed_dim;
@@ -540,8 +664,6 @@ static int forward_impl(rba_model* m, const void* images, int img_dtype, int B, 
   RBA_RUN(patch_embed(images, img_dtype, B, H, W, Hp, Wp, c.pixel_mean, c.pixel_std, F.W("backbone.patch_embed.proj.weight"),
                       F.W("backbone.patch_embed.proj.bias"), F.W("backbone.patch_embed.norm.weight"),
                       F.W("backbone.patch_embed.norm.bias"), C, x, st));
-  Planes resp[4];
-  int resH[4], resW[4], resC[4];
   for (int i = 0; i < 4; ++i) {
     const int64_t N = (int64_t)Hs * Wsz, T = (int64_t)B * N;
     const int heads = c.num_heads[i];
@@ -616,6 +738,8 @@ static int forward_impl(rba_model* m, const void* images, int img_dtype, int B, 
       x = xn;
       Hs /= 2; Wsz /= 2; C *= 2;
     }
+  }
+
   }
 
   // ================= pixel decoder (msdeformattn.py:323-367) =================

@@ -13,6 +13,13 @@ int groupnorm(const float* x, int64_t x_bs, const float* gamma, const float* bet
 int patch_embed(const void* images, int img_dtype, int B, int H, int W, int Hp, int Wp, const float* mean,
                 const float* stdv, const float* conv_w, const float* conv_b, const float* gamma, const float* beta, int C,
                 float* tokens, cudaStream_t st);
+int stem_conv(const void* images, int img_dtype, int B, int H, int W, int Hp, int Wp, const float* mean, const float* stdv,
+              const float* w, const float* bias, float* out, cudaStream_t st);
+int maxpool3x3s2(const float* x, int B, int H, int W, int C, float* y, uint16_t* y_hi, uint16_t* y_lo, cudaStream_t st);
+int bias_act_sub(const float* x, const float* bias, int B, int H, int W, int C, int stride, int relu, float* y, uint16_t* y_hi,
+                 uint16_t* y_lo, cudaStream_t st);
+int bn_fold_conv(const float* w, const float* gamma, const float* beta, const float* mean, const float* var, float eps, int O,
+                 int64_t I, float* w_out, float* b_out, cudaStream_t st);
 int ew_add(const float* a, const float* b, int64_t rows, int cols, int64_t period, float* y, uint16_t* y_hi,
            uint16_t* y_lo, cudaStream_t st);
 int gemm(const rba_gemm_args& a, cudaStream_t st);

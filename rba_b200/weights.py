@@ -25,6 +25,45 @@ def param_specs(mc):
     """OrderedDict name -> (shape, init kind) in the reference's registration order."""
     S = OrderedDict()
     C0, ws, D = mc.embed_dim, mc.window_size, mc.conv_dim
+    FC = mc.feature_channels
+    if mc.backbone == "resnet":
+        _resnet_specs(S, mc)
+    else:
+        _swin_specs(S, mc)
+    _head_specs(S, mc, FC)
+    return S
+
+
+RESNET_BLOCKS = {50: [3, 4, 6, 3], 101: [3, 4, 23, 3]}
+
+
+def _resnet_specs(S, mc):
+    """detectron2 ResNet state_dict names (= tools/convert-torchvision-to-d2.py:33-44 applied to torchvision's), batch norm
+    with running statistics (RESNETS.NORM "SyncBN" at training time; an affine map in eval)."""
+    def conv_bn(p, cout, cin, k):
+        S[p + "weight"] = ((cout, cin, k, k), "msra")
+        S[p + "norm.weight"] = ((cout,), "ones")
+        S[p + "norm.bias"] = ((cout,), "zeros")
+        S[p + "norm.running_mean"] = ((cout,), "bn_mean")
+        S[p + "norm.running_var"] = ((cout,), "bn_var")
+        S[p + "norm.num_batches_tracked"] = ((), "counter")
+    conv_bn("backbone.stem.conv1.", 64, 3, 7)
+    cin, width = 64, 64
+    for i, n in enumerate(RESNET_BLOCKS[mc.resnet_depth]):
+        cout = width * 4
+        for j in range(n):
+            p = f"backbone.res{i + 2}.{j}."
+            if cin != cout:
+                conv_bn(p + "shortcut.", cout, cin, 1)
+            conv_bn(p + "conv1.", width, cin, 1)
+            conv_bn(p + "conv2.", width, width, 3)
+            conv_bn(p + "conv3.", cout, width, 1)
+            cin = cout
+        width *= 2
+
+
+def _swin_specs(S, mc):
+    C0, ws = mc.embed_dim, mc.window_size
     S["backbone.patch_embed.proj.weight"] = ((C0, 3, 4, 4), "conv")
     S["backbone.patch_embed.proj.bias"] = ((C0,), "conv_bias:48")
     S["backbone.patch_embed.norm.weight"] = ((C0,), "ones")
@@ -55,10 +94,14 @@ def param_specs(mc):
     for i in range(4):
         S[f"backbone.norm{i}.weight"] = ((C0 << i,), "ones")
         S[f"backbone.norm{i}.bias"] = ((C0 << i,), "zeros")
+
+
+def _head_specs(S, mc, FC):
+    D = mc.conv_dim
     pd = "sem_seg_head.pixel_decoder."
     L = mc.num_enc_levels
     for idx in range(L):
-        Cin = C0 << (3 - idx)
+        Cin = FC[3 - idx]
         S[f"{pd}input_proj.{idx}.0.weight"] = ((D, Cin, 1, 1), "xavier")
         S[f"{pd}input_proj.{idx}.0.bias"] = ((D,), "zeros")
         S[f"{pd}input_proj.{idx}.1.weight"] = ((D,), "ones")
@@ -87,7 +130,7 @@ def param_specs(mc):
     S[pd + "mask_features.bias"] = ((mc.mask_dim,), "zeros")
     num_fpn = 3 if L == 1 else 1
     for k in range(1, num_fpn + 1):
-        Cin = C0 << (k - 1)
+        Cin = FC[k - 1]
         S[f"{pd}adapter_{k}.weight"] = ((D, Cin, 1, 1), "c2_xavier")
         S[f"{pd}adapter_{k}.norm.weight"] = ((D,), "ones")
         S[f"{pd}adapter_{k}.norm.bias"] = ((D,), "zeros")
@@ -131,7 +174,6 @@ def param_specs(mc):
         S[pr + "ood_pred.conv.weight"] = ((2, D, 1, 1), "conv")
         S[pr + "ood_pred.conv.bias"] = ((2,), f"conv_bias:{D}")
     S["criterion.empty_weight"] = ((mc.num_classes + 1,), "ones")  # training buffer kept for key parity
-    return S
 
 
 def _fans(shape):
@@ -167,6 +209,11 @@ def init_state_dict(mc, seed=0, perturb=0.0):
             t = torch.ones(shape) + (10.0 * perturb * torch.randn(shape, generator=g)).abs()
             sd[name] = t.float().contiguous()
             continue
+        elif kind == "bn_mean":                                  # running mean: 0 (+ perturbation below)
+            t = torch.zeros(shape)
+        elif kind == "msra":                                     # c2_msra_fill: kaiming_normal_(mode="fan_out", relu)
+            _, fan_out = _fans(shape)
+            t = torch.randn(shape, generator=g) * math.sqrt(2.0 / fan_out)
         elif kind == "trunc02":
             t = torch.nn.init.trunc_normal_(torch.empty(shape), std=0.02, generator=g)
         elif kind == "normal":

@@ -32,8 +32,9 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    # rba_config: 25 int32 + 6 float; rba_gemm_args must round-trip through the C side unchanged (checked on GPU by use)
-    assert ctypes.sizeof(_lib.RbaConfig) == 4 * (1 + 4 + 4 + 1 + 12) + 4 * 6
+    # rba_config: 22 int32 + 6 float + backbone_type, resnet_depth; rba_gemm_args must round-trip through the C side unchanged
+    # (checked on GPU by use)
+    assert ctypes.sizeof(_lib.RbaConfig) == 4 * (1 + 4 + 4 + 1 + 12) + 4 * 6 + 4 * 2
     assert ctypes.sizeof(_lib.RbaGemmArgs) % 8 == 0
 
 
@@ -67,11 +68,14 @@ def test_config_presets_and_validation():
     b, l = config.swin_b_1dl(), config.swin_l_1dl()
     assert b.embed_dim == 128 and l.embed_dim == 192 and b.num_enc_levels == 1 and b.dec_layers == 1
     assert config.swin_b_full().num_enc_levels == 3
-    y = {"MODEL": {"BACKBONE": {"NAME": "build_resnet_backbone"}}}
+    y = {"MODEL": {"BACKBONE": {"NAME": "D2MixVisionTransformer"}}}
     with pytest.raises(ValueError):
         config.model_config_from_cfg(y)
+    r = config.r50_1dl()
+    assert r.backbone == "resnet" and r.to_ctypes().backbone_type == 1 and r.to_ctypes().resnet_depth == 50
+    assert config.r50_full().num_enc_levels == 3 and config.r50_1dl(101).resnet_depth == 101
     c = b.to_ctypes()
-    assert list(c.depths) == [2, 2, 18, 2] and c.num_enc_levels == 1 and abs(c.pixel_std[2] - 57.375) < 1e-6
+    assert c.backbone_type == 0 and list(c.depths) == [2, 2, 18, 2] and c.num_enc_levels == 1 and abs(c.pixel_std[2] - 57.375) < 1e-6
 
 
 def test_weight_inventory_and_state_dict_roundtrip():

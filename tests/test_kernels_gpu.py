@@ -590,3 +590,64 @@ def test_window_attention_tensor_core(dev, H, W, shift, B, heads, kernel):
     out = fn(qp, table.to(dev), B, H, W, C, heads, ws, shift)
     err = (unplanes(out) - ref).abs()
     assert err.max() < 3e-4, (float(err.max()), int(err.argmax()) // C, int(err.argmax()) % C)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# ResNet backbone pieces (detectron2 build_resnet_backbone; resnet.cu)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.uint8, torch.float32])
+def test_resnet_stem_conv_and_maxpool(dev, dtype):
+    """normalise + zero-pad + 7x7/2 conv + folded BN + ReLU, then the 3x3/2 max-pool, against torch."""
+    import ctypes
+    from rba_b200 import _lib
+    g = torch.Generator().manual_seed(31)
+    B, H, W, Hp, Wp = 2, 70, 100, 96, 128
+    img = torch.randint(0, 256, (B, 3, H, W), generator=g).to(dtype)
+    w = torch.randn(64, 3, 7, 7, generator=g) * 0.1
+    bias = torch.randn(64, generator=g) * 0.1
+    mean, std = [123.675, 116.28, 103.53], [58.395, 57.12, 57.375]
+    xn = (img.float() - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)
+    xn = F.pad(xn, (0, Wp - W, 0, Hp - H))
+    ref = F.relu(F.conv2d(xn, w, bias, stride=2, padding=3))
+    ref_pool = F.max_pool2d(ref, 3, 2, 1)
+    out = torch.empty(B, Hp // 2, Wp // 2, 64, device=dev)
+    L = _lib.lib()
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    imd, wd, bd = img.to(dev).contiguous(), w.reshape(64, -1).to(dev).contiguous(), bias.to(dev)
+    _lib.check(L.rba_k_stem_conv(p(imd), 0 if dtype == torch.uint8 else 1, B, H, W, Hp, Wp, (ctypes.c_float * 3)(*mean),
+                                 (ctypes.c_float * 3)(*std), p(wd), p(bd), p(out), st))
+    assert (out.cpu().permute(0, 3, 1, 2) - ref).abs().max() < 2e-4
+    y = torch.empty(B, Hp // 4, Wp // 4, 64, device=dev)
+    hi = torch.empty(B, Hp // 4, Wp // 4, 64, dtype=torch.bfloat16, device=dev)
+    lo = torch.empty_like(hi)
+    _lib.check(L.rba_k_maxpool3x3s2(p(out), B, Hp // 2, Wp // 2, 64, p(y), p(hi), p(lo), st))
+    assert (y.cpu().permute(0, 3, 1, 2) - ref_pool).abs().max() < 2e-4
+    assert (hi.float() + lo.float() - y).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("stride,relu,with_bias", [(1, 1, True), (2, 1, True), (2, 0, False), (1, 1, False)])
+def test_resnet_bias_act_sub(dev, stride, relu, with_bias):
+    import ctypes
+    from rba_b200 import _lib
+    g = torch.Generator().manual_seed(32)
+    B, H, W, C = 2, 12, 20, 64
+    x = torch.randn(B, H, W, C, generator=g)
+    bias = torch.randn(C, generator=g) if with_bias else None
+    ref = x[:, ::stride, ::stride] + (bias if with_bias else 0.0)
+    if relu:
+        ref = ref.relu()
+    xd = x.to(dev)
+    y = torch.empty(B, H // stride, W // stride, C, device=dev)
+    hi = torch.empty(y.shape, dtype=torch.bfloat16, device=dev)
+    lo = torch.empty_like(hi)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
+    _lib.check(_lib.lib().rba_k_bias_act_sub(p(xd), p(bias.to(dev) if with_bias else None), B, H, W, C, stride, relu, p(y), p(hi),
+                                             p(lo), st))
+    assert torch.equal(y.cpu(), ref)
+    assert (hi.float() + lo.float() - y).abs().max() < 1e-4
+    if stride == 1:                                              # in place
+        _lib.check(_lib.lib().rba_k_bias_act_sub(p(xd), p(bias.to(dev) if with_bias else None), B, H, W, C, 1, relu, p(xd), None,
+                                                 None, st))
+        assert torch.equal(xd.cpu(), ref)
