@@ -326,8 +326,20 @@ def run_ours(args):
     host_imgs = [torch.randint(0, 256, (B, 3, H, W), dtype=torch.uint8, generator=g).pin_memory() for _ in range(2)]
     dev_imgs = [h.to(dev) for h in host_imgs]
     host_out = torch.empty((B, H, W), dtype=torch.float32).pin_memory()
-    from rba_b200.parallel import OverlappedGather
-    og = OverlappedGather((B, H, W), dev) if world > 1 else None      # the all-gather of step i overlaps the forward of step i+1
+    from rba_b200.parallel import OverlappedGather, PeerGather
+    # the one exchange of the path: score maps to rank 0 (what evaluate_ood consumes).  Default: copy-engine peer writes into
+    # rank 0's symmetric-memory buffer (no collective kernel on the SMs); RBA_GATHER=nccl: one NCCL all-gather per step
+    og, collective = None, None
+    if world > 1:
+        if os.environ.get("RBA_GATHER", "peer") == "peer":
+            try:
+                og = PeerGather((B, H, W), dev)
+                collective = "copy-engine peer writes of the score maps into rank 0's symmetric-memory buffer (NVLink), side stream"
+            except Exception as ex:                      # report the transport that actually ran
+                print(f"[bench] symmetric-memory gather unavailable ({type(ex).__name__}: {ex}); using NCCL all-gather", file=sys.stderr)
+        if og is None:
+            og = OverlappedGather((B, H, W), dev)
+            collective = "one NCCL all-gather of the score maps per step, side stream"
 
     # one eager forward: warms position tables / function attributes and counts this library's launches per step
     n0 = rba_b200.launch_count()
@@ -527,7 +539,7 @@ def run_ours(args):
                                + ("(BASELINE.json configs[1])" if args.model == "swin_b_1dl" and B == 8 else ""),
                    "gemm_backend": backend, "cuda_graph": use_graph,
                    "l2": "activations are several GB per step (>> 126 MB L2); two input batches alternate",
-                   "parallelism": f"dp{world}: images sharded, weights replicated" + (", one NCCL all-gather of score maps per step" if world > 1 else "")},
+                   "parallelism": f"dp{world}: images sharded, weights replicated" + (f"; {collective}" if world > 1 else "")},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * 3 * H * W, "d2h_bytes_per_step": B * H * W * 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches_per_step * args.steps),

@@ -106,3 +106,64 @@ class OverlappedGather:
     def wait(self):
         if self.stream is not None:
             torch.cuda.current_stream(self.stage[0].device).wait_stream(self.stream)
+
+
+class PeerGather:
+    """Gather of the per-step score maps to ONE rank (what evaluate_ood's OODEvaluator consumes, support.py:353-399) without
+    a collective kernel: every rank pushes its (n_local, H, W) maps straight into the root's buffer over NVLink with a
+    copy-engine peer copy (the buffer is CUDA symmetric memory: torch.distributed._symmetric_memory, peer-mapped on every
+    rank), on a side stream under the next step's forward.  No SM is taken from the forward (the NCCL all-gather kernel of
+    `OverlappedGather` competes with the persistent one-CTA-per-SM kernels of the forward for SMs), and 1/world of the
+    all-gather's bytes move.  Two slots; arrival and slot-free hand-shakes are symmetric-memory signals (stream ordered).
+
+        pg = PeerGather((n_local, H, W), device)      # collective: every rank constructs it
+        out = pg.submit(local)                         # every rank, every step; root gets (world, n_local, H, W) or None
+        pg.wait()                                      # current stream waits for this rank's part (root: for all arrivals)
+
+    `out` on the root is valid after `wait()` until the submission after next."""
+
+    def __init__(self, shape, device, dtype=torch.float32, group=None, root=0):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank, self.root = dist.get_world_size(self.group), dist.get_rank(self.group), root
+        self.shape = tuple(shape)
+        full = (2, self.world) + self.shape
+        self.buf = symm.empty(full, dtype=dtype, device=device)
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        self.root_buf = self.buf if self.rank == root else self.hdl.get_buffer(root, full, dtype)
+        self.stream = torch.cuda.Stream(device)
+        self.stage = [torch.empty(self.shape, dtype=dtype, device=device) for _ in range(2)]   # snapshots: the producer may
+        self.ev_ready = [torch.cuda.Event(), torch.cuda.Event()]                               # overwrite `local` at once
+        self.ev_done = [torch.cuda.Event(), torch.cuda.Event()]
+        self.n = 0
+        self.hdl.barrier()
+
+    def submit(self, local):
+        k = self.n & 1
+        comp = torch.cuda.current_stream(local.device)
+        if self.n >= 2:
+            comp.wait_event(self.ev_done[k])               # the peer copy that last read stage[k]
+        self.stage[k].copy_(local, non_blocking=True)      # ~20 us on-device snapshot
+        self.ev_ready[k].record(comp)                      # earlier results have been consumed by now (stream order)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(self.ev_ready[k])
+            if self.rank == self.root:
+                if self.n >= 2:                            # slot k (step n - 2) has been consumed: peers may overwrite it
+                    for r in range(self.world):
+                        if r != self.root:
+                            self.hdl.put_signal(r, channel=k)
+                self.root_buf[k, self.rank].copy_(self.stage[k], non_blocking=True)
+                for r in range(self.world):                # arrivals of this step
+                    if r != self.root:
+                        self.hdl.wait_signal(r, channel=2 + k)
+            else:
+                if self.n >= 2:
+                    self.hdl.wait_signal(self.root, channel=k)
+                self.root_buf[k, self.rank].copy_(self.stage[k], non_blocking=True)    # copy-engine peer write over NVLink
+                self.hdl.put_signal(self.root, channel=2 + k)
+            self.ev_done[k].record(self.stream)
+        self.n += 1
+        return self.root_buf[k] if self.rank == self.root else None
+
+    def wait(self):
+        torch.cuda.current_stream(self.buf.device).wait_stream(self.stream)
