@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")
     ap.add_argument("--height", type=int, default=1024)
     ap.add_argument("--width", type=int, default=2048)
-    ap.add_argument("--model", default="swin_b_1dl", choices=["swin_b_1dl", "swin_l_1dl", "swin_b_full", "tiny"])
+    ap.add_argument("--model", default="swin_b_1dl", choices=["swin_b_1dl", "swin_l_1dl", "swin_b_full", "r50_1dl", "r50_full", "tiny"])
     ap.add_argument("--backend", default=os.environ.get("RBA_GEMM_BACKEND", "auto"), choices=["auto", "ffma", "tc"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -57,7 +57,7 @@ def parse():
 def model_config(name):
     from rba_b200 import config
     return {"swin_b_1dl": config.swin_b_1dl, "swin_l_1dl": config.swin_l_1dl, "swin_b_full": config.swin_b_full,
-            "tiny": config.tiny_test}[name]()
+            "r50_1dl": config.r50_1dl, "r50_full": config.r50_full, "tiny": config.tiny_test}[name]()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -139,7 +139,8 @@ def cpu_port_images_per_s(mc, H, W, n_images, warmup, steps, budget_s=240.0):
 # ------------------------------------------------------------------------------------------------
 # the UNMODIFIED reference modules (baseline/_ref, installed by tools/make_baseline_ref.py; travels to the GPU box)
 # ------------------------------------------------------------------------------------------------
-REF_CKPT = {"swin_b_1dl": "swin_b_1dl", "swin_l_1dl": "swin_l_1dl", "swin_b_full": "swin_b_1dl"}
+REF_CKPT = {"swin_b_1dl": "swin_b_1dl", "swin_l_1dl": "swin_l_1dl", "swin_b_full": "swin_b_1dl", "r50_1dl": "swin_b_1dl",
+            "r50_full": "swin_b_1dl"}
 
 
 def reference_available(model_name):
@@ -159,6 +160,8 @@ def build_reference(model_name, mc, device, native_msda):
     if model_name == "swin_b_full":
         over = {"MODEL.SEM_SEG_HEAD.DEFORMABLE_TRANSFORMER_ENCODER_IN_FEATURES": ["res3", "res4", "res5"],
                 "MODEL.MASK_FORMER.DEC_LAYERS": mc.dec_layers + 1}
+    if model_name.startswith("r50"):     # the reference's modules around the detectron2 ResNet stand-in (oracle/ref_shims)
+        over.update(ref_loader.r50_overrides(dec_layers=mc.dec_layers, levels=mc.num_enc_levels))
     cfg = ref_loader.load_cfg(REF_CKPT[model_name], over)
     model = ref_loader.build_reference_model(cfg, seed=0)
     ref_loader.load_state_dict_into(model, weights.init_state_dict(mc, seed=0))

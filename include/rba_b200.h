@@ -249,6 +249,11 @@ typedef struct rba_gemm_args {
    * token row map(r) of `c`/`residual`, rows that fall in the window padding are dropped. */
   int32_t swin_map; int32_t sw_H, sw_W, sw_ws, sw_shift;
   int32_t backend;               /* RBA_GEMM_* */
+  /* Optional (tensor-core backend, split-plane output only): write the planes in the (window, part, head) tiled layout the
+   * tcgen05 window attention reads with ONE bulk copy per operand tile -- the tcgen05 "core matrix" order
+   *   [row / 144][col / C][(col % C) / 32][(col % 32) / 8][row % 144][col % 8]
+   * (N = 3C: q | k | v blocks of `qkv_tile_heads` heads of 32 channels).  0 = plain row-major planes. */
+  int32_t qkv_tile_heads;
 } rba_gemm_args;
 int rba_k_gemm(const rba_gemm_args* args, void* stream);
 
@@ -282,6 +287,10 @@ int64_t rba_k_window_attn_bias_floats(int heads);
 int rba_k_window_attn_prepare_bias(const float* bias_table, int heads, float* prepared, void* stream);
 int rba_k_window_attn_tc(const uint16_t* qkv_hi, const uint16_t* qkv_lo, const float* bias_prepared, int B, int H, int W, int C,
                          int heads, int ws, int shift, uint16_t* out_hi, uint16_t* out_lo, void* stream);
+/* Same kernel with q / k / v in the tiled layout of rba_gemm_args.qkv_tile_heads (what the engine runs: every operand tile
+ * is 9216 contiguous bytes and arrives by one cp.async.bulk instead of 144 64-byte TMA box rows). */
+int rba_k_window_attn_tc_tiled(const uint16_t* qkv_hi, const uint16_t* qkv_lo, const float* bias_prepared, int B, int H, int W,
+                               int C, int heads, int ws, int shift, uint16_t* out_hi, uint16_t* out_lo, void* stream);
 
 /* nn.MultiheadAttention core for the decoder (mask2former_transformer_decoder.py:52-53,110-113):
  * q [B,Lq,E], k,v [B,Lk,E] fp32 (already projected, q NOT yet scaled), mask (B,Lq,Lk) uint8 (1 = blocked, shared by

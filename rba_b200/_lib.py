@@ -44,7 +44,7 @@ class RbaGemmArgs(Structure):
         ("c", c_void_p), ("ldc", c_int64), ("c_bstride", c_int64),
         ("c_hi", c_void_p), ("c_lo", c_void_p), ("ldcp", c_int64), ("cp_bstride", c_int64),
         ("swin_map", c_int32), ("sw_H", c_int32), ("sw_W", c_int32), ("sw_ws", c_int32), ("sw_shift", c_int32),
-        ("backend", c_int32),
+        ("backend", c_int32), ("qkv_tile_heads", c_int32),
     ]
 
 
@@ -94,6 +94,7 @@ PROTOTYPES = {
     "rba_k_window_attn_bias_floats": (c_int64, [c_int]),
     "rba_k_window_attn_prepare_bias": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "rba_k_window_attn_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "rba_k_window_attn_tc_tiled": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "rba_k_mha_workspace_floats": (c_int64, [c_int, c_int, c_int, c_int]),
     "rba_k_mha": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                           c_void_p]),

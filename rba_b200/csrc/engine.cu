@@ -678,11 +678,24 @@ static int forward_impl(rba_model* m, const void* images, int img_dtype, int B, 
                         a1.lo, st));
       Planes ao = A.planes(RW * C);
       if (m->attn_backend == 2) {
+        // q | k | v leave the QKV GEMM already in the (window, part, head) tiled layout: one bulk copy per operand tile
         Planes qkv = A.planes(RW * 3 * C);
-        RBA_TRY(F.lin(a1, C, RW, C, F.P(p + "attn.qkv.weight"), 3 * C, F.W(p + "attn.qkv.bias"), RBA_ACT_NONE, nullptr, nullptr, 0,
-                      qkv, 3 * C));
+        const bool tiled = F.backend == RBA_GEMM_TC;
+        {
+          rba_gemm_args ga;
+          memset(&ga, 0, sizeof(ga));
+          Planes w = F.P(p + "attn.qkv.weight");
+          ga.a_hi = a1.hi; ga.a_lo = a1.lo; ga.lda = C;
+          ga.w_hi = w.hi; ga.w_lo = w.lo; ga.ldw = C;
+          ga.M = (int)RW; ga.N = 3 * C; ga.K = C; ga.batch = 1;
+          ga.bias = F.W(p + "attn.qkv.bias");
+          ga.c_hi = qkv.hi; ga.c_lo = qkv.lo; ga.ldcp = 3 * C;
+          ga.qkv_tile_heads = tiled ? heads : 0;
+          ga.backend = F.backend;
+          RBA_RUN(gemm(ga, st));
+        }
         RBA_RUN(window_attn_tc(qkv.hi, qkv.lo, F.W(p + "attn.relative_position_bias_prepared"), B, Hs, Wsz, C, heads, ws, shift,
-                               ao.hi, ao.lo, st));
+                               ao.hi, ao.lo, st, tiled ? 1 : 0));
       } else if (m->attn_backend == 1) {
         Planes qkv = A.planes(RW * 3 * C);
         RBA_TRY(F.lin(a1, C, RW, C, F.P(p + "attn.qkv.weight"), 3 * C, F.W(p + "attn.qkv.bias"), RBA_ACT_NONE, nullptr, nullptr, 0,

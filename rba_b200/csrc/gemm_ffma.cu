@@ -224,6 +224,7 @@ int gemm(const rba_gemm_args& a, cudaStream_t st) {
   if (a.M == 0) return RBA_OK;
   if (a.backend == RBA_GEMM_TC) return gemm_tc_launch(a, st);
   RBA_CHECK(a.backend == RBA_GEMM_FFMA, "gemm: bad backend %d", a.backend);
+  RBA_CHECK(a.qkv_tile_heads == 0, "gemm: the tiled q|k|v plane layout is written by the tensor-core backend only");
   GemmParams p;
   p.a_hi = a.a_hi; p.a_lo = a.a_lo; p.lda = a.lda;
   p.w_hi = a.w_hi; p.w_lo = a.w_lo; p.ldw = a.ldw;

@@ -42,6 +42,7 @@ struct TcParams {
   int cH, cW, cCin, tilesW, tilesH;
   // persistent tile schedule
   int tilesM, tilesN, ntiles;
+  int qkv_heads, qkv_C;            // > 0: planes written in the (window, part, head) tiled layout (see rba_gemm_args.qkv_tile_heads)
   int debug;   // RBA_TC_DEBUG: 1 = skip global stores, 2 = skip the whole epilogue after the TMEM load (profiling aid)
 };
 
@@ -327,7 +328,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             if (nb + j < p.N) x[j] += res[orow * ldr + nb + j];
         }
         // ---- stores ----
-        const bool staged = STG && full32 && ((OUTP ? (p.ldcp & 7) : (p.ldc & 3)) == 0) && !(!OUTP && c_hi);   // warp-uniform
+        const bool staged = STG && full32 && ((OUTP ? (p.ldcp & 7) : (p.ldc & 3)) == 0) && !(!OUTP && c_hi) && !(OUTP && p.qkv_heads);   // warp-uniform
         if (p.debug & 1) {
         } else if (staged) {
           // Row-per-lane registers -> swizzled shared-memory tile -> coalesced 16-byte global stores.
@@ -391,7 +392,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 if (nb + j < p.N) store_split1(c_hi, c_lo, orow * p.ldcp + nb + j, x[j]);
             }
           } else {
-            const int64_t ob = orow * p.ldcp + nb;
+            int64_t ob = orow * p.ldcp + nb;
+            int64_t cs = 8;                                 // elements between the four 8-column chunks of this row segment
+            if (p.qkv_heads) {
+              // tiled q | k | v planes: this warp's 32 columns are exactly one head of one part; consecutive lanes (rows) are
+              // 16 bytes apart inside a chunk plane, so every store instruction writes 512 contiguous bytes
+              const int part = nb / p.qkv_C, head = (nb - part * p.qkv_C) >> 5;
+              const int64_t tile = orow / 144;
+              const int r = (int)(orow - tile * 144);
+              ob = (((tile * 3 + part) * p.qkv_heads + head) * 4) * (int64_t)(144 * 8) + r * 8;
+              cs = 144 * 8;
+            }
             if (full32 && (p.ldcp & 7) == 0) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {                 // 8 columns -> one 16-byte store per plane
@@ -400,8 +411,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 split_pack2(x[8 * j + 2], x[8 * j + 3], Hh.y, Ll.y);
                 split_pack2(x[8 * j + 4], x[8 * j + 5], Hh.z, Ll.z);
                 split_pack2(x[8 * j + 6], x[8 * j + 7], Hh.w, Ll.w);
-                *reinterpret_cast<uint4*>(c_hi + ob + 8 * j) = Hh;
-                *reinterpret_cast<uint4*>(c_lo + ob + 8 * j) = Ll;
+                *reinterpret_cast<uint4*>(c_hi + ob + cs * j) = Hh;
+                *reinterpret_cast<uint4*>(c_lo + ob + cs * j) = Ll;
               }
             } else {
 #pragma unroll
@@ -479,11 +490,16 @@ static void fill_epilogue(TcParams& p, const rba_gemm_args& a) {
   p.c = a.c; p.ldc = a.ldc; p.c_bs = a.c_bstride;
   p.c_hi = a.c_hi; p.c_lo = a.c_lo; p.ldcp = a.ldcp; p.cp_bs = a.cp_bstride;
   p.swin_map = a.swin_map;
+  p.qkv_heads = a.qkv_tile_heads; p.qkv_C = a.qkv_tile_heads * 32;
   p.geom = make_swin_geom(a.sw_H > 0 ? a.sw_H : 1, a.sw_W > 0 ? a.sw_W : 1, a.sw_ws > 0 ? a.sw_ws : 1, a.sw_shift);
 }
 
 int gemm_tc_launch(const rba_gemm_args& a, cudaStream_t st) {
   RBA_CHECK(a.K % 8 == 0, "gemm(tc): K must be a multiple of 8");
+  if (a.qkv_tile_heads)
+    RBA_CHECK(a.qkv_tile_heads > 0 && a.N == 3 * 32 * a.qkv_tile_heads && a.M % 144 == 0 && a.c == nullptr && a.c_hi && a.c_lo &&
+                  !a.swin_map && a.batch == 1 && (a.ldcp & 7) == 0,
+              "gemm(tc): the tiled q|k|v layout needs N = 96 heads, M a multiple of 144, split-plane output only");
   RBA_CHECK(((uintptr_t)a.a_hi & 15) == 0 && ((uintptr_t)a.a_lo & 15) == 0 && ((uintptr_t)a.w_hi & 15) == 0 &&
                 ((uintptr_t)a.w_lo & 15) == 0, "gemm(tc): operand planes must be 16-byte aligned");
   TcParams p;

@@ -31,7 +31,7 @@ int window_attn_planes(const uint16_t* qkv_hi, const uint16_t* qkv_lo, const flo
                        int B, int H, int W, int C, int heads, int ws, int shift, uint16_t* out_hi, uint16_t* out_lo,
                        cudaStream_t st);
 int window_attn_tc(const uint16_t* qkv_hi, const uint16_t* qkv_lo, const float* bias_prepared, int B, int H, int W, int C,
-                   int heads, int ws, int shift, uint16_t* out_hi, uint16_t* out_lo, cudaStream_t st);
+                   int heads, int ws, int shift, uint16_t* out_hi, uint16_t* out_lo, cudaStream_t st, int tiled = 0);
 int window_attn_bias_floats(int heads);
 int window_attn_prepare_bias(const float* table, int heads, float* out, cudaStream_t st);
 int mha(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv, const uint8_t* mask, int B,

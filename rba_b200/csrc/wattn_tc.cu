@@ -17,10 +17,11 @@
 //   O          tcgen05.mma M=128 N=32 K=144 with A = P read from TENSOR MEMORY and B = v straight from the TMA tile
 //              (MN-major descriptor: no transpose anywhere), 27 MMAs per tile.
 //   epilogue   O rows * 1 / row sum -> bf16 hi/lo -> global planes.
-// The MMAs of item i+1 (S) run under the softmax of item i; TMA runs two items ahead.  Warps: 0 and 12 = softmax of the
-// 16-row tile (TMEM lane quadrant 0), 1 = TMA producer, 2 = MMA issuer of the 128-row tile + TMEM owner, 3 = MMA issuer of
-// the 16-row tile (two issuers: 66 small MMAs per item are issue-bound from one thread, and the two tiles' chains stay
-// independent), 4..11 = softmax of the 128-row tile (quadrant w % 4, key half (w - 4) / 4).
+// The MMAs of item i+1 (S) run under the softmax of item i; TMA runs two items ahead.  Warps: 0 = TMA producer, 1 = MMA
+// issuer of the 128-row tile + TMEM owner, 2 = MMA issuer of the 16-row tile (two issuers keep the two tiles' chains
+// independent), 3 idle, 4..11 = softmax (quadrant w % 4, key half (w - 4) / 4): every warp serves the 128-row tile of every
+// item, and the two warps of quadrant i % 4 also serve the 16-row tile of item i, whose rows the issuer places on that
+// quadrant's lanes.
 // TMEM columns: S1[0] 0..143 | S1[1] 144..287 | S2 288..431 | O1 432..463 | O2 464..495 (496 of 512: S2 cannot be double
 // buffered; an M=64 variant that would have packed two items' 16-row tiles into one block at lane offsets 0 / 16 gave
 // wrong results at offset 16 on this hardware / toolchain and was dropped).
@@ -40,7 +41,7 @@ constexpr int WT_BIAS_FLOATS = 532;                       // == WM_BIAS_PITCH of
 constexpr int WT_BIAS_BYTES = WT_BIAS_FLOATS * 4;         // 2128 (multiple of 16: bulk-copy granularity)
 constexpr int WT_STAGE_BYTES = 6 * WT_TILE_BYTES + 3072;  // 58368 = 57 * 1024
 constexpr int WT_STAGES = 3;
-constexpr int WT_THREADS = 13 * 32;
+constexpr int WT_THREADS = 12 * 32;
 constexpr uint32_t WT_TMEM_COLS = 512;
 constexpr int WT_COL_S1 = 0, WT_COL_S2 = 288, WT_COL_O1 = 432, WT_COL_O2 = 464;
 constexpr int WT_EXCH_FLOATS = 2 /*parity*/ * 2 /*half*/ * 160 /*rows (144, padded)*/;
@@ -53,6 +54,8 @@ struct WtParams {
   int C, heads, nWh, nWw, shift;
   int64_t nitems;           // B * nWh * nWw * heads
   float scale_log2e;        // head_dim^-0.5 * log2(e)
+  const uint16_t* t_hi;     // tiled q | k | v planes (rba_gemm_args.qkv_tile_heads layout) or null: row-major planes via tensor maps
+  const uint16_t* t_lo;
   int debug;
   long long* tl;            // profiling aid (RBA_WT_TIMELINE): clock64 stamps of CTA 0, [item < 32][16 events]
 };
@@ -80,6 +83,18 @@ __device__ __forceinline__ uint64_t make_sdesc64(uint32_t smem_addr) {
   d |= (uint64_t)(512 >> 4) << 32;                   // stride byte offset: 8 rows x 64 B
   d |= (uint64_t)1 << 46;                            // version 1 (Blackwell)
   d |= (uint64_t)4 << 61;                            // SWIZZLE_64B
+  return d;
+}
+// SWIZZLE_NONE descriptor over the tiled ("core matrix") operand layout: a 144 x 32 bf16 tile is stored as 4 chunk planes
+// (8 channels = 16 B wide) of 144 rows x 16 B, i.e. 8 x 16 B core matrices of 128 contiguous bytes.
+//   K-major  (q, k):  ((8,n),2):((1,SBO),LBO) in 16-byte units  ->  SBO = 128 B (next 8 rows), LBO = 2304 B (next 8 channels)
+//   MN-major (v):     ((1,n),(8,k)):((X,SBO),(1,LBO))           ->  SBO = 2304 B (next 8 channels), LBO = 128 B (next 8 keys)
+__device__ __forceinline__ uint64_t make_sdesc_ns(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;                            // version 1 (Blackwell); layout type 0 = no swizzle
   return d;
 }
 // kind::f16 instruction descriptor: D fp32, A / B bf16, A K-major, B K-major or MN-major (bit 16)
@@ -160,158 +175,187 @@ __device__ __forceinline__ void wt_item(const WtParams& p, int64_t it, int64_t& 
   head = (int)(it - win * p.heads);
 }
 
-// The softmax + epilogue role.  TILE2 = false: one of the eight warps of the 128-row tile; true: one of the two warps that own
-// query rows 128..143 (lanes 0..15; lanes 16..31 run along on rows that are never stored).
+// Per-thread state of a softmax warp: quadrant = TMEM lane quadrant (= SM sub-partition) of the warp, half = which 72 of the
+// 144 keys this thread owns.
+struct WtThread {
+  int quadrant, half, lane;
+  uint32_t lane_addr;
+  int pair_bar;
+};
+
+// One softmax pass over one S tile of item `lt`: logits (72 keys of one query row) -> bias (+ mask) -> row max across the two
+// halves -> exp2 -> bf16 hi / lo of the un-normalised probabilities written back over S -> "P ready".  TILE2 = the 16-row tile
+// (query rows 128..143 on lanes 0..15 of this warp's quadrant; lanes 16..31 run along on rows that are never stored).
 template <bool TILE2>
-__device__ __forceinline__ void wt_softmax_role(const WtParams& p, uint8_t* smem, WtBars* bars, float* exch_max, float* exch_sum,
-                                                uint32_t tmem_base, int quadrant, int half, int lane) {
-  const int row = TILE2 ? 128 + lane : quadrant * 32 + lane;      // query index inside the window (garbage rows: >= 144)
-  const int rowc = row < WT_N ? row : WT_N - 1;                    // clamped for address arithmetic only
+__device__ __forceinline__ void wt_pass(const WtParams& p, const WtThread& T, uint8_t* smem, WtBars* bars, float* exch_max,
+                                        float* exch_sum, uint32_t tmem_base, uint32_t lt, bool lastrow, bool lastcol) {
+  const int lane = T.lane, half = T.half;
+  const int row = TILE2 ? 128 + lane : T.quadrant * 32 + lane;     // query index inside the window (garbage rows: >= 144)
+  const int rowc = row < WT_N ? row : WT_N - 1;                     // clamped for address arithmetic only
   const int iy = rowc / WT_WS, ix = rowc - iy * WT_WS;
   // bias index of (query i, key j) = (iy - jy + 11) * 23 + (ix - jx + 11) = base - (jy * 23 + jx)
   const int bias_base = (iy + WT_WS - 1) * (2 * WT_WS - 1) + ix + WT_WS - 1 - half * 6 * (2 * WT_WS - 1);
-  const uint32_t lane_addr = (uint32_t)(quadrant * 32) << 16;
-  const int pair_bar = TILE2 ? 5 : 1 + quadrant;
-  // slot of this thread's row in the max / sum exchange arrays (160 per half: rows 0..127 of the big tile, 144..159 = rows
-  // 128..143 of the small tile, 128..143 = scratch for the small tile's lanes 16..31, whose rows do not exist)
+  // slot of this row in the max / sum exchange arrays (160 per half: rows 0..127 of the big tile, 144..159 = rows 128..143 of
+  // the small tile, 128..143 = scratch for the small tile's lanes 16..31, whose rows do not exist)
   const int er = TILE2 ? (lane < 16 ? 144 + lane : 128 + (lane - 16)) : row;
   const bool rf = iy >= WT_WS - p.shift, cf = ix >= WT_WS - p.shift;   // region flags of this query in a boundary window
   const float NEG = -100.0f * 1.4426950408889634f;
+  const int s = lt % WT_STAGES, b = lt & 1;
+  const float* sBias = reinterpret_cast<const float*>(smem + s * WT_STAGE_BYTES + 6 * WT_TILE_BYTES) + bias_base;
+  mbar_wait(&bars->full[s], (lt / WT_STAGES) & 1);                 // the bias table of this stage has landed
+  if (TILE2) mbar_wait(&bars->s2_full, lt & 1); else mbar_wait(&bars->s1_full[b], (lt >> 1) & 1);
+  tc_fence_after();
+  const bool stamp = !TILE2 && T.quadrant == 0 && half == 0 && lane == 0;
+  if (stamp) WT_STAMP(lt, 6);
+  const uint32_t saddr = tmem_base + T.lane_addr + (TILE2 ? WT_COL_S2 : WT_COL_S1 + b * WT_N);
+  float x[72];
+  uint32_t* xv = reinterpret_cast<uint32_t*>(x);
+  // shift mask (swin.py:416-440): -100 where query and key lie in different regions of a boundary window.  Keys of this half
+  // all have jy >= 6 iff half == 1; jx >= 6 is a compile-time property of the unrolled index.
+  const bool masked = lastrow || lastcol;
+  const bool rowdiff = lastrow && ((half == 1) != rf);
+  const float mlo = (rowdiff || (lastcol && cf)) ? NEG : 0.f, mhi = (rowdiff || (lastcol && !cf)) ? NEG : 0.f;
+  float mm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};        // four independent max chains
+  // x = S * scale * log2(e) + bias (+ mask) for keys [J0, J1), software-pipelined against the TMEM loads of the next chunk
+  auto logits = [&](auto j0c, auto j1c) {
+    constexpr int J0 = decltype(j0c)::value, J1 = decltype(j1c)::value;
+    if (p.debug & 1) return;
+    if (masked) {
+#pragma unroll
+      for (int jj = J0; jj < J1; ++jj) {
+        const int off = (jj / WT_WS) * (2 * WT_WS - 1) + (jj % WT_WS);
+        x[jj] = fmaf(x[jj], p.scale_log2e, sBias[-off]) + ((jj % WT_WS) < WT_WS / 2 ? mlo : mhi);
+        mm[jj & 3] = fmaxf(mm[jj & 3], x[jj]);
+      }
+    } else {
+#pragma unroll
+      for (int jj = J0; jj < J1; ++jj) {
+        const int off = (jj / WT_WS) * (2 * WT_WS - 1) + (jj % WT_WS);
+        x[jj] = fmaf(x[jj], p.scale_log2e, sBias[-off]);
+        mm[jj & 3] = fmaxf(mm[jj & 3], x[jj]);
+      }
+    }
+  };
+  tmem_ld32(saddr + half * 72, xv);
+  tmem_ld_wait_dep<32>(xv);
+  tmem_ld32(saddr + half * 72 + 32, xv + 32);                       // in flight under the first chunk's arithmetic
+  logits(std::integral_constant<int, 0>{}, std::integral_constant<int, 32>{});
+  tmem_ld_wait_dep<32>(xv + 32);
+  tmem_ld8(saddr + half * 72 + 64, xv + 64);
+  logits(std::integral_constant<int, 32>{}, std::integral_constant<int, 64>{});
+  tmem_ld_wait_dep<8>(xv + 64);
+  logits(std::integral_constant<int, 64>{}, std::integral_constant<int, 72>{});
+  if (stamp) WT_STAMP(lt, 7);
+  float m = (p.debug & 1) ? 0.f : fmaxf(fmaxf(mm[0], mm[1]), fmaxf(mm[2], mm[3]));
+  // ---- row max across the two halves (every S column of this row has been read once both threads are here) ----
+  float* emax = exch_max + (b * 2) * 160;
+  emax[half * 160 + er] = m;
+  wt_pair_bar(T.pair_bar);
+  m = fmaxf(m, emax[(half ^ 1) * 160 + er]);
+  if (stamp) WT_STAMP(lt, 8);
+  // ---- un-normalised probabilities, bf16 hi / lo, written back over S: hi -> columns [0,72), lo -> [72,144) ----
+  float sum = 0.f;
+  uint32_t ph[36], pl[36];
+  if (p.debug & 2) {                       // ablation: no exp / split
+#pragma unroll
+    for (int jj = 0; jj < 36; ++jj) { ph[jj] = __float_as_uint(x[jj]); pl[jj] = __float_as_uint(x[jj + 36]); }
+    sum = 1.f;
+  } else {
+    float ss[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int jj = 0; jj < 72; jj += 2) {
+      const float e0 = wt_ex2(x[jj] - m), e1 = wt_ex2(x[jj + 1] - m);
+      ss[(jj >> 1) & 3] += e0 + e1;
+      split_pack2(e0, e1, ph[jj >> 1], pl[jj >> 1]);
+    }
+    sum = (ss[0] + ss[1]) + (ss[2] + ss[3]);
+  }
+  tmem_st32(saddr + half * 36, ph);
+  tmem_st4(saddr + half * 36 + 32, ph + 32);
+  tmem_st32(saddr + 72 + half * 36, pl);
+  tmem_st4(saddr + 72 + half * 36 + 32, pl + 32);
+  if (stamp) WT_STAMP(lt, 9);
+  tmem_st_wait();
+  tc_fence_before();
+  if (stamp) WT_STAMP(lt, 10);
+  exch_sum[(b * 2 + half) * 160 + er] = sum;
+  __syncwarp();
+  if (lane == 0) mbar_arrive(TILE2 ? &bars->p2_ready : &bars->p1_ready[b]);
+}
+
+// Epilogue of one tile of item `lt`: O rows * 1 / row sum -> bf16 hi / lo planes.  The partner's partial sum is visible: both
+// threads of a row have passed a pair barrier (or the final one) since it was written.
+template <bool TILE2>
+__device__ __forceinline__ void wt_epilogue(const WtParams& p, const WtThread& T, WtBars* bars, const float* exch_sum,
+                                            uint32_t tmem_base, uint32_t lt, int64_t row0, int head, bool release) {
+  const int lane = T.lane;
+  const int row = TILE2 ? 128 + lane : T.quadrant * 32 + lane;
+  const int er = TILE2 ? (lane < 16 ? 144 + lane : 128 + (lane - 16)) : row;
+  mbar_wait(TILE2 ? &bars->o2_full : &bars->o1_full, lt & 1);
+  tc_fence_after();
+  const float* ps = exch_sum + ((lt & 1) * 2) * 160;
+  const float inv = 1.0f / (ps[er] + ps[160 + er]);
+  uint32_t o[16];
+  tmem_ld16(tmem_base + T.lane_addr + (TILE2 ? WT_COL_O2 : WT_COL_O1) + T.half * 16, o);
+  tmem_ld_wait();
+  tc_fence_before();
+  if (release) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(TILE2 ? &bars->o2_empty : &bars->o1_empty);
+  }
+  if (!TILE2 || lane < 16) {
+    const int64_t g = (row0 + row) * p.C + head * WT_D + T.half * 16;
+    wt_store16(p.out_hi, p.out_lo, g, o, inv);
+  }
+}
+
+// The softmax + epilogue role of warps 4..11.  Every warp serves the 128-row tile of every item (its quadrant's 32 rows, its
+// half of the keys); the 16-row tile of item i is placed on the lanes of quadrant i % 4 (the MMA issuer offsets the q rows
+// accordingly) and served by that quadrant's two warps, so the extra pass rotates over the four SM sub-partitions instead of
+// loading one of them with 4 of 10 heavy warp-passes (measured: that sub-partition bounded the kernel).
+__device__ __forceinline__ void wt_softmax_role(const WtParams& p, uint8_t* smem, WtBars* bars, float* exch_max, float* exch_sum,
+                                                uint32_t tmem_base, int quadrant, int half, int lane) {
+  WtThread T;
+  T.quadrant = quadrant; T.half = half; T.lane = lane;
+  T.lane_addr = (uint32_t)(quadrant * 32) << 16;
+  T.pair_bar = 1 + quadrant;
+  const bool tile2 = !(p.debug & 4);
   uint32_t lt = 0;
   int64_t prev_row0 = 0;
   int prev_head = 0;
-  const uint32_t nitems = (uint32_t)p.nitems, uheads = (uint32_t)p.heads;       // < 2^31 (checked on the host): 32-bit divides
+  // item -> (window, head, boundary flags) without divisions in the loop: all counters advance by gridDim.x items per step
+  const uint32_t nitems = (uint32_t)p.nitems, uheads = (uint32_t)p.heads, nWw = (uint32_t)p.nWw, nW = (uint32_t)(p.nWh * p.nWw);
+  const uint32_t step_win = gridDim.x / uheads, step_head = gridDim.x % uheads;
+  uint32_t win = blockIdx.x / uheads, head = blockIdx.x % uheads;
+  uint32_t wxm = win % nWw, wim = win % nW;                       // window column / window index inside its image
+  const uint32_t step_wx = step_win % nWw, step_wi = step_win % nW;
   for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x, ++lt) {
-    const int s = lt % WT_STAGES, b = lt & 1;
-    const uint32_t win = it / uheads;
-    const int head = (int)(it - win * uheads);
-    const uint32_t wrow = win / (uint32_t)p.nWw;
-    const int wx = (int)(win - wrow * (uint32_t)p.nWw), wy = (int)(wrow % (uint32_t)p.nWh);
-    const bool lastrow = p.shift > 0 && wy == p.nWh - 1, lastcol = p.shift > 0 && wx == p.nWw - 1;
-    uint8_t* st = smem + s * WT_STAGE_BYTES;
-    const float* sBias = reinterpret_cast<const float*>(st + 6 * WT_TILE_BYTES) + bias_base;
-    // ---- logits of this thread: 72 keys of one query ----
-    mbar_wait(&bars->full[s], (lt / WT_STAGES) & 1);                 // the bias table of this stage has landed
-    if (TILE2) mbar_wait(&bars->s2_full, lt & 1); else mbar_wait(&bars->s1_full[b], (lt >> 1) & 1);
-    tc_fence_after();
-    const bool stamp = !TILE2 && quadrant == 0 && half == 0 && lane == 0;
-    if (stamp) WT_STAMP(lt, 6);
-    const uint32_t scol = TILE2 ? WT_COL_S2 : WT_COL_S1 + b * WT_N;
-    const uint32_t saddr = tmem_base + lane_addr + scol;
-    float x[72];
-    uint32_t* xv = reinterpret_cast<uint32_t*>(x);
-    // shift mask (swin.py:416-440): -100 where query and key lie in different regions of a boundary window.  Keys of this
-    // half all have jy >= 6 iff half == 1; jx >= 6 is a compile-time property of the unrolled index.
-    const bool masked = lastrow || lastcol;
-    const bool rowdiff = lastrow && ((half == 1) != rf);
-    const float mlo = (rowdiff || (lastcol && cf)) ? NEG : 0.f, mhi = (rowdiff || (lastcol && !cf)) ? NEG : 0.f;
-    float mm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};        // four independent max chains
-    // x = S * scale * log2(e) + bias (+ mask) for keys [J0, J1), software-pipelined against the TMEM loads of the next chunk
-    auto logits = [&](auto j0c, auto j1c) {
-      constexpr int J0 = decltype(j0c)::value, J1 = decltype(j1c)::value;
-      if (p.debug & 1) return;
-      if (masked) {
-#pragma unroll
-        for (int jj = J0; jj < J1; ++jj) {
-          const int off = (jj / WT_WS) * (2 * WT_WS - 1) + (jj % WT_WS);
-          x[jj] = fmaf(x[jj], p.scale_log2e, sBias[-off]) + ((jj % WT_WS) < WT_WS / 2 ? mlo : mhi);
-          mm[jj & 3] = fmaxf(mm[jj & 3], x[jj]);
-        }
-      } else {
-#pragma unroll
-        for (int jj = J0; jj < J1; ++jj) {
-          const int off = (jj / WT_WS) * (2 * WT_WS - 1) + (jj % WT_WS);
-          x[jj] = fmaf(x[jj], p.scale_log2e, sBias[-off]);
-          mm[jj & 3] = fmaxf(mm[jj & 3], x[jj]);
-        }
-      }
-    };
-    tmem_ld32(saddr + half * 72, xv);
-    tmem_ld_wait_dep<32>(xv);
-    tmem_ld32(saddr + half * 72 + 32, xv + 32);                       // in flight under the first chunk's arithmetic
-    logits(std::integral_constant<int, 0>{}, std::integral_constant<int, 32>{});
-    tmem_ld_wait_dep<32>(xv + 32);
-    tmem_ld8(saddr + half * 72 + 64, xv + 64);
-    logits(std::integral_constant<int, 32>{}, std::integral_constant<int, 64>{});
-    tmem_ld_wait_dep<8>(xv + 64);
-    logits(std::integral_constant<int, 64>{}, std::integral_constant<int, 72>{});
-    if (stamp) WT_STAMP(lt, 7);
-    float m = (p.debug & 1) ? 0.f : fmaxf(fmaxf(mm[0], mm[1]), fmaxf(mm[2], mm[3]));
-    // ---- row max across the two halves (every S column of this row has been read once both threads are here) ----
-    float* emax = exch_max + (b * 2) * 160;
-    emax[half * 160 + er] = m;
-    wt_pair_bar(pair_bar);
-    m = fmaxf(m, emax[(half ^ 1) * 160 + er]);
-    if (stamp) WT_STAMP(lt, 8);
-    // ---- un-normalised probabilities, bf16 hi / lo, written back over S: hi -> columns [0,72), lo -> [72,144) ----
-    float sum = 0.f;
-    uint32_t ph[36], pl[36];
-    if (p.debug & 2) {                       // ablation: no exp / split
-#pragma unroll
-      for (int jj = 0; jj < 36; ++jj) { ph[jj] = __float_as_uint(x[jj]); pl[jj] = __float_as_uint(x[jj + 36]); }
-      sum = 1.f;
-    } else {
-      float ss[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int jj = 0; jj < 72; jj += 2) {
-        const float e0 = wt_ex2(x[jj] - m), e1 = wt_ex2(x[jj + 1] - m);
-        ss[(jj >> 1) & 3] += e0 + e1;
-        split_pack2(e0, e1, ph[jj >> 1], pl[jj >> 1]);
-      }
-      sum = (ss[0] + ss[1]) + (ss[2] + ss[3]);
-    }
-    tmem_st32(saddr + half * 36, ph);
-    tmem_st4(saddr + half * 36 + 32, ph + 32);
-    tmem_st32(saddr + 72 + half * 36, pl);
-    tmem_st4(saddr + 72 + half * 36 + 32, pl + 32);
-    if (stamp) WT_STAMP(lt, 9);
-    tmem_st_wait();
-    tc_fence_before();
-    if (stamp) WT_STAMP(lt, 10);
-    float* esum = exch_sum + (b * 2) * 160;
-    esum[half * 160 + er] = sum;
-    __syncwarp();
-    if (lane == 0) mbar_arrive(TILE2 ? &bars->p2_ready : &bars->p1_ready[b]);
-    // ---- epilogue of the PREVIOUS item (its P.v has had a whole softmax to finish) ----
-    if (lt > 0) {
-      const uint32_t pl_ = lt - 1;
-      if (stamp) WT_STAMP(lt, 11);
-      mbar_wait(TILE2 ? &bars->o2_full : &bars->o1_full, pl_ & 1);
-      tc_fence_after();
-      if (stamp) WT_STAMP(lt, 12);
-      const float* ps = exch_sum + ((pl_ & 1) * 2) * 160;
-      const float inv = 1.0f / (ps[er] + ps[160 + er]);
-      uint32_t o[16];
-      tmem_ld16(tmem_base + lane_addr + (TILE2 ? WT_COL_O2 : WT_COL_O1) + half * 16, o);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(TILE2 ? &bars->o2_empty : &bars->o1_empty);
-      if (stamp) WT_STAMP(lt, 13);
-      if (!TILE2 || lane < 16) {
-        const int64_t g = (prev_row0 + row) * p.C + prev_head * WT_D + half * 16;
-wt_store16(p.out_hi, p.out_lo, g, o, inv);
-      }
-    }
-    if (stamp) WT_STAMP(lt, 14);
+    const bool lastrow = p.shift > 0 && wim >= nW - nWw, lastcol = p.shift > 0 && wxm == nWw - 1;
+    wt_pass<false>(p, T, smem, bars, exch_max, exch_sum, tmem_base, lt, lastrow, lastcol);
+    // the 16-row tile of the previous item, if this quadrant served it (its P.v was issued a whole pass ago, and the O2
+    // buffer is needed again only after another quadrant's 16-row pass of this item)
+    if (tile2 && lt > 0 && (int)((lt - 1) & 3) == quadrant) wt_epilogue<true>(p, T, bars, exch_sum, tmem_base, lt - 1, prev_row0, prev_head, true);
+    if (tile2 && (int)(lt & 3) == quadrant) wt_pass<true>(p, T, smem, bars, exch_max, exch_sum, tmem_base, lt, lastrow, lastcol);
+    // the 128-row tile of the previous item (its P.v has had a whole softmax to finish)
+    if (lt > 0) wt_epilogue<false>(p, T, bars, exch_sum, tmem_base, lt - 1, prev_row0, prev_head, true);
+    if (!half && quadrant == 0 && lane == 0) WT_STAMP(lt, 14);
     prev_row0 = (int64_t)win * WT_N;
-    prev_head = head;
+    prev_head = (int)head;
+    head += step_head;
+    uint32_t carry = 0;
+    if (head >= uheads) { head -= uheads; carry = 1; }
+    win += step_win + carry;
+    wxm += step_wx + carry;
+    if (wxm >= nWw) wxm -= nWw;
+    if (wxm >= nWw) wxm -= nWw;
+    wim += step_wi + carry;
+    if (wim >= nW) wim -= nW;
+    if (wim >= nW) wim -= nW;
   }
-  if (lt > 0) {                                   // epilogue of the last item
-    const uint32_t pl_ = lt - 1;
-    mbar_wait(TILE2 ? &bars->o2_full : &bars->o1_full, pl_ & 1);
-    tc_fence_after();
-    wt_pair_bar(pair_bar);                        // the partner's sum of the last item is in shared memory
-    const float* ps = exch_sum + ((pl_ & 1) * 2) * 160;
-    const float inv = 1.0f / (ps[er] + ps[160 + er]);
-    uint32_t o[16];
-    tmem_ld16(tmem_base + lane_addr + (TILE2 ? WT_COL_O2 : WT_COL_O1) + half * 16, o);
-    tmem_ld_wait();
-    tc_fence_before();
-    if (!TILE2 || lane < 16) {
-      const int64_t g = (prev_row0 + row) * p.C + prev_head * WT_D + half * 16;
-wt_store16(p.out_hi, p.out_lo, g, o, inv);
-    }
+  if (lt > 0) {                                   // epilogues of the last item
+    wt_pair_bar(T.pair_bar);                      // the partner's sums of the last item are in shared memory
+    if (tile2 && (int)((lt - 1) & 3) == quadrant) wt_epilogue<true>(p, T, bars, exch_sum, tmem_base, lt - 1, prev_row0, prev_head, false);
+    wt_epilogue<false>(p, T, bars, exch_sum, tmem_base, lt - 1, prev_row0, prev_head, false);
   }
 }
 
@@ -333,7 +377,7 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_co
     mbar_init(&bars->o2_full, 1); mbar_init(&bars->o2_empty, 2);
     fence_barrier_init();
   }
-  if (warp == 2) {
+  if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_slot)), "r"(WT_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -342,7 +386,7 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_slot;
 
-  if (warp == 1) {
+  if (warp == 0) {
     // ===================== TMA producer (whole warp, one elected lane issues) =====================
     const uint32_t n = (uint32_t)((p.nitems - (int64_t)blockIdx.x + (int64_t)gridDim.x - 1) / (int64_t)gridDim.x);
     uint32_t s = 0, ph = 1;                               // fresh "empty" barriers pass a wait on parity 1
@@ -356,29 +400,40 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_co
       if (elect_one()) {
         uint8_t* st = smem + s * WT_STAGE_BYTES;
         mbar_expect_tx(&bars->full[s], 6 * WT_TILE_BYTES + WT_BIAS_BYTES);
-        const int r0 = (int)(win * WT_N);
+        if (p.t_hi) {                                       // tiled planes: every operand tile is 9216 contiguous bytes
 #pragma unroll
-        for (int part = 0; part < 3; ++part) {              // q, k, v column blocks of this head
-          const int c0 = part * p.C + head * WT_D;
-          tma_load_2d(st + (2 * part) * WT_TILE_BYTES, &tm_hi, &bars->full[s], c0, r0);
-          tma_load_2d(st + (2 * part + 1) * WT_TILE_BYTES, &tm_lo, &bars->full[s], c0, r0);
+          for (int part = 0; part < 3; ++part) {
+            const size_t off = ((size_t)(win * 3 + part) * p.heads + head) * (WT_TILE_BYTES / 2);
+            bulk_load(st + (2 * part) * WT_TILE_BYTES, p.t_hi + off, WT_TILE_BYTES, &bars->full[s]);
+            bulk_load(st + (2 * part + 1) * WT_TILE_BYTES, p.t_lo + off, WT_TILE_BYTES, &bars->full[s]);
+          }
+        } else {
+          const int r0 = (int)(win * WT_N);
+#pragma unroll
+          for (int part = 0; part < 3; ++part) {            // q, k, v column blocks of this head
+            const int c0 = part * p.C + head * WT_D;
+            tma_load_2d(st + (2 * part) * WT_TILE_BYTES, &tm_hi, &bars->full[s], c0, r0);
+            tma_load_2d(st + (2 * part + 1) * WT_TILE_BYTES, &tm_lo, &bars->full[s], c0, r0);
+          }
         }
         bulk_load(st + 6 * WT_TILE_BYTES, p.bias + (size_t)head * WT_BIAS_FLOATS, WT_BIAS_BYTES, &bars->full[s]);
       }
       __syncwarp();
       if (++s == WT_STAGES) { s = 0; ph ^= 1; }
     }
-  } else if (warp == 2 || warp == 3) {
-    // ===================== MMA issuers: warp 2 = 128-row tile, warp 3 = 16-row tile =====================
+  } else if (warp == 1 || warp == 2) {
+    // ===================== MMA issuers: warp 1 = 128-row tile, warp 2 = 16-row tile =====================
     // The WHOLE warp walks the loop (uniform control flow, 32-bit uniform counters) and one elected lane issues: descriptors
     // then live in uniform registers.  (Under `if (lane == 0)` ptxas wraps every tcgen05.mma in an ELECT / R2UR.BROADCAST /
     // BRA.U.ANY loop -- measured ~70 clk per MMA, which made 66 small MMAs per item the bottleneck of the whole kernel.)
     constexpr uint32_t idS = wt_idesc(128, WT_N, false), idO = wt_idesc(128, WT_D, true);
-    const bool t2 = warp == 3;
+    const bool t2 = warp == 2;
+    const bool tiled = p.t_hi != nullptr;
     uint32_t n = (uint32_t)((p.nitems - (int64_t)blockIdx.x + (int64_t)gridDim.x - 1) / (int64_t)gridDim.x);
     if (t2 && (p.debug & 4)) n = 0;
     const uint32_t smem0 = smem_u32(smem);
-    const uint32_t q_off = t2 ? 128u * WT_D * 2u : 0u;       // first q row of this issuer's tile, in bytes
+    // first q row of this issuer's tile, in bytes.  The 16-row tile of item i is computed as q rows [128 - 32 (i & 3), + 128)
+    // so that rows 128..143 land on TMEM lanes 32 (i & 3) .. + 15: the lanes of the quadrant whose softmax warps serve it
     uint32_t s_i = 0, ph_i = 0;                              // stage / phase of item i   (S issue)
     uint32_t s_j = 0;                                        // stage of item j = i - 1   (P v issue)
     const bool run = !(t2 && (p.debug & 4));
@@ -391,10 +446,12 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_co
         tc_fence_after();
         if (elect_one()) {
           const uint32_t sb = smem0 + s_j * WT_STAGE_BYTES;
-          const uint64_t vh = make_sdesc64(sb + 4 * WT_TILE_BYTES), vl = make_sdesc64(sb + 5 * WT_TILE_BYTES);
+          const uint64_t vh = tiled ? make_sdesc_ns(sb + 4 * WT_TILE_BYTES, 128, 2304) : make_sdesc64(sb + 4 * WT_TILE_BYTES);
+          const uint64_t vl = tiled ? make_sdesc_ns(sb + 5 * WT_TILE_BYTES, 128, 2304) : make_sdesc64(sb + 5 * WT_TILE_BYTES);
+          const uint32_t vstep = tiled ? 16u * 16u : 16u * 64u;                             // bytes per 16 keys
 #pragma unroll
           for (int k = 0; k < ((p.debug & 8) ? 0 : WT_N / 16); ++k) {
-            const uint64_t adv = (uint64_t)(k * 16 * 64 >> 4);     // 16 keys = 16 rows of 64 B
+            const uint64_t adv = (uint64_t)((k * vstep) >> 4);
             umma_bf16_ts(tmem_base + WT_COL_O2, tmem_base + WT_COL_S2 + k * 8, vh + adv, idO, k != 0);
             umma_bf16_ts(tmem_base + WT_COL_O2, tmem_base + WT_COL_S2 + k * 8, vl + adv, idO, 1);
             umma_bf16_ts(tmem_base + WT_COL_O2, tmem_base + WT_COL_S2 + 72 + k * 8, vh + adv, idO, 1);
@@ -413,11 +470,16 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_co
         if (elect_one()) {
           const uint32_t sb = smem0 + s_i * WT_STAGE_BYTES;
           const uint32_t dcol = tmem_base + (t2 ? (uint32_t)WT_COL_S2 : (uint32_t)WT_COL_S1 + (i & 1) * WT_N);
-          const uint64_t qh = make_sdesc64(sb + q_off), ql = make_sdesc64(sb + WT_TILE_BYTES + q_off);
-          const uint64_t kh = make_sdesc64(sb + 2 * WT_TILE_BYTES), kl = make_sdesc64(sb + 3 * WT_TILE_BYTES);
+          const uint32_t q_row = t2 ? 128u - 32u * (i & 3u) : 0u;
+          const uint32_t q_off = q_row * (tiled ? 16u : (uint32_t)(WT_D * 2));           // bytes to the tile's first q row
+          const uint64_t qh = tiled ? make_sdesc_ns(sb + q_off, 2304, 128) : make_sdesc64(sb + q_off);
+          const uint64_t ql = tiled ? make_sdesc_ns(sb + WT_TILE_BYTES + q_off, 2304, 128) : make_sdesc64(sb + WT_TILE_BYTES + q_off);
+          const uint64_t kh = tiled ? make_sdesc_ns(sb + 2 * WT_TILE_BYTES, 2304, 128) : make_sdesc64(sb + 2 * WT_TILE_BYTES);
+          const uint64_t kl = tiled ? make_sdesc_ns(sb + 3 * WT_TILE_BYTES, 2304, 128) : make_sdesc64(sb + 3 * WT_TILE_BYTES);
+          const uint32_t kstep = tiled ? 2u * 2304u : 32u;                                  // bytes per 16 channels
 #pragma unroll
           for (int k = 0; k < ((p.debug & 16) ? 0 : WT_D / 16); ++k) {
-            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+            const uint64_t adv = (uint64_t)((k * kstep) >> 4);
             umma_bf16(dcol, qh + adv, kh + adv, idS, k != 0);
             umma_bf16(dcol, qh + adv, kl + adv, idS, 1);
             umma_bf16(dcol, ql + adv, kh + adv, idS, 1);
@@ -438,10 +500,12 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_co
         if (elect_one()) {
           const uint32_t sb = smem0 + s_j * WT_STAGE_BYTES;
           const uint32_t pcol = tmem_base + WT_COL_S1 + (j & 1) * WT_N;
-          const uint64_t vh = make_sdesc64(sb + 4 * WT_TILE_BYTES), vl = make_sdesc64(sb + 5 * WT_TILE_BYTES);
+          const uint64_t vh = tiled ? make_sdesc_ns(sb + 4 * WT_TILE_BYTES, 128, 2304) : make_sdesc64(sb + 4 * WT_TILE_BYTES);
+          const uint64_t vl = tiled ? make_sdesc_ns(sb + 5 * WT_TILE_BYTES, 128, 2304) : make_sdesc64(sb + 5 * WT_TILE_BYTES);
+          const uint32_t vstep = tiled ? 16u * 16u : 16u * 64u;
 #pragma unroll
           for (int k = 0; k < ((p.debug & 8) ? 0 : WT_N / 16); ++k) {
-            const uint64_t adv = (uint64_t)(k * 16 * 64 >> 4);
+            const uint64_t adv = (uint64_t)((k * vstep) >> 4);
             umma_bf16_ts(tmem_base + WT_COL_O1, pcol + k * 8, vh + adv, idO, k != 0);
             umma_bf16_ts(tmem_base + WT_COL_O1, pcol + k * 8, vl + adv, idO, 1);
             umma_bf16_ts(tmem_base + WT_COL_O1, pcol + 72 + k * 8, vh + adv, idO, 1);
@@ -455,14 +519,12 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_co
         s_j = s_j + 1 == WT_STAGES ? 0 : s_j + 1;
       }
     }
-  } else if (warp >= 4 && warp < 12) {
-    wt_softmax_role<false>(p, smem, bars, exch_max, exch_sum, tmem_base, warp & 3, (warp - 4) >> 2, lane);
-  } else if ((warp == 0 || warp == 12) && !(p.debug & 4)) {
-    wt_softmax_role<true>(p, smem, bars, exch_max, exch_sum, tmem_base, 0, warp == 12 ? 1 : 0, lane);
+  } else if (warp >= 4) {
+    wt_softmax_role(p, smem, bars, exch_max, exch_sum, tmem_base, warp & 3, (warp - 4) >> 2, lane);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(WT_TMEM_COLS) : "memory");
   }
@@ -483,7 +545,7 @@ static int make_map_wattn(CUtensorMap* m, const uint16_t* ptr, int64_t rows, int
 }
 
 int window_attn_tc(const uint16_t* qkv_hi, const uint16_t* qkv_lo, const float* bias_prepared, int B, int H, int W, int C,
-                   int heads, int ws, int shift, uint16_t* out_hi, uint16_t* out_lo, cudaStream_t st) {
+                   int heads, int ws, int shift, uint16_t* out_hi, uint16_t* out_lo, cudaStream_t st, int tiled) {
   RBA_CHECK(qkv_hi && qkv_lo && bias_prepared && out_hi && out_lo, "window_attn_tc: null pointer");
   RBA_CHECK(ws == WT_WS, "window_attn_tc: only window_size 12 is built (got %d)", ws);
   RBA_CHECK(heads > 0 && C == heads * WT_D, "window_attn_tc: head_dim must be 32 (C=%d heads=%d)", C, heads);
@@ -495,10 +557,15 @@ int window_attn_tc(const uint16_t* qkv_hi, const uint16_t* qkv_lo, const float* 
   if (nwin == 0) return RBA_OK;
   RBA_CHECK(nwin * WT_N < (1LL << 31), "window_attn_tc: too many rows");
   CUtensorMap tm_hi, tm_lo;
-  RBA_TRY_(make_map_wattn(&tm_hi, qkv_hi, nwin * WT_N, 3 * (int64_t)C));
-  RBA_TRY_(make_map_wattn(&tm_lo, qkv_lo, nwin * WT_N, 3 * (int64_t)C));
+  memset(&tm_hi, 0, sizeof(tm_hi));
+  memset(&tm_lo, 0, sizeof(tm_lo));
+  if (!tiled) {
+    RBA_TRY_(make_map_wattn(&tm_hi, qkv_hi, nwin * WT_N, 3 * (int64_t)C));
+    RBA_TRY_(make_map_wattn(&tm_lo, qkv_lo, nwin * WT_N, 3 * (int64_t)C));
+  }
   WtParams p;
   memset(&p, 0, sizeof(p));
+  if (tiled) { p.t_hi = qkv_hi; p.t_lo = qkv_lo; }
   p.bias = bias_prepared; p.out_hi = out_hi; p.out_lo = out_lo;
   p.C = C; p.heads = heads; p.nWh = g.nWh; p.nWw = g.nWw; p.shift = shift;
   p.nitems = nwin * heads;
@@ -538,6 +605,11 @@ int window_attn_tc(const uint16_t* qkv_hi, const uint16_t* qkv_lo, const float* 
 
 extern "C" int rba_k_window_attn_tc(const uint16_t* qkv_hi, const uint16_t* qkv_lo, const float* bias_prepared, int B, int H, int W,
                                     int C, int heads, int ws, int shift, uint16_t* out_hi, uint16_t* out_lo, void* stream) {
-  return rba::window_attn_tc(qkv_hi, qkv_lo, bias_prepared, B, H, W, C, heads, ws, shift, out_hi, out_lo, (cudaStream_t)stream);
+  return rba::window_attn_tc(qkv_hi, qkv_lo, bias_prepared, B, H, W, C, heads, ws, shift, out_hi, out_lo, (cudaStream_t)stream, 0);
+}
+extern "C" int rba_k_window_attn_tc_tiled(const uint16_t* qkv_hi, const uint16_t* qkv_lo, const float* bias_prepared, int B, int H,
+                                          int W, int C, int heads, int ws, int shift, uint16_t* out_hi, uint16_t* out_lo,
+                                          void* stream) {
+  return rba::window_attn_tc(qkv_hi, qkv_lo, bias_prepared, B, H, W, C, heads, ws, shift, out_hi, out_lo, (cudaStream_t)stream, 1);
 }
 

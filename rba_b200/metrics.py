@@ -90,19 +90,27 @@ class OODEvaluator:
         return {k: r[k] for k in ("auroc", "aupr", "fpr95")}
 
     @torch.no_grad()
-    def evaluate_dataset(self, dataset, batch=8, workers=8, upper_limit=None, metrics=None, use_graph=True):
+    def evaluate_dataset(self, dataset, batch=8, workers=8, upper_limit=None, metrics=None, use_graph=True, group=None):
         """The same evaluation over an indexable dataset of (image, label) pairs (the reference's dataset classes), fully
         pipelined: threaded decode into pinned batches (PinnedBatcher), H2D of batch i+1 overlapping the forward of batch i
-        (ScoreStream with d2h=False), scores and labels accumulated on the device.  One 40-byte D2H at the end."""
+        (ScoreStream with d2h=False), scores and labels accumulated on the device.  One 40-byte D2H at the end.
+
+        Multi-GPU (one process per GPU, torch.distributed initialised): image i goes to rank i % world, every rank fills its
+        own histogram and ONE all-reduce of the 2 x 2^24 counters at the end gives every rank the metrics over all pixels --
+        no score map ever crosses the link (the reference gathers every map to the host, support.py:353-399)."""
+        import torch.distributed as dist
         from .pipeline import PinnedBatcher, ScoreStream
         dev = self.model.device
         metrics = metrics or StreamingOODMetrics(dev)
         n = len(dataset) if upper_limit is None else min(len(dataset), int(upper_limit))
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank(group) if world > 1 else 0
+        mine = range(rank, n, world)
         eng = self.model.engine()
         eng.set_score(self.score_func, include_void=False)
         stream, ybuf, ev_lab = None, None, None
         comp = torch.cuda.current_stream(dev)
-        for it, (images, labels, n_valid) in enumerate(PinnedBatcher(dataset, batch, indices=range(n), workers=workers)):
+        for it, (images, labels, n_valid) in enumerate(PinnedBatcher(dataset, batch, indices=mine, workers=workers)):
             if stream is None:
                 stream = ScoreStream(eng, images.shape[0], images.shape[2], images.shape[3], use_graph=use_graph, d2h=False)
                 ybuf = [torch.empty(labels.shape, dtype=torch.uint8, device=dev) for _ in range(2)]
@@ -122,5 +130,7 @@ class OODEvaluator:
             # ring; the forward keeps running while the next batch is fetched
             stream.ev_in_ready[k].synchronize()
             ev_lab[k].synchronize()
+        if world > 1:
+            dist.all_reduce(metrics._hist, group=group)           # int64 counters: exact, order-independent
         r = metrics.compute()
         return {k: r[k] for k in ("auroc", "aupr", "fpr95")}

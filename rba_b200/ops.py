@@ -215,7 +215,7 @@ def outlier_loss(pred_masks, pred_logits, outlier_masks, outlier_loss_target="nl
 
 
 def gemm(a, w, bias=None, act=RBA_ACT_NONE, residual=None, out_planes=False, out_f32=True, bias_per_row=False,
-         swin=None, backend=RBA_GEMM_FFMA, out=None):
+         swin=None, backend=RBA_GEMM_FFMA, out=None, qkv_tile_heads=0):
     """C = act(A W^T + bias) (+ residual).  a: (hi, lo) planes [M,K] or [batch,M,K]; w: planes [N,K] or [batch,N,K].
     swin = (B, H, W, ws, shift) scatters windowed rows to token rows (output has B*H*W rows)."""
     a_hi, a_lo = a
@@ -257,6 +257,7 @@ def gemm(a, w, bias=None, act=RBA_ACT_NONE, residual=None, out_planes=False, out
     if swin is not None:
         g.swin_map, g.sw_H, g.sw_W, g.sw_ws, g.sw_shift = 1, swin[1], swin[2], swin[3], swin[4]
     g.backend = backend
+    g.qkv_tile_heads = int(qkv_tile_heads)        # planes in the (window, part, head) tiled layout (tensor-core backend only)
     _lib.check(_lib.lib().rba_k_gemm(ctypes.byref(g), _stream()))
     if out_planes and c is not None:
         return c, (c_hi, c_lo)
@@ -319,9 +320,19 @@ def window_attn_planes(qkv, bias_table, B, H, W, C, heads, ws, shift):
     return hi, lo
 
 
-def window_attn_tc(qkv, bias_table, B, H, W, C, heads, ws, shift):
-    """tcgen05 + TMA window attention; qkv = (hi, lo) planes [rows, 3C]; bias_table is the reference's
-    relative_position_bias_table [(2ws-1)^2, heads] (prepared per call here; the engine prepares it once at load)."""
+def qkv_to_tiles(planes, heads):
+    """Row-major q|k|v planes [rows, 3C] -> the tiled layout rba_gemm_args.qkv_tile_heads writes (torch permute; test aid)."""
+    out = []
+    for t in planes:
+        rows = t.shape[0]
+        out.append(t.view(rows // 144, 144, 3, heads, 4, 8).permute(0, 2, 3, 4, 1, 5).contiguous().view(rows, -1))
+    return tuple(out)
+
+
+def window_attn_tc(qkv, bias_table, B, H, W, C, heads, ws, shift, tiled=False):
+    """tcgen05 + TMA window attention; qkv = (hi, lo) planes [rows, 3C] (tiled=True: in the tiled layout of qkv_to_tiles /
+    the QKV GEMM's qkv_tile_heads mode); bias_table is the reference's relative_position_bias_table [(2ws-1)^2, heads]
+    (prepared per call here; the engine prepares it once at load)."""
     q_hi, q_lo = qkv
     _chk_cuda(q_hi, q_lo, bias_table)
     rows = q_hi.shape[0]
@@ -330,7 +341,8 @@ def window_attn_tc(qkv, bias_table, B, H, W, C, heads, ws, shift):
     _lib.check(L.rba_k_window_attn_prepare_bias(_p(bias_table), heads, _p(prep), _stream()))
     hi = torch.empty((rows, C), dtype=torch.bfloat16, device=q_hi.device)
     lo = torch.empty((rows, C), dtype=torch.bfloat16, device=q_hi.device)
-    _lib.check(L.rba_k_window_attn_tc(_p(q_hi), _p(q_lo), _p(prep), B, H, W, C, heads, ws, shift, _p(hi), _p(lo), _stream()))
+    fn = L.rba_k_window_attn_tc_tiled if tiled else L.rba_k_window_attn_tc
+    _lib.check(fn(_p(q_hi), _p(q_lo), _p(prep), B, H, W, C, heads, ws, shift, _p(hi), _p(lo), _stream()))
     return hi, lo
 
 

@@ -562,7 +562,7 @@ def test_conv3x3_tc(dev, H, W, Cout):
     assert (y.cpu() - ref).abs().max() < TC_TOL * max(1.0, float(ref.abs().max()))
 
 
-@pytest.mark.parametrize("kernel", ["tcgen05", "mma_sync"])
+@pytest.mark.parametrize("kernel", ["tcgen05_tiled", "tcgen05", "mma_sync"])
 @pytest.mark.parametrize("H,W,shift,B,heads", [(24, 24, 0, 2, 2), (30, 41, 6, 2, 2), (12, 12, 6, 2, 2), (12, 12, 0, 1, 1),
                                                (96, 180, 6, 3, 4), (40, 40, 6, 1, 16)])
 def test_window_attention_tensor_core(dev, H, W, shift, B, heads, kernel):
@@ -586,8 +586,11 @@ def test_window_attention_tensor_core(dev, H, W, shift, B, heads, kernel):
         mask = O.shift_attn_mask(H, W, ws, shift)
         attn = (attn.view(B, nW, heads, ws * ws, ws * ws) + mask.unsqueeze(1).unsqueeze(0)).view(-1, heads, ws * ws, ws * ws)
     ref = (attn.softmax(-1) @ v).transpose(1, 2).reshape(B * nW * ws * ws, C)
-    fn = ops.window_attn_tc if kernel == "tcgen05" else ops.window_attn_planes
-    out = fn(qp, table.to(dev), B, H, W, C, heads, ws, shift)
+    if kernel == "tcgen05_tiled":      # q|k|v in the tiled layout the engine's QKV GEMM writes: one bulk copy per operand tile
+        out = ops.window_attn_tc(ops.qkv_to_tiles(qp, heads), table.to(dev), B, H, W, C, heads, ws, shift, tiled=True)
+    else:
+        fn = ops.window_attn_tc if kernel == "tcgen05" else ops.window_attn_planes
+        out = fn(qp, table.to(dev), B, H, W, C, heads, ws, shift)
     err = (unplanes(out) - ref).abs()
     assert err.max() < 3e-4, (float(err.max()), int(err.argmax()) // C, int(err.argmax()) % C)
 
@@ -651,3 +654,22 @@ def test_resnet_bias_act_sub(dev, stride, relu, with_bias):
         _lib.check(_lib.lib().rba_k_bias_act_sub(p(xd), p(bias.to(dev) if with_bias else None), B, H, W, C, 1, relu, p(xd), None,
                                                  None, st))
         assert torch.equal(xd.cpu(), ref)
+
+
+def test_gemm_tc_writes_tiled_qkv_planes(dev):
+    """rba_gemm_args.qkv_tile_heads: the QKV GEMM's planes in the (window, part, head) tiled layout equal a permutation of its
+    plain row-major planes (bitwise)."""
+    g = torch.Generator().manual_seed(41)
+    heads, nwin = 4, 5
+    C, M = 32 * heads, 144 * nwin
+    a = torch.randn(M, C, generator=g)
+    w = torch.randn(3 * C, C, generator=g) / math.sqrt(C)
+    bias = torch.randn(3 * C, generator=g)
+    ap, _ = planes(a, dev)
+    wp, _ = planes(w, dev)
+    plain = ops.gemm(ap, wp, bias=bias.to(dev), out_planes=True, out_f32=False, backend=ops.RBA_GEMM_TC)
+    tiled = ops.gemm(ap, wp, bias=bias.to(dev), out_planes=True, out_f32=False, backend=ops.RBA_GEMM_TC, qkv_tile_heads=heads)
+    want = ops.qkv_to_tiles(plain, heads)
+    assert torch.equal(tiled[0].view(-1), want[0].view(-1)) and torch.equal(tiled[1].view(-1), want[1].view(-1))
+    with pytest.raises(ops.RbaError):
+        ops.gemm(ap, wp, out_planes=True, out_f32=False, backend=ops.RBA_GEMM_FFMA, qkv_tile_heads=heads)

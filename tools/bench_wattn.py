@@ -13,7 +13,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 dev = torch.device("cuda", 0)
 stages = [(256, 512, 128, 4, 2), (128, 256, 256, 8, 2), (64, 128, 512, 16, 18), (32, 64, 1024, 32, 2)]   # H, W, C, heads, blocks
 res = {"B": B, "stages": []}
-tot = {"tcgen05": 0.0, "mma_sync": 0.0}
+tot = {"tcgen05": 0.0, "tcgen05_rowmajor": 0.0, "mma_sync": 0.0}
 for H, W, C, heads, blocks in stages:
     nW = -(-H // 12) * -(-W // 12)
     rows = B * nW * 144
@@ -24,7 +24,9 @@ for H, W, C, heads, blocks in stages:
     row = {"H": H, "W": W, "C": C, "heads": heads, "blocks": blocks, "items": B * nW * heads,
            "algorithmic_bytes": rows * C * 4 * 4}            # q, k, v in + o out, 4 B per element (hi + lo planes)
     outs = {}
-    for name, fn in (("tcgen05", ops.window_attn_tc), ("mma_sync", ops.window_attn_planes)):
+    qt = ops.qkv_to_tiles(qp, heads)
+    tiled_fn = lambda q, *a: ops.window_attn_tc(qt, *a, tiled=True)  # noqa: E731
+    for name, fn in (("tcgen05", tiled_fn), ("tcgen05_rowmajor", ops.window_attn_tc), ("mma_sync", ops.window_attn_planes)):
         for shift in (0, 6):
             for _ in range(3):
                 o = fn(qp, table, B, H, W, C, heads, 12, shift)

@@ -16,13 +16,16 @@ nW = -(-H // 12) * -(-W // 12)
 g = torch.Generator(device=dev).manual_seed(1)
 qp = ops.split_planes(torch.randn(B * nW * 144, 3 * C, device=dev, generator=g))
 table = torch.randn(529, heads, device=dev, generator=g)
+tiled = os.environ.get("RBA_WT_ROWMAJOR") is None
+if tiled:
+    qp = ops.qkv_to_tiles(qp, heads)
 for _ in range(3):
-    ops.window_attn_tc(qp, table, B, H, W, C, heads, 12, 0)
+    ops.window_attn_tc(qp, table, B, H, W, C, heads, 12, 0, tiled=tiled)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(reps):
-    ops.window_attn_tc(qp, table, B, H, W, C, heads, 12, 0)
+    ops.window_attn_tc(qp, table, B, H, W, C, heads, 12, 0, tiled=tiled)
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
