@@ -7,7 +7,12 @@ score maps never leave the device and the metrics never touch sklearn.
 `StreamingOODMetrics` is the accumulator underneath: `update(score, gt)` adds a batch of (score, label) pixels to a
 two-class 2^24-bin histogram of order-preserving float keys (csrc/ood_metrics.cu), `compute()` sweeps it.  The
 result equals sklearn's roc_curve/auc/average_precision_score on scores quantised to 2^-15 relative resolution
-(exactly), and the reference's numbers within ~1e-5 on real score maps."""
+(exactly), and the reference's numbers within ~1e-5 on real score maps.
+
+One documented difference: `fpr95` is the FPR at the FIRST threshold whose TPR exceeds 0.95.  The reference's
+`calculate_auroc` (support.py:247-268) walks sklearn's `roc_curve` output with its default `drop_intermediate=True`, which
+removes collinear ROC points, so the first RETAINED point with TPR > 0.95 can be a later one with a slightly higher FPR.  AUROC
+and AUPR are unaffected; on the committed goldens all three metrics agree with the reference's within the tolerance of tests/test_ood_metrics.py."""
 import ctypes
 
 import numpy as np
