@@ -18,8 +18,25 @@ from .config import ModelConfig, model_config_from_cfg
 from .engine import Engine
 
 
+def _opt(node, key, default):
+    try:
+        return node[key] if isinstance(node, dict) else getattr(node, key)
+    except (KeyError, AttributeError):
+        return default
+
+
+def _thing_ids(cfg):
+    """MetadataCatalog.get(cfg.DATASETS.TRAIN[0]).thing_dataset_id_to_contiguous_id.values() (maskformer_model.py:204,424)."""
+    try:
+        from detectron2.data import MetadataCatalog
+        ds = cfg["DATASETS"]["TRAIN"][0] if isinstance(cfg, dict) else cfg.DATASETS.TRAIN[0]
+        return sorted(int(v) for v in MetadataCatalog.get(ds).thing_dataset_id_to_contiguous_id.values())
+    except Exception:
+        return []
+
+
 class MaskFormer(nn.Module):
-    """B200-native drop-in for the reference meta-architecture (eval / semantic branch)."""
+    """B200-native drop-in for the reference meta-architecture (eval branch: semantic + panoptic / open-panoptic)."""
 
     def __init__(self, cfg, seed=0):
         super().__init__()
@@ -28,6 +45,25 @@ class MaskFormer(nn.Module):
         self.size_divisibility = self.mc.size_divisibility
         self.semantic_on, self.panoptic_on, self.instance_on = True, False, False
         self.sem_seg_postprocess_before_inference = False
+        # panoptic / open-panoptic inference (maskformer_model.py:202-220,336-340,394-481): host-side post-processing of the
+        # head outputs, rba_b200/panoptic.py
+        self.object_mask_threshold, self.overlap_threshold, self.open_panoptic = 0.8, 0.8, True
+        self.thing_ids = []
+        if not isinstance(cfg, ModelConfig):
+            M = cfg["MODEL"] if isinstance(cfg, dict) else cfg.MODEL
+            mf = M["MASK_FORMER"] if isinstance(M, dict) else M.MASK_FORMER
+            test = _opt(mf, "TEST", None)
+            if test is not None:
+                self.panoptic_on = bool(_opt(test, "PANOPTIC_ON", False))
+                self.semantic_on = bool(_opt(test, "SEMANTIC_ON", True))
+                self.object_mask_threshold = float(_opt(test, "OBJECT_MASK_THRESHOLD", 0.8))
+                self.overlap_threshold = float(_opt(test, "OVERLAP_THRESHOLD", 0.8))
+                if bool(_opt(test, "INSTANCE_ON", False)):
+                    raise RbaError("MODEL.MASK_FORMER.TEST.INSTANCE_ON is not built")
+            self.open_panoptic = bool(_opt(mf, "OPEN_PANOPTIC", True))
+            if self.panoptic_on:
+                self.thing_ids = _thing_ids(cfg)
+        self.sem_seg_postprocess_before_inference = self.panoptic_on
         # host master copy of the reference-layout state_dict (what DetectionCheckpointer reads and writes)
         self._sd = weights.init_state_dict(self.mc, seed=seed)
         self._device = torch.device("cpu")
@@ -118,10 +154,12 @@ class MaskFormer(nn.Module):
 
     @torch.no_grad()
     def forward(self, batched_inputs, include_void=False, return_separately=False, return_aux=False,
-                return_ood_pred=False, **kwargs):
-        """maskformer_model.py:227-356, eval + SEMANTIC_ON branch."""
-        if return_aux or kwargs.get("return_panoptic_ood"):
-            raise RbaError("return_aux / panoptic outputs are not built (SURVEY §8f-3)")
+                return_ood_pred=False, panoptic_ood_threshold=-0.3, panoptic_pixel_min=200, return_panoptic_ood=False):
+        """maskformer_model.py:227-356, eval branch (SEMANTIC_ON, and PANOPTIC_ON with the open-panoptic OoD segments)."""
+        if return_aux:
+            raise RbaError("return_aux (auxiliary decoder outputs) is not built")
+        if self.panoptic_on:
+            return self._forward_panoptic(batched_inputs, include_void, panoptic_ood_threshold, panoptic_pixel_min, return_panoptic_ood)
         if return_ood_pred and not self.mc.ood_prediction:
             raise RbaError("return_ood_pred needs the DenseHybrid head (MODEL.MASK_FORMER.DENSE_HYBRID_LOSS: True)")
         images = self._batch(batched_inputs)
@@ -143,6 +181,37 @@ class MaskFormer(nn.Module):
             return results, out["pred_logits"][-1], up
         if return_ood_pred:                                  # maskformer_model.py:303-305,350-351
             return results, out["ood_pred"]
+        return results
+
+    def _forward_panoptic(self, batched_inputs, include_void, ood_threshold, pixel_min, return_panoptic_ood):
+        """PANOPTIC_ON: sem_seg_postprocess runs BEFORE inference (maskformer_model.py:206-209,318-322), then semantic and panoptic
+        inference on the post-processed masks (:325-340).  The engine supplies sem_seg, the RbA score (= the open-panoptic
+        branch's ood_mask, :456-458) and the head outputs in one forward."""
+        from .panoptic import panoptic_inference
+        images = self._batch(batched_inputs)
+        B, _, H, W = images.shape
+        eng = self.engine()
+        eng.set_score("rba", include_void=include_void)
+        out = eng.forward(images, rba=True, sem_seg=self.semantic_on, logits=True, masks=True)
+        Hp, Wp = eng.padded_hw(H, W)
+        results = []
+        for b, inp in enumerate(batched_inputs):
+            h, w = inp.get("height", H), inp.get("width", W)
+            up = F.interpolate(out["pred_masks"][b:b + 1], size=(Hp, Wp), mode="bilinear", align_corners=False)[:, :, :H, :W]
+            rba = out["rba"][b]
+            r = {}
+            if (h, w) != (H, W):                 # sem_seg_postprocess: crop (above) + bilinear resize to the requested size
+                up = F.interpolate(up, size=(h, w), mode="bilinear", align_corners=False)
+                rba = None                       # the score of the resized masks is recomputed from them
+            if self.semantic_on:
+                sem = out["sem_seg"][b]
+                if (h, w) != (H, W):
+                    sem = F.interpolate(sem[None], size=(h, w), mode="bilinear", align_corners=False)[0]
+                r["sem_seg"] = sem
+            r["panoptic_seg"] = panoptic_inference(out["pred_logits"][b], up[0], self.mc.num_classes, self.object_mask_threshold,
+                                                   self.overlap_threshold, self.thing_ids, self.open_panoptic, ood_threshold,
+                                                   pixel_min, return_panoptic_ood, ood_mask=rba)
+            results.append(r)
         return results
 
     @torch.no_grad()

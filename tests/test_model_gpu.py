@@ -518,3 +518,47 @@ def test_arena_growth_keeps_captured_graphs_valid(dev):
     assert torch.equal(o2["rba"], want)
     del filler
     e.release_retired()
+
+
+def test_panoptic_on_model_matches_host_inference(dev):
+    """MODEL.MASK_FORMER.TEST.PANOPTIC_ON: `model(x)[0]["panoptic_seg"]` (maskformer_model.py:336-340) = the reference's
+    panoptic_inference restated in rba_b200/panoptic.py (pinned on the reference in tests/test_panoptic.py) applied to this
+    model's own post-processed head outputs; the OoD segments come from the fused kernel's RbA score."""
+    from rba_b200.panoptic import panoptic_inference
+    case = CASES["tiny_1dl"]
+    mc = case_model_config(case)
+    sd = weights.init_state_dict(mc, seed=case["seed"], perturb=case["perturb"])
+    y = {"MODEL": {"META_ARCHITECTURE": "MaskFormer", "PIXEL_MEAN": list(mc.pixel_mean), "PIXEL_STD": list(mc.pixel_std),
+                   "BACKBONE": {"NAME": "D2SwinTransformer"},
+                   "SWIN": {"EMBED_DIM": mc.embed_dim, "DEPTHS": list(mc.depths), "NUM_HEADS": list(mc.num_heads), "WINDOW_SIZE": 12,
+                            "MLP_RATIO": 4.0, "PATCH_SIZE": 4, "APE": False, "QKV_BIAS": True, "PATCH_NORM": True},
+                   "SEM_SEG_HEAD": {"PIXEL_DECODER_NAME": "MSDeformAttnPixelDecoder", "NORM": "GN", "CONVS_DIM": 256, "MASK_DIM": 256,
+                                    "NUM_CLASSES": mc.num_classes, "IN_FEATURES": ["res2", "res3", "res4", "res5"],
+                                    "DEFORMABLE_TRANSFORMER_ENCODER_IN_FEATURES": list(mc.transformer_in_features),
+                                    "COMMON_STRIDE": 4, "TRANSFORMER_ENC_LAYERS": mc.enc_layers},
+                   "MASK_FORMER": {"TRANSFORMER_DECODER_NAME": "MultiScaleMaskedTransformerDecoder", "PRE_NORM": False, "NHEADS": 8,
+                                   "HIDDEN_DIM": 256, "DIM_FEEDFORWARD": 2048, "DEC_LAYERS": mc.dec_layers + 1,
+                                   "NUM_OBJECT_QUERIES": mc.num_queries, "SIZE_DIVISIBILITY": 32, "OPEN_PANOPTIC": True,
+                                   "TEST": {"SEMANTIC_ON": True, "PANOPTIC_ON": True, "INSTANCE_ON": False,
+                                            "OBJECT_MASK_THRESHOLD": 0.0, "OVERLAP_THRESHOLD": 0.3}}},
+         "DATASETS": {"TRAIN": ["cityscapes_fine_sem_seg_train"]}}
+    model = rba_b200.MaskFormer(y)
+    assert model.panoptic_on and model.open_panoptic
+    model.thing_ids = [11, 12, 13, 14, 15, 16, 17, 18]
+    model.load_state_dict(sd)
+    model.to(dev).eval()
+    x = case_images(case)[0].to(dev)
+    H, W = x.shape[-2:]
+    out = model([{"image": x}], panoptic_ood_threshold=-15.0, panoptic_pixel_min=4, return_panoptic_ood=True)[0]
+    pan, info, ood = out["panoptic_seg"]
+    assert pan.shape == (H, W) and pan.dtype == torch.int32 and out["sem_seg"].shape == (mc.num_classes, H, W)
+    # the same from the plain model's head outputs
+    plain = rba_b200.MaskFormer(mc)
+    plain.load_state_dict(sd)
+    plain.to(dev).eval()
+    res, cls, up = plain([{"image": x}], return_separately=True)
+    want = panoptic_inference(cls, up[:, :H, :W], mc.num_classes, 0.0, 0.3, model.thing_ids, True, -15.0, 4, True)
+    assert (ood - want[2]).abs().max() < 2e-4                       # fused-kernel RbA vs the reference arithmetic on the masks
+    agree = (pan == want[0]).float().mean().item()
+    assert agree > 0.999 and len(info) == len(want[1]), (agree, len(info), len(want[1]))
+    assert (out["sem_seg"] - res[0]["sem_seg"]).abs().max() < 1e-5
