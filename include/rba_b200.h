@@ -156,6 +156,10 @@ int rba_score_fused(const float* pred_masks, const float* pred_logits, int B, in
 int rba_einsum_score_fused(const uint16_t* embed_hi, const uint16_t* embed_lo, const float* bias, const uint16_t* feat_hi,
                            const uint16_t* feat_lo, const float* pred_logits, int B, int Q, int K, int D, int h, int w,
                            int H, int W, int score_func, int include_void, float* score, float* sem_seg, void* stream);
+/* Test / profiling hook.  RbA-only launches (sem_seg NULL, RBA_SCORE_RBA) run on the second-generation kernel
+ * (interpolation and class contraction on tcgen05, csrc/score_fused2.cu); variant 1 selects the first-generation kernel
+ * (mma.sync score phase, csrc/score_fused.cu) for them as well.  Process-wide; env RBA_FS_VARIANT sets the initial value. */
+int rba_k_set_fused_score_variant(int variant);
 
 /* ---- streaming OoD metrics (replaces OODEvaluator.evaluate_ood / calculate_auroc, support.py:247-303, and the
  * per-image host round trip of compute_anomaly_scores, support.py:353-399) ----

@@ -23,6 +23,7 @@
 //               quad shuffles.  The MMAs of tile i+1 overlap the score phase of tile i (the accumulator is drained first).
 #include <cuda_fp16.h>
 
+#include "kernels.cuh"
 #include "tcgen05.cuh"
 
 namespace rba {
@@ -201,19 +202,12 @@ __device__ __forceinline__ float fs_rsum2(float v0, float v1) {
   const float a0 = 1.0f + fs_ex2(fminf(v0, FS_UMAX)), a1 = 1.0f + fs_ex2(fminf(v1, FS_UMAX));
   return (a0 + a1) * fs_rcp(a0 * a1);
 }
-// A fragments (f16 hi / lo) of one k16 step from 8 + 8 interpolated logits.  RCPM 1: one reciprocal per pair, 2: per quad.
+// A fragments (f16 hi / lo) of one k16 step from 8 + 8 interpolated logits.  The clamp that keeps the batched reciprocals
+// finite is applied to the INTERPOLATED value (fs_sigmoid2 / fs_sigmoid4): clamping the taps instead (an earlier revision did,
+// to save one FMNMX per sigmoid) changes the interpolated logit wherever a tap beyond the clamp sits next to a small one.
 template <int ABL, int RCPM>
 __device__ __forceinline__ void fs_sig_frag_u(const float* u0, const float* u1, uint32_t* ah, uint32_t* al) {
-  if (ABL != 0 || RCPM == 0 || RCPM == 3) { fs_sig_frag<ABL, RCPM>(u0, u1, ah, al); return; }
-  float s0[4], s1[4];
-  if (RCPM == 1) {
-    fs_sigmoid2u(u0[0], u0[1], s0[0], s0[1]); fs_sigmoid2u(u0[2], u0[3], s0[2], s0[3]);
-    fs_sigmoid2u(u1[0], u1[1], s1[0], s1[1]); fs_sigmoid2u(u1[2], u1[3], s1[2], s1[3]);
-  } else {
-    fs_sigmoid4u(u0, s0); fs_sigmoid4u(u1, s1);
-  }
-  fs_split_fast(s0[0], s0[1], ah[0], al[0]); fs_split_fast(s0[2], s0[3], ah[1], al[1]);
-  fs_split_fast(s1[0], s1[1], ah[2], al[2]); fs_split_fast(s1[2], s1[3], ah[3], al[3]);
+  fs_sig_frag<ABL, RCPM>(u0, u1, ah, al);
 }
 
 // per-lane constants of the score phase
@@ -333,7 +327,7 @@ __device__ __forceinline__ void fs_score_cells(const FsParams& p, const FsLane& 
 #pragma unroll
           for (int e = 0; e < 4; ++e) s0[e] = fs_sigmoid_scaled(u0[c][e]);
         } else {
-          fs_sigmoid4u(u0[c], s0);
+          fs_sigmoid4(u0[c], s0);
         }
         fs_split_fast(s0[0], s0[1], ah0, al0);
         fs_split_fast(s0[2], s0[3], ah1, al1);
@@ -577,10 +571,10 @@ rba_einsum_score_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid
             for (int j = 0; j < 4; ++j) {
               const float4 b4 = *reinterpret_cast<const float4*>(sBias + q0 + 4 * j);
               float4 o;
-              o.x = fminf(fmaf(__uint_as_float(v[4 * j]), SCALE, b4.x), FS_UMAX);
-              o.y = fminf(fmaf(__uint_as_float(v[4 * j + 1]), SCALE, b4.y), FS_UMAX);
-              o.z = fminf(fmaf(__uint_as_float(v[4 * j + 2]), SCALE, b4.z), FS_UMAX);
-              o.w = fminf(fmaf(__uint_as_float(v[4 * j + 3]), SCALE, b4.w), FS_UMAX);
+              o.x = fmaf(__uint_as_float(v[4 * j]), SCALE, b4.x);
+              o.y = fmaf(__uint_as_float(v[4 * j + 1]), SCALE, b4.y);
+              o.z = fmaf(__uint_as_float(v[4 * j + 2]), SCALE, b4.z);
+              o.w = fmaf(__uint_as_float(v[4 * j + 3]), SCALE, b4.w);
               *reinterpret_cast<float4*>(prow + q0 + 4 * j) = o;
             }
           } else {
@@ -590,10 +584,10 @@ rba_einsum_score_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid
             for (int j = 0; j < 2; ++j) {
               const float4 b4 = *reinterpret_cast<const float4*>(sBias + q0 + 4 * j);
               float4 o;
-              o.x = fminf(fmaf(__uint_as_float(v[4 * j]), SCALE, b4.x), FS_UMAX);
-              o.y = fminf(fmaf(__uint_as_float(v[4 * j + 1]), SCALE, b4.y), FS_UMAX);
-              o.z = fminf(fmaf(__uint_as_float(v[4 * j + 2]), SCALE, b4.z), FS_UMAX);
-              o.w = fminf(fmaf(__uint_as_float(v[4 * j + 3]), SCALE, b4.w), FS_UMAX);
+              o.x = fmaf(__uint_as_float(v[4 * j]), SCALE, b4.x);
+              o.y = fmaf(__uint_as_float(v[4 * j + 1]), SCALE, b4.y);
+              o.z = fmaf(__uint_as_float(v[4 * j + 2]), SCALE, b4.z);
+              o.w = fmaf(__uint_as_float(v[4 * j + 3]), SCALE, b4.w);
               *reinterpret_cast<float4*>(prow + q0 + 4 * j) = o;
             }
           }
@@ -636,6 +630,17 @@ rba_einsum_score_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid
   }
 }
 
+static std::atomic<int> g_fs_variant{-1};
+int fused_score_variant() {
+  int v = g_fs_variant.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("RBA_FS_VARIANT");
+    v = e ? atoi(e) : 1;   // second-generation kernel is opt-in until it is the faster one
+    g_fs_variant.store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
 int einsum_score_supported(int Q, int K, int D) { return Q > 0 && Q <= FS_QP && K > 0 && K + 1 <= FS_NT * 8 && D % TC_BK == 0; }
 
 int einsum_score_launch(const uint16_t* e_hi, const uint16_t* e_lo, const float* bias, const uint16_t* y_hi,
@@ -644,6 +649,10 @@ int einsum_score_launch(const uint16_t* e_hi, const uint16_t* e_lo, const float*
   RBA_CHECK(einsum_score_supported(Q, K, D), "einsum_score: unsupported Q=%d (<= %d) K=%d (<= %d) D=%d (multiple of %d)", Q,
             FS_QP, K, FS_NT * 8 - 1, D, TC_BK);
   RBA_CHECK(score_func == RBA_SCORE_RBA || score_func == RBA_SCORE_ENERGY, "einsum_score: unknown score function %d", score_func);
+  // RbA-only launches (the hot path) run on the second-generation kernel (score_fused2.cu); sem_seg / energy launches and
+  // RBA_FS_VARIANT=1 (or rba_k_set_fused_score_variant(1)) stay on this one
+  if (!sem && score_func == RBA_SCORE_RBA && fused_score_variant() != 1)
+    return einsum_score2_launch(e_hi, e_lo, bias, y_hi, y_lo, logits, B, Q, K, D, h, w, H, W, include_void, rba, st);
   RBA_CHECK(((uintptr_t)e_hi & 15) == 0 && ((uintptr_t)e_lo & 15) == 0 && ((uintptr_t)y_hi & 15) == 0 && ((uintptr_t)y_lo & 15) == 0,
             "einsum_score: operand planes must be 16-byte aligned");
   FsParams p;
@@ -700,6 +709,12 @@ int einsum_score_launch(const uint16_t* e_hi, const uint16_t* e_lo, const float*
 
 // mask_embed (B,Q,D) and features (B,h,w,D) as bf16 split planes; bias (B,Q) fp32 or NULL; pred_logits (B,Q,K+1);
 // sem_seg (B, K or K+1, H, W) or NULL.
+// test / profiling hook: 1 = first-generation kernel (mma.sync score phase), 2 = second generation (default)
+extern "C" int rba_k_set_fused_score_variant(int v) {
+  rba::g_fs_variant.store(v == 1 ? 1 : 2, std::memory_order_relaxed);
+  return RBA_OK;
+}
+
 extern "C" int rba_einsum_score_fused(const uint16_t* embed_hi, const uint16_t* embed_lo, const float* bias,
                                       const uint16_t* feat_hi, const uint16_t* feat_lo, const float* pred_logits, int B, int Q,
                                       int K, int D, int h, int w, int H, int W, int score_func, int include_void,

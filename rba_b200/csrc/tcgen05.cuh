@@ -135,6 +135,87 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem, const void* gptr, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem)), "l"(gptr), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// SWIZZLE_64B shared-memory matrix descriptor: 64-byte rows, 8-row groups 512 B apart.  The same encoding serves the
+// K-major operands (q, k: ((8,n),2):((4,SBO),1) in 16-byte units) and the MN-major operand (v: ((4,n),(8,k)):((1,LBO),(4,SBO))).
+__device__ __forceinline__ uint64_t make_sdesc64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(512 >> 4) << 16;                   // leading byte offset (one 64-byte column block; unused: N = 32)
+  d |= (uint64_t)(512 >> 4) << 32;                   // stride byte offset: 8 rows x 64 B
+  d |= (uint64_t)1 << 46;                            // version 1 (Blackwell)
+  d |= (uint64_t)4 << 61;                            // SWIZZLE_64B
+  return d;
+}
+// SWIZZLE_NONE descriptor over the tiled ("core matrix") operand layout: a 144 x 32 bf16 tile is stored as 4 chunk planes
+// (8 channels = 16 B wide) of 144 rows x 16 B, i.e. 8 x 16 B core matrices of 128 contiguous bytes.
+//   K-major  (q, k):  ((8,n),2):((1,SBO),LBO) in 16-byte units  ->  SBO = 128 B (next 8 rows), LBO = 2304 B (next 8 channels)
+//   MN-major (v):     ((1,n),(8,k)):((X,SBO),(1,LBO))           ->  SBO = 2304 B (next 8 channels), LBO = 128 B (next 8 keys)
+__device__ __forceinline__ uint64_t make_sdesc_ns(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;                            // version 1 (Blackwell); layout type 0 = no swizzle
+  return d;
+}
+// kind::f16 instruction descriptor: D fp32, A / B bf16, A K-major, B K-major or MN-major (bit 16)
+__host__ __device__ constexpr uint32_t wt_idesc(int M, int N, bool b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// tcgen05.wait::ld that also names the destination registers, so that the compiler cannot schedule their first use above it
+// when independent work is interleaved between a tcgen05.ld and its wait
+template <int N>
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t* v) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < N; ++i) asm volatile("" : "+r"(v[i]));
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),
+      "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),
+      "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float wt_ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 // ---------------------------------------------------------------------------------------------------------
 // host side: tensor maps + launch
 // ---------------------------------------------------------------------------------------------------------

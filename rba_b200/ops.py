@@ -84,6 +84,12 @@ def einsum_score_fused(mask_embed, features, pred_logits, out_hw, bias=None, wan
     return (rba, sem) if want_sem_seg else rba
 
 
+def set_fused_score_variant(variant):
+    """Test / profiling hook: 2 (default) = tcgen05 score phase (score_fused2.cu) for RbA-only launches, 1 = the mma.sync
+    kernel (score_fused.cu) for every launch."""
+    _lib.check(_lib.lib().rba_k_set_fused_score_variant(int(variant)))
+
+
 def _dev_i64(t, like):
     return t.is_cuda and t.device == like.device and t.dtype == torch.int64 and t.is_contiguous()
 
