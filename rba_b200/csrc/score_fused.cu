@@ -709,9 +709,9 @@ int einsum_score_launch(const uint16_t* e_hi, const uint16_t* e_lo, const float*
 
 // mask_embed (B,Q,D) and features (B,h,w,D) as bf16 split planes; bias (B,Q) fp32 or NULL; pred_logits (B,Q,K+1);
 // sem_seg (B, K or K+1, H, W) or NULL.
-// test / profiling hook: 1 = first-generation kernel (mma.sync score phase), 2 = second generation (default)
+// test / profiling hook: 1 = first-generation kernel (mma.sync score phase), 2 = second generation, 0 = default
 extern "C" int rba_k_set_fused_score_variant(int v) {
-  rba::g_fs_variant.store(v == 1 ? 1 : 2, std::memory_order_relaxed);
+  rba::g_fs_variant.store(v == 0 ? -1 : (v == 1 ? 1 : 2), std::memory_order_relaxed);   // 0: back to the default / RBA_FS_VARIANT
   return RBA_OK;
 }
 

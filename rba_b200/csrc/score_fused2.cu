@@ -1,6 +1,5 @@
-// Fused mask einsum + RbA score, second generation: EVERY contraction of the path on tcgen05, the CUDA cores only evaluate
-// the sigmoids / tanh (SURVEY §8d "Variant A"; replaces score_fused.cu for the RbA-only launch, which is the kernel
-// BASELINE.json's metric names).
+// Fused mask einsum + RbA score, second generation (SURVEY §8d "Variant A"; opt-in replacement of score_fused.cu for the
+// RbA-only launch, the kernel BASELINE.json's metric names).
 //
 // Per image (mask2former_transformer_decoder.py:479, maskformer_model.py:294-299,381-386, evaluate_ood.py:148-150):
 //   m[q,i,j]   = sum_c E'[q,c] y[i,j,c] + b'[q]                          einsum "bqc,bchw->bqhw"
@@ -8,29 +7,33 @@
 //   s[k,Y,X]   = sum_q softmax(logits[q,:])[k] * sigmoid(u[q,Y,X])        semantic_inference
 //   rba[Y,X]   = -sum_k tanh(s[k,Y,X])                                    get_RbA
 //
-// What changed against score_fused.cu (mma.sync interpolation + contraction, 15.5 thread-instructions and 1.5 MUFU per
+// What changed against score_fused.cu (mma.sync interpolation + contraction; 15.5 thread-instructions and 1.5 MUFU per
 // sigmoid):
 //   * a thread owns a RUN: the four horizontally adjacent output pixels of one output row inside one interpolation cell.
 //     Along a run the interpolated logit is linear, u_j = x0 + j d, so 2^u_j = 2^x0 (2^d)^j: TWO ex2 give the four
-//     exponentials (plus two paired reciprocals): 1 MUFU per sigmoid instead of 1.5, ~6 instructions instead of 15.5.
-//   * x0 and d are themselves linear in the four taps: the interpolation is a tcgen05 GEMM D2[run, q] = A[run, tap] P[tap, q]
-//     with constant weight matrices A (exact in f16) and the drained patch P (f16 hi + lo planes) as the MN-major B operand.
-//   * the (run, q) x (q, class) contraction is a tcgen05 GEMM with the sigmoids (f16 hi / lo) written to TENSOR MEMORY as the
-//     A operand (tcgen05.st) and the class probabilities [W_hi | W_lo] (N = 48) as B: D3[run, px] = S_hi [W_hi|W_lo] + S_lo W_hi.
+//     exponentials (plus two paired reciprocals): 1 MUFU per sigmoid instead of 1.5.  x0 and d come from the four taps with
+//     7 FP32 instructions per query (shared by the 4 sigmoids).
+//   * the (run, q) x (q, class) contraction is a tcgen05 GEMM: the sigmoids (f16 hi / lo) are written to TENSOR MEMORY as the
+//     A operand (tcgen05.st), the class probabilities (f16 hi / lo, interleaved, N = 48) are the B operand in shared memory:
+//     D3[run, px] += (S_hi + S_lo) W.  No fragment shuffling, no mma.sync.
 //   Range: the product form needs every tap |u| <= 60 (|mask logit| <= 41.6); the drain records the tile's max |u| and a tile
 //   that exceeds it takes the exact path (four ex2 of individually clamped u_j) -- no clamp ever touches a tap.
 //   Image borders: out-of-range taps are REPLICATED from the edge in the patch (what the clamped source index of
-//   align_corners=False amounts to), so one weight matrix serves every tile.
+//   align_corners=False amounts to), so interior weights serve every tile.
+//   (A first revision also ran the interpolation on tcgen05 -- D2[run, q] = A[run, tap] P[tap, q] with constant weight
+//   matrices -- and was bound by the tensor pipe: an M128 x N<=64 x K16 MMA costs ~40-80 clk whatever N is)
 //
 // Persistent kernel, one CTA per SM, 18 warps.  Tile = 8 x 16 low-resolution pixels (M = 128 rows of the einsum), 7 x 15 cells,
-// processed as 4 blocks of two cell rows (8 output rows x 15 cells = 120 runs = 120 TMEM lanes; the 4th block has one row).
+// processed as 4 blocks of two cell rows (2 x 15 cells x 4 output rows = 120 runs = 120 TMEM lanes; the 4th block has one row).
 //   warp 0      TMA producer (feature planes NHWC + E' planes, K blocks of 32 channels, 4-stage ring, SWIZZLE_64B) AND issuer of
-//               the einsum MMAs of the NEXT tile (bf16x3), so that they never queue behind the score-phase MMAs
-//   warp 1      score-phase MMA issuer: per block and 32-query item the interpolation (f16 hi/lo, K = 48 taps) of item n + 1,
-//               then the contraction of item n
-//   warps 2-17  drain D1 -> patch planes; then 4 groups x 4 TMEM lane quadrants: group g evaluates queries 8g..8g+7 of every
-//               32-query item for its 32 runs and, in the epilogue of a block, output pixel g of each run.
-// TMEM columns: D1 0..111 | D3 112..303 (4 pixels x 48) | P 304..431 (4 pixels x (hi 16 | lo 16)) | D2 432..495 (x0 32 | d 32).
+//               the einsum MMAs of the NEXT tile (bf16x3)
+//   warp 1      contraction issuer: per block and k16 step (16 queries), 8 MMAs (4 pixels x hi / lo) once the step's sigmoids
+//               are in tensor memory
+//   warps 2-17  drain D1 -> fp32 patch; then two PAIRS of warp groups (pair X owns the k16 steps ks = X mod 2 and operand slot
+//               X; group e of a pair evaluates queries 16 ks + 8 e .. + 7; each group is 4 warps = the 4 TMEM lane quadrants):
+//               the pairs run independently, so one keeps the MUFU pipe busy while the other stores / waits.  In the epilogue
+//               of a block, group g = 2 X + e finishes output pixel g of each run.
+// TMEM columns: D1 0..111 | D3 112..303 (4 pixels x 48) | P 304..431 (2 slots x 4 pixels x (hi 8 | lo 8)).
 #include <cuda_fp16.h>
 
 #include "tcgen05.cuh"
@@ -44,25 +47,22 @@ constexpr int F2_A_BYTES = TC_BM * F2_BK * 2;               // 8 KB: one plane o
 constexpr int F2_E_BYTES = F2_NQ * F2_BK * 2;               // 7 KB: one plane of E'
 constexpr int F2_STAGE_BYTES = 2 * F2_A_BYTES + 2 * F2_E_BYTES;   // 30 KB
 constexpr int F2_QCH = F2_NQ / 8;                           // 14 chunks of 8 queries
-constexpr int F2_PLANE_BYTES = F2_QCH * TC_BM * 16;         // 28 KB: patch plane [q chunk][pixel][8 q] f16 (MN-major B operand)
-constexpr int F2_KT = 48;                                   // taps of a block: 3 patch rows x 16
-constexpr int F2_AMAT_BYTES = (F2_KT / 8) * TC_BM * 16;     // 12 KB: weight matrix [tap chunk][run][8 taps] f16 (K-major A operand)
-constexpr int F2_WN = 48;                                   // [W_hi (24) | W_lo (24)]
+constexpr int F2_PITCH = 132;                               // patch pitch (words): = 4 (mod 32) -> 8 lanes x 16 B hit 8 bank groups
+constexpr int F2_PATCH_BYTES = TC_BM * F2_PITCH * 4;        // 66 KB: patch[pixel][query] fp32, scaled by -log2(e), bias added
+constexpr int F2_WN = 48;                                   // class columns: 2c = hi, 2c + 1 = lo of class c
 constexpr int F2_W_BYTES = F2_QCH * F2_WN * 16;             // 10.5 KB: [q chunk][column][8 q] f16 (K-major B operand)
 constexpr int F2_CW = 16;                                   // compute warps
 constexpr int F2_THREADS = (2 + F2_CW) * 32;
 constexpr int F2_OFF_PATCH = F2_STAGES * F2_STAGE_BYTES;
-constexpr int F2_OFF_AMAT = F2_OFF_PATCH + 2 * F2_PLANE_BYTES;
-constexpr int F2_OFF_W = F2_OFF_AMAT + 2 * F2_AMAT_BYTES;
+constexpr int F2_OFF_W = F2_OFF_PATCH + F2_PATCH_BYTES;
 constexpr int F2_OFF_BIAS = F2_OFF_W + 2 * F2_W_BYTES;
 constexpr int F2_OFF_BARS = F2_OFF_BIAS + 512;
 constexpr int F2_SMEM = F2_OFF_BARS + 256 + 1024;
 constexpr uint32_t F2_TMEM_COLS = 512;
-constexpr uint32_t F2_COL_D1 = 0, F2_COL_D3 = 112, F2_COL_P = 304, F2_COL_D2 = 432;
+constexpr uint32_t F2_COL_D1 = 0, F2_COL_D3 = 112, F2_COL_P = 304;
 constexpr int F2_NBLK = 4;                                  // blocks (pairs of cell rows) per tile
 constexpr int F2_CELLS_X = TC_CONV_TW - 1, F2_CELLS_Y = TC_CONV_TH - 1;   // 15 x 7
 constexpr float F2_UFAST = 60.0f;                           // product form valid while every tap |u| <= 60
-constexpr float F2_UCLAMP = 30000.0f;                       // f16 range of the patch planes (|mask logit| > 2e4 is clamped)
 
 struct F2Params {
   const float* logits;   // (B, Q, K+1)
@@ -73,7 +73,7 @@ struct F2Params {
   int nkb;               // D / 32
   int tilesX, tilesY, ntiles;
   int debug;             // RBA_FS_DEBUG (profiling aid): 1 = always the exact path, 2 = no sigmoid math, 4 = no epilogue math
-  long long* tl;         // profiling aid (RBA_FS_TIMELINE): clock64 stamps of CTA 0, [item < 64][16 events]
+  long long* tl;         // profiling aid (RBA_FS_TIMELINE): clock64 stamps of CTA 0, [step < 64][16 events]
 };
 #define F2_STAMP(item, ev)                                                                   \
   do {                                                                                       \
@@ -82,10 +82,8 @@ struct F2Params {
 
 struct F2Bars {
   uint64_t full[F2_STAGES], empty[F2_STAGES];
-  uint64_t acc_full;                 // D1 of a tile complete (tcgen05.commit)
-  uint64_t patch_ready, patch_free;  // patch planes written (16 warps) / last interpolation of the tile has read them (commit)
-  uint64_t d2_full, d2_empty;        // interpolated item in TMEM (commit) / loaded by the 16 warps
-  uint64_t p_ready, p_empty;         // sigmoid operand of an item written (16 warps) / read by its contraction (commit)
+  uint64_t acc_full, acc_empty;      // D1 of a tile complete (tcgen05.commit) / drained by the 16 warps
+  uint64_t p_ready[2], p_empty[2];   // per warp pair: its k16 step of sigmoids is in its slot (8 warps) / has been read (commit)
   uint64_t d3_full, d3_empty;        // class sums of a block complete (commit) / loaded by the 16 warps
   uint32_t tmem_slot;
   uint32_t amax[2];                  // max |u| of the tile's taps (float bits), by tile parity
@@ -111,7 +109,7 @@ __device__ __forceinline__ void f2_split_f16(float a, float b, uint32_t& hi, uin
       : "r"(hi), "h"(m1), "f"(a), "f"(b));
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
 }
-// kind::f16 instruction descriptor with f16 (not bf16) operands: D fp32, A K-major, B K- or MN-major
+// kind::f16 instruction descriptor with f16 (not bf16) operands: D fp32, A K-major (or tensor memory), B K- or MN-major
 __host__ __device__ constexpr uint32_t f2_idesc(int M, int N, bool b_mn_major) {
   return (1u << 4) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
@@ -155,6 +153,42 @@ __device__ __forceinline__ float f2_rsum4(float v0, float v1, float v2, float v3
   return fmaf(cd, a0 + a1, ab * (a2 + a3)) * f2_rcp(ab * cd);
 }
 
+// One step of one run: 8 queries (nq of them real) x 4 output pixels.  tap -> patch[top-left tap][first query]; taps a b / c d.
+//   x0 = L + (R - L) / 8, d = (R - L) / 4 with L = ly1 a + ly c, R = ly1 b + ly d  (k1 = ly1 / 4, k2 = ly / 4)
+// Output: f16 hi / lo operand words, hi[px][k] = pack(s_px(query 2k), s_px(query 2k + 1)).
+template <bool FAST, bool FULL>
+__device__ __forceinline__ void f2_step_math(const float* __restrict__ tap, int nq, float ly, float ly1, float k1, float k2,
+                                             uint32_t (*hi)[4], uint32_t (*lo)[4]) {
+#pragma unroll
+  for (int h4 = 0; h4 < 2; ++h4) {
+    // 4 queries at a time: 16 live tap registers
+    const float4 a4 = *reinterpret_cast<const float4*>(tap + 4 * h4);
+    const float4 b4 = *reinterpret_cast<const float4*>(tap + F2_PITCH + 4 * h4);
+    const float4 c4 = *reinterpret_cast<const float4*>(tap + TC_CONV_TW * F2_PITCH + 4 * h4);
+    const float4 d4 = *reinterpret_cast<const float4*>(tap + (TC_CONV_TW + 1) * F2_PITCH + 4 * h4);
+    const float ta[4] = {a4.x, a4.y, a4.z, a4.w}, tb[4] = {b4.x, b4.y, b4.z, b4.w};
+    const float tc[4] = {c4.x, c4.y, c4.z, c4.w}, td[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+    for (int k2i = 0; k2i < 2; ++k2i) {
+      const int k = 2 * h4 + k2i;
+      if (FULL || 2 * k < nq) {
+        float sa[4], sb[4];
+        const float d0 = fmaf(k2, td[2 * k2i] - tc[2 * k2i], k1 * (tb[2 * k2i] - ta[2 * k2i]));
+        const float x0 = fmaf(0.5f, d0, fmaf(ly, tc[2 * k2i], ly1 * ta[2 * k2i]));
+        const float d1 = fmaf(k2, td[2 * k2i + 1] - tc[2 * k2i + 1], k1 * (tb[2 * k2i + 1] - ta[2 * k2i + 1]));
+        const float x1 = fmaf(0.5f, d1, fmaf(ly, tc[2 * k2i + 1], ly1 * ta[2 * k2i + 1]));
+        f2_sig4<FAST>(x0, d0, sa);
+        f2_sig4<FAST>(x1, d1, sb);
+#pragma unroll
+        for (int px = 0; px < 4; ++px) f2_split_f16(sa[px], sb[px], hi[px][k], lo[px][k]);
+      } else {
+#pragma unroll
+        for (int px = 0; px < 4; ++px) { hi[px][k] = 0u; lo[px][k] = 0u; }
+      }
+    }
+  }
+}
+
 struct F2Tile {
   int b, r0, c0;
 };
@@ -174,8 +208,7 @@ rba_einsum_score2_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __gri
                          const F2Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sPatch = smem + F2_OFF_PATCH;                    // [plane hi | lo][q chunk][pixel][8 q]
-  uint8_t* sAmat = smem + F2_OFF_AMAT;                      // [x0 | d][tap chunk][run][8 taps]
+  float* sPatch = reinterpret_cast<float*>(smem + F2_OFF_PATCH);   // [pixel][query], pitch F2_PITCH
   uint8_t* sW = smem + F2_OFF_W;                            // [buffer 0 | 1][q chunk][column][8 q]
   float* sBias = reinterpret_cast<float*>(smem + F2_OFF_BIAS);
   F2Bars* bars = reinterpret_cast<F2Bars*>(smem + F2_OFF_BARS);
@@ -185,10 +218,8 @@ rba_einsum_score2_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __gri
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmY_hi); prefetch_tmap(&tmY_lo); prefetch_tmap(&tmE_hi); prefetch_tmap(&tmE_lo);
     for (int s = 0; s < F2_STAGES; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-    mbar_init(&bars->acc_full, 1);
-    mbar_init(&bars->patch_ready, F2_CW); mbar_init(&bars->patch_free, 1);
-    mbar_init(&bars->d2_full, 1); mbar_init(&bars->d2_empty, F2_CW);
-    mbar_init(&bars->p_ready, F2_CW); mbar_init(&bars->p_empty, 1);
+    mbar_init(&bars->acc_full, 1); mbar_init(&bars->acc_empty, F2_CW);
+    for (int x = 0; x < 2; ++x) { mbar_init(&bars->p_ready[x], F2_CW / 2); mbar_init(&bars->p_empty[x], 1); }
     mbar_init(&bars->d3_full, 1); mbar_init(&bars->d3_empty, F2_CW);
     bars->amax[0] = 0u; bars->amax[1] = 0u;
     fence_barrier_init();
@@ -197,33 +228,12 @@ rba_einsum_score2_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __gri
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_slot)), "r"(F2_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // ---- constant interpolation weight matrices (interior weights; borders are handled by edge replication of the patch).
-  // run m = (cell row cr, output row dy, cell bc) = (m / 60, (m % 60) / 15, m % 15); tap k = (patch row k / 16, column k % 16).
-  //   x0 = u at the first pixel of the run = (1 - ly) (7/8 P[cr][bc] + 1/8 P[cr][bc+1]) + ly (7/8 P[cr+1][bc] + 1/8 P[cr+1][bc+1])
-  //   d  = step along the run               = (1 - ly) (P[cr][bc+1] - P[cr][bc]) / 4     + ly (P[cr+1][bc+1] - P[cr+1][bc]) / 4
-  // with ly = 1/8 + dy/4.  All products are odd / 64 or odd / 32: exact in f16.
-  for (int e = threadIdx.x; e < TC_BM * F2_KT; e += F2_THREADS) {
-    const int m = e / F2_KT, k = e - m * F2_KT;
-    float wx0 = 0.f, wd = 0.f;
-    if (m < 120) {
-      const int cr = m / 60, rem = m - 60 * cr, dy = rem / 15, bc = rem - 15 * dy;
-      const int rr = k >> 4, cc = k & 15;
-      const float ly = 0.125f + 0.25f * (float)dy;
-      const float wy = rr == cr ? 1.0f - ly : (rr == cr + 1 ? ly : 0.f);
-      wx0 = wy * (cc == bc ? 0.875f : (cc == bc + 1 ? 0.125f : 0.f));
-      wd = wy * (cc == bc ? -0.25f : (cc == bc + 1 ? 0.25f : 0.f));
-    }
-    const int off = ((k >> 3) * TC_BM + m) * 8 + (k & 7);
-    reinterpret_cast<__half*>(sAmat)[off] = __float2half_rn(wx0);
-    reinterpret_cast<__half*>(sAmat + F2_AMAT_BYTES)[off] = __float2half_rn(wd);
-  }
-  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_slot;
-  const int nit = (p.Q + 31) >> 5;                          // 32-query items per block
   const int nks = (p.Q + 15) >> 4;                          // k16 steps of the contraction
+  const int nturns = (nks + 1) & ~1;                        // turns per block: both pairs take the same number (the last may be empty)
 
   if (warp == 0) {
     // ===================== TMA producer + einsum issuer (one warp, software-pipelined over the stage ring) =====================
@@ -256,7 +266,7 @@ rba_einsum_score2_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __gri
     for (int lt = 0; lt < my_tiles; ++lt) {
       issue_loads_upto(g + F2_STAGES);                     // the first stages of this tile load under the previous tile's score phase
       if (lt > 0) {
-        mbar_wait_sleep(&bars->patch_ready, (uint32_t)(lt - 1) & 1);   // D1 of the previous tile has been drained
+        mbar_wait_sleep(&bars->acc_empty, (uint32_t)(lt - 1) & 1);   // D1 of the previous tile has been drained
         tc_fence_after();
       }
       for (int kb = 0; kb < p.nkb; ++kb, ++g) {
@@ -282,191 +292,155 @@ rba_einsum_score2_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __gri
       }
     }
   } else if (warp == 1) {
-    // ===================== score-phase MMA issuer (whole warp in uniform control flow, one elected lane issues) ==========
-    // Descriptors are (constant high word, low word = address / 16 | LBO / 16 << 16): every MMA of an item is the item's base
-    // low word plus a compile-time offset, so the issue loop is straight-line UTCHMMA with immediate adds.
-    constexpr uint32_t idI32 = f2_idesc(TC_BM, 32, true), idI16 = f2_idesc(TC_BM, 16, true);        // interpolation: B MN-major
-    constexpr uint32_t idC48 = f2_idesc(TC_BM, F2_WN, false), idC32 = f2_idesc(TC_BM, 32, false);   // contraction: K-major
-    constexpr uint32_t A_HI = 0x4000u | (128u >> 4);                // version 1, SBO = 128 B (next 8 runs)
-    constexpr uint32_t B_HI = 0x4000u | ((uint32_t)(TC_BM * 16) >> 4);   // SBO = 2048 B (next 8 queries)
-    constexpr uint32_t W_HI = 0x4000u | (128u >> 4);                // SBO = 128 B (next 8 columns)
-    const uint32_t smem0 = smem_u32(smem);
-    const uint32_t a_lo0 = ((smem0 + F2_OFF_AMAT) >> 4) | (((uint32_t)(TC_BM * 16) >> 4) << 16);   // LBO = 2048 B (next 8 taps)
-    const uint32_t b_lo0 = ((smem0 + F2_OFF_PATCH) >> 4) | ((128u >> 4) << 16);                    // LBO = 128 B (next 8 taps)
-    const uint32_t w_lo0 = ((smem0 + F2_OFF_W) >> 4) | (((uint32_t)(F2_WN * 16) >> 4) << 16);      // LBO = 768 B (next 8 queries)
-    uint32_t nd2 = 0, npc = 0, nb3 = 0;                     // interpolations / contractions / blocks issued so far
+    // ===================== contraction issuer (whole warp in uniform control flow, one elected lane issues) ==========
+    constexpr uint32_t idC = f2_idesc(TC_BM, F2_WN, false);         // f16 operands, B K-major
+    constexpr uint32_t W_HI = 0x4000u | (128u >> 4);                // version 1, SBO = 128 B (next 8 columns)
+    const uint32_t w_lo0 = ((smem_u32(smem) + F2_OFF_W) >> 4) | (((uint32_t)(F2_WN * 16) >> 4) << 16);   // LBO = 768 B (next 8 queries)
+    uint32_t nb3 = 0, ntx0 = 0, ntx1 = 0;                   // blocks / turns of pair 0, 1 issued so far
     int cur_b = -1;
     uint32_t wsel = 1;                                      // W buffer of the current image (toggles at every image change)
-    // interpolation of item (blk, i): D2 = [A_x0 ; A_d] P[taps of the block, queries 32 i ..]; K = 48 taps (32 in the last block)
-    auto interp = [&](int blk, int i, bool last_of_tile) {
-      F2_STAMP(nd2, 0);
-      mbar_wait(&bars->d2_empty, (nd2 & 1) ^ 1);            // every warp has loaded the previous item
-      tc_fence_after();
-      F2_STAMP(nd2, 1);
-      if (elect_one()) {
-        const uint32_t id = 32 * i + 16 >= F2_NQ ? idI16 : idI32;   // the last item of the 112-query patch holds 16 queries
-        const uint32_t b_lo = b_lo0 + (uint32_t)(512 * i + 32 * blk);   // (4 i chunks x 2048 B + 32 blk pixels x 16 B) / 16
-        const uint32_t d0 = tmem_base + F2_COL_D2;
-#pragma unroll
-        for (int kind = 0; kind < 2; ++kind) {
-#pragma unroll
-          for (int ks = 0; ks < 3; ++ks) {
-            if (ks == 2 && blk == F2_NBLK - 1) break;
-            const uint64_t ad = f2_desc(a_lo0 + kind * (F2_AMAT_BYTES >> 4) + ks * 256, A_HI);
-            umma_bf16(d0 + kind * 32, ad, f2_desc(b_lo + ks * 16, B_HI), id, ks != 0);
-            umma_bf16(d0 + kind * 32, ad, f2_desc(b_lo + ks * 16 + (F2_PLANE_BYTES >> 4), B_HI), id, 1);
-          }
-        }
-        umma_commit(&bars->d2_full);
-        if (last_of_tile) umma_commit(&bars->patch_free);
-      }
-      __syncwarp();
-      F2_STAMP(nd2, 2);
-      ++nd2;
-    };
-    // contraction of item i of a block: k16 steps 2 i and 2 i + 1 of D3[px] += S_hi [W_hi | W_lo] + S_lo W_hi
-    auto contraction = [&](int i) {
-      mbar_wait(&bars->p_ready, npc & 1);
-      if (i == 0) mbar_wait(&bars->d3_empty, (nb3 & 1) ^ 1);        // the previous block's class sums have been loaded
-      tc_fence_after();
-      F2_STAMP(npc, 3);
-      if (elect_one()) {
-        const uint32_t w_lo = w_lo0 + wsel * (F2_W_BYTES >> 4) + (uint32_t)(2 * i) * (2 * F2_WN);   // 2 chunks x 768 B per k16 step
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          if (2 * i + s < nks) {
-            const uint64_t wd = f2_desc(w_lo + s * (2 * F2_WN), W_HI);
-#pragma unroll
-            for (int px = 0; px < 4; ++px) {
-              const uint32_t dcol = tmem_base + F2_COL_D3 + px * F2_WN;
-              const uint32_t acol = tmem_base + F2_COL_P + px * 32 + s * 8;
-              umma_bf16_ts(dcol, acol, wd, idC48, (2 * i + s) != 0);        // S_hi [W_hi | W_lo]
-              umma_bf16_ts(dcol, acol + 16, wd, idC32, 1);                  // S_lo W_hi (+ S_lo W_lo[0:8], second order)
-            }
-          }
-        }
-        umma_commit(&bars->p_empty);
-        if (2 * i + 2 >= nks) umma_commit(&bars->d3_full);
-      }
-      __syncwarp();
-      F2_STAMP(npc, 4);
-      ++npc;
-      if (2 * i + 2 >= nks) ++nb3;
-    };
-    const int nitems = F2_NBLK * nit;
-    uint32_t lt = 0;
-    for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++lt) {
+    for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
       const F2Tile T = f2_tile(p, t);
       if (T.b != cur_b) { cur_b = T.b; wsel ^= 1; }
-      mbar_wait(&bars->patch_ready, lt & 1);                // patch planes written
-      tc_fence_after();
-      interp(0, 0, nitems == 1);
-      int blk = 0, i = 0;
 #pragma unroll 1
-      for (int n = 0; n < nitems; ++n) {
-        int nblk = blk, ni = i + 1;
-        if (ni == nit) { ni = 0; ++nblk; }
-        if (n + 1 < nitems) interp(nblk, ni, n + 2 == nitems);   // runs under the sigmoid math of item n
-        contraction(i);
-        blk = nblk; i = ni;
+      for (int blk = 0; blk < F2_NBLK; ++blk) {
+#pragma unroll 1
+        for (int ks = 0; ks < nturns; ++ks) {
+          // turn ks: D3[px] += (S_hi + S_lo)[runs, 16 ks ..] W[16 ks .., classes] from pair ks & 1's slot
+          const int x = ks & 1;
+          const uint32_t tx = x ? ntx1 : ntx0;
+          mbar_wait(&bars->p_ready[x], tx & 1);
+          if (ks == 0) mbar_wait(&bars->d3_empty, (nb3 & 1) ^ 1);   // the previous block's class sums have been loaded
+          tc_fence_after();
+          F2_STAMP(ntx0 + ntx1, 3);
+          if (elect_one()) {
+            if (ks < nks) {
+              const uint64_t wd = f2_desc(w_lo0 + wsel * (F2_W_BYTES >> 4) + (uint32_t)ks * (2 * F2_WN), W_HI);   // 2 chunks x 768 B / step
+#pragma unroll
+              for (int px = 0; px < 4; ++px) {
+                const uint32_t dcol = tmem_base + F2_COL_D3 + px * F2_WN;
+                const uint32_t acol = tmem_base + F2_COL_P + x * 64 + px * 16;
+                umma_bf16_ts(dcol, acol, wd, idC, ks != 0);
+                umma_bf16_ts(dcol, acol + 8, wd, idC, 1);
+              }
+            }
+            umma_commit(&bars->p_empty[x]);
+            if (ks == nturns - 1) umma_commit(&bars->d3_full);
+          }
+          __syncwarp();
+          F2_STAMP(ntx0 + ntx1, 4);
+          if (x) ++ntx1; else ++ntx0;
+        }
+        ++nb3;
       }
     }
   } else {
-    // ===================== drain + sigmoid + epilogue: warps 2..17 =====================
+    // ===================== drain + interpolation + sigmoid + epilogue: warps 2..17 =====================
     const int cw = warp - 2;
     const int ctid = cw * 32 + lane;
-    const int qd = warp & 3, grp = cw >> 2;                // TMEM lane quadrant; query sub-chunk / output pixel of this warp
+    const int qd = warp & 3, grp = cw >> 2;                // TMEM lane quadrant; warp group (= output pixel of the epilogue)
+    const int X = grp >> 1, e = grp & 1;                   // warp pair (owner of the k16 steps ks = X mod 2); 8-query half of a step
     const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
-    const int m = qd * 32 + lane;                          // run index inside a block (TMEM lane)
-    const int cr = m >= 60 ? 1 : 0, rem = m - 60 * cr, dy = rem / 15, bc = rem - 15 * dy;
+    const int m = qd * 32 + lane;                          // TMEM lane: low-res pixel in the drain, run in the score phase
+    // run m = (cell row cr, cell bc, output row dy), dy fastest: the 4 lanes of a cell read the same taps (broadcast)
+    const int mc = m < 120 ? m : 119;
+    const int cr = mc >= 60 ? 1 : 0, rem = mc - 60 * cr, bc = rem >> 2, dy = m & 3;     // (60 and 64 are multiples of 4)
+    // the half block (one cell row, 60 runs) sits on lanes 0..59 on even tiles and on lanes 64..123 on odd ones, so that over two
+    // tiles every SM sub-partition (TMEM lane quadrant) evaluates the same number of steps
+    const int mh = (m & 63) < 60 ? (m & 63) : 59, bch = mh >> 2;
+    const float ly = 0.125f + 0.25f * (float)dy, ly1 = 1.0f - ly, k1 = 0.25f * ly1, k2 = 0.25f * ly;
     const float SCALE = -1.4426950408889634f;
     const int dbg = p.debug;
     const bool stamp = cw == 0 && lane == 0;
-    uint32_t nd2 = 0, nb3 = 0, npc = 0;                    // D2 items loaded / blocks / P items stored so far
+    uint32_t nb3 = 0, ntx = 0;                             // block epilogues / turns of this pair so far
     int cur_b = -1;
     uint32_t wsel = 1;
     F2Tile prevT = {0, 0, 0};
 
-    // epilogue of block `blk` of tile T: output pixel `grp` of this thread's run
-    auto epilogue = [&](const F2Tile& T, int blk) {
+    // epilogue of block `blk` of tile T: output pixel `grp` of this thread's run.  D3 columns 2c / 2c + 1 hold the W_hi / W_lo
+    // parts of class c, scaled by 2 log2(e): sum_c tanh(s_c) = n - 2 sum_c 1 / (1 + 2^(s'_c)); classes in groups of four,
+    // padded classes hold exactly 0 and contribute tanh(0) = 0.  Loaded 8 classes at a time (16 registers).
+    auto epilogue = [&](const F2Tile& T, int blk, bool flip) {
       mbar_wait(&bars->d3_full, nb3 & 1);
       tc_fence_after();
-      uint32_t v[F2_WN];
-      tmem_ld32(tmem_base + lane_addr + F2_COL_D3 + grp * F2_WN, v);
-      tmem_ld16(tmem_base + lane_addr + F2_COL_D3 + grp * F2_WN + 32, v + 32);
-      tmem_ld_wait();
+      float r = 0.f;
+      int n = 0;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        if (8 * ch < p.Kc) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + lane_addr + F2_COL_D3 + grp * F2_WN + ch * 16, v);
+          tmem_ld_wait();
+          if (dbg & 4) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) r += __uint_as_float(v[c]);
+          } else {
+#pragma unroll
+            for (int g4 = 0; g4 < 2; ++g4) {
+              if (8 * ch + 4 * g4 < p.Kc) {
+                const int c = 8 * g4;
+                r += f2_rsum4(__uint_as_float(v[c]) + __uint_as_float(v[c + 1]), __uint_as_float(v[c + 2]) + __uint_as_float(v[c + 3]),
+                              __uint_as_float(v[c + 4]) + __uint_as_float(v[c + 5]), __uint_as_float(v[c + 6]) + __uint_as_float(v[c + 7]));
+                n += 4;
+              }
+            }
+          }
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->d3_empty);
       ++nb3;
-      const int i = T.r0 + 2 * blk + cr, j = T.c0 + bc;    // low-res coordinates of the cell's top-left tap
+      const bool half = blk == F2_NBLK - 1;                // the half block: 60 runs on lanes 0..59 or (flipped tiles) 64..123
+      const int i = T.r0 + 2 * blk + (half ? 0 : cr), j = T.c0 + (half ? bch : bc);   // low-res coordinates of the cell's top-left tap
       const int y = 4 * i + 2 + dy, x = 4 * j + 2 + grp;
-      const bool ok = m < (blk == F2_NBLK - 1 ? 60 : 120) && i <= p.h - 1 && j <= p.w - 1 && y >= 0 && y < p.H && x >= 0 && x < p.W;
-      if (!ok) return;
-      // class sums arrive scaled by 2 log2(e): sum_c tanh(s_c) = n - 2 sum_c 1 / (1 + 2^(s'_c)); classes in groups of four,
-      // padded classes hold exactly 0 and contribute tanh(0) = 0
-      float r = 0.f;
-      int n = 0;
-      if (dbg & 4) {
-#pragma unroll
-        for (int c = 0; c < 24; ++c) r += __uint_as_float(v[c]) + __uint_as_float(v[24 + c]);
-      } else {
-#pragma unroll
-        for (int g4 = 0; g4 < 6; ++g4) {
-          if (4 * g4 < p.Kc) {
-            const int c = 4 * g4;
-            r += f2_rsum4(__uint_as_float(v[c]) + __uint_as_float(v[24 + c]), __uint_as_float(v[c + 1]) + __uint_as_float(v[25 + c]),
-                          __uint_as_float(v[c + 2]) + __uint_as_float(v[26 + c]), __uint_as_float(v[c + 3]) + __uint_as_float(v[27 + c]));
-            n += 4;
-          }
-        }
-      }
-      p.rba[((size_t)T.b * p.H + y) * p.W + x] = fmaf(2.0f, r, -(float)n);
+      const bool ok = (half ? (flip ? m >= 64 && m < 124 : m < 60) : m < 120) && i <= p.h - 1 && j <= p.w - 1 && y >= 0 && y < p.H &&
+                      x >= 0 && x < p.W;
+      if (ok) p.rba[((size_t)T.b * p.H + y) * p.W + x] = fmaf(2.0f, r, -(float)n);
     };
 
     uint32_t lt = 0;
     for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++lt) {
       const F2Tile T = f2_tile(p, t);
       const bool newimg = T.b != cur_b;
+      if (ctid == 0) bars->amax[lt & 1] = 0u;               // last read two tiles ago
+      f2_bar_compute();                                     // every warp has finished the previous tile's steps: patch and bias are free
       if (newimg) {
-        // every warp is past the previous tile's drain (its items needed all 16 warps): the bias table is free
         cur_b = T.b;
         wsel ^= 1;
         if (ctid < F2_NQ) sBias[ctid] = (p.bias && ctid < p.Q) ? p.bias[(size_t)T.b * p.Q + ctid] * SCALE : 0.f;
         f2_bar_compute();
       }
-      // ---- drain the accumulator: TMEM lane = low-res pixel, column = query -> f16 hi / lo patch planes ----
-      mbar_wait(&bars->patch_free, (lt & 1) ^ 1);           // the previous tile's interpolations have read the patch
+      // ---- drain the accumulator: TMEM lane = low-res pixel, column = query -> patch[pixel][query] ----
       mbar_wait(&bars->acc_full, lt & 1);
       tc_fence_after();
-      if (ctid == 0) bars->amax[(lt + 1) & 1] = 0u;         // (read by every warp at the previous tile's first item)
       float am = 0.f;
       for (int chunk = grp; chunk * 16 < F2_NQ; chunk += 4) {
         const int q0 = chunk * 16;
         uint32_t v[16];
         tmem_ld16(tmem_base + lane_addr + F2_COL_D1 + (uint32_t)q0, v);
         tmem_ld_wait();
-        uint32_t hw[8], lw[8];
+        float* prow = sPatch + m * F2_PITCH + q0;
 #pragma unroll
-        for (int j2 = 0; j2 < 8; ++j2) {
-          float ua = fmaf(__uint_as_float(v[2 * j2]), SCALE, sBias[q0 + 2 * j2]);
-          float ub = fmaf(__uint_as_float(v[2 * j2 + 1]), SCALE, sBias[q0 + 2 * j2 + 1]);
-          am = fmaxf(am, fmaxf(fabsf(ua), fabsf(ub)));
-          ua = fminf(fmaxf(ua, -F2_UCLAMP), F2_UCLAMP);
-          ub = fminf(fmaxf(ub, -F2_UCLAMP), F2_UCLAMP);
-          f2_split_f16(ua, ub, hw[j2], lw[j2]);
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(sBias + q0 + 4 * j4);
+          float4 o;
+          o.x = fmaf(__uint_as_float(v[4 * j4]), SCALE, b4.x);
+          o.y = fmaf(__uint_as_float(v[4 * j4 + 1]), SCALE, b4.y);
+          o.z = fmaf(__uint_as_float(v[4 * j4 + 2]), SCALE, b4.z);
+          o.w = fmaf(__uint_as_float(v[4 * j4 + 3]), SCALE, b4.w);
+          am = fmaxf(fmaxf(am, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
+          *reinterpret_cast<float4*>(prow + 4 * j4) = o;
         }
-        uint8_t* dst = sPatch + (size_t)(2 * chunk) * (TC_BM * 16) + (size_t)m * 16;
-        *reinterpret_cast<uint4*>(dst) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        *reinterpret_cast<uint4*>(dst + TC_BM * 16) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
-        *reinterpret_cast<uint4*>(dst + F2_PLANE_BYTES) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-        *reinterpret_cast<uint4*>(dst + F2_PLANE_BYTES + TC_BM * 16) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
       }
       tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->acc_empty);         // the einsum of the next tile may start
       {
         const uint32_t wm = __reduce_max_sync(0xffffffffu, __float_as_uint(am));   // non-negative floats order like their bits
         if (lane == 0) atomicMax(&bars->amax[lt & 1], wm);
       }
+      f2_bar_compute();                                     // every pixel of the patch has been written
       // ---- image borders: replicate the edge into the out-of-range taps (CTA-uniform) ----
       {
         const int rtop = T.r0 < 0 ? 0 : -1;                                   // patch row above the image
@@ -474,42 +448,38 @@ rba_einsum_score2_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __gri
         const int cleft = T.c0 < 0 ? 0 : -1;
         const int cright = p.w - T.c0 <= TC_CONV_TW - 1 ? p.w - T.c0 : -1;
         if (rtop >= 0 || rbot >= 0 || cleft >= 0 || cright >= 0) {
-          f2_bar_compute();                                  // every pixel of the patch has been written
-          // rows first, then columns (so that the corners pick up the diagonal neighbour)
-          for (int e = ctid; e < 2 * TC_CONV_TW * 2 * F2_QCH; e += F2_CW * 32) {
-            const int which = e / (TC_CONV_TW * 2 * F2_QCH), r2 = e - which * (TC_CONV_TW * 2 * F2_QCH);
-            const int col = r2 / (2 * F2_QCH), pc = r2 - col * (2 * F2_QCH);    // pc = plane * 14 + q chunk
+          // rows first, then columns (so that the corners pick up the diagonal neighbour); F2_NQ / 4 = 28 float4 per pixel
+          for (int e4 = ctid; e4 < 2 * TC_CONV_TW * (F2_NQ / 4); e4 += F2_CW * 32) {
+            const int which = e4 / (TC_CONV_TW * (F2_NQ / 4)), r2 = e4 - which * (TC_CONV_TW * (F2_NQ / 4));
+            const int col = r2 / (F2_NQ / 4), q4 = r2 - col * (F2_NQ / 4);
             const int dstrow = which ? rbot : rtop;
             if (dstrow < 0) continue;
             const int srcrow = which ? rbot - 1 : 1;
-            uint8_t* base = sPatch + (size_t)(pc / F2_QCH) * F2_PLANE_BYTES + (size_t)(pc % F2_QCH) * (TC_BM * 16);
-            *reinterpret_cast<uint4*>(base + (dstrow * TC_CONV_TW + col) * 16) =
-                *reinterpret_cast<const uint4*>(base + (srcrow * TC_CONV_TW + col) * 16);
+            *reinterpret_cast<float4*>(sPatch + (dstrow * TC_CONV_TW + col) * F2_PITCH + 4 * q4) =
+                *reinterpret_cast<const float4*>(sPatch + (srcrow * TC_CONV_TW + col) * F2_PITCH + 4 * q4);
           }
           f2_bar_compute();
-          for (int e = ctid; e < 2 * TC_CONV_TH * 2 * F2_QCH; e += F2_CW * 32) {
-            const int which = e / (TC_CONV_TH * 2 * F2_QCH), r2 = e - which * (TC_CONV_TH * 2 * F2_QCH);
-            const int row = r2 / (2 * F2_QCH), pc = r2 - row * (2 * F2_QCH);
+          for (int e4 = ctid; e4 < 2 * TC_CONV_TH * (F2_NQ / 4); e4 += F2_CW * 32) {
+            const int which = e4 / (TC_CONV_TH * (F2_NQ / 4)), r2 = e4 - which * (TC_CONV_TH * (F2_NQ / 4));
+            const int row = r2 / (F2_NQ / 4), q4 = r2 - row * (F2_NQ / 4);
             const int dstcol = which ? cright : cleft;
             if (dstcol < 0) continue;
             const int srccol = which ? cright - 1 : 1;
-            uint8_t* base = sPatch + (size_t)(pc / F2_QCH) * F2_PLANE_BYTES + (size_t)(pc % F2_QCH) * (TC_BM * 16);
-            *reinterpret_cast<uint4*>(base + (row * TC_CONV_TW + dstcol) * 16) =
-                *reinterpret_cast<const uint4*>(base + (row * TC_CONV_TW + srccol) * 16);
+            *reinterpret_cast<float4*>(sPatch + (row * TC_CONV_TW + dstcol) * F2_PITCH + 4 * q4) =
+                *reinterpret_cast<const float4*>(sPatch + (row * TC_CONV_TW + srccol) * F2_PITCH + 4 * q4);
           }
+          f2_bar_compute();
         }
       }
-      fence_proxy_async();                                   // patch planes (generic-proxy stores) -> tcgen05.mma (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->patch_ready);
+      const bool fast = !(dbg & 1) && bars->amax[lt & 1] <= __float_as_uint(F2_UFAST);
       // ---- deferred: the last block of the previous tile (its contraction ran under this drain) ----
-      if (lt > 0) epilogue(prevT, F2_NBLK - 1);
+      if (lt > 0) epilogue(prevT, F2_NBLK - 1, ((lt - 1) & 1) != 0);
       if (newimg) {
-        // ---- per image: class probabilities as the f16 B operand [q chunk][column: hi 0..23 | lo 24..47][8 q], scaled by
-        // 2 log2(e) (tanh(s) = 1 - 2 / (1 + 2^(2 log2(e) s))).  Buffer wsel: the other one may still feed the previous
-        // image's last contraction ----
+        // ---- per image: class probabilities as the f16 B operand [q chunk][column][8 q], scaled by 2 log2(e)
+        // (tanh(s) = 1 - 2 / (1 + 2^(2 log2(e) s))), column 2c = hi, 2c + 1 = lo of class c.  Buffer wsel: the other one may
+        // still feed the previous image's last contraction ----
         uint4* wz = reinterpret_cast<uint4*>(sW + wsel * F2_W_BYTES);
-        for (int e = ctid; e < F2_W_BYTES / 16; e += F2_CW * 32) wz[e] = make_uint4(0u, 0u, 0u, 0u);
+        for (int e4 = ctid; e4 < F2_W_BYTES / 16; e4 += F2_CW * 32) wz[e4] = make_uint4(0u, 0u, 0u, 0u);
         f2_bar_compute();
         if (ctid < p.Q) {
           const int q = ctid;
@@ -523,102 +493,68 @@ rba_einsum_score2_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __gri
           for (int c = 0; c < p.Kc; ++c) {
             const float pv = expf(lg[c] - mx) * inv;
             const __half hh = __float2half_rn(pv);
-            base[c * 8] = hh;
-            base[(24 + c) * 8] = __float2half_rn(pv - __half2float(hh));
+            base[(2 * c) * 8] = hh;
+            base[(2 * c + 1) * 8] = __float2half_rn(pv - __half2float(hh));
           }
         }
-        fence_proxy_async();
+        fence_proxy_async();                                 // generic-proxy stores -> tcgen05.mma (async proxy) reads
         f2_bar_compute();
       }
-      // ---- sigmoid items: per block, per 32 queries; the D2 registers of item n + 1 are fetched under the math of item n ----
-      uint32_t cx[8], cd[8], nx[8], nd[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) { cx[e] = cd[e] = nx[e] = nd[e] = 0u; }
-      mbar_wait(&bars->d2_full, nd2 & 1);
-      tc_fence_after();
-      const bool fast = !(dbg & 1) && bars->amax[lt & 1] <= __float_as_uint(F2_UFAST);
-      if (8 * grp < p.Q) {
-        tmem_ld8(tmem_base + lane_addr + F2_COL_D2 + (uint32_t)(8 * grp), cx);
-        tmem_ld8(tmem_base + lane_addr + F2_COL_D2 + 32 + (uint32_t)(8 * grp), cd);
-      }
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->d2_empty);
-      ++nd2;
+      // ---- score steps: block blk, k16 step ks = 2 kk + X, queries qb = 16 ks + 8 e .. + 7 of this thread's run ----
 #pragma unroll 1
       for (int blk = 0; blk < F2_NBLK; ++blk) {
-        const bool active = blk < F2_NBLK - 1 || qd < 2;     // the last block holds 60 runs: lanes 0..59
+        const bool flip = (lt & 1) != 0;
+        const bool active = blk < F2_NBLK - 1 || (flip ? qd >= 2 : qd < 2);   // the last block holds 60 runs
+        const float* tap = sPatch + (blk < F2_NBLK - 1 ? (2 * blk + cr) * TC_CONV_TW + bc : 2 * blk * TC_CONV_TW + bch) * F2_PITCH;
 #pragma unroll 1
-        for (int i = 0; i < nit; ++i) {
-          const int qb = 32 * i + 8 * grp;                   // first query of this warp's sub-chunk
+        for (int kk = 0; kk < nturns / 2; ++kk) {
+          const int ks = 2 * kk + X;
+          const int qb = 16 * ks + 8 * e;
           const bool work = active && qb < p.Q && !(dbg & 2);
-          const bool last = blk == F2_NBLK - 1 && i == nit - 1;
-          const int ni = i + 1 < nit ? i + 1 : 0, nblk = i + 1 < nit ? blk : blk + 1;
-          const bool nwork = (nblk < F2_NBLK - 1 || qd < 2) && 32 * ni + 8 * grp < p.Q;
-          if (stamp) F2_STAMP(npc, 8);
+          if (stamp) F2_STAMP(ntx, 8);
           uint32_t hi[4][4], lo[4][4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (k == 3 && !last) {
-              // D2 of the next item (its interpolation was issued when this item's registers were loaded)
-              if (stamp) F2_STAMP(npc, 9);
-              mbar_wait(&bars->d2_full, nd2 & 1);
-              tc_fence_after();
-              if (stamp) F2_STAMP(npc, 10);
-              if (nwork) {
-                tmem_ld8(tmem_base + lane_addr + F2_COL_D2 + (uint32_t)(8 * grp), nx);
-                tmem_ld8(tmem_base + lane_addr + F2_COL_D2 + 32 + (uint32_t)(8 * grp), nd);
-              }
-            }
-            if (work && qb + 2 * k < p.Q) {
-              float sa[4], sb[4];
-              if (fast) {
-                f2_sig4<true>(__uint_as_float(cx[2 * k]), __uint_as_float(cd[2 * k]), sa);
-                f2_sig4<true>(__uint_as_float(cx[2 * k + 1]), __uint_as_float(cd[2 * k + 1]), sb);
-              } else {
-                f2_sig4<false>(__uint_as_float(cx[2 * k]), __uint_as_float(cd[2 * k]), sa);
-                f2_sig4<false>(__uint_as_float(cx[2 * k + 1]), __uint_as_float(cd[2 * k + 1]), sb);
-              }
-#pragma unroll
-              for (int px = 0; px < 4; ++px) f2_split_f16(sa[px], sb[px], hi[px][k], lo[px][k]);
+          if (work) {
+            // straight-line variants (no branch inside: the scheduler interleaves the 8 queries' MUFU chains)
+            const int nq = p.Q - qb >= 8 ? 8 : p.Q - qb;
+            if (fast) {
+              if (nq == 8) f2_step_math<true, true>(tap + qb, 8, ly, ly1, k1, k2, hi, lo);
+              else f2_step_math<true, false>(tap + qb, nq, ly, ly1, k1, k2, hi, lo);
             } else {
-#pragma unroll
-              for (int px = 0; px < 4; ++px) { hi[px][k] = 0u; lo[px][k] = 0u; }
+              if (nq == 8) f2_step_math<false, true>(tap + qb, 8, ly, ly1, k1, k2, hi, lo);
+              else f2_step_math<false, false>(tap + qb, nq, ly, ly1, k1, k2, hi, lo);
             }
+          } else {
+#pragma unroll
+            for (int px = 0; px < 4; ++px)
+#pragma unroll
+              for (int k = 0; k < 4; ++k) { hi[px][k] = 0u; lo[px][k] = 0u; }
           }
-          if (stamp) F2_STAMP(npc, 11);
-          mbar_wait(&bars->p_empty, (npc & 1) ^ 1);          // the contraction of the previous item has read the operand
+          if (stamp) F2_STAMP(ntx, 11);
+          // the previous block's class sums (its last contraction was issued about a step ago); must precede the wait for the
+          // slot: the first contraction of this block needs every warp's d3_empty
+          if (kk == 0 && blk > 0) epilogue(T, blk - 1, false);
+          mbar_wait(&bars->p_empty[X], (ntx & 1) ^ 1);      // the contraction of this pair's previous step has read the slot
           tc_fence_after();
-          if (stamp) F2_STAMP(npc, 12);
-          if (active) {
-            const uint32_t pa = tmem_base + lane_addr + F2_COL_P + (uint32_t)(4 * grp);
+          if (stamp) F2_STAMP(ntx, 12);
+          if (active && ks < nks) {
+            const uint32_t pa = tmem_base + lane_addr + F2_COL_P + (uint32_t)(X * 64 + 4 * e);
 #pragma unroll
             for (int px = 0; px < 4; ++px) {
-              tmem_st4v(pa + px * 32, hi[px][0], hi[px][1], hi[px][2], hi[px][3]);
-              tmem_st4v(pa + px * 32 + 16, lo[px][0], lo[px][1], lo[px][2], lo[px][3]);
+              tmem_st4v(pa + px * 16, hi[px][0], hi[px][1], hi[px][2], hi[px][3]);
+              tmem_st4v(pa + px * 16 + 8, lo[px][0], lo[px][1], lo[px][2], lo[px][3]);
             }
+            tmem_st_wait();
           }
-          tmem_ld_wait();
-          tmem_st_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) {
-            if (!last) mbar_arrive(&bars->d2_empty);
-            mbar_arrive(&bars->p_ready);
-          }
-          if (stamp) F2_STAMP(npc, 13);
-          if (!last) ++nd2;
-          ++npc;
-          if (i == 0 && blk > 0) epilogue(T, blk - 1);
-          if (stamp) F2_STAMP(npc - 1, 14);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) { cx[e] = nx[e]; cd[e] = nd[e]; }
+          if (lane == 0) mbar_arrive(&bars->p_ready[X]);
+          if (stamp) F2_STAMP(ntx, 13);
+          ++ntx;
         }
       }
       prevT = T;
     }
-    if (lt > 0) epilogue(prevT, F2_NBLK - 1);
+    if (lt > 0) epilogue(prevT, F2_NBLK - 1, ((lt - 1) & 1) != 0);
     tc_fence_before();
   }
   __syncthreads();
@@ -696,16 +632,17 @@ int einsum_score2_launch(const uint16_t* e_hi, const uint16_t* e_lo, const float
   rba_einsum_score2_kernel<<<grid, F2_THREADS, F2_SMEM, st>>>(ty_hi, ty_lo, te_hi, te_lo, p);
   RBA_LAUNCHED();
   if (timeline) {
-    static long long h[64 * 16];
+    static long long h2[64 * 16];
     RBA_CUDA(cudaStreamSynchronize(st));
-    RBA_CUDA(cudaMemcpy(h, tl_dev, sizeof(h), cudaMemcpyDeviceToHost));
-    const long long t0 = h[0];
-    fprintf(stderr, "[score2 timeline, CTA 0, clocks since the first interpolation wait]\n item | mma: start d2empty interp contr einsum | cmp: start d2full loaded mathdone pempty stored end\n");
+    RBA_CUDA(cudaMemcpy(h2, tl_dev, sizeof(h2), cudaMemcpyDeviceToHost));
+    long long t0 = h2[8];
+    fprintf(stderr, "[score2 timeline, CTA 0, clocks since the first step]\n turn | mma: p_ready issued | pair-0 warp: start mathdone slotfree stored\n");
     for (int i = 0; i < 40; ++i) {
       fprintf(stderr, "%5d |", i);
-      for (int e = 0; e < 5; ++e) fprintf(stderr, " %7lld", h[i * 16 + e] ? h[i * 16 + e] - t0 : -1);
+      for (int ev = 3; ev < 5; ++ev) fprintf(stderr, " %7lld", h2[i * 16 + ev] ? h2[i * 16 + ev] - t0 : -1);
       fprintf(stderr, " |");
-      for (int e = 8; e < 15; ++e) fprintf(stderr, " %7lld", h[i * 16 + e] ? h[i * 16 + e] - t0 : -1);
+      const int evs[4] = {8, 11, 12, 13};
+      for (int k = 0; k < 4; ++k) fprintf(stderr, " %7lld", h2[i * 16 + evs[k]] ? h2[i * 16 + evs[k]] - t0 : -1);
       fprintf(stderr, "\n");
     }
   }

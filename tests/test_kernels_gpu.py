@@ -439,15 +439,14 @@ def test_einsum_score_fused(dev, B, Q, K, D, h, w, crop):
     rba, sem = ops.einsum_score_fused(e_pl, f_pl, logits.to(dev), (H, W), bias=bias.to(dev), want_sem_seg=True)
     assert (sem.cpu() - sem_ref).abs().max() < 5e-5, float((sem.cpu() - sem_ref).abs().max())
     assert (rba.cpu() - rba_ref).abs().max() < 5e-5
-    rba2 = ops.einsum_score_fused(e_pl, f_pl, logits.to(dev), (H, W), bias=bias.to(dev))
-    assert (rba2 - rba).abs().max() < 2e-5      # score-only launches run on the tcgen05 score phase: same value, other rounding
-    assert (rba2.cpu() - rba_ref).abs().max() < 5e-5
-    try:                                        # the first-generation kernel on the same RbA-only launch
-        ops.set_fused_score_variant(1)
-        rba1 = ops.einsum_score_fused(e_pl, f_pl, logits.to(dev), (H, W), bias=bias.to(dev))
-    finally:
-        ops.set_fused_score_variant(2)
-    assert (rba1.cpu() - rba_ref).abs().max() < 5e-5
+    for variant in (1, 2):                      # RbA-only launch on the mma.sync / on the tcgen05 score phase
+        try:
+            ops.set_fused_score_variant(variant)
+            rba2 = ops.einsum_score_fused(e_pl, f_pl, logits.to(dev), (H, W), bias=bias.to(dev))
+        finally:
+            ops.set_fused_score_variant(0)
+        assert (rba2 - rba).abs().max() < 2e-5, variant     # same value as the sem_seg launch, other rounding
+        assert (rba2.cpu() - rba_ref).abs().max() < 5e-5, variant
     # same answer as the two-kernel path (GEMM -> pred_masks -> rba_score_fused)
     rba3 = ops.score_fused(masks.to(dev), logits.to(dev), (H, W))
     assert (rba3 - rba).abs().max() < 5e-5
@@ -484,11 +483,43 @@ def test_einsum_score_fused_large_logits(dev, variant, scale, bias_shift):
         ops.set_fused_score_variant(variant)
         rba = ops.einsum_score_fused(e_pl, f_pl, logits.to(dev), (H, W), bias=bias.to(dev))
     finally:
-        ops.set_fused_score_variant(2)
+        ops.set_fused_score_variant(0)
     # fp32 einsum of logits of magnitude `scale * 3` carries ~1e-7 relative error into the exponent
     tol = 5e-5 if scale <= 30 else 2e-4
     err = (rba.cpu().double() - ref).abs().max().item()
     assert err < tol, err
+
+
+@pytest.mark.parametrize("variant", [2, 1])
+def test_einsum_score_fused_many_tiles_per_cta(dev, variant):
+    """More tiles than SMs (each persistent CTA walks 3-4 tiles and crosses image boundaries): the deferred epilogue of a tile's
+    last block, the per-image class-probability buffers and the alternating half block of the second-generation kernel.
+    Reference: the same arithmetic in PyTorch fp32 on the GPU."""
+    B, Q, K, D, h, w = 3, 100, 19, 64, 96, 160
+    g = torch.Generator().manual_seed(11)
+    E = torch.randn(B, Q, D, generator=g) / math.sqrt(D) * 3.0
+    Fm = torch.randn(B, h, w, D, generator=g)
+    bias = torch.randn(B, Q, generator=g) - 1.0
+    logits = torch.randn(B, Q, K + 1, generator=g) * 2.0
+    H, W = 4 * h - 3, 4 * w
+    (e_hi, e_lo), Ex = planes(E.view(B * Q, D), dev)
+    (f_hi, f_lo), Fx = planes(Fm.view(-1, D), dev)
+    e_pl = (e_hi.view(B, Q, D), e_lo.view(B, Q, D))
+    f_pl = (f_hi.view(B, h, w, D), f_lo.view(B, h, w, D))
+    masks = (torch.einsum("bqc,bhwc->bqhw", Ex.view(B, Q, D).double().to(dev), Fx.view(B, h, w, D).double().to(dev))
+             + bias.double().to(dev)[:, :, None, None]).float()
+    ref = torch.empty(B, H, W, device=dev)
+    for b in range(B):
+        up = F.interpolate(masks[b:b + 1], size=(4 * h, 4 * w), mode="bilinear", align_corners=False)[0, :, :H, :W]
+        sem = torch.einsum("qc,qhw->chw", logits[b].to(dev).softmax(-1)[:, :-1], up.sigmoid())
+        ref[b] = -sem.tanh().sum(0)
+    try:
+        ops.set_fused_score_variant(variant)
+        rba = ops.einsum_score_fused(e_pl, f_pl, logits.to(dev), (H, W), bias=bias.to(dev))
+    finally:
+        ops.set_fused_score_variant(0)
+    err = (rba - ref).abs().max().item()
+    assert err < 5e-5, err
 
 
 def test_einsum_score_fused_energy_and_void(dev):
