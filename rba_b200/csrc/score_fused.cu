@@ -175,9 +175,9 @@ __device__ __forceinline__ void fs_interp8(const float* tp, uint32_t a0, uint32_
   fs_mma_tf32(u, a0, a1, hi, __float_as_uint(lo));
 }
 
-// ---- unclamped batched sigmoids: the drain clamps every patch value to <= FS_UMAX, and the interpolation weights are
-// convex, so u <= FS_UMAX here and products of up to four (1 + 2^u) stay below 2^121 ----
-constexpr float FS_UMAX = 30.0f;      // sigmoid(x) for -x log2(e) > 30 is < 2^-30: the clamp changes nothing visible in fp32
+// ---- unclamped batched sigmoids (kept for the profiling variants; the launch path clamps the interpolated value, see
+// fs_sig_frag_u): valid only when the caller guarantees u <= FS_UMAX ----
+constexpr float FS_UMAX = 30.0f;      // sigmoid(x) for -x log2(e) > 30 is < 2^-30
 __device__ __forceinline__ void fs_sigmoid2u(float u0, float u1, float& s0, float& s1) {
   const float a0 = 1.0f + fs_ex2(u0), a1 = 1.0f + fs_ex2(u1);
   const float r = fs_rcp(a0 * a1);

@@ -142,15 +142,22 @@ class MaskFormer(nn.Module):
         return self._engine
 
     def _batch(self, batched_inputs):
+        """(B,3,Hmax,Wmax) batch + the per-image (h, w).  Images of different sizes are padded bottom / right to the largest one
+        like detectron2's ImageList.from_tensors does (maskformer_model.py:255-257: zeros AFTER normalisation, i.e. the pixel
+        mean before it); the engine then pads the batch to SIZE_DIVISIBILITY the same way."""
         ims = [x["image"] for x in batched_inputs]
-        shapes = {tuple(im.shape) for im in ims}
-        if len(shapes) != 1:
-            raise RbaError("rba_b200.MaskFormer: images of one batch must share one size "
-                           f"(got {sorted(shapes)}); call per image like evaluate_ood.py does")
-        dt = {im.dtype for im in ims}
-        tgt = torch.uint8 if dt == {torch.uint8} else torch.float32
-        ims = [im.to(self._device, tgt, non_blocking=True) for im in ims]
-        return torch.stack(ims).contiguous()
+        sizes = [(int(im.shape[-2]), int(im.shape[-1])) for im in ims]
+        if len(set(sizes)) == 1:
+            dt = {im.dtype for im in ims}
+            tgt = torch.uint8 if dt == {torch.uint8} else torch.float32
+            ims = [im.to(self._device, tgt, non_blocking=True) for im in ims]
+            return torch.stack(ims).contiguous(), sizes
+        Hm, Wm = max(h for h, _ in sizes), max(w for _, w in sizes)
+        mean = torch.tensor(self.mc.pixel_mean, dtype=torch.float32, device=self._device).view(3, 1, 1)
+        batch = mean.expand(3, Hm, Wm).repeat(len(ims), 1, 1, 1).contiguous()
+        for b, im in enumerate(ims):
+            batch[b, :, :sizes[b][0], :sizes[b][1]] = im.to(self._device, torch.float32, non_blocking=True)
+        return batch, sizes
 
     @torch.no_grad()
     def forward(self, batched_inputs, include_void=False, return_separately=False, return_aux=False,
@@ -162,7 +169,7 @@ class MaskFormer(nn.Module):
             return self._forward_panoptic(batched_inputs, include_void, panoptic_ood_threshold, panoptic_pixel_min, return_panoptic_ood)
         if return_ood_pred and not self.mc.ood_prediction:
             raise RbaError("return_ood_pred needs the DenseHybrid head (MODEL.MASK_FORMER.DENSE_HYBRID_LOSS: True)")
-        images = self._batch(batched_inputs)
+        images, sizes = self._batch(batched_inputs)
         B, _, H, W = images.shape
         eng = self.engine()
         eng.set_score("rba", include_void=include_void)     # semantic_inference_with_void (maskformer_model.py:388-392)
@@ -170,9 +177,10 @@ class MaskFormer(nn.Module):
                           ood_pred=return_ood_pred)
         results = []
         for b, inp in enumerate(batched_inputs):
-            r = out["sem_seg"][b]
-            h, w = inp.get("height", H), inp.get("width", W)
-            if (h, w) != (H, W):  # sem_seg_postprocess resize (detectron2): bilinear, align_corners=False
+            hi, wi = sizes[b]
+            r = out["sem_seg"][b][:, :hi, :wi]               # sem_seg_postprocess: crop to the image ...
+            h, w = inp.get("height", hi), inp.get("width", wi)
+            if (h, w) != (hi, wi):  # ... and resize (detectron2): bilinear, align_corners=False
                 r = F.interpolate(r[None], size=(h, w), mode="bilinear", align_corners=False)[0]
             results.append({"sem_seg": r})
         if return_separately:
@@ -188,7 +196,9 @@ class MaskFormer(nn.Module):
         inference on the post-processed masks (:325-340).  The engine supplies sem_seg, the RbA score (= the open-panoptic
         branch's ood_mask, :456-458) and the head outputs in one forward."""
         from .panoptic import panoptic_inference
-        images = self._batch(batched_inputs)
+        images, sizes = self._batch(batched_inputs)
+        if len(set(sizes)) != 1:
+            raise RbaError("rba_b200.MaskFormer: the panoptic branch takes images of one size per batch")
         B, _, H, W = images.shape
         eng = self.engine()
         eng.set_score("rba", include_void=include_void)
@@ -224,11 +234,15 @@ class MaskFormer(nn.Module):
     def score(self, batched_inputs, score_func="rba"):
         """Fused anomaly score of evaluate_ood.py --score_func: "rba" (get_RbA, :143-150), "pebal"/"energy"
         (get_energy, :152-159: -logsumexp over the class planes) or "dense_hybrid" (get_densehybrid_score, :161-173:
-        energy + log p(outlier) from the ood_pred head).  sem_seg is never materialised."""
-        images = self._batch(batched_inputs)
+        energy + log p(outlier) from the ood_pred head).  sem_seg is never materialised.  Returns (B,H,W), or a list of per-image
+        maps when the images of the batch differ in size."""
+        images, sizes = self._batch(batched_inputs)
         eng = self.engine()
         eng.set_score(score_func, include_void=False)
-        return eng.forward(images, rba=True)["rba"]
+        score = eng.forward(images, rba=True)["rba"]
+        if len(set(sizes)) == 1:
+            return score
+        return [score[b, :h, :w] for b, (h, w) in enumerate(sizes)]      # mixed sizes: one cropped map per image
 
 
 def build_model(cfg):

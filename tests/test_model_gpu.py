@@ -562,3 +562,26 @@ def test_panoptic_on_model_matches_host_inference(dev):
     agree = (pan == want[0]).float().mean().item()
     assert agree > 0.999 and len(info) == len(want[1]), (agree, len(info), len(want[1]))
     assert (out["sem_seg"] - res[0]["sem_seg"]).abs().max() < 1e-5
+
+
+def test_mixed_size_batch_is_padded_like_image_list(dev):
+    """Images of different sizes in one batch: detectron2's ImageList.from_tensors pads them (zeros after normalisation) to the
+    largest one (maskformer_model.py:255-257) and sem_seg_postprocess crops each result to its image (:318-322).  Oracle: the
+    restatement of exactly that (oracle.preprocess / forward)."""
+    case = CASES["tiny_1dl"]
+    mc = case_model_config(case)
+    sd = weights.init_state_dict(mc, seed=case["seed"], perturb=case["perturb"])
+    g = torch.Generator().manual_seed(5)
+    ims = [torch.randint(0, 256, (3, 64, 96), generator=g, dtype=torch.uint8),
+           torch.randint(0, 256, (3, 48, 80), generator=g, dtype=torch.uint8),
+           torch.randint(0, 256, (3, 64, 70), generator=g, dtype=torch.uint8)]
+    ref = O.forward(sd, mc, ims)
+    model = rba_b200.MaskFormer(mc)
+    model.load_state_dict(sd)
+    model.to(dev).eval()
+    out = model([{"image": im.to(dev)} for im in ims])
+    scores = model.rba([{"image": im.to(dev)} for im in ims])
+    for b, im in enumerate(ims):
+        assert out[b]["sem_seg"].shape[-2:] == im.shape[-2:] == scores[b].shape
+        assert (out[b]["sem_seg"].cpu() - ref["sem_seg"][b]).abs().max() < 1e-3
+        assert (scores[b].cpu() - ref["rba"][b]).abs().max() < 1e-3
