@@ -11,15 +11,16 @@
 //              (bulk copy) into one of three shared-memory stages                                     55.3 KB in flight / stage
 //   S          tcgen05.mma M=128 N=144 K=32: query rows 0..127 -> TMEM buffer S1[item & 1]; query rows 128..143 (+112 rows
 //              that are never read) -> S2.  A = q (K-major), B = k (K-major), 6 MMAs each.
-//   softmax    thread per (row, half of the 144 keys): tcgen05.ld its 72 logits, bias (+ mask), max / sum exchanged with
-//              the thread that owns the other half, exp2, bf16 hi/lo split of the UN-normalised probabilities written
+//   softmax    thread per (row, quarter of the 144 keys): tcgen05.ld its 36 logits, bias (+ mask), max / sum exchanged with
+//              the threads that own the other quarters, exp2, bf16 hi/lo split of the UN-normalised probabilities written
 //              back over S with tcgen05.st (P aliases S: 144 fp32 columns = 72 + 72 packed bf16x2 columns).
 //   O          tcgen05.mma M=128 N=32 K=144 with A = P read from TENSOR MEMORY and B = v straight from the TMA tile
 //              (MN-major descriptor: no transpose anywhere), 27 MMAs per tile.
 //   epilogue   O rows * 1 / row sum -> bf16 hi/lo -> global planes.
 // The MMAs of item i+1 (S) run under the softmax of item i; TMA runs two items ahead.  Warps: 0 = TMA producer, 1 = MMA
 // issuer of the 128-row tile + TMEM owner, 2 = MMA issuer of the 16-row tile (two issuers keep the two tiles' chains
-// independent), 3 idle, 4..11 = softmax (quadrant w % 4, key half (w - 4) / 4): every warp serves the 128-row tile of every
+// independent), 3 idle, 4..19 = softmax (quadrant w % 4, key quarter (w - 4) / 4; RBA_WT_PARTS=2 restores the 12-warp form
+// with 72 keys per thread: 7.0 instead of 5.8 ms per 8 images, profiles/r2i_wattn_*): every warp serves the 128-row tile of every
 // item, and the two warps of quadrant i % 4 also serve the 16-row tile of item i, whose rows the issuer places on that
 // quadrant's lanes.
 // TMEM columns: S1[0] 0..143 | S1[1] 144..287 | S2 288..431 | O1 432..463 | O2 464..495 (496 of 512: S2 cannot be double
@@ -41,10 +42,11 @@ constexpr int WT_BIAS_FLOATS = 532;                       // == WM_BIAS_PITCH of
 constexpr int WT_BIAS_BYTES = WT_BIAS_FLOATS * 4;         // 2128 (multiple of 16: bulk-copy granularity)
 constexpr int WT_STAGE_BYTES = 6 * WT_TILE_BYTES + 3072;  // 58368 = 57 * 1024
 constexpr int WT_STAGES = 3;
-constexpr int WT_THREADS = 12 * 32;
+constexpr int WT_MAXPARTS = 4;                             // softmax warps per TMEM lane quadrant (key partitions of a row): 2 or 4
+constexpr int WT_THREADS_MAX = (4 + 4 * WT_MAXPARTS) * 32;
 constexpr uint32_t WT_TMEM_COLS = 512;
 constexpr int WT_COL_S1 = 0, WT_COL_S2 = 288, WT_COL_O1 = 432, WT_COL_O2 = 464;
-constexpr int WT_EXCH_FLOATS = 2 /*parity*/ * 2 /*half*/ * 160 /*rows (144, padded)*/;
+constexpr int WT_EXCH_FLOATS = 2 /*parity*/ * WT_MAXPARTS /*key partition*/ * 160 /*rows (144, padded)*/;
 constexpr int WT_SMEM = WT_STAGES * WT_STAGE_BYTES + 2 * WT_EXCH_FLOATS * 4 + 256 + 1024;
 
 struct WtParams {
@@ -64,7 +66,7 @@ struct WtParams {
     if (p.tl && blockIdx.x == 0 && (item) < 32) p.tl[(item) * 16 + (ev)] = clock64();        \
   } while (0)
 
-__device__ __forceinline__ void wt_pair_bar(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void wt_part_bar(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 // 16 consecutive output values * inv -> bf16 hi / lo planes, two 16-byte stores each (g is a multiple of 16 elements)
 __device__ __forceinline__ void wt_store16(uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo, int64_t g, const uint32_t* o, float inv) {
@@ -77,6 +79,14 @@ __device__ __forceinline__ void wt_store16(uint16_t* __restrict__ out_hi, uint16
   ph[1] = make_uint4(h[4], h[5], h[6], h[7]);
   pl[0] = make_uint4(l[0], l[1], l[2], l[3]);
   pl[1] = make_uint4(l[4], l[5], l[6], l[7]);
+}
+
+__device__ __forceinline__ void wt_store8(uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo, int64_t g, const uint32_t* o, float inv) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split_pack2(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv, h[i], l[i]);
+  *reinterpret_cast<uint4*>(out_hi + g) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(out_lo + g) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 // barriers (shared memory, 8 bytes each)
@@ -97,7 +107,7 @@ __device__ __forceinline__ void wt_item(const WtParams& p, int64_t it, int64_t& 
 // Per-thread state of a softmax warp: quadrant = TMEM lane quadrant (= SM sub-partition) of the warp, half = which 72 of the
 // 144 keys this thread owns.
 struct WtThread {
-  int quadrant, half, lane;
+  int quadrant, half, lane;      // half = key partition index (0 .. PARTS - 1)
   uint32_t lane_addr;
   int pair_bar;
 };
@@ -105,7 +115,7 @@ struct WtThread {
 // One softmax pass over one S tile of item `lt`: logits (72 keys of one query row) -> bias (+ mask) -> row max across the two
 // halves -> exp2 -> bf16 hi / lo of the un-normalised probabilities written back over S -> "P ready".  TILE2 = the 16-row tile
 // (query rows 128..143 on lanes 0..15 of this warp's quadrant; lanes 16..31 run along on rows that are never stored).
-template <bool TILE2>
+template <bool TILE2, int PARTS>
 __device__ __forceinline__ void wt_pass(const WtParams& p, const WtThread& T, uint8_t* smem, WtBars* bars, float* exch_max,
                                         float* exch_sum, uint32_t tmem_base, uint32_t lt, bool lastrow, bool lastcol) {
   const int lane = T.lane, half = T.half;
@@ -113,7 +123,8 @@ __device__ __forceinline__ void wt_pass(const WtParams& p, const WtThread& T, ui
   const int rowc = row < WT_N ? row : WT_N - 1;                     // clamped for address arithmetic only
   const int iy = rowc / WT_WS, ix = rowc - iy * WT_WS;
   // bias index of (query i, key j) = (iy - jy + 11) * 23 + (ix - jx + 11) = base - (jy * 23 + jx)
-  const int bias_base = (iy + WT_WS - 1) * (2 * WT_WS - 1) + ix + WT_WS - 1 - half * 6 * (2 * WT_WS - 1);
+  constexpr int KP = WT_N / PARTS, PK = KP / 2;                    // keys / packed operand words of this thread (72 / 36 or 36 / 18)
+  const int bias_base = (iy + WT_WS - 1) * (2 * WT_WS - 1) + ix + WT_WS - 1 - half * (KP / WT_WS) * (2 * WT_WS - 1);
   // slot of this row in the max / sum exchange arrays (160 per half: rows 0..127 of the big tile, 144..159 = rows 128..143 of
   // the small tile, 128..143 = scratch for the small tile's lanes 16..31, whose rows do not exist)
   const int er = TILE2 ? (lane < 16 ? 144 + lane : 128 + (lane - 16)) : row;
@@ -127,12 +138,12 @@ __device__ __forceinline__ void wt_pass(const WtParams& p, const WtThread& T, ui
   const bool stamp = !TILE2 && T.quadrant == 0 && half == 0 && lane == 0;
   if (stamp) WT_STAMP(lt, 6);
   const uint32_t saddr = tmem_base + T.lane_addr + (TILE2 ? WT_COL_S2 : WT_COL_S1 + b * WT_N);
-  float x[72];
+  float x[KP];
   uint32_t* xv = reinterpret_cast<uint32_t*>(x);
   // shift mask (swin.py:416-440): -100 where query and key lie in different regions of a boundary window.  Keys of this half
   // all have jy >= 6 iff half == 1; jx >= 6 is a compile-time property of the unrolled index.
   const bool masked = lastrow || lastcol;
-  const bool rowdiff = lastrow && ((half == 1) != rf);
+  const bool rowdiff = lastrow && ((half >= PARTS / 2) != rf);       // keys of this partition all have jy >= 6 iff it is in the upper half
   const float mlo = (rowdiff || (lastcol && cf)) ? NEG : 0.f, mhi = (rowdiff || (lastcol && !cf)) ? NEG : 0.f;
   float mm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};        // four independent max chains
   // x = S * scale * log2(e) + bias (+ mask) for keys [J0, J1), software-pipelined against the TMEM loads of the next chunk
@@ -155,56 +166,73 @@ __device__ __forceinline__ void wt_pass(const WtParams& p, const WtThread& T, ui
       }
     }
   };
-  tmem_ld32(saddr + half * 72, xv);
-  tmem_ld_wait_dep<32>(xv);
-  tmem_ld32(saddr + half * 72 + 32, xv + 32);                       // in flight under the first chunk's arithmetic
-  logits(std::integral_constant<int, 0>{}, std::integral_constant<int, 32>{});
-  tmem_ld_wait_dep<32>(xv + 32);
-  tmem_ld8(saddr + half * 72 + 64, xv + 64);
-  logits(std::integral_constant<int, 32>{}, std::integral_constant<int, 64>{});
-  tmem_ld_wait_dep<8>(xv + 64);
-  logits(std::integral_constant<int, 64>{}, std::integral_constant<int, 72>{});
+  if (PARTS == 2) {
+    tmem_ld32(saddr + half * KP, xv);
+    tmem_ld_wait_dep<32>(xv);
+    tmem_ld32(saddr + half * KP + 32, xv + 32);                     // in flight under the first chunk's arithmetic
+    logits(std::integral_constant<int, 0>{}, std::integral_constant<int, 32>{});
+    tmem_ld_wait_dep<32>(xv + 32);
+    tmem_ld8(saddr + half * KP + 64, xv + 64);
+    logits(std::integral_constant<int, 32>{}, std::integral_constant<int, 64>{});
+    tmem_ld_wait_dep<8>(xv + 64);
+    logits(std::integral_constant<int, 64>{}, std::integral_constant<int, KP>{});
+  } else {
+    tmem_ld32(saddr + half * KP, xv);
+    tmem_ld_wait_dep<32>(xv);
+    tmem_ld4(saddr + half * KP + 32, xv + 32);
+    logits(std::integral_constant<int, 0>{}, std::integral_constant<int, 32>{});
+    tmem_ld_wait_dep<4>(xv + 32);
+    logits(std::integral_constant<int, 32>{}, std::integral_constant<int, KP>{});
+  }
   if (stamp) WT_STAMP(lt, 7);
   float m = (p.debug & 1) ? 0.f : fmaxf(fmaxf(mm[0], mm[1]), fmaxf(mm[2], mm[3]));
   // ---- row max across the two halves (every S column of this row has been read once both threads are here) ----
-  float* emax = exch_max + (b * 2) * 160;
+  float* emax = exch_max + (b * PARTS) * 160;
   emax[half * 160 + er] = m;
-  wt_pair_bar(T.pair_bar);
-  m = fmaxf(m, emax[(half ^ 1) * 160 + er]);
+  wt_part_bar(T.pair_bar, 32 * PARTS);
+#pragma unroll
+  for (int o = 1; o < PARTS; ++o) m = fmaxf(m, emax[((half + o) % PARTS) * 160 + er]);
   if (stamp) WT_STAMP(lt, 8);
   // ---- un-normalised probabilities, bf16 hi / lo, written back over S: hi -> columns [0,72), lo -> [72,144) ----
   float sum = 0.f;
-  uint32_t ph[36], pl[36];
+  uint32_t ph[PK], pl[PK];
   if (p.debug & 2) {                       // ablation: no exp / split
 #pragma unroll
-    for (int jj = 0; jj < 36; ++jj) { ph[jj] = __float_as_uint(x[jj]); pl[jj] = __float_as_uint(x[jj + 36]); }
+    for (int jj = 0; jj < PK; ++jj) { ph[jj] = __float_as_uint(x[jj]); pl[jj] = __float_as_uint(x[jj + PK]); }
     sum = 1.f;
   } else {
     float ss[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int jj = 0; jj < 72; jj += 2) {
+    for (int jj = 0; jj < KP; jj += 2) {
       const float e0 = wt_ex2(x[jj] - m), e1 = wt_ex2(x[jj + 1] - m);
       ss[(jj >> 1) & 3] += e0 + e1;
       split_pack2(e0, e1, ph[jj >> 1], pl[jj >> 1]);
     }
     sum = (ss[0] + ss[1]) + (ss[2] + ss[3]);
   }
-  tmem_st32(saddr + half * 36, ph);
-  tmem_st4(saddr + half * 36 + 32, ph + 32);
-  tmem_st32(saddr + 72 + half * 36, pl);
-  tmem_st4(saddr + 72 + half * 36 + 32, pl + 32);
+  if (PARTS == 2) {
+    tmem_st32(saddr + half * PK, ph);
+    tmem_st4(saddr + half * PK + 32, ph + 32);
+    tmem_st32(saddr + 72 + half * PK, pl);
+    tmem_st4(saddr + 72 + half * PK + 32, pl + 32);
+  } else {
+    tmem_st16(saddr + half * PK, ph);
+    tmem_st2(saddr + half * PK + 16, ph + 16);
+    tmem_st16(saddr + 72 + half * PK, pl);
+    tmem_st2(saddr + 72 + half * PK + 16, pl + 16);
+  }
   if (stamp) WT_STAMP(lt, 9);
   tmem_st_wait();
   tc_fence_before();
   if (stamp) WT_STAMP(lt, 10);
-  exch_sum[(b * 2 + half) * 160 + er] = sum;
+  exch_sum[(b * PARTS + half) * 160 + er] = sum;
   __syncwarp();
   if (lane == 0) mbar_arrive(TILE2 ? &bars->p2_ready : &bars->p1_ready[b]);
 }
 
 // Epilogue of one tile of item `lt`: O rows * 1 / row sum -> bf16 hi / lo planes.  The partner's partial sum is visible: both
 // threads of a row have passed a pair barrier (or the final one) since it was written.
-template <bool TILE2>
+template <bool TILE2, int PARTS>
 __device__ __forceinline__ void wt_epilogue(const WtParams& p, const WtThread& T, WtBars* bars, const float* exch_sum,
                                             uint32_t tmem_base, uint32_t lt, int64_t row0, int head, bool release) {
   const int lane = T.lane;
@@ -212,10 +240,15 @@ __device__ __forceinline__ void wt_epilogue(const WtParams& p, const WtThread& T
   const int er = TILE2 ? (lane < 16 ? 144 + lane : 128 + (lane - 16)) : row;
   mbar_wait(TILE2 ? &bars->o2_full : &bars->o1_full, lt & 1);
   tc_fence_after();
-  const float* ps = exch_sum + ((lt & 1) * 2) * 160;
-  const float inv = 1.0f / (ps[er] + ps[160 + er]);
-  uint32_t o[16];
-  tmem_ld16(tmem_base + T.lane_addr + (TILE2 ? WT_COL_O2 : WT_COL_O1) + T.half * 16, o);
+  constexpr int OC = WT_D / PARTS;                                  // output channels of this thread (16 or 8)
+  const float* ps = exch_sum + ((lt & 1) * PARTS) * 160;
+  float tot = 0.f;
+#pragma unroll
+  for (int o = 0; o < PARTS; ++o) tot += ps[o * 160 + er];
+  const float inv = 1.0f / tot;
+  uint32_t o[OC];
+  if (PARTS == 2) tmem_ld16(tmem_base + T.lane_addr + (TILE2 ? WT_COL_O2 : WT_COL_O1) + T.half * OC, o);
+  else tmem_ld8(tmem_base + T.lane_addr + (TILE2 ? WT_COL_O2 : WT_COL_O1) + T.half * OC, o);
   tmem_ld_wait();
   tc_fence_before();
   if (release) {
@@ -223,8 +256,8 @@ __device__ __forceinline__ void wt_epilogue(const WtParams& p, const WtThread& T
     if (lane == 0) mbar_arrive(TILE2 ? &bars->o2_empty : &bars->o1_empty);
   }
   if (!TILE2 || lane < 16) {
-    const int64_t g = (row0 + row) * p.C + head * WT_D + T.half * 16;
-    wt_store16(p.out_hi, p.out_lo, g, o, inv);
+    const int64_t g = (row0 + row) * p.C + head * WT_D + T.half * OC;
+    if (PARTS == 2) wt_store16(p.out_hi, p.out_lo, g, o, inv); else wt_store8(p.out_hi, p.out_lo, g, o, inv);
   }
 }
 
@@ -232,6 +265,7 @@ __device__ __forceinline__ void wt_epilogue(const WtParams& p, const WtThread& T
 // half of the keys); the 16-row tile of item i is placed on the lanes of quadrant i % 4 (the MMA issuer offsets the q rows
 // accordingly) and served by that quadrant's two warps, so the extra pass rotates over the four SM sub-partitions instead of
 // loading one of them with 4 of 10 heavy warp-passes (measured: that sub-partition bounded the kernel).
+template <int PARTS>
 __device__ __forceinline__ void wt_softmax_role(const WtParams& p, uint8_t* smem, WtBars* bars, float* exch_max, float* exch_sum,
                                                 uint32_t tmem_base, int quadrant, int half, int lane) {
   WtThread T;
@@ -250,13 +284,13 @@ __device__ __forceinline__ void wt_softmax_role(const WtParams& p, uint8_t* smem
   const uint32_t step_wx = step_win % nWw, step_wi = step_win % nW;
   for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x, ++lt) {
     const bool lastrow = p.shift > 0 && wim >= nW - nWw, lastcol = p.shift > 0 && wxm == nWw - 1;
-    wt_pass<false>(p, T, smem, bars, exch_max, exch_sum, tmem_base, lt, lastrow, lastcol);
+    wt_pass<false, PARTS>(p, T, smem, bars, exch_max, exch_sum, tmem_base, lt, lastrow, lastcol);
     // the 16-row tile of the previous item, if this quadrant served it (its P.v was issued a whole pass ago, and the O2
     // buffer is needed again only after another quadrant's 16-row pass of this item)
-    if (tile2 && lt > 0 && (int)((lt - 1) & 3) == quadrant) wt_epilogue<true>(p, T, bars, exch_sum, tmem_base, lt - 1, prev_row0, prev_head, true);
-    if (tile2 && (int)(lt & 3) == quadrant) wt_pass<true>(p, T, smem, bars, exch_max, exch_sum, tmem_base, lt, lastrow, lastcol);
+    if (tile2 && lt > 0 && (int)((lt - 1) & 3) == quadrant) wt_epilogue<true, PARTS>(p, T, bars, exch_sum, tmem_base, lt - 1, prev_row0, prev_head, true);
+    if (tile2 && (int)(lt & 3) == quadrant) wt_pass<true, PARTS>(p, T, smem, bars, exch_max, exch_sum, tmem_base, lt, lastrow, lastcol);
     // the 128-row tile of the previous item (its P.v has had a whole softmax to finish)
-    if (lt > 0) wt_epilogue<false>(p, T, bars, exch_sum, tmem_base, lt - 1, prev_row0, prev_head, true);
+    if (lt > 0) wt_epilogue<false, PARTS>(p, T, bars, exch_sum, tmem_base, lt - 1, prev_row0, prev_head, true);
     if (!half && quadrant == 0 && lane == 0) WT_STAMP(lt, 14);
     prev_row0 = (int64_t)win * WT_N;
     prev_head = (int)head;
@@ -272,13 +306,14 @@ __device__ __forceinline__ void wt_softmax_role(const WtParams& p, uint8_t* smem
     if (wim >= nW) wim -= nW;
   }
   if (lt > 0) {                                   // epilogues of the last item
-    wt_pair_bar(T.pair_bar);                      // the partner's sums of the last item are in shared memory
-    if (tile2 && (int)((lt - 1) & 3) == quadrant) wt_epilogue<true>(p, T, bars, exch_sum, tmem_base, lt - 1, prev_row0, prev_head, false);
-    wt_epilogue<false>(p, T, bars, exch_sum, tmem_base, lt - 1, prev_row0, prev_head, false);
+    wt_part_bar(T.pair_bar, 32 * PARTS);           // the partners' sums of the last item are in shared memory
+    if (tile2 && (int)((lt - 1) & 3) == quadrant) wt_epilogue<true, PARTS>(p, T, bars, exch_sum, tmem_base, lt - 1, prev_row0, prev_head, false);
+    wt_epilogue<false, PARTS>(p, T, bars, exch_sum, tmem_base, lt - 1, prev_row0, prev_head, false);
   }
 }
 
-__global__ void __launch_bounds__(WT_THREADS, 1)
+template <int PARTS>
+__global__ void __launch_bounds__((4 + 4 * PARTS) * 32, 1)
 window_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const WtParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -290,10 +325,10 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_co
   if (threadIdx.x == 0) {
     prefetch_tmap(&tm_hi); prefetch_tmap(&tm_lo);
     for (int s = 0; s < WT_STAGES; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 2); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&bars->s1_full[b], 1); mbar_init(&bars->p1_ready[b], 8); }
-    mbar_init(&bars->o1_full, 1); mbar_init(&bars->o1_empty, 8);
-    mbar_init(&bars->s2_full, 1); mbar_init(&bars->p2_ready, 2);
-    mbar_init(&bars->o2_full, 1); mbar_init(&bars->o2_empty, 2);
+    for (int b = 0; b < 2; ++b) { mbar_init(&bars->s1_full[b], 1); mbar_init(&bars->p1_ready[b], 4 * PARTS); }
+    mbar_init(&bars->o1_full, 1); mbar_init(&bars->o1_empty, 4 * PARTS);
+    mbar_init(&bars->s2_full, 1); mbar_init(&bars->p2_ready, PARTS);
+    mbar_init(&bars->o2_full, 1); mbar_init(&bars->o2_empty, PARTS);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -439,7 +474,7 @@ window_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_co
       }
     }
   } else if (warp >= 4) {
-    wt_softmax_role(p, smem, bars, exch_max, exch_sum, tmem_base, warp & 3, (warp - 4) >> 2, lane);
+    wt_softmax_role<PARTS>(p, smem, bars, exch_max, exch_sum, tmem_base, warp & 3, (warp - 4) >> 2, lane);
   }
   tc_fence_before();
   __syncthreads();
@@ -490,9 +525,12 @@ int window_attn_tc(const uint16_t* qkv_hi, const uint16_t* qkv_lo, const float* 
   p.nitems = nwin * heads;
   p.scale_log2e = 1.4426950408889634f / sqrtf((float)WT_D);
   { static const int dbg = []() { const char* e = getenv("RBA_WT_DEBUG"); return e ? atoi(e) : 0; }(); p.debug = dbg; }   // profiling ablations
+  // RBA_WT_PARTS: softmax warps per TMEM lane quadrant (2: 12 warps, 72 keys per thread; 4: 20 warps, 36 keys per thread)
+  static const int parts = []() { const char* e = getenv("RBA_WT_PARTS"); const int v = e ? atoi(e) : 4; return v == 2 ? 2 : 4; }();
   static PerDeviceOnce once;
   if (once.needed()) {
-    RBA_CUDA(cudaFuncSetAttribute(window_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM));
+    RBA_CUDA(cudaFuncSetAttribute(window_attn_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM));
+    RBA_CUDA(cudaFuncSetAttribute(window_attn_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM));
     once.done();
   }
   const unsigned grid = (unsigned)std::min<int64_t>(p.nitems, num_sms());
@@ -503,7 +541,8 @@ int window_attn_tc(const uint16_t* qkv_hi, const uint16_t* qkv_lo, const float* 
     RBA_CUDA(cudaMemsetAsync(tl_dev, 0, 32 * 16 * sizeof(long long), st));
     p.tl = tl_dev;
   }
-  window_attn_tc_kernel<<<grid, WT_THREADS, WT_SMEM, st>>>(tm_hi, tm_lo, p);
+  if (parts == 2) window_attn_tc_kernel<2><<<grid, (4 + 4 * 2) * 32, WT_SMEM, st>>>(tm_hi, tm_lo, p);
+  else window_attn_tc_kernel<4><<<grid, (4 + 4 * 4) * 32, WT_SMEM, st>>>(tm_hi, tm_lo, p);
   RBA_LAUNCHED();
   if (timeline) {
     long long h[32 * 16];
