@@ -42,7 +42,7 @@ constexpr int WT_BIAS_FLOATS = 532;                       // == WM_BIAS_PITCH of
 constexpr int WT_BIAS_BYTES = WT_BIAS_FLOATS * 4;         // 2128 (multiple of 16: bulk-copy granularity)
 constexpr int WT_STAGE_BYTES = 6 * WT_TILE_BYTES + 3072;  // 58368 = 57 * 1024
 constexpr int WT_STAGES = 3;
-constexpr int WT_MAXPARTS = 4;                             // softmax warps per TMEM lane quadrant (key partitions of a row): 2 or 4
+constexpr int WT_MAXPARTS = 6;                             // softmax warps per TMEM lane quadrant (key partitions of a row): 2 or 4
 constexpr int WT_THREADS_MAX = (4 + 4 * WT_MAXPARTS) * 32;
 constexpr uint32_t WT_TMEM_COLS = 512;
 constexpr int WT_COL_S1 = 0, WT_COL_S2 = 288, WT_COL_O1 = 432, WT_COL_O2 = 464;
@@ -176,13 +176,20 @@ __device__ __forceinline__ void wt_pass(const WtParams& p, const WtThread& T, ui
     logits(std::integral_constant<int, 32>{}, std::integral_constant<int, 64>{});
     tmem_ld_wait_dep<8>(xv + 64);
     logits(std::integral_constant<int, 64>{}, std::integral_constant<int, KP>{});
-  } else {
+  } else if (PARTS == 4) {
     tmem_ld32(saddr + half * KP, xv);
     tmem_ld_wait_dep<32>(xv);
     tmem_ld4(saddr + half * KP + 32, xv + 32);
     logits(std::integral_constant<int, 0>{}, std::integral_constant<int, 32>{});
     tmem_ld_wait_dep<4>(xv + 32);
     logits(std::integral_constant<int, 32>{}, std::integral_constant<int, KP>{});
+  } else {
+    tmem_ld16(saddr + half * KP, xv);
+    tmem_ld_wait_dep<16>(xv);
+    tmem_ld8(saddr + half * KP + 16, xv + 16);
+    logits(std::integral_constant<int, 0>{}, std::integral_constant<int, 16>{});
+    tmem_ld_wait_dep<8>(xv + 16);
+    logits(std::integral_constant<int, 16>{}, std::integral_constant<int, KP>{});
   }
   if (stamp) WT_STAMP(lt, 7);
   float m = (p.debug & 1) ? 0.f : fmaxf(fmaxf(mm[0], mm[1]), fmaxf(mm[2], mm[3]));
@@ -215,11 +222,16 @@ __device__ __forceinline__ void wt_pass(const WtParams& p, const WtThread& T, ui
     tmem_st4(saddr + half * PK + 32, ph + 32);
     tmem_st32(saddr + 72 + half * PK, pl);
     tmem_st4(saddr + 72 + half * PK + 32, pl + 32);
-  } else {
+  } else if (PARTS == 4) {
     tmem_st16(saddr + half * PK, ph);
     tmem_st2(saddr + half * PK + 16, ph + 16);
     tmem_st16(saddr + 72 + half * PK, pl);
     tmem_st2(saddr + 72 + half * PK + 16, pl + 16);
+  } else {
+    tmem_st8(saddr + half * PK, ph);
+    tmem_st4(saddr + half * PK + 8, ph + 8);
+    tmem_st8(saddr + 72 + half * PK, pl);
+    tmem_st4(saddr + 72 + half * PK + 8, pl + 8);
   }
   if (stamp) WT_STAMP(lt, 9);
   tmem_st_wait();
@@ -240,7 +252,8 @@ __device__ __forceinline__ void wt_epilogue(const WtParams& p, const WtThread& T
   const int er = TILE2 ? (lane < 16 ? 144 + lane : 128 + (lane - 16)) : row;
   mbar_wait(TILE2 ? &bars->o2_full : &bars->o1_full, lt & 1);
   tc_fence_after();
-  constexpr int OC = WT_D / PARTS;                                  // output channels of this thread (16 or 8)
+  constexpr int OC = PARTS == 2 ? 16 : 8;                           // output channels of this thread; with 6 partitions only 0..3 carry any
+  const bool has_out = T.half * OC < WT_D;
   const float* ps = exch_sum + ((lt & 1) * PARTS) * 160;
   float tot = 0.f;
 #pragma unroll
@@ -248,14 +261,14 @@ __device__ __forceinline__ void wt_epilogue(const WtParams& p, const WtThread& T
   const float inv = 1.0f / tot;
   uint32_t o[OC];
   if (PARTS == 2) tmem_ld16(tmem_base + T.lane_addr + (TILE2 ? WT_COL_O2 : WT_COL_O1) + T.half * OC, o);
-  else tmem_ld8(tmem_base + T.lane_addr + (TILE2 ? WT_COL_O2 : WT_COL_O1) + T.half * OC, o);
+  else if (has_out) tmem_ld8(tmem_base + T.lane_addr + (TILE2 ? WT_COL_O2 : WT_COL_O1) + T.half * OC, o);
   tmem_ld_wait();
   tc_fence_before();
   if (release) {
     __syncwarp();
     if (lane == 0) mbar_arrive(TILE2 ? &bars->o2_empty : &bars->o1_empty);
   }
-  if (!TILE2 || lane < 16) {
+  if (has_out && (!TILE2 || lane < 16)) {
     const int64_t g = (row0 + row) * p.C + head * WT_D + T.half * OC;
     if (PARTS == 2) wt_store16(p.out_hi, p.out_lo, g, o, inv); else wt_store8(p.out_hi, p.out_lo, g, o, inv);
   }
@@ -526,11 +539,12 @@ int window_attn_tc(const uint16_t* qkv_hi, const uint16_t* qkv_lo, const float* 
   p.scale_log2e = 1.4426950408889634f / sqrtf((float)WT_D);
   { static const int dbg = []() { const char* e = getenv("RBA_WT_DEBUG"); return e ? atoi(e) : 0; }(); p.debug = dbg; }   // profiling ablations
   // RBA_WT_PARTS: softmax warps per TMEM lane quadrant (2: 12 warps, 72 keys per thread; 4: 20 warps, 36 keys per thread)
-  static const int parts = []() { const char* e = getenv("RBA_WT_PARTS"); const int v = e ? atoi(e) : 4; return v == 2 ? 2 : 4; }();
+  static const int parts = []() { const char* e = getenv("RBA_WT_PARTS"); const int v = e ? atoi(e) : 4; return v == 2 || v == 6 ? v : 4; }();
   static PerDeviceOnce once;
   if (once.needed()) {
     RBA_CUDA(cudaFuncSetAttribute(window_attn_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM));
     RBA_CUDA(cudaFuncSetAttribute(window_attn_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM));
+    RBA_CUDA(cudaFuncSetAttribute(window_attn_tc_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM));
     once.done();
   }
   const unsigned grid = (unsigned)std::min<int64_t>(p.nitems, num_sms());
@@ -542,6 +556,7 @@ int window_attn_tc(const uint16_t* qkv_hi, const uint16_t* qkv_lo, const float* 
     p.tl = tl_dev;
   }
   if (parts == 2) window_attn_tc_kernel<2><<<grid, (4 + 4 * 2) * 32, WT_SMEM, st>>>(tm_hi, tm_lo, p);
+  else if (parts == 6) window_attn_tc_kernel<6><<<grid, (4 + 4 * 6) * 32, WT_SMEM, st>>>(tm_hi, tm_lo, p);
   else window_attn_tc_kernel<4><<<grid, (4 + 4 * 4) * 32, WT_SMEM, st>>>(tm_hi, tm_lo, p);
   RBA_LAUNCHED();
   if (timeline) {
