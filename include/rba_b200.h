@@ -161,6 +161,14 @@ int rba_einsum_score_fused(const uint16_t* embed_hi, const uint16_t* embed_lo, c
  * (mma.sync score phase, csrc/score_fused.cu) for them as well.  Process-wide; env RBA_FS_VARIANT sets the initial value. */
 int rba_k_set_fused_score_variant(int variant);
 
+/* ---- input pipeline, device side: JPEG bitstreams -> planar RGB uint8 (n,3,H,W) on the device ----
+ * Replaces the host-side decode + ToTensorV2 of the reference's dataset classes (support.py:73-81, datasets/*.py) for JPEG
+ * inputs; the planes are what rba_model_forward reads (RBA_IMG_U8).  Decoder: nvJPEG, bound at run time (rba_jpeg_available()
+ * is 0 and the calls fail with RBA_ERR_CUDA when libnvjpeg is absent).  data[i] are HOST pointers; stream-ordered. */
+int rba_jpeg_available(void);
+int rba_jpeg_info(const uint8_t* data, int64_t nbytes, int* height, int* width, int* channels);
+int rba_jpeg_decode(const uint8_t* const* data, const int64_t* nbytes, int n, uint8_t* out, int H, int W, void* stream);
+
 /* ---- streaming OoD metrics (replaces OODEvaluator.evaluate_ood / calculate_auroc, support.py:247-303, and the
  * per-image host round trip of compute_anomaly_scores, support.py:353-399) ----
  * A two-class histogram of order-preserving float keys (2 x 2^24 uint64 counters = rba_ood_hist_bytes() device bytes,

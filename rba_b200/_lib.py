@@ -69,6 +69,9 @@ PROTOTYPES = {
     "rba_einsum_score_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                        c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "rba_k_set_fused_score_variant": (c_int, [c_int]),
+    "rba_jpeg_available": (c_int, []),
+    "rba_jpeg_info": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "rba_jpeg_decode": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
     "rba_ood_hist_bytes": (c_int64, []),
     "rba_ood_workspace_bytes": (c_int64, []),
     "rba_ood_hist_update": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p]),

@@ -208,6 +208,109 @@ msda_fused_kernel(const float* __restrict__ value, MsdaLevels lv, const float* _
   store_split4(out_hi, out_lo, idx * 4, acc.x, acc.y, acc.z, acc.w);
 }
 
+// Second form of the fused kernel for head_dim 32 (every shipped configuration): the 8 lanes of a head SHARE the per-sample
+// scalar work instead of repeating it.  `ncu --set full` of the form above at 3 levels (profiles/r2j: 43008 queries x 12
+// samples) showed it issue-bound, not memory-bound: 507 M warp instructions per 2 images (~245 per lane and sample: expf,
+// two float divisions, 64-bit index arithmetic and four bounds tests, all eight times per head), instruction-cache misses
+// from the 16-way unrolled body, L1 hit rate 67 %, L2 13 % busy.  Here lane j of a head owns samples j and j + 8: it forms
+// their softmax terms (max / sum by three xor-shuffles inside the 8-lane group), sampling location, the four CLAMPED 32-bit
+// tap offsets and the four bilinear weights (zero for a tap outside the map: same sum as the skipped tap of the reference,
+// ms_deform_im2col_cuda.cuh:242-304) and parks them in shared memory; after a __syncwarp every lane walks the samples with
+// three broadcast LDS, four unconditional 16-byte gathers and 20 FP32 instructions each.  Same arithmetic, same association.
+// lv.X[l] for a run-time l without spilling the kernel-parameter struct to local memory (constant-bank selects)
+__device__ __forceinline__ int msda_sel(const int* a, int l) {
+  int v = a[0];
+#pragma unroll
+  for (int k = 1; k < MSDA_MAX_LEVELS; ++k) v = l == k ? a[k] : v;
+  return v;
+}
+
+template <int MAXLP>
+__global__ void __launch_bounds__(256)
+msda_fused_d32_kernel(const float* __restrict__ value, MsdaLevels lv, const float* __restrict__ oa, uint32_t ngroups, int S, int M,
+                      int L, int P, uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo) {
+  constexpr int D = 32;
+  __shared__ int4 sOff[8][4][MAXLP];
+  __shared__ float4 sWgt[8][4][MAXLP];
+  __shared__ float sAw[8][4][MAXLP];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane & 7, gw = lane >> 3;
+  const uint32_t g0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;       // (b, q, head) of this 8-lane group
+  const bool live = g0 < ngroups;
+  const uint32_t g = live ? g0 : ngroups - 1;                             // dead groups shadow the last one (warp-wide shuffles)
+  const uint32_t t = g / (uint32_t)M, m = g - t * (uint32_t)M;            // t = b * S + q
+  const uint32_t b = t / (uint32_t)S, q = t - b * (uint32_t)S;
+  int lq = 0;
+#pragma unroll
+  for (int l = 1; l < MSDA_MAX_LEVELS; ++l)
+    if (l < L && (int)q >= lv.start[l]) lq = l;
+  const int Wq = msda_sel(lv.W, lq), Hq = msda_sel(lv.H, lq), sq = msda_sel(lv.start, lq);
+  const int qi = ((int)q - sq) / Wq, qj = ((int)q - sq) - qi * Wq;
+  const float ref_x = (qj + 0.5f) / (float)Wq, ref_y = (qi + 0.5f) / (float)Hq;
+  const int LP = L * P;
+  const float* row = oa + (size_t)t * (size_t)(M * LP * 3);
+  const float* offp = row + (size_t)m * LP * 2;
+  const float* lgp = row + (size_t)M * LP * 2 + (size_t)m * LP;
+  // ---- softmax over the L*P logits: this lane's terms are samples sub and sub + 8 ----
+  const bool has0 = sub < LP, has1 = sub + 8 < LP;
+  float e0 = has0 ? lgp[sub] : -INFINITY, e1 = has1 ? lgp[sub + 8] : -INFINITY;
+  float mx = fmaxf(e0, e1);
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  e0 = has0 ? expf(e0 - mx) : 0.f;
+  e1 = has1 ? expf(e1 - mx) : 0.f;
+  float sum = e0 + e1;
+  // same left-to-right order as the serial sum of the first form would need a serial loop; the 8-lane tree is used instead and
+  // differs from it by fp32 rounding of the denominator only (<= 1 ulp of the attention weights)
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.f / sum;
+  // ---- per-sample tap offsets and weights ----
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int i = sub + 8 * k;
+    if (i < LP) {
+      const int l = i / P;
+      const int H = msda_sel(lv.H, l), W = msda_sel(lv.W, l);
+      const float x = ref_x + offp[2 * i] / (float)W;
+      const float y = ref_y + offp[2 * i + 1] / (float)H;
+      const float h_im = y * H - 0.5f;
+      const float w_im = x * W - 0.5f;
+      const bool inside = h_im > -1.f && w_im > -1.f && h_im < H && w_im < W;
+      const int h0 = (int)floorf(h_im), w0 = (int)floorf(w_im);
+      const float lh = h_im - h0, lw = w_im - w0;
+      const float hh = 1.f - lh, hw = 1.f - lw;
+      const int h1 = h0 + 1, w1 = w0 + 1;
+      const bool okh0 = inside && h0 >= 0, okh1 = inside && h1 <= H - 1, okw0 = w0 >= 0, okw1 = w1 <= W - 1;
+      const int h0c = min(max(h0, 0), H - 1), h1c = min(max(h1, 0), H - 1), w0c = min(max(w0, 0), W - 1), w1c = min(max(w1, 0), W - 1);
+      const int base = msda_sel(lv.start, l);
+      const int stride = M * D;
+      sOff[warp][gw][i] = make_int4((base + h0c * W + w0c) * stride, (base + h0c * W + w1c) * stride, (base + h1c * W + w0c) * stride,
+                                    (base + h1c * W + w1c) * stride);
+      sWgt[warp][gw][i] = make_float4(okh0 && okw0 ? hh * hw : 0.f, okh0 && okw1 ? hh * lw : 0.f, okh1 && okw0 ? lh * hw : 0.f,
+                                      okh1 && okw1 ? lh * lw : 0.f);
+      sAw[warp][gw][i] = (k ? e1 : e0) * inv;
+    }
+  }
+  __syncwarp();
+  const float* vb = value + ((size_t)b * S * M + m) * D + 4 * sub;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int i = 0; i < LP; ++i) {
+    const int4 o = sOff[warp][gw][i];
+    const float4 w = sWgt[warp][gw][i];
+    const float aw = sAw[warp][gw][i];
+    const float4 v00 = __ldg(reinterpret_cast<const float4*>(vb + o.x));
+    const float4 v01 = __ldg(reinterpret_cast<const float4*>(vb + o.y));
+    const float4 v10 = __ldg(reinterpret_cast<const float4*>(vb + o.z));
+    const float4 v11 = __ldg(reinterpret_cast<const float4*>(vb + o.w));
+    acc.x = fmaf(aw, w.x * v00.x + w.y * v01.x + w.z * v10.x + w.w * v11.x, acc.x);
+    acc.y = fmaf(aw, w.x * v00.y + w.y * v01.y + w.z * v10.y + w.w * v11.y, acc.y);
+    acc.z = fmaf(aw, w.x * v00.z + w.y * v01.z + w.z * v10.z + w.w * v11.z, acc.z);
+    acc.w = fmaf(aw, w.x * v00.w + w.y * v01.w + w.z * v10.w + w.w * v11.w, acc.w);
+  }
+  if (live) store_split4(out_hi, out_lo, ((int64_t)g * 8 + sub) * 4, acc.x, acc.y, acc.z, acc.w);
+}
+
 int msda_fused(const float* value, const int* Hs, const int* Ws, const float* oa, int B, int S, int M, int D, int L,
                int P, uint16_t* out_hi, uint16_t* out_lo, cudaStream_t st) {
   RBA_CHECK(L <= MSDA_MAX_LEVELS && L * P <= 16, "msda_fused: L=%d P=%d unsupported", L, P);
@@ -217,6 +320,13 @@ int msda_fused(const float* value, const int* Hs, const int* Ws, const float* oa
   for (int l = 0; l < L; ++l) { lv.H[l] = Hs[l]; lv.W[l] = Ws[l]; lv.start[l] = start; start += Hs[l] * Ws[l]; }
   RBA_CHECK(start == S, "msda_fused: level sizes do not sum to S");
   const int64_t total = (int64_t)B * S * M * (D / 4);
+  static const bool first_form = getenv("RBA_MSDA_FORM1") != nullptr;      // profiling: the one-thread-does-everything form
+  if (D == 32 && !first_form && (int64_t)B * S * M < (1LL << 28) && (int64_t)S * M * D < (1LL << 31)) {
+    msda_fused_d32_kernel<16><<<(unsigned)cdiv(total, 256), 256, 0, st>>>(value, lv, oa, (uint32_t)((int64_t)B * S * M), S, M, L, P,
+                                                                            out_hi, out_lo);
+    RBA_LAUNCHED();
+    return RBA_OK;
+  }
   msda_fused_kernel<16><<<(unsigned)cdiv(total, 256), 256, 0, st>>>(value, lv, oa, total, S, M, D, L, P, out_hi, out_lo);
   RBA_LAUNCHED();
   return RBA_OK;

@@ -254,3 +254,54 @@ class PinnedBatcher:
             stop.set()
             if prev is not None and self._bufs is not None:
                 self.release(prev)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Device-side JPEG decode: bitstreams -> planar RGB uint8 in HBM
+# ---------------------------------------------------------------------------------------------------------
+def jpeg_available():
+    """True when the nvJPEG run-time library could be bound (rba_jpeg_available)."""
+    from . import _lib
+    return bool(_lib.lib().rba_jpeg_available())
+
+
+def jpeg_info(data):
+    """(height, width, channels) of one JPEG bitstream (bytes / bytearray / uint8 array)."""
+    import ctypes
+    from . import _lib
+    buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+    h, w, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    _lib.check(_lib.lib().rba_jpeg_info(buf.ctypes.data, buf.size, ctypes.byref(h), ctypes.byref(w), ctypes.byref(c)))
+    return h.value, w.value, c.value
+
+
+def decode_jpeg_batch(streams, device=None, out=None):
+    """streams: sequence of JPEG bitstreams (bytes or uint8 arrays, or paths of .jpg files) of ONE image size.
+    Returns a (n,3,H,W) uint8 CUDA tensor of planar RGB -- the layout `Engine.forward` / `ScoreStream.submit` take --
+    decoded on the device by nvJPEG (`rba_jpeg_decode`), stream-ordered on the current CUDA stream.  Replaces
+    `cv2.imread` / `PIL.Image.open` + `ToTensorV2` of the reference's dataset classes (support.py:73-81) for JPEG inputs."""
+    import ctypes
+    from . import _lib
+    if not torch.cuda.is_available():
+        raise RbaError("decode_jpeg_batch needs a CUDA device: the product path has no CPU fallback")
+    bufs = []
+    for s in streams:
+        if isinstance(s, str):
+            with open(s, "rb") as f:
+                s = f.read()
+        bufs.append(np.frombuffer(s, dtype=np.uint8) if not isinstance(s, np.ndarray) else np.ascontiguousarray(s, dtype=np.uint8))
+    n = len(bufs)
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if n == 0:
+        return torch.empty((0, 3, 0, 0), dtype=torch.uint8, device=dev)
+    H, W, _ = jpeg_info(bufs[0])
+    if out is None:
+        out = torch.empty((n, 3, H, W), dtype=torch.uint8, device=dev)
+    elif tuple(out.shape) != (n, 3, H, W) or out.dtype != torch.uint8 or not out.is_cuda or not out.is_contiguous():
+        raise RbaError(f"decode_jpeg_batch: out must be a contiguous uint8 CUDA tensor of shape {(n, 3, H, W)}")
+    ptrs = (ctypes.c_void_p * n)(*[b.ctypes.data for b in bufs])
+    sizes = (ctypes.c_int64 * n)(*[b.size for b in bufs])
+    with torch.cuda.device(out.device):
+        st = torch.cuda.current_stream(out.device).cuda_stream
+        _lib.check(_lib.lib().rba_jpeg_decode(ptrs, sizes, n, out.data_ptr(), H, W, ctypes.c_void_p(st)))
+    return out
