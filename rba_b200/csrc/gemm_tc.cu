@@ -60,11 +60,14 @@ constexpr int TC_THREADS2 = (2 + TC_EPI_WARPS) * 32;    // 576
 // STG = "store-staged" configuration for store-bound shapes (K <= 256): a 2-stage operand ring leaves room for a
 // 4 KB per-warp staging buffer through which the epilogue turns its row-per-lane registers into coalesced 16-byte
 // global stores (4 full lines per instruction instead of 32 partial ones).
-template <int BN, bool STG = false>
+// CG2 = CTA pair (`tcgen05.mma.cta_group::2`): the two CTAs of a cluster compute ONE 256 x 256 tile; each loads its own 128
+// rows of A and HALF of the 256 W rows (the tensor core of either SM reads the other half from the peer's shared memory), so
+// a stage is 64 KB per SM for twice the MMA work of the 128 x 128 tile: half the L2 -> shared-memory bytes per FLOP.
+template <int BN, bool STG = false, bool CG2 = false>
 struct TcSmem {
-  static constexpr int STAGES = (BN > 128 || STG) ? 2 : 3;   // 96 KB stages for BN = 256, 64 KB (48 KB) otherwise
+  static constexpr int STAGES = CG2 ? 3 : ((BN > 128 || STG) ? 2 : 3);   // 96 KB stages for BN = 256, 64 KB (48 KB) otherwise
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;      // one plane of A per stage (16 KB)
-  static constexpr int W_BYTES = BN * TC_BK * 2;
+  static constexpr int W_BYTES = (CG2 ? 128 : BN) * TC_BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
   static constexpr int NG = BN > 128 ? BN / 128 : 1;     // 128-column groups per tile (epilogue passes)
   static constexpr int BIAS_BYTES = TC_EPI_WARPS * 32 * NG * 4;
@@ -78,8 +81,8 @@ struct TileCoord {
   int cvb, cvh0, cvw0;      // conv
 };
 
-template <int BN, bool CONV>
-__device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int t) {
+template <int BN, bool CONV, bool CG2 = false>
+__device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int t, int rank = 0) {
   TileCoord c;
   const int tn = t % p.tilesN;
   int r = t / p.tilesN;
@@ -91,7 +94,7 @@ __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int t) {
     c.cvh0 = (r % p.tilesH) * TC_CONV_TH;
     c.cvb = r / p.tilesH;
   } else {
-    c.m0 = (r % p.tilesM) * TC_BM;
+    c.m0 = CG2 ? (r % p.tilesM) * (2 * TC_BM) + rank * TC_BM : (r % p.tilesM) * TC_BM;   // CG2: tilesM counts 256-row tiles
     c.bz = r / p.tilesM;
   }
   return c;
@@ -124,12 +127,57 @@ __device__ __forceinline__ float tc_act(float x) {
 
 // ACT: RBA_ACT_*; OUTP: false = fp32 output (c), true = split-plane output (c_hi/c_lo) [both: handled by the fp32 variant
 // falling back to scalar plane stores].
-template <int BN, bool CONV, int ACT, bool OUTP, bool STG>
+// ---- CTA-pair helpers ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are signalled on an mbarrier that may live in the peer CTA (shared::cluster address)
+__device__ __forceinline__ void tma_load_3d_cg2(void* smem, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit of the pair's MMAs: arrives on the barrier at this shared-memory offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_cg2(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
+template <int BN, bool CONV, int ACT, bool OUTP, bool STG, bool CG2 = false>
 __global__ void __launch_bounds__(TC_THREADS2, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, const TcParams p) {
-  using S = TcSmem<BN, STG>;
+  static_assert(!CG2 || (BN == 256 && !CONV && !STG), "the CTA-pair form is the 256 x 256 GEMM tile");
+  using S = TcSmem<BN, STG, CG2>;
   constexpr int TC_STAGES = S::STAGES;
+  const int rank = CG2 ? (int)cluster_ctarank() : 0;     // CTA of the pair: 0 = leader (issues the MMAs)
+  const int cta0 = CG2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, nctas = CG2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   // align to 1024 B (128B-swizzle atoms) with pointer arithmetic on the __shared__ array so that the compiler keeps the
   // shared address space (LDS/STS instead of generic LD/ST)
@@ -150,29 +198,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmW_hi); prefetch_tmap(&tmW_lo);
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], (BN >= 128 ? 4 : BN / 32) * 4); }   // one arrival per active epilogue warp
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], (BN >= 128 ? 4 : BN / 32) * 4 * (CG2 ? 2 : 1)); }   // one arrival per active epilogue warp (of both CTAs of a pair)
     fence_barrier_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG2) cluster_sync_all(); else __syncthreads();      // (pair: the peer's barriers must be initialised before anything signals them)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      uint32_t it = 0;                                 // running K-block counter (ring position)
-      for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
-        const TileCoord tc = tile_coord<BN, CONV>(p, t);
-        for (int kb = 0; kb < p.nkb; ++kb, ++it) {
-          const int s = it % TC_STAGES;
-          const uint32_t ph = (it / TC_STAGES) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
+    // ===================== TMA producer (whole warp in uniform control flow, one elected lane issues) =====================
+    uint32_t s = 0, ph = 1;                                // fresh "empty" barriers pass a wait on parity 1
+    for (int t = cta0; t < p.ntiles; t += nctas) {
+      const TileCoord tc = tile_coord<BN, CONV, CG2>(p, t, rank);
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        mbar_wait(&empty[s], ph);
+        if (elect_one()) {
           uint8_t* st = smem + s * S::STAGE_BYTES;
+          if (CG2) {
+            // both CTAs' bytes complete on the LEADER's barrier (armed by the leader for 2 x 64 KB); W: this CTA's half of the rows
+            const uint32_t fb = mapa_u32(smem_u32(&full[s]), 0);
+            if (rank == 0) mbar_expect_tx(&full[s], 2 * S::STAGE_BYTES);
+            tma_load_3d_cg2(st, &tmA_hi, fb, kb * TC_BK, tc.m0, p.a_batched ? tc.bz : 0);
+            tma_load_3d_cg2(st + S::A_BYTES, &tmA_lo, fb, kb * TC_BK, tc.m0, p.a_batched ? tc.bz : 0);
+            tma_load_3d_cg2(st + 2 * S::A_BYTES, &tmW_hi, fb, kb * TC_BK, tc.n0 + rank * 128, p.w_batched ? tc.bz : 0);
+            tma_load_3d_cg2(st + 2 * S::A_BYTES + S::W_BYTES, &tmW_lo, fb, kb * TC_BK, tc.n0 + rank * 128, p.w_batched ? tc.bz : 0);
+          } else {
           mbar_expect_tx(&full[s], S::STAGE_BYTES);
           if (CONV) {
             const int cpb = p.cCin / TC_BK;               // channel blocks per tap
@@ -186,37 +246,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           }
           tma_load_3d(st + 2 * S::A_BYTES, &tmW_hi, &full[s], kb * TC_BK, tc.n0, p.w_batched ? tc.bz : 0);
           tma_load_3d(st + 2 * S::A_BYTES + S::W_BYTES, &tmW_lo, &full[s], kb * TC_BK, tc.n0, p.w_batched ? tc.bz : 0);
+          }
         }
+        __syncwarp();
+        if (++s == TC_STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(TC_BM, BN);
-      uint32_t it = 0, lt = 0;                           // ring position, local tile counter
-      for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++lt) {
-        const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
-        mbar_wait(&acc_empty[as], aph ^ 1);              // epilogue has drained this accumulator buffer
+    // The WHOLE warp walks the loop (uniform control flow, uniform counters) and one elected lane issues.  Under
+    // `if (lane == 0)` ptxas wraps every tcgen05.mma in an ELECT / BRA.U.ANY loop (seen in the SASS of every instantiation of
+    // the first revision; measured ~70 clk per MMA in the window-attention kernel): with 64 clk of math per 128x128x16 MMA that
+    // made the BN = 128 GEMMs issue-bound at ~56 % tensor-pipe activity (profiles/r2f_ncu_kernels.md).  Descriptors are a
+    // constant high word plus a low word (address / 16 | LBO) that advances by compile-time offsets.
+    constexpr uint32_t idesc = make_idesc(CG2 ? 2 * TC_BM : TC_BM, BN);
+    constexpr uint32_t D_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
+    const uint32_t lo0 = (smem_u32(smem) >> 4) | (1u << 16);
+    uint32_t lt = 0;
+    uint32_t s = 0, ph = 0;
+    for (int t = cta0; (!CG2 || rank == 0) && t < p.ntiles; t += nctas, ++lt) {     // pair: only the leader issues
+      const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
+      mbar_wait(&acc_empty[as], aph ^ 1);                // epilogue (of both CTAs) has drained this accumulator buffer
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * BN;
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        mbar_wait(&full[s], ph);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * BN;
-        for (int kb = 0; kb < p.nkb; ++kb, ++it) {
-          const int s = it % TC_STAGES;
-          const uint32_t ph = (it / TC_STAGES) & 1;
-          mbar_wait(&full[s], ph);
-          tc_fence_after();
-          const uint32_t base = smem_u32(smem + s * S::STAGE_BYTES);
-          const uint64_t a_hi = make_sdesc(base), a_lo = make_sdesc(base + S::A_BYTES);
-          const uint64_t w_hi = make_sdesc(base + 2 * S::A_BYTES), w_lo = make_sdesc(base + 2 * S::A_BYTES + S::W_BYTES);
+        if (elect_one()) {
+          const uint32_t a_hi = lo0 + s * (S::STAGE_BYTES >> 4), a_lo = a_hi + (S::A_BYTES >> 4);
+          const uint32_t w_hi = a_hi + (2 * S::A_BYTES >> 4), w_lo = w_hi + (S::W_BYTES >> 4);
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
-            const uint64_t adv = (uint64_t)(k * 32 >> 4);  // +32 B along K inside the 128 B swizzle span
-            umma_bf16(tmem_d, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
-            umma_bf16(tmem_d, a_hi + adv, w_lo + adv, idesc, 1);
-            umma_bf16(tmem_d, a_lo + adv, w_hi + adv, idesc, 1);
+            const uint32_t adv = (uint32_t)(k * 32 >> 4);  // +32 B along K inside the 128 B swizzle span
+            if (CG2) {
+              umma_bf16_cg2(tmem_d, tc_desc(a_hi + adv, D_HI), tc_desc(w_hi + adv, D_HI), idesc, (kb | k) != 0);
+              umma_bf16_cg2(tmem_d, tc_desc(a_hi + adv, D_HI), tc_desc(w_lo + adv, D_HI), idesc, 1);
+              umma_bf16_cg2(tmem_d, tc_desc(a_lo + adv, D_HI), tc_desc(w_hi + adv, D_HI), idesc, 1);
+            } else {
+              umma_bf16(tmem_d, tc_desc(a_hi + adv, D_HI), tc_desc(w_hi + adv, D_HI), idesc, (kb | k) != 0);
+              umma_bf16(tmem_d, tc_desc(a_hi + adv, D_HI), tc_desc(w_lo + adv, D_HI), idesc, 1);
+              umma_bf16(tmem_d, tc_desc(a_lo + adv, D_HI), tc_desc(w_hi + adv, D_HI), idesc, 1);
+            }
           }
-          umma_commit(&empty[s]);                         // frees the smem stage when these MMAs retire
+          if (CG2) {
+            umma_commit_cg2(&empty[s]);                     // frees the stage in BOTH CTAs when these MMAs retire
+            if (kb == p.nkb - 1) umma_commit_cg2(&acc_full[as]);
+          } else {
+            umma_commit(&empty[s]);                         // frees the smem stage when these MMAs retire
+            if (kb == p.nkb - 1) umma_commit(&acc_full[as]);   // accumulator complete
+          }
         }
-        umma_commit(&acc_full[as]);                       // accumulator complete
+        __syncwarp();
+        if (++s == TC_STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else {
@@ -233,8 +314,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       uint8_t* mystage = sstage + ew * 4096;
       const int row_in_tile = quad * 32 + lane;
       uint32_t lt = 0;
-      for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++lt) {
-        const TileCoord tc = tile_coord<BN, CONV>(p, t);
+      for (int t = cta0; t < p.ntiles; t += nctas, ++lt) {
+        const TileCoord tc = tile_coord<BN, CONV, CG2>(p, t, rank);
         const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
         const int bz = tc.bz;
         int64_t orow = -1;                                  // output row (or -1: nothing to store)
@@ -296,7 +377,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (g2 == NG - 1) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[as]);       // this warp is done with the TMEM buffer
+          if (lane == 0) {                                  // this warp is done with the TMEM buffer (pair: tell the leader)
+            if (CG2) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[as]), 0)); else mbar_arrive(&acc_empty[as]);
+          }
         }
         if ((p.debug & 2) || nb >= p.N) { __syncwarp(); continue; }   // warp-uniform
         // ---- bias, activation, residual in the TMEM layout (lane <-> row, register j <-> column nb + j) ----
@@ -427,10 +510,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
     tc_fence_before();
   }
-  __syncthreads();
+  if (CG2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if (CG2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// CTA-pair launch: 2-CTA clusters, grid = 2 x min(#256x256 tiles, #SMs / 2)
+template <int ACT, bool OUTP>
+static int launch_cg2(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
+                      const TcParams& p, cudaStream_t st) {
+  constexpr int smem = TcSmem<256, false, true>::TOTAL;
+  auto kern = gemm_tc_kernel<256, false, ACT, OUTP, false, true>;
+  static PerDeviceOnce once;
+  if (once.needed()) {
+    RBA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    once.done();
+  }
+  const int npairs = std::min<int>(p.ntiles, num_sms() / 2);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(2 * npairs));
+  cfg.blockDim = dim3(TC_THREADS2);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  RBA_CUDA(cudaLaunchKernelEx(&cfg, kern, a_hi, a_lo, w_hi, w_lo, p));
+  RBA_LAUNCHED();
+  return RBA_OK;
+}
+static int launch_tc_cg2(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
+                         const TcParams& p, cudaStream_t st) {
+  const bool outp = p.c == nullptr;                       // planes only
+  switch (p.act) {
+    case RBA_ACT_RELU:
+      return outp ? launch_cg2<RBA_ACT_RELU, true>(a_hi, a_lo, w_hi, w_lo, p, st) : launch_cg2<RBA_ACT_RELU, false>(a_hi, a_lo, w_hi, w_lo, p, st);
+    case RBA_ACT_GELU:
+      return outp ? launch_cg2<RBA_ACT_GELU, true>(a_hi, a_lo, w_hi, w_lo, p, st) : launch_cg2<RBA_ACT_GELU, false>(a_hi, a_lo, w_hi, w_lo, p, st);
+    default:
+      return outp ? launch_cg2<RBA_ACT_NONE, true>(a_hi, a_lo, w_hi, w_lo, p, st) : launch_cg2<RBA_ACT_NONE, false>(a_hi, a_lo, w_hi, w_lo, p, st);
   }
 }
 
@@ -511,7 +635,23 @@ int gemm_tc_launch(const rba_gemm_args& a, cudaStream_t st) {
   p.w_batched = a.batch > 1 && a.w_bstride != 0;
   int BN = a.N > 64 ? 128 : 64;
   if (a.N % 256 == 0 && (g_tc_bn256 == 1 || (g_tc_bn256 == 2 && a.K >= 1024))) BN = 256;   // K = 512, N >= 2048 measured slower
+  // CTA pairs (256 x 256 tiles over two SMs): RBA_TC_CG2 = 0 never, 1 (default) when N % 256 == 0, K % 64 == 0, K >= 512 and
+  // M >= 512 (measured, profiles/r2o_gemm_cta_pairs.txt: +4 ... +13 % on the K >= 512 shapes; the store-bound K = 128 shapes
+  // lose the staged stores and a 256 x 256 tile there is two K blocks long: 2 = also those, for the record)
+  static const int g_tc_cg2 = []() { const char* e = getenv("RBA_TC_CG2"); return e ? atoi(e) : 1; }();
+  const bool cg2 = g_tc_cg2 != 0 && a.N % 256 == 0 && a.K % TC_BK == 0 && a.M >= 512 && (a.K >= 512 || g_tc_cg2 == 2);
   CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
+  if (cg2) {
+    RBA_TRY_(make_map_3d(&ta_hi, a.a_hi, a.K, a.M, a.lda, p.a_batched ? a.batch : 1, a.a_bstride, TC_BM));
+    RBA_TRY_(make_map_3d(&ta_lo, a.a_lo, a.K, a.M, a.lda, p.a_batched ? a.batch : 1, a.a_bstride, TC_BM));
+    RBA_TRY_(make_map_3d(&tw_hi, a.w_hi, a.K, a.N, a.ldw, p.w_batched ? a.batch : 1, a.w_bstride, 128));
+    RBA_TRY_(make_map_3d(&tw_lo, a.w_lo, a.K, a.N, a.ldw, p.w_batched ? a.batch : 1, a.w_bstride, 128));
+    p.tilesM = (int)cdiv(a.M, 2 * TC_BM); p.tilesN = a.N / 256;
+    const int64_t nt2 = (int64_t)p.tilesM * p.tilesN * a.batch;
+    RBA_CHECK(nt2 < (1LL << 31), "gemm(tc): too many tiles");
+    p.ntiles = (int)nt2;
+    return launch_tc_cg2(ta_hi, ta_lo, tw_hi, tw_lo, p, st);
+  }
   RBA_TRY_(make_map_3d(&ta_hi, a.a_hi, a.K, a.M, a.lda, p.a_batched ? a.batch : 1, a.a_bstride, TC_BM));
   RBA_TRY_(make_map_3d(&ta_lo, a.a_lo, a.K, a.M, a.lda, p.a_batched ? a.batch : 1, a.a_bstride, TC_BM));
   RBA_TRY_(make_map_3d(&tw_hi, a.w_hi, a.K, a.N, a.ldw, p.w_batched ? a.batch : 1, a.w_bstride, BN));

@@ -90,6 +90,12 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                            // SWIZZLE_128B, bits [61,64)
   return d;
 }
+// 64-bit descriptor from its two words (low: start address / 16 | LBO / 16 << 16; high: SBO / 16 | version << 14 | layout << 29)
+__device__ __forceinline__ uint64_t tc_desc(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
 // Instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16: D fp32, A/B bf16, both K-major, M x N.
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);

@@ -571,7 +571,8 @@ TC_TOL = 2e-4
 
 
 @pytest.mark.parametrize("M,N,K", [(300, 20, 256), (129, 96, 128), (1000, 384, 64), (5, 1, 256), (257, 130, 2304),
-                                   (128, 128, 32), (700, 512, 512), (300, 512, 1024), (129, 256, 2048)])   # last two: 256-wide N tiles
+                                   (128, 128, 32), (700, 512, 512), (300, 512, 1024), (129, 256, 2048),   # last two: 256-wide N tiles
+                                   (1024, 256, 512), (2049, 768, 576), (40000, 1536, 512)])   # CTA pairs (M >= 512, N % 256 == 0, K >= 512), > 1 tile per pair
 @pytest.mark.parametrize("act", [ops.RBA_ACT_NONE, ops.RBA_ACT_GELU])
 def test_gemm_tc(dev, M, N, K, act):
     g = torch.Generator().manual_seed(M + N + K + 1)
