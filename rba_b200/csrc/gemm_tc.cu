@@ -65,7 +65,7 @@ constexpr int TC_THREADS2 = (2 + TC_EPI_WARPS) * 32;    // 576
 // a stage is 64 KB per SM for twice the MMA work of the 128 x 128 tile: half the L2 -> shared-memory bytes per FLOP.
 template <int BN, bool STG = false, bool CG2 = false>
 struct TcSmem {
-  static constexpr int STAGES = CG2 ? 3 : ((BN > 128 || STG) ? 2 : 3);   // 96 KB stages for BN = 256, 64 KB (48 KB) otherwise
+  static constexpr int STAGES = CG2 ? (STG ? 2 : 3) : ((BN > 128 || STG) ? 2 : 3);   // 96 KB stages for BN = 256, 64 KB (48 KB) otherwise
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;      // one plane of A per stage (16 KB)
   static constexpr int W_BYTES = (CG2 ? 128 : BN) * TC_BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
@@ -173,7 +173,7 @@ template <int BN, bool CONV, int ACT, bool OUTP, bool STG, bool CG2 = false>
 __global__ void __launch_bounds__(TC_THREADS2, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, const TcParams p) {
-  static_assert(!CG2 || (BN == 256 && !CONV && !STG), "the CTA-pair form is the 256 x 256 GEMM tile");
+  static_assert(!CG2 || (BN == 256 && !CONV), "the CTA-pair form is the 256 x 256 GEMM tile");
   using S = TcSmem<BN, STG, CG2>;
   constexpr int TC_STAGES = S::STAGES;
   const int rank = CG2 ? (int)cluster_ctarank() : 0;     // CTA of the pair: 0 = leader (issues the MMAs)
@@ -518,12 +518,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   }
 }
 
+static const int g_tc_stg_maxk = []() { const char* e = getenv("RBA_TC_STG_MAXK"); return e ? atoi(e) : 512; }();
+
 // CTA-pair launch: 2-CTA clusters, grid = 2 x min(#256x256 tiles, #SMs / 2)
-template <int ACT, bool OUTP>
-static int launch_cg2(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
-                      const TcParams& p, cudaStream_t st) {
-  constexpr int smem = TcSmem<256, false, true>::TOTAL;
-  auto kern = gemm_tc_kernel<256, false, ACT, OUTP, false, true>;
+template <int ACT, bool OUTP, bool STG>
+static int launch_cg2s(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
+                       const TcParams& p, cudaStream_t st) {
+  constexpr int smem = TcSmem<256, STG, true>::TOTAL;
+  auto kern = gemm_tc_kernel<256, false, ACT, OUTP, STG, true>;
   static PerDeviceOnce once;
   if (once.needed()) {
     RBA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -544,6 +546,14 @@ static int launch_cg2(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CU
   RBA_CUDA(cudaLaunchKernelEx(&cfg, kern, a_hi, a_lo, w_hi, w_lo, p));
   RBA_LAUNCHED();
   return RBA_OK;
+}
+// short K loops are store-bound: 2-stage ring + staged coalesced stores (as for the single-CTA tiles); RBA_TC_CG2_STG=0 disables
+template <int ACT, bool OUTP>
+static int launch_cg2(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
+                      const TcParams& p, cudaStream_t st) {
+  static const int stg = []() { const char* e = getenv("RBA_TC_CG2_STG"); return e ? atoi(e) : 1; }();
+  if (stg && p.K <= g_tc_stg_maxk) return launch_cg2s<ACT, OUTP, true>(a_hi, a_lo, w_hi, w_lo, p, st);
+  return launch_cg2s<ACT, OUTP, false>(a_hi, a_lo, w_hi, w_lo, p, st);
 }
 static int launch_tc_cg2(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
                          const TcParams& p, cudaStream_t st) {
@@ -577,7 +587,6 @@ static int launch_tc3(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CU
 // 4-7 % on the K >= 1024 shapes and lose on K = 512 / 128 (profiles/r1e_gemm_power_sustained.txt): RBA_TC_BN256 = 0 never,
 // 1 always (when N % 256 == 0), 2 (default) for K >= 1024.
 static const int g_tc_bn256 = []() { const char* e = getenv("RBA_TC_BN256"); return e ? atoi(e) : 2; }();
-static const int g_tc_stg_maxk = []() { const char* e = getenv("RBA_TC_STG_MAXK"); return e ? atoi(e) : 512; }();
 
 template <int BN, bool CONV, int ACT, bool OUTP>
 static int launch_tc2(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
