@@ -46,6 +46,10 @@ int einsum_score2_supported(int Q, int K, int D);
 int einsum_score2_launch(const uint16_t* e_hi, const uint16_t* e_lo, const float* bias, const uint16_t* y_hi, const uint16_t* y_lo,
                          const float* logits, int B, int Q, int K, int D, int h, int w, int H, int W, int include_void, float* rba,
                          cudaStream_t st);
+int einsum_score3_supported(int Q, int K, int D);
+int einsum_score3_launch(const uint16_t* e_hi, const uint16_t* e_lo, const float* bias, const uint16_t* y_hi, const uint16_t* y_lo,
+                         const float* logits, int B, int Q, int K, int D, int h, int w, int H, int W, int include_void, float* rba,
+                         cudaStream_t st);
 int fused_score_variant();
 int ood_pred_resize(const float* logits, int B, int h, int w, int H, int W, float* ood_pred, float* score, cudaStream_t st);
 int msda_fused(const float* value, const int* Hs, const int* Ws, const float* oa, int B, int S, int M, int D, int L,

@@ -635,7 +635,7 @@ int fused_score_variant() {
   int v = g_fs_variant.load(std::memory_order_relaxed);
   if (v < 0) {
     const char* e = getenv("RBA_FS_VARIANT");
-    v = e ? atoi(e) : 1;   // second-generation kernel is opt-in until it is the faster one
+    v = e ? atoi(e) : 3;   // third generation (score_fused3.cu) by default; 1 / 2 select the earlier kernels
     g_fs_variant.store(v, std::memory_order_relaxed);
   }
   return v;
@@ -649,9 +649,12 @@ int einsum_score_launch(const uint16_t* e_hi, const uint16_t* e_lo, const float*
   RBA_CHECK(einsum_score_supported(Q, K, D), "einsum_score: unsupported Q=%d (<= %d) K=%d (<= %d) D=%d (multiple of %d)", Q,
             FS_QP, K, FS_NT * 8 - 1, D, TC_BK);
   RBA_CHECK(score_func == RBA_SCORE_RBA || score_func == RBA_SCORE_ENERGY, "einsum_score: unknown score function %d", score_func);
-  // RbA-only launches (the hot path) run on the second-generation kernel (score_fused2.cu); sem_seg / energy launches and
-  // RBA_FS_VARIANT=1 (or rba_k_set_fused_score_variant(1)) stay on this one
-  if (!sem && score_func == RBA_SCORE_RBA && fused_score_variant() != 1)
+  // RbA-only launches (the hot path) run on the third-generation kernel (score_fused3.cu: runs in registers, 1.33 ms per
+  // 8 images against 1.45 here); RBA_FS_VARIANT / rba_k_set_fused_score_variant select 2 (score_fused2.cu, tcgen05 score
+  // phase, 1.54 ms) or 1 (this file); sem_seg / energy launches always run here
+  if (!sem && score_func == RBA_SCORE_RBA && fused_score_variant() == 3)
+    return einsum_score3_launch(e_hi, e_lo, bias, y_hi, y_lo, logits, B, Q, K, D, h, w, H, W, include_void, rba, st);
+  if (!sem && score_func == RBA_SCORE_RBA && fused_score_variant() == 2)
     return einsum_score2_launch(e_hi, e_lo, bias, y_hi, y_lo, logits, B, Q, K, D, h, w, H, W, include_void, rba, st);
   RBA_CHECK(((uintptr_t)e_hi & 15) == 0 && ((uintptr_t)e_lo & 15) == 0 && ((uintptr_t)y_hi & 15) == 0 && ((uintptr_t)y_lo & 15) == 0,
             "einsum_score: operand planes must be 16-byte aligned");
@@ -709,9 +712,10 @@ int einsum_score_launch(const uint16_t* e_hi, const uint16_t* e_lo, const float*
 
 // mask_embed (B,Q,D) and features (B,h,w,D) as bf16 split planes; bias (B,Q) fp32 or NULL; pred_logits (B,Q,K+1);
 // sem_seg (B, K or K+1, H, W) or NULL.
-// test / profiling hook: 1 = first-generation kernel (mma.sync score phase), 2 = second generation, 0 = default
+// test / profiling hook: 1 = first-generation kernel (mma.sync cells), 2 = second (tcgen05 score phase), 3 = third (runs in
+// registers), 0 = default (RBA_FS_VARIANT, else 3)
 extern "C" int rba_k_set_fused_score_variant(int v) {
-  rba::g_fs_variant.store(v == 0 ? -1 : (v == 1 ? 1 : 2), std::memory_order_relaxed);   // 0: back to the default / RBA_FS_VARIANT
+  rba::g_fs_variant.store(v == 0 ? -1 : (v == 1 ? 1 : (v == 3 ? 3 : 2)), std::memory_order_relaxed);   // 0: back to the default / RBA_FS_VARIANT
   return RBA_OK;
 }
 

@@ -564,33 +564,6 @@ rba_einsum_score2_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __gri
   }
 }
 
-// bf16 NHWC [B][H][W][C] -> 4-D map, box = (32 ch, 16 w, 8 h, 1), SWIZZLE_64B
-static int f2_map_nhwc(CUtensorMap* m, const uint16_t* ptr, int B, int H, int W, int C) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) return fail(RBA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)F2_BK, TC_CONV_TW, TC_CONV_TH, 1};
-  cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(RBA_ERR_CUDA, "cuTensorMapEncodeTiled(score2 nhwc) failed with %d", (int)r);
-  return RBA_OK;
-}
-// bf16 [B][Q][D] -> 3-D map, box = (32, 112, 1), SWIZZLE_64B (rows >= Q zero-filled)
-static int f2_map_embed(CUtensorMap* m, const uint16_t* ptr, int B, int Q, int D) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) return fail(RBA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-  cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)Q, (cuuint64_t)B};
-  cuuint64_t strides[2] = {(cuuint64_t)D * 2, (cuuint64_t)Q * D * 2};
-  cuuint32_t box[3] = {(cuuint32_t)F2_BK, (cuuint32_t)F2_NQ, 1};
-  cuuint32_t es[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(RBA_ERR_CUDA, "cuTensorMapEncodeTiled(score2 embed) failed with %d", (int)r);
-  return RBA_OK;
-}
-
 int einsum_score2_supported(int Q, int K, int D) { return Q > 0 && Q <= 104 && K > 0 && K + 1 <= 24 && D % 64 == 0; }
 
 // RbA-only launch (no sem_seg, score function RbA); same operands as einsum_score_launch
@@ -612,10 +585,10 @@ int einsum_score2_launch(const uint16_t* e_hi, const uint16_t* e_lo, const float
   RBA_CHECK(nt < (1LL << 31), "einsum_score2: too many tiles");
   p.ntiles = (int)nt;
   CUtensorMap ty_hi, ty_lo, te_hi, te_lo;
-  RBA_TRY_(f2_map_nhwc(&ty_hi, y_hi, B, h, w, D));
-  RBA_TRY_(f2_map_nhwc(&ty_lo, y_lo, B, h, w, D));
-  RBA_TRY_(f2_map_embed(&te_hi, e_hi, B, Q, D));
-  RBA_TRY_(f2_map_embed(&te_lo, e_lo, B, Q, D));
+  RBA_TRY_(make_map_nhwc_k32(&ty_hi, y_hi, B, h, w, D));
+  RBA_TRY_(make_map_nhwc_k32(&ty_lo, y_lo, B, h, w, D));
+  RBA_TRY_(make_map_embed_k32(&te_hi, e_hi, B, Q, D));
+  RBA_TRY_(make_map_embed_k32(&te_lo, e_lo, B, Q, D));
   static PerDeviceOnce once;
   if (once.needed()) {
     RBA_CUDA(cudaFuncSetAttribute(rba_einsum_score2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));

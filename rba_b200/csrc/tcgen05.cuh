@@ -292,6 +292,34 @@ static int make_map_nhwc(CUtensorMap* m, const uint16_t* ptr, int B, int H, int 
   return RBA_OK;
 }
 
+// bf16 NHWC [B][H][W][C] -> 4-D map, box = (32 ch, tw, th, 1) (16 x 8 pixels by default), SWIZZLE_64B
+static int make_map_nhwc_k32(CUtensorMap* m, const uint16_t* ptr, int B, int H, int W, int C, int tw = TC_CONV_TW,
+                             int th = TC_CONV_TH) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(RBA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {32, (cuuint32_t)tw, (cuuint32_t)th, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(RBA_ERR_CUDA, "cuTensorMapEncodeTiled(score2 nhwc) failed with %d", (int)r);
+  return RBA_OK;
+}
+// bf16 [B][Q][D] -> 3-D map, box = (32, 112, 1) (the fused score kernels' E' operand), SWIZZLE_64B (rows >= Q zero-filled)
+static int make_map_embed_k32(CUtensorMap* m, const uint16_t* ptr, int B, int Q, int D) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(RBA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)Q, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)D * 2, (cuuint64_t)Q * D * 2};
+  cuuint32_t box[3] = {32, 112, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(RBA_ERR_CUDA, "cuTensorMapEncodeTiled(score2 embed) failed with %d", (int)r);
+  return RBA_OK;
+}
+
 static int num_sms() {
   static int n = 0;
   if (n == 0) {

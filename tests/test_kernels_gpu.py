@@ -439,7 +439,7 @@ def test_einsum_score_fused(dev, B, Q, K, D, h, w, crop):
     rba, sem = ops.einsum_score_fused(e_pl, f_pl, logits.to(dev), (H, W), bias=bias.to(dev), want_sem_seg=True)
     assert (sem.cpu() - sem_ref).abs().max() < 5e-5, float((sem.cpu() - sem_ref).abs().max())
     assert (rba.cpu() - rba_ref).abs().max() < 5e-5
-    for variant in (1, 2):                      # RbA-only launch on the mma.sync / on the tcgen05 score phase
+    for variant in (1, 2, 3):                   # RbA-only launch: mma.sync cells / tcgen05 score phase / runs in registers
         try:
             ops.set_fused_score_variant(variant)
             rba2 = ops.einsum_score_fused(e_pl, f_pl, logits.to(dev), (H, W), bias=bias.to(dev))
@@ -456,7 +456,7 @@ def test_einsum_score_fused(dev, B, Q, K, D, h, w, crop):
     assert (rba0.cpu() - rba_ref0).abs().max() < 5e-5
 
 
-@pytest.mark.parametrize("variant", [2, 1])
+@pytest.mark.parametrize("variant", [3, 2, 1])
 @pytest.mark.parametrize("scale,bias_shift", [(12.0, 0.0), (30.0, 0.0), (60.0, -20.0), (400.0, 50.0)])
 def test_einsum_score_fused_large_logits(dev, variant, scale, bias_shift):
     """Mask logits far outside the comfortable range (|x| up to several hundred, sharp sign changes between neighbouring
@@ -490,7 +490,7 @@ def test_einsum_score_fused_large_logits(dev, variant, scale, bias_shift):
     assert err < tol, err
 
 
-@pytest.mark.parametrize("variant", [2, 1])
+@pytest.mark.parametrize("variant", [3, 2, 1])
 def test_einsum_score_fused_many_tiles_per_cta(dev, variant):
     """More tiles than SMs (each persistent CTA walks 3-4 tiles and crosses image boundaries): the deferred epilogue of a tile's
     last block, the per-image class-probability buffers and the alternating half block of the second-generation kernel.
