@@ -15,7 +15,7 @@ ckpts/swin_b_1dl architecture (no network for checkpoints), synthetic uint8 imag
          pinned H2D of its uint8 batch, its forward and the D2H of its score maps are inside the timed region; the
          three legs of consecutive steps overlap on three CUDA streams.
   roofline     the fused mask-einsum + upsample + sigmoid + contraction + tanh score kernel (the kernel BASELINE's metric
-               names; score_fused.cu), timed alone with CUDA events on its launch stream on inputs > L2 (1.07 GB at B=8).
+               names; score_fused3.cu), timed alone with CUDA events on its launch stream on inputs > L2 (1.07 GB at B=8).
   cpu_baseline the oracle port (oracle/rba_oracle.py, PyTorch CPU fp32, all host threads) on a bounded sample.
 
 `--impl reference` times that CPU port of the reference's path as the reference arm (rank 0 only).
@@ -431,7 +431,7 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    # ---- roofline of the fused mask-einsum + RbA score kernel (score_fused.cu), timed ALONE (before the long timed loops
+    # ---- roofline of the fused mask-einsum + RbA score kernel (score_fused3.cu), timed ALONE (before the long timed loops
     # put the GPU at its power cap) with CUDA events on the stream it is launched
     # on; its inputs (feature planes 134 MB/img) exceed L2 at every batch size ----
     Q, K, D = mc.num_queries, mc.num_classes, mc.conv_dim
@@ -466,9 +466,9 @@ def run_ours(args):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     # DRAM traffic of this kernel from the committed `ncu --set full` capture (dram__bytes_read.sum + dram__bytes_write.sum,
-    # per image; profiles/r1_fused_score_traffic.json), scaled to this launch's batch
+    # per image; profiles/r2s_fused_score_traffic.json), scaled to this launch's batch
     traffic, issue = None, None
-    tp = os.path.join(ROOT, "profiles", "r2_fused_score_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r2s_fused_score_traffic.json")
     other_bounds = None
     if os.path.exists(tp):
         cap = json.load(open(tp))
@@ -486,14 +486,14 @@ def run_ours(args):
                     f_ms = cap[key] * B / sm_clock_hz * 1e3
                     other_bounds[name] = {"floor_ms": f_ms, "frac": f_ms / k_ms}
             other_bounds["issue"] = {"floor_ms": floor_ms, "frac": floor_ms / k_ms}
-    roofline = {"kernel": "rba_einsum_score_kernel (tcgen05 mask einsum -> x4 bilinear on tf32 MMA -> sigmoid -> (Q,K) contraction "
-                          "on f16 hi/lo MMA -> tanh -> class sum; one HBM pass)", "bound": "hbm",
+    roofline = {"kernel": "rba_einsum_score3_kernel (tcgen05 mask einsum -> x4 bilinear in the thread -> run-form sigmoids -> (Q,K) "
+                          "contraction on f16 hi/lo mma.sync -> tanh -> class sum; one HBM pass)", "bound": "hbm",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst, kernel timed alone)" if peaks else "fallback 6.65 TB/s",
                 "traffic": traffic, "ms_per_launch": k_ms, "algorithmic_bytes_per_launch": alg_bytes, "issue_bound": issue,
                 "binding_bounds": other_bounds,
                 "note": "fp32 semantics make this kernel issue/MUFU-bound, not HBM-bound (SURVEY §0.5): per output pixel "
-                        "Q sigmoids of individually interpolated logits (2 MUFU each) + 2*K*Q contraction FLOP vs 68 B"}
+                        "Q sigmoids of individually interpolated logits (1 MUFU + ~9 other instructions each) + 2*K*Q contraction FLOP vs 68 B"}
 
     del f_pl, e_pl, kbias, klogits
     torch.cuda.empty_cache()
