@@ -85,8 +85,9 @@ def einsum_score_fused(mask_embed, features, pred_logits, out_hw, bias=None, wan
 
 
 def set_fused_score_variant(variant):
-    """Test / profiling hook: 2 (default) = tcgen05 score phase (score_fused2.cu) for RbA-only launches, 1 = the mma.sync
-    kernel (score_fused.cu) for every launch."""
+    """Test / profiling hook for RbA-only launches: 3 (default) = runs in registers (score_fused3.cu), 2 = tcgen05 score
+    phase (score_fused2.cu), 1 = the mma.sync cell kernel (score_fused.cu, which serves every sem_seg / energy launch);
+    0 restores the default."""
     _lib.check(_lib.lib().rba_k_set_fused_score_variant(int(variant)))
 
 

@@ -522,6 +522,41 @@ def test_einsum_score_fused_many_tiles_per_cta(dev, variant):
     assert err < 5e-5, err
 
 
+@pytest.mark.parametrize("Q,K,void", [(96, 19, False), (91, 19, False), (85, 7, True), (16, 19, False), (5, 3, False), (104, 22, True),
+                                      (100, 19, True)])
+def test_einsum_score_fused_v3_query_counts(dev, Q, K, void):
+    """Third-generation kernel (score_fused3.cu): every shape of its query loop -- whole k16 steps only (96, 16), a remainder
+    above 8 that takes a full step (91), the k8 tail step with two (85, 104) and with one query per lane (100, 5; 5 has no full
+    step at all) -- and semantic_inference_with_void (K + 1 class columns, up to the 24 the three class tiles hold).
+    Reference: fp64 interpolate -> sigmoid -> class sums -> tanh on the values the planes hold."""
+    B, D, h, w = 2, 64, 13, 21
+    g = torch.Generator().manual_seed(Q * 31 + K)
+    E = torch.randn(B, Q, D, generator=g) / math.sqrt(D) * 3.0
+    Fm = torch.randn(B, h, w, D, generator=g)
+    bias = torch.randn(B, Q, generator=g) - 0.5
+    logits = torch.randn(B, Q, K + 1, generator=g) * 2.0
+    H, W = 4 * h - 1, 4 * w - 3
+    (e_hi, e_lo), Ex = planes(E.view(B * Q, D), dev)
+    (f_hi, f_lo), Fx = planes(Fm.view(-1, D), dev)
+    e_pl = (e_hi.view(B, Q, D), e_lo.view(B, Q, D))
+    f_pl = (f_hi.view(B, h, w, D), f_lo.view(B, h, w, D))
+    masks = torch.einsum("bqc,bhwc->bqhw", Ex.view(B, Q, D).double(), Fx.view(B, h, w, D).double()) + bias.double()[:, :, None, None]
+    up = F.interpolate(masks.float().double(), size=(4 * h, 4 * w), mode="bilinear", align_corners=False)[:, :, :H, :W]
+    probs = logits.double().softmax(-1)
+    sem = torch.einsum("bqc,bqhw->bchw", probs if void else probs[..., :-1], up.sigmoid())
+    ref = -sem.tanh().sum(1)
+    out = {}
+    for variant in (3, 1):
+        try:
+            ops.set_fused_score_variant(variant)
+            out[variant] = ops.einsum_score_fused(e_pl, f_pl, logits.to(dev), (H, W), bias=bias.to(dev), include_void=void)
+        finally:
+            ops.set_fused_score_variant(0)
+        err = (out[variant].cpu().double() - ref).abs().max().item()
+        assert err < 5e-5, (variant, err)
+    assert (out[3] - out[1]).abs().max() < 2e-5
+
+
 def test_einsum_score_fused_energy_and_void(dev):
     """Other score heads on the same kernel: get_energy (evaluate_ood.py:152-159) and
     semantic_inference_with_void (maskformer_model.py:388-392)."""
