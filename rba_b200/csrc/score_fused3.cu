@@ -27,10 +27,14 @@
 // for a fourth round (an 8 x 16 tile has 105 cells = 52.5 units: 17 % of the warp cycles stalled on that barrier).
 // The queries beyond the last full k16 step (Q = 100: 4) take a k8 step with one (or two) queries per lane instead of a
 // seventh full step that would compute 12 padded queries.
-//   warp 0      TMA producer (feature planes NHWC + E' planes, K blocks of 32 channels, 4-stage ring, SWIZZLE_64B) and issuer of
-//               the einsum MMAs of the NEXT tile (they run under the score phase of the current one)
+//   warp 0      TMA producer (feature planes NHWC + E' planes, K blocks of 32 channels, SWIZZLE_64B ring) and issuer of the einsum
+//               MMAs of the tiles to come (they run under the score phases)
 //   warp 1      tensor-memory allocation only
-//   warps 2-17  drain D1 -> fp32 patch[pixel][query] (scaled by -log2 e, bias added), then the units of the tile
+//   warps 2-17  two GROUPS of 8 compute warps (RBA_F3_GROUPS=1: one group of 16).  The CTA's tiles alternate between the groups;
+//               each group has its own tensor-memory accumulator, patch, class-probability tables and named barrier, drains D1
+//               -> fp32 patch[pixel][query] (scaled by -log2 e, bias added) and scores the 48 units of its tile, 6 per warp.
+//               While one group drains / waits at its tile barrier (7 % of a tile) the other keeps the schedulers busy:
+//               1.329 -> 1.303 ms per 8 images.
 #include <cuda_fp16.h>
 
 #include "kernels.cuh"
@@ -43,31 +47,39 @@ namespace rba {
 #endif
 constexpr int F3_NQ = 112;                                  // einsum N: queries padded to a multiple of 16
 constexpr int F3_BK = 32;
-constexpr int F3_STAGES = 4;
+#ifndef RBA_F3_GROUPS
+#define RBA_F3_GROUPS 2                                      // 1: one group of 16 compute warps; 2: two groups of 8 on alternating tiles
+#endif
+constexpr int F3_NG = RBA_F3_GROUPS;
+constexpr int F3_STAGES = F3_NG == 2 ? 2 : 4;
 constexpr int F3_A_BYTES = TC_BM * F3_BK * 2;               // 8 KB: one plane of the feature tile per K block (119 rows loaded)
 constexpr int F3_E_BYTES = F3_NQ * F3_BK * 2;               // 7 KB: one plane of E'
 constexpr int F3_STAGE_BYTES = 2 * F3_A_BYTES + 2 * F3_E_BYTES;   // 30 KB
 constexpr int F3_PITCH = 132;                               // patch pitch (words): = 4 (mod 32) -> 8 lanes x 16 B hit 8 bank groups
-constexpr int F3_PATCH_BYTES = TC_BM * F3_PITCH * 4;        // 66 KB
+constexpr int F3_PATCH_ROWS = 120;                           // 119 pixels + the tap prefetch past the last one
+constexpr int F3_PATCH_BYTES = F3_PATCH_ROWS * F3_PITCH * 4;  // 62 KB per group
 constexpr int F3_KS = F3_NQ / 16;                           // 7 k16 steps
 constexpr int F3_NT = 3;                                    // n8 class tiles (K + 1 <= 24)
 constexpr int F3_P_BYTES = F3_NT * F3_KS * 32 * 16;         // [class tile][k16 step][lane] x {b0_hi, b1_hi, b0_lo, b1_lo}
 constexpr int F3_CW = 16;                                   // compute warps
+constexpr int F3_GW = F3_CW / F3_NG;                         // compute warps per group
+static_assert(F3_NG == 1 || F3_NG == 2, "one or two groups");
 constexpr int F3_SW = 2;                                    // service warps: TMA + einsum issue; tensor-memory allocation
 constexpr int F3_THREADS = (F3_SW + F3_CW) * 32;
+// per group: patch | sP | sPt | bias
 constexpr int F3_OFF_PATCH = F3_STAGES * F3_STAGE_BYTES;
-constexpr int F3_OFF_P = F3_OFF_PATCH + F3_PATCH_BYTES;
 constexpr int F3_PT_BYTES = F3_NT * 32 * 8;                  // tail step: [class tile][lane] x {hi pair, lo pair}
-constexpr int F3_OFF_PT = F3_OFF_P + F3_P_BYTES;
-constexpr int F3_OFF_BIAS = F3_OFF_PT + F3_PT_BYTES;
-constexpr int F3_OFF_BARS = F3_OFF_BIAS + 512;
+constexpr int F3_GOFF_P = F3_PATCH_BYTES, F3_GOFF_PT = F3_GOFF_P + F3_P_BYTES, F3_GOFF_BIAS = F3_GOFF_PT + F3_PT_BYTES;
+constexpr int F3_GROUP_BYTES = F3_GOFF_BIAS + 512;
+constexpr int F3_OFF_BARS = F3_OFF_PATCH + F3_NG * F3_GROUP_BYTES;
 constexpr int F3_SMEM = F3_OFF_BARS + 256 + 1024;
-constexpr uint32_t F3_TMEM_COLS = 128;
+constexpr uint32_t F3_TMEM_COLS = F3_NG == 2 ? 256 : 128;     // one 112-column accumulator per group (columns 0 / 128)
+static_assert(F3_SMEM <= 227 * 1024, "shared memory");
 constexpr int F3_TW = 17, F3_TH = 7;                        // tile = 7 x 17 low-resolution pixels (119 of the 128 einsum rows)
 constexpr int F3_CELLS_X = F3_TW - 1, F3_CELLS_Y = F3_TH - 1;   // 16 x 6 cells
 constexpr int F3_NCELL = F3_CELLS_X * F3_CELLS_Y;           // 96
 constexpr int F3_NUNIT = F3_NCELL / 2;                      // 48 units of two cells = 3 per compute warp, no remainder
-static_assert(F3_TW * F3_TH <= TC_BM && F3_NCELL % 2 == 0 && F3_NUNIT % 16 == 0, "tile geometry");
+static_assert(F3_TW * F3_TH <= TC_BM && F3_TW * F3_TH < F3_PATCH_ROWS && F3_NCELL % 2 == 0 && F3_NUNIT % F3_GW == 0, "tile geometry");
 constexpr int F3_A_TX = F3_TW * F3_TH * F3_BK * 2;             // bytes one feature-plane box delivers
 constexpr int F3_STAGE_TX = 2 * F3_A_TX + 2 * F3_E_BYTES;
 constexpr float F3_UFAST = 60.0f;                           // product form valid while every tap |u| <= 60
@@ -92,9 +104,9 @@ struct F3Params {
 
 struct F3Bars {
   uint64_t full[F3_STAGES], empty[F3_STAGES];
-  uint64_t acc_full, acc_empty;      // D1 of a tile complete (tcgen05.commit) / drained by the 16 warps
+  uint64_t acc_full[2], acc_empty[2];   // per group: D1 of a tile complete (tcgen05.commit) / drained by the group's warps
   uint32_t tmem_slot;
-  uint32_t amax[2];                  // max |u| of the tile's taps (float bits), by tile parity
+  uint32_t amax[2][2];                  // max |u| of the tile's taps (float bits), by group and tile parity
 };
 
 __device__ __forceinline__ float f3_rcp(float x) {
@@ -127,7 +139,8 @@ __device__ __forceinline__ void f3_mma_k8(float* c, uint32_t a0, uint32_t a1, ui
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a0), "r"(a1), "r"(b0));
 }
-__device__ __forceinline__ void f3_bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(F3_CW * 32) : "memory"); }
+// barrier of one group's compute warps (named barrier 1 + group)
+__device__ __forceinline__ void f3_bar_group(int grp) { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(F3_GW * 32) : "memory"); }
 
 // The four sigmoids 1 / (1 + 2^(x0 + j d)), j = 0..3, of one run and one query.
 //   FAST: 2^x0 and 2^d once, the other three exponentials by multiplication (every intermediate is 2^(u_j) or (2^d)^j with
@@ -345,10 +358,6 @@ rba_einsum_score3_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __gri
                          const F3Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  float* sPatch = reinterpret_cast<float*>(smem + F3_OFF_PATCH);   // [pixel][query], pitch F3_PITCH
-  uint4* sP = reinterpret_cast<uint4*>(smem + F3_OFF_P);
-  uint2* sPt = reinterpret_cast<uint2*>(smem + F3_OFF_PT);
-  float* sBias = reinterpret_cast<float*>(smem + F3_OFF_BIAS);
   F3Bars* bars = reinterpret_cast<F3Bars*>(smem + F3_OFF_BARS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -356,8 +365,10 @@ rba_einsum_score3_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __gri
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmY_hi); prefetch_tmap(&tmY_lo); prefetch_tmap(&tmE_hi); prefetch_tmap(&tmE_lo);
     for (int s = 0; s < F3_STAGES; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-    mbar_init(&bars->acc_full, 1); mbar_init(&bars->acc_empty, F3_CW);
-    bars->amax[0] = 0u; bars->amax[1] = 0u;
+    for (int g2 = 0; g2 < 2; ++g2) {
+      mbar_init(&bars->acc_full[g2], 1); mbar_init(&bars->acc_empty[g2], F3_GW);
+      bars->amax[g2][0] = 0u; bars->amax[g2][1] = 0u;
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -399,8 +410,11 @@ rba_einsum_score3_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __gri
     int g = 0;
     for (int lt = 0; lt < my_tiles; ++lt) {
       issue_loads_upto(g + F3_STAGES);                     // the first stages of this tile load under the previous tile's score phase
-      if (lt > 0) {
-        mbar_wait_sleep(&bars->acc_empty, (uint32_t)(lt - 1) & 1);   // D1 of the previous tile has been drained
+      const int pg = F3_NG == 2 ? (lt & 1) : 0;            // group that scores this tile; its accumulator
+      const int plt = F3_NG == 2 ? (lt >> 1) : lt;         // tile count of that group
+      const uint32_t dcol = tmem_base + (uint32_t)(pg * 128);
+      if (plt > 0) {
+        mbar_wait_sleep(&bars->acc_empty[pg], (uint32_t)(plt - 1) & 1);   // the group has drained its previous tile's D1
         tc_fence_after();
       }
       for (int kb = 0; kb < p.nkb; ++kb, ++g) {
@@ -414,12 +428,12 @@ rba_einsum_score3_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __gri
 #pragma unroll
           for (int k = 0; k < F3_BK / 16; ++k) {
             const uint64_t adv = (uint64_t)(k * 32 >> 4);
-            umma_bf16(tmem_base, a_hi + adv, e_hi + adv, idE, (kb | k) != 0);
-            umma_bf16(tmem_base, a_hi + adv, e_lo + adv, idE, 1);
-            umma_bf16(tmem_base, a_lo + adv, e_hi + adv, idE, 1);
+            umma_bf16(dcol, a_hi + adv, e_hi + adv, idE, (kb | k) != 0);
+            umma_bf16(dcol, a_hi + adv, e_lo + adv, idE, 1);
+            umma_bf16(dcol, a_lo + adv, e_hi + adv, idE, 1);
           }
           umma_commit(&bars->empty[ms]);
-          if (kb == p.nkb - 1) umma_commit(&bars->acc_full);
+          if (kb == p.nkb - 1) umma_commit(&bars->acc_full[pg]);
         }
         __syncwarp();
         if (++ms == F3_STAGES) { ms = 0; mph ^= 1; }
@@ -428,8 +442,15 @@ rba_einsum_score3_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __gri
   } else if (warp >= F3_SW) {
     // ===================== drain + score: warps 2..17 =====================
     const int cw = warp - F3_SW;
-    const int ctid = cw * 32 + lane;
-    const int qd = warp & 3, grp = cw >> 2;                // TMEM lane quadrant; chunk group of the drain
+    const int gi = cw / F3_GW, gw = cw - gi * F3_GW;       // group; warp inside the group
+    const int ctid = gw * 32 + lane;                       // thread inside the group
+    const int qd = warp & 3, grp = gw >> 2;                // TMEM lane quadrant; chunk group of the drain
+    uint8_t* gsm = smem + F3_OFF_PATCH + gi * F3_GROUP_BYTES;
+    float* sPatch = reinterpret_cast<float*>(gsm);         // [pixel][query], pitch F3_PITCH
+    uint4* sP = reinterpret_cast<uint4*>(gsm + F3_GOFF_P);
+    uint2* sPt = reinterpret_cast<uint2*>(gsm + F3_GOFF_PT);
+    float* sBias = reinterpret_cast<float*>(gsm + F3_GOFF_BIAS);
+    const uint32_t dcol = tmem_base + (uint32_t)(gi * 128);
     const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
     const int m = qd * 32 + lane;                          // TMEM lane = low-res pixel of the drain
     const int g = lane >> 2, t = lane & 3;                 // run of the unit; query quad of the step / output pixel of the store
@@ -445,19 +466,19 @@ rba_einsum_score3_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __gri
     const uint2* bt = sPt + lane;
     int cur_b = -1;
     uint32_t lt = 0;
-    for (int tt = blockIdx.x; tt < p.ntiles; tt += gridDim.x, ++lt) {
+    for (int tt = blockIdx.x + gi * gridDim.x; tt < p.ntiles; tt += F3_NG * gridDim.x, ++lt) {   // the CTA's tiles alternate between the groups
       const F3Tile T = f3_tile(p, tt);
       F3_STAMP(lt, 0);
-      if (ctid == 0) bars->amax[lt & 1] = 0u;               // last read one tile ago, before that tile's closing barrier
-      f3_bar_compute();                                     // every warp has finished the previous tile: patch, bias and sP are free
+      if (ctid == 0) bars->amax[gi][lt & 1] = 0u;               // last read one tile ago, before that tile's closing barrier
+      f3_bar_group(gi);                                     // every warp has finished the previous tile: patch, bias and sP are free
       if (T.b != cur_b) {
         // ---- per image: scaled bias; class probabilities as f16 hi/lo B fragments, scaled by 2 log2(e)
         // (tanh(s) = 1 - 2 / (1 + 2^(2 log2(e) s))): entry [class tile][k16 step][lane (g, t)] = {b0_hi, b1_hi, b0_lo, b1_lo},
         // class 8 nt + g, b0 = queries 16 ks + 4t + {0, 1}, b1 = queries 16 ks + 4t + {2, 3} ----
         cur_b = T.b;
         if (ctid < F3_NQ) sBias[ctid] = (p.bias && ctid < p.Q) ? p.bias[(size_t)T.b * p.Q + ctid] * SCALE : 0.f;
-        for (int e4 = ctid; e4 < (F3_P_BYTES + F3_PT_BYTES) / 16; e4 += F3_CW * 32) sP[e4] = make_uint4(0u, 0u, 0u, 0u);   // sP and sPt
-        f3_bar_compute();
+        for (int e4 = ctid; e4 < (F3_P_BYTES + F3_PT_BYTES) / 16; e4 += F3_GW * 32) sP[e4] = make_uint4(0u, 0u, 0u, 0u);   // sP and sPt
+        f3_bar_group(gi);
         if (ctid < p.Q) {
           const int q = ctid;
           const float* lg = p.logits + ((size_t)T.b * p.Q + q) * (p.K + 1);
@@ -483,20 +504,20 @@ rba_einsum_score3_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __gri
             }
           }
         }
-        f3_bar_compute();
+        f3_bar_group(gi);
       }
       // ---- drain the accumulator: TMEM lane = low-res pixel, column = query -> patch[pixel][query] ----
       F3_STAMP(lt, 1);
-      mbar_wait(&bars->acc_full, lt & 1);
+      mbar_wait(&bars->acc_full[gi], lt & 1);
       tc_fence_after();
       F3_STAMP(lt, 2);
       float am = 0.f;
-      for (int chunk = grp; chunk * 16 < F3_NQ; chunk += 4) {
+      for (int chunk = grp; chunk * 16 < F3_NQ; chunk += F3_GW / 4) {
         const int q0 = chunk * 16;
         uint32_t v[16];
-        tmem_ld16(tmem_base + lane_addr + (uint32_t)q0, v);
+        tmem_ld16(dcol + lane_addr + (uint32_t)q0, v);
         tmem_ld_wait();
-        float* prow = sPatch + m * F3_PITCH + q0;
+        float* prow = sPatch + (m < F3_PATCH_ROWS ? m : F3_PATCH_ROWS - 1) * F3_PITCH + q0;   // rows >= 119: garbage, parked on the spare row
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
           const float4 b4 = *reinterpret_cast<const float4*>(sBias + q0 + 4 * j4);
@@ -512,13 +533,13 @@ rba_einsum_score3_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __gri
       if (m >= F3_TW * F3_TH) am = 0.f;                     // rows beyond the box: whatever the stage held before
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->acc_empty);         // the einsum of the next tile may start
+      if (lane == 0) mbar_arrive(&bars->acc_empty[gi]);         // the einsum of the next tile may start
       {
         const uint32_t wm = __reduce_max_sync(0xffffffffu, __float_as_uint(am));   // non-negative floats order like their bits
-        if (lane == 0) atomicMax(&bars->amax[lt & 1], wm);
+        if (lane == 0) atomicMax(&bars->amax[gi][lt & 1], wm);
       }
       F3_STAMP(lt, 3);
-      f3_bar_compute();                                     // every pixel of the patch has been written
+      f3_bar_group(gi);                                     // every pixel of the patch has been written
       F3_STAMP(lt, 4);
       // ---- image borders: replicate the edge into the out-of-range taps (CTA-uniform) ----
       {
@@ -528,7 +549,7 @@ rba_einsum_score3_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __gri
         const int cright = p.w - T.c0 <= F3_TW - 1 ? p.w - T.c0 : -1;
         if (rtop >= 0 || rbot >= 0 || cleft >= 0 || cright >= 0) {
           // rows first, then columns (so that the corners pick up the diagonal neighbour); F3_NQ / 4 = 28 float4 per pixel
-          for (int e4 = ctid; e4 < 2 * F3_TW * (F3_NQ / 4); e4 += F3_CW * 32) {
+          for (int e4 = ctid; e4 < 2 * F3_TW * (F3_NQ / 4); e4 += F3_GW * 32) {
             const int which = e4 / (F3_TW * (F3_NQ / 4)), r2 = e4 - which * (F3_TW * (F3_NQ / 4));
             const int col = r2 / (F3_NQ / 4), q4 = r2 - col * (F3_NQ / 4);
             const int dstrow = which ? rbot : rtop;
@@ -537,8 +558,8 @@ rba_einsum_score3_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __gri
             *reinterpret_cast<float4*>(sPatch + (dstrow * F3_TW + col) * F3_PITCH + 4 * q4) =
                 *reinterpret_cast<const float4*>(sPatch + (srcrow * F3_TW + col) * F3_PITCH + 4 * q4);
           }
-          f3_bar_compute();
-          for (int e4 = ctid; e4 < 2 * F3_TH * (F3_NQ / 4); e4 += F3_CW * 32) {
+          f3_bar_group(gi);
+          for (int e4 = ctid; e4 < 2 * F3_TH * (F3_NQ / 4); e4 += F3_GW * 32) {
             const int which = e4 / (F3_TH * (F3_NQ / 4)), r2 = e4 - which * (F3_TH * (F3_NQ / 4));
             const int row = r2 / (F3_NQ / 4), q4 = r2 - row * (F3_NQ / 4);
             const int dstcol = which ? cright : cleft;
@@ -547,16 +568,16 @@ rba_einsum_score3_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __gri
             *reinterpret_cast<float4*>(sPatch + (row * F3_TW + dstcol) * F3_PITCH + 4 * q4) =
                 *reinterpret_cast<const float4*>(sPatch + (row * F3_TW + srccol) * F3_PITCH + 4 * q4);
           }
-          f3_bar_compute();
+          f3_bar_group(gi);
         }
       }
-      const bool fast = !(dbg & 1) && bars->amax[lt & 1] <= __float_as_uint(F3_UFAST);
+      const bool fast = !(dbg & 1) && bars->amax[gi][lt & 1] <= __float_as_uint(F3_UFAST);
       F3_STAMP(lt, 5);
       if (dbg & 2) continue;
       // ---- score phase: unit u = cells 2u, 2u + 1 (row-major over the 6 x 16 cells) ----
       float* const rba_b = p.rba + (size_t)T.b * p.H * p.W;
 #pragma unroll 1
-      for (int u = cw; u < F3_NUNIT; u += F3_CW) {
+      for (int u = gw; u < F3_NUNIT; u += F3_GW) {
         const int cell = 2 * u + half;
         const int br = cell / F3_CELLS_X, bc = cell - br * F3_CELLS_X;
         const float* tap = sPatch + (br * F3_TW + bc) * F3_PITCH + 4 * t;
