@@ -8,9 +8,9 @@
 
 constexpr int ITERS = 2048, CHAINS = 8;
 
-enum Op { EX2, RCP, TANH, F2FP, F2FP_BF16, SPLIT_F16, SPLIT_BF16T, HADD2F32, PRMT, LOP, FMNMX, FFMA, FADD, HMMA_F16, HMMA_BF16, HMMA_TF32, LDS32, MIX_SIG, MIX_MUFU_HMMA, MIX_MUFU_FFMA4, FHFMA_OP, HMMA_F16_K8, NOPS };
+enum Op { EX2, RCP, TANH, F2FP, F2FP_BF16, SPLIT_F16, SPLIT_BF16T, HADD2F32, PRMT, LOP, FMNMX, FFMA, FADD, HMMA_F16, HMMA_BF16, HMMA_TF32, LDS32, MIX_SIG, MIX_MUFU_HMMA, MIX_MUFU_FFMA4, FHFMA_OP, HMMA_F16_K8, MIX_HMMA_FFMA4, MIX_HMMA_FFMA8, NOPS };
 const char* names[] = {"MUFU.EX2", "MUFU.RCP", "MUFU.TANH", "F2FP.F16.F32.PACK", "F2FP.BF16.F32.PACK", "split f16 (6 ops)", "split bf16 trunc (6 ops)", "HADD2.F32 (h->f)", "PRMT", "LOP3", "FMNMX",
-                       "FFMA", "FADD", "HMMA.16816.F32 f16", "HMMA.16816.F32 bf16", "HMMA.1688.F32.TF32", "LDS.32", "EX2+FADD+RCP", "EX2+HMMA", "EX2+4xFFMA", "FHFMA (f32 += f16*f16)", "HMMA.1688.F32 f16"};
+                       "FFMA", "FADD", "HMMA.16816.F32 f16", "HMMA.16816.F32 bf16", "HMMA.1688.F32.TF32", "LDS.32", "EX2+FADD+RCP", "EX2+HMMA", "EX2+4xFFMA", "FHFMA (f32 += f16*f16)", "HMMA.1688.F32 f16", "HMMA+4xFFMA", "HMMA+8xFFMA"};
 
 template <int OP>
 __global__ void __launch_bounds__(256) k(float* out, long long* clk, float seed) {
@@ -88,6 +88,22 @@ __global__ void __launch_bounds__(256) k(float* out, long long* clk, float seed)
         asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
                      : "+f"(acc[c][0]), "+f"(acc[c][1]), "+f"(acc[c][2]), "+f"(acc[c][3])
                      : "r"(u[0]), "r"(u[1]), "r"(u[4]));
+      if (OP == MIX_HMMA_FFMA4 || OP == MIX_HMMA_FFMA8) {
+        // does the legacy tensor path overlap FMA-pipe issue?  (HMMA alone: 5 clk per sub-partition)
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(acc[c][0]), "+f"(acc[c][1]), "+f"(acc[c][2]), "+f"(acc[c][3])
+                     : "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]));
+        asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(x[c]) : "f"(seed));
+        asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(x[(c + 1) % CHAINS]) : "f"(seed));
+        asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(x[(c + 2) % CHAINS]) : "f"(seed));
+        asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(x[(c + 3) % CHAINS]) : "f"(seed));
+        if (OP == MIX_HMMA_FFMA8) {
+          asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(x[c]) : "f"(seed));
+          asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(x[(c + 1) % CHAINS]) : "f"(seed));
+          asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(x[(c + 2) % CHAINS]) : "f"(seed));
+          asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(x[(c + 3) % CHAINS]) : "f"(seed));
+        }
+      }
       if (OP == MIX_SIG) {
         asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[c]));
         asm volatile("add.f32 %0, %0, 1.0;" : "+f"(x[c]));
@@ -121,7 +137,7 @@ void run(int sms, int ctas_per_sm) {
   long long* h = new long long[grid];
   cudaMemcpy(h, clk, grid * 8, cudaMemcpyDeviceToHost);
   double avg = 0; for (int i = 0; i < grid; ++i) avg += h[i]; avg /= grid;
-  const double per_op = (OP == MIX_SIG) ? 3.0 : (OP == MIX_MUFU_HMMA) ? 2.0 : (OP == MIX_MUFU_FFMA4) ? 5.0 : (OP == SPLIT_F16 || OP == SPLIT_BF16T) ? 6.0 : 1.0;
+  const double per_op = (OP == MIX_SIG) ? 3.0 : (OP == MIX_MUFU_HMMA) ? 2.0 : (OP == MIX_MUFU_FFMA4 || OP == MIX_HMMA_FFMA4) ? 5.0 : (OP == MIX_HMMA_FFMA8) ? 9.0 : (OP == SPLIT_F16 || OP == SPLIT_BF16T) ? 6.0 : 1.0;
   const double winst_per_cta = 8.0 * ITERS * CHAINS * per_op;     // 8 warps
   // per-SM rate from the in-kernel clocks (each SM runs ctas_per_sm CTAs concurrently for ~avg clocks)
   printf("%-22s ctas/SM=%d  %.3f warp-inst/clk/SM  (%.1f lanes/clk/SM)  [%.3f ms, %.0f clk]\n", names[OP], ctas_per_sm,
@@ -136,7 +152,7 @@ int main() {
   for (int c : {2, 4}) {
     run<EX2>(sms, c); run<RCP>(sms, c); run<TANH>(sms, c); run<MIX_SIG>(sms, c); run<F2FP>(sms, c); run<F2FP_BF16>(sms, c); run<SPLIT_F16>(sms, c); run<SPLIT_BF16T>(sms, c); run<HADD2F32>(sms, c);
     run<PRMT>(sms, c); run<LOP>(sms, c); run<FMNMX>(sms, c); run<FFMA>(sms, c); run<FADD>(sms, c);
-    run<HMMA_F16>(sms, c); run<HMMA_BF16>(sms, c); run<HMMA_TF32>(sms, c); run<LDS32>(sms, c); run<MIX_MUFU_HMMA>(sms, c); run<MIX_MUFU_FFMA4>(sms, c); run<FHFMA_OP>(sms, c); run<HMMA_F16_K8>(sms, c);
+    run<HMMA_F16>(sms, c); run<HMMA_BF16>(sms, c); run<HMMA_TF32>(sms, c); run<LDS32>(sms, c); run<MIX_MUFU_HMMA>(sms, c); run<MIX_MUFU_FFMA4>(sms, c); run<FHFMA_OP>(sms, c); run<HMMA_F16_K8>(sms, c); run<MIX_HMMA_FFMA4>(sms, c); run<MIX_HMMA_FFMA8>(sms, c);
   }
   return 0;
 }
