@@ -417,10 +417,14 @@ __global__ void __launch_bounds__(256)
 patch_embed_kernel(const T* __restrict__ img, int B, int H, int W, int Hp, int Wp, float m0, float m1, float m2, float s0,
                    float s1, float s2, const float* __restrict__ cw, const float* __restrict__ cb,
                    const float* __restrict__ gamma, const float* __restrict__ beta, int C, float* __restrict__ tokens) {
+  // A warp takes PE_TOK = 8 horizontally adjacent tokens at a time (round 2: 2 -> 8): per conv tap one 16-byte weight load and two
+  // broadcast 16-byte input loads feed 32 FFMA (11 instructions per 8 FFMA before), and the image rows are read 32 pixels wide.
+  // The FMA order per output channel is unchanged (bias, then taps 0..47), so the result is bitwise the same.
+  constexpr int PE_TOK = 8;
   extern __shared__ __align__(16) float pe_smem[];
   const int CP = 128 * G;              // padded channel count in smem
   float* sW = pe_smem;                 // [48][CP]
-  float* sIn = pe_smem + 48 * CP;      // [8 warps][2 tokens][48]
+  float* sIn = pe_smem + 48 * CP;      // [8 warps][48 taps][PE_TOK tokens]
   for (int e = threadIdx.x; e < 48 * CP; e += blockDim.x) {
     const int k = e / CP, c = e - k * CP;
     sW[e] = (c < C) ? cw[c * 48 + k] : 0.f;
@@ -428,50 +432,61 @@ patch_embed_kernel(const T* __restrict__ img, int B, int H, int W, int Hp, int W
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Th = Hp >> 2, Tw = Wp >> 2;
-  const int64_t npair = (int64_t)B * Th * (Tw >> 1);           // Tw is even (Wp is a multiple of 32)
-  float* in = sIn + warp * 96;
-  for (int64_t pr = (int64_t)blockIdx.x * 8 + warp; pr < npair; pr += (int64_t)gridDim.x * 8) {
-    const int tx = (int)(pr % (Tw >> 1)) * 2;
-    int64_t t = pr / (Tw >> 1);
+  const int ngx = (Tw + PE_TOK - 1) / PE_TOK;                    // the engine pads to multiples of 32 (Tw % 8 == 0); others: partial last group
+  const int64_t ngrp = (int64_t)B * Th * ngx;
+  float* in = sIn + warp * (48 * PE_TOK);
+  for (int64_t pr = (int64_t)blockIdx.x * 8 + warp; pr < ngrp; pr += (int64_t)gridDim.x * 8) {
+    const int tx = (int)(pr % ngx) * PE_TOK;
+    int64_t t = pr / ngx;
     const int ty = (int)(t % Th);
     const int b = (int)(t / Th);
     __syncwarp();
-    for (int e = lane; e < 96; e += 32) {                      // e = ch*32 + ky*8 + kx8 : 8 consecutive pixels per (ch, ky)
-      const int ch = e >> 5, ky = (e >> 3) & 3, kx8 = e & 7;
-      const int yy = ty * 4 + ky, xx = tx * 4 + kx8;
-      float v = 0.f;                                            // ImageList pads the NORMALISED image with 0
+#pragma unroll
+    for (int r = 0; r < 12; ++r) {                               // r = ch * 4 + ky: one image row segment of 32 pixels, lane = pixel
+      const int ch = r >> 2, ky = r & 3;
+      const int yy = ty * 4 + ky, xx = tx * 4 + lane;
+      float v = 0.f;                                             // ImageList pads the NORMALISED image with 0
       if (yy < H && xx < W) {
         const float raw = (float)img[(((int64_t)b * 3 + ch) * H + yy) * W + xx];
         const float mean = ch == 0 ? m0 : (ch == 1 ? m1 : m2);
         const float sd = ch == 0 ? s0 : (ch == 1 ? s1 : s2);
         v = (raw - mean) / sd;
       }
-      in[(kx8 >> 2) * 48 + ch * 16 + ky * 4 + (kx8 & 3)] = v;  // token (kx8 >> 2), conv index ch*16 + ky*4 + kx
+      in[(ch * 16 + ky * 4 + (lane & 3)) * PE_TOK + (lane >> 2)] = v;   // tap ch*16 + ky*4 + kx of token (lane >> 2)
     }
     __syncwarp();
-    float acc[2][4 * G];
+    float acc[PE_TOK][4 * G];
 #pragma unroll
     for (int gch = 0; gch < G; ++gch) {
       const int c0 = gch * 128 + 4 * lane;
       float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
       if (c0 < C) bb = *reinterpret_cast<const float4*>(cb + c0);
 #pragma unroll
-      for (int tk = 0; tk < 2; ++tk) { acc[tk][4 * gch] = bb.x; acc[tk][4 * gch + 1] = bb.y; acc[tk][4 * gch + 2] = bb.z; acc[tk][4 * gch + 3] = bb.w; }
+      for (int tk = 0; tk < PE_TOK; ++tk) { acc[tk][4 * gch] = bb.x; acc[tk][4 * gch + 1] = bb.y; acc[tk][4 * gch + 2] = bb.z; acc[tk][4 * gch + 3] = bb.w; }
     }
-#pragma unroll 4
+#pragma unroll 2
     for (int e = 0; e < 48; ++e) {
-      const float i0 = in[e], i1 = in[48 + e];
+      const float4 ia = *reinterpret_cast<const float4*>(in + e * PE_TOK), ib = *reinterpret_cast<const float4*>(in + e * PE_TOK + 4);
+      const float iv[PE_TOK] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w};
 #pragma unroll
       for (int gch = 0; gch < G; ++gch) {
         const float4 w4 = *reinterpret_cast<const float4*>(sW + e * CP + gch * 128 + 4 * lane);
-        acc[0][4 * gch] = fmaf(w4.x, i0, acc[0][4 * gch]); acc[0][4 * gch + 1] = fmaf(w4.y, i0, acc[0][4 * gch + 1]);
-        acc[0][4 * gch + 2] = fmaf(w4.z, i0, acc[0][4 * gch + 2]); acc[0][4 * gch + 3] = fmaf(w4.w, i0, acc[0][4 * gch + 3]);
-        acc[1][4 * gch] = fmaf(w4.x, i1, acc[1][4 * gch]); acc[1][4 * gch + 1] = fmaf(w4.y, i1, acc[1][4 * gch + 1]);
-        acc[1][4 * gch + 2] = fmaf(w4.z, i1, acc[1][4 * gch + 2]); acc[1][4 * gch + 3] = fmaf(w4.w, i1, acc[1][4 * gch + 3]);
+#pragma unroll
+        for (int tk = 0; tk < PE_TOK; ++tk) {
+          acc[tk][4 * gch] = fmaf(w4.x, iv[tk], acc[tk][4 * gch]); acc[tk][4 * gch + 1] = fmaf(w4.y, iv[tk], acc[tk][4 * gch + 1]);
+          acc[tk][4 * gch + 2] = fmaf(w4.z, iv[tk], acc[tk][4 * gch + 2]); acc[tk][4 * gch + 3] = fmaf(w4.w, iv[tk], acc[tk][4 * gch + 3]);
+        }
       }
     }
+    float4 g4[G], b4[G];
 #pragma unroll
-    for (int tk = 0; tk < 2; ++tk) {
+    for (int gch = 0; gch < G; ++gch) {
+      const int c0 = gch * 128 + 4 * lane;
+      g4[gch] = b4[gch] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c0 < C) { g4[gch] = *reinterpret_cast<const float4*>(gamma + c0); b4[gch] = *reinterpret_cast<const float4*>(beta + c0); }
+    }
+#pragma unroll
+    for (int tk = 0; tk < PE_TOK; ++tk) {
       float sum = 0.f;
 #pragma unroll
       for (int j = 0; j < 4 * G; ++j) {
@@ -490,13 +505,12 @@ patch_embed_kernel(const T* __restrict__ img, int B, int H, int W, int Hp, int W
 #pragma unroll
       for (int gch = 0; gch < G; ++gch) {
         const int c0 = gch * 128 + 4 * lane;
-        if (c0 < C) {
-          const float4 g4 = *reinterpret_cast<const float4*>(gamma + c0), b4 = *reinterpret_cast<const float4*>(beta + c0);
+        if (c0 < C && tx + tk < Tw) {
           float4 o;
-          o.x = (acc[tk][4 * gch] - mean) * rstd * g4.x + b4.x;
-          o.y = (acc[tk][4 * gch + 1] - mean) * rstd * g4.y + b4.y;
-          o.z = (acc[tk][4 * gch + 2] - mean) * rstd * g4.z + b4.z;
-          o.w = (acc[tk][4 * gch + 3] - mean) * rstd * g4.w + b4.w;
+          o.x = (acc[tk][4 * gch] - mean) * rstd * g4[gch].x + b4[gch].x;
+          o.y = (acc[tk][4 * gch + 1] - mean) * rstd * g4[gch].y + b4[gch].y;
+          o.z = (acc[tk][4 * gch + 2] - mean) * rstd * g4[gch].z + b4[gch].z;
+          o.w = (acc[tk][4 * gch + 3] - mean) * rstd * g4[gch].w + b4[gch].w;
           *reinterpret_cast<float4*>(tokens + tok * C + c0) = o;
         }
       }
@@ -510,11 +524,11 @@ int patch_embed(const void* images, int img_dtype, int B, int H, int W, int Hp, 
   RBA_CHECK(images && conv_w && conv_b && gamma && beta && tokens, "patch_embed: null pointer");
   RBA_CHECK(Hp % 8 == 0 && Wp % 8 == 0 && Hp >= H && Wp >= W, "patch_embed: padded size must be a multiple of 8");
   RBA_CHECK(C <= 256 && C % 4 == 0, "patch_embed: C=%d unsupported", C);
-  const int64_t npair = (int64_t)B * (Hp / 4) * (Wp / 8);
-  if (npair == 0) return RBA_OK;
-  dim3 grid((unsigned)std::min<int64_t>(cdiv(npair, 8), 148 * 4));
+  const int64_t ngrp = (int64_t)B * (Hp / 4) * cdiv(Wp / 4, 8);          // groups of 8 tokens, one per warp iteration
+  if (ngrp == 0) return RBA_OK;
+  dim3 grid((unsigned)std::min<int64_t>(cdiv(ngrp, 8), 148 * 4));
   const int G = C > 128 ? 2 : 1;
-  const size_t smem = (size_t)(48 * 128 * G + 8 * 96) * sizeof(float);
+  const size_t smem = (size_t)(48 * 128 * G + 8 * 48 * 8) * sizeof(float);
 #define RBA_PE(T, GG)                                                                                                   \
   do {                                                                                                                  \
     RBA_CUDA(cudaFuncSetAttribute(patch_embed_kernel<T, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \

@@ -223,11 +223,12 @@ def test_groupnorm_fused(dev, with_prev, relu):
     assert (unplanes(p) - ref).abs().max() < 2e-4
 
 
+@pytest.mark.parametrize("Wp,C", [(64, 32), (56, 128), (96, 192)])   # 56: the last group of 8 tokens is partial; 192: two channel groups
 @pytest.mark.parametrize("dtype", [torch.uint8, torch.float32])
-def test_patch_embed(dev, dtype):
+def test_patch_embed(dev, dtype, Wp, C):
     """maskformer_model.py:255-257 + swin.py:479-495"""
-    B, H, W, C = 2, 30, 45, 32
-    Hp, Wp = 32, 64
+    B, H, W = 2, 30, 45
+    Hp = 32
     g = torch.Generator().manual_seed(11)
     img = torch.randint(0, 256, (B, 3, H, W), dtype=torch.uint8, generator=g).to(dtype)
     cw, cb = torch.randn(C, 3, 4, 4, generator=g) / 7, torch.randn(C, generator=g)
