@@ -303,10 +303,12 @@ __device__ __forceinline__ void bilin_coeff(int o, int in, int out, int& i0, int
   l1 = src - (float)i0;
 }
 
-// One CTA iteration covers 256 / (C/4) consecutive pixels x all channel quads; the (pixel-in-group, quad) split of a thread,
-// its gamma / beta and all strides are fixed for the kernel, and each thread keeps UNR pixels in flight.  (The first version
-// decomposed a flat 64-bit element index with three divisions per float4 and had one load in flight per thread: 2x off the
-// HBM floor on the 1/4-resolution FPN level.)
+// A CTA walks image ROWS (grid-stride over the B * H rows); inside a row one iteration covers 256 / (C/4) consecutive pixels x all
+// channel quads, and each thread keeps UNR pixels in flight.  The image index, the row and the vertical interpolation
+// coefficients are computed once per row, the horizontal scale once per kernel: the previous form decomposed a flat pixel index
+// with two integer divisions and two float divisions per float4 (the one before that with three 64-bit divisions), ~120
+// instructions per 16 bytes, and ran at 44 % (with the up-sampled addend) / 62 % of its HBM floor on the FPN levels.
+// The arithmetic per element is unchanged.
 template <bool PREV, int UNR>
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const float* __restrict__ x, int64_t x_bs, const float* __restrict__ gamma,
@@ -319,53 +321,61 @@ gn_apply_kernel(const float* __restrict__ x, int64_t x_bs, const float* __restri
   if (pl >= ppi) return;
   const int c = 4 * cq;
   const int g = c / (C / groups);
-  const int HW = H * W;
-  const int npix = B * HW;                               // < 2^31 (checked by the launcher)
   const float4 gm = *reinterpret_cast<const float4*>(gamma + c);
   const float4 bt = *reinterpret_cast<const float4*>(beta + c);
-  const int step = gridDim.x * ppi;
-  for (int p0 = blockIdx.x * ppi + pl; p0 < npix; p0 += step * UNR) {
-    float4 v[UNR];
-    int bb[UNR], rem[UNR];
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const int p = p0 + u * step;
-      bb[u] = -1;
-      if (p < npix) {
-        bb[u] = p / HW;
-        rem[u] = p - bb[u] * HW;
-        v[u] = *reinterpret_cast<const float4*>(x + (int64_t)bb[u] * x_bs + (int64_t)rem[u] * C + c);
-      }
+  const float xscale = PREV ? (float)wp / (float)W : 0.f;   // bilin_coeff's scale (same expression: same bits)
+  const int nrows = B * H;
+  for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const int b = row / H, yh = row - b * H;
+    const float2 mr = *reinterpret_cast<const float2*>(mean_rstd + ((int64_t)b * groups + g) * 2);
+    const float* xr = x + (int64_t)b * x_bs + (int64_t)yh * W * C + c;
+    const int64_t orow = (int64_t)b * y_bs + (int64_t)yh * W * C + c;
+    int y0 = 0, y1 = 0; float ly = 0.f;
+    const float* pb0 = nullptr; const float* pb1 = nullptr;
+    if (PREV) {
+      bilin_coeff(yh, hp, H, y0, y1, ly);
+      pb0 = prev + (int64_t)b * prev_bs + (int64_t)y0 * wp * C + c;
+      pb1 = prev + (int64_t)b * prev_bs + (int64_t)y1 * wp * C + c;
     }
+    for (int x0p = pl; x0p < W; x0p += ppi * UNR) {
+      float4 v[UNR];
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      if (bb[u] < 0) continue;
-      const float2 mr = *reinterpret_cast<const float2*>(mean_rstd + ((int64_t)bb[u] * groups + g) * 2);
-      float4 o;
-      o.x = (v[u].x - mr.x) * mr.y * gm.x + bt.x;
-      o.y = (v[u].y - mr.x) * mr.y * gm.y + bt.y;
-      o.z = (v[u].z - mr.x) * mr.y * gm.z + bt.z;
-      o.w = (v[u].w - mr.x) * mr.y * gm.w + bt.w;
-      if (PREV) {
-        const int yh = rem[u] / W, xw = rem[u] - yh * W;
-        int y0, y1, x0, x1; float ly, lx;
-        bilin_coeff(yh, hp, H, y0, y1, ly);
-        bilin_coeff(xw, wp, W, x0, x1, lx);
-        const float* pb = prev + (int64_t)bb[u] * prev_bs + c;
-        const float4 p00 = *reinterpret_cast<const float4*>(pb + ((int64_t)y0 * wp + x0) * C);
-        const float4 p01 = *reinterpret_cast<const float4*>(pb + ((int64_t)y0 * wp + x1) * C);
-        const float4 p10 = *reinterpret_cast<const float4*>(pb + ((int64_t)y1 * wp + x0) * C);
-        const float4 p11 = *reinterpret_cast<const float4*>(pb + ((int64_t)y1 * wp + x1) * C);
-        const float hy = 1.f - ly, hx = 1.f - lx;
-        o.x += hy * (hx * p00.x + lx * p01.x) + ly * (hx * p10.x + lx * p11.x);
-        o.y += hy * (hx * p00.y + lx * p01.y) + ly * (hx * p10.y + lx * p11.y);
-        o.z += hy * (hx * p00.z + lx * p01.z) + ly * (hx * p10.z + lx * p11.z);
-        o.w += hy * (hx * p00.w + lx * p01.w) + ly * (hx * p10.w + lx * p11.w);
+      for (int u = 0; u < UNR; ++u) {
+        const int xw = x0p + u * ppi;
+        if (xw < W) v[u] = *reinterpret_cast<const float4*>(xr + (int64_t)xw * C);
       }
-      if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-      const int64_t ob = (int64_t)bb[u] * y_bs + (int64_t)rem[u] * C + c;
-      if (y) *reinterpret_cast<float4*>(y + ob) = o;
-      if (y_hi) store_split4(y_hi, y_lo, ob, o.x, o.y, o.z, o.w);
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int xw = x0p + u * ppi;
+        if (xw >= W) continue;
+        float4 o;
+        o.x = (v[u].x - mr.x) * mr.y * gm.x + bt.x;
+        o.y = (v[u].y - mr.x) * mr.y * gm.y + bt.y;
+        o.z = (v[u].z - mr.x) * mr.y * gm.z + bt.z;
+        o.w = (v[u].w - mr.x) * mr.y * gm.w + bt.w;
+        if (PREV) {
+          // bilin_coeff(xw, wp, W, ...) with the scale hoisted
+          float src = ((float)xw + 0.5f) * xscale - 0.5f;
+          if (src < 0.f) src = 0.f;
+          int x0 = (int)src;
+          if (x0 > wp - 1) x0 = wp - 1;
+          const int x1 = min(x0 + 1, wp - 1);
+          const float lx = src - (float)x0;
+          const float4 p00 = *reinterpret_cast<const float4*>(pb0 + (int64_t)x0 * C);
+          const float4 p01 = *reinterpret_cast<const float4*>(pb0 + (int64_t)x1 * C);
+          const float4 p10 = *reinterpret_cast<const float4*>(pb1 + (int64_t)x0 * C);
+          const float4 p11 = *reinterpret_cast<const float4*>(pb1 + (int64_t)x1 * C);
+          const float hy = 1.f - ly, hx = 1.f - lx;
+          o.x += hy * (hx * p00.x + lx * p01.x) + ly * (hx * p10.x + lx * p11.x);
+          o.y += hy * (hx * p00.y + lx * p01.y) + ly * (hx * p10.y + lx * p11.y);
+          o.z += hy * (hx * p00.z + lx * p01.z) + ly * (hx * p10.z + lx * p11.z);
+          o.w += hy * (hx * p00.w + lx * p01.w) + ly * (hx * p10.w + lx * p11.w);
+        }
+        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        const int64_t ob = orow + (int64_t)xw * C;
+        if (y) *reinterpret_cast<float4*>(y + ob) = o;
+        if (y_hi) store_split4(y_hi, y_lo, ob, o.x, o.y, o.z, o.w);
+      }
     }
   }
 }
@@ -393,8 +403,7 @@ int groupnorm(const float* x, int64_t x_bs, const float* gamma, const float* bet
   gn_finalize_kernel<<<B, 256, 0, st>>>(part, nchunks, groups, (int64_t)HW * (C / groups), eps, mean_rstd);
   RBA_LAUNCHED();
   RBA_CHECK((int64_t)B * HW < (1LL << 31), "groupnorm: too many pixels");
-  const int ppi = 256 / (C / 4);
-  int blocks = (int)std::min<int64_t>(cdiv((int64_t)B * HW, ppi), 148 * 8);
+  int blocks = (int)std::min<int64_t>((int64_t)B * H, 148 * 8);          // grid-stride over image rows
   if (prev)
     gn_apply_kernel<true, 2><<<blocks, 256, 0, st>>>(x, x_bs, gamma, beta, mean_rstd, B, H, W, C, groups, prev, prev_bs, hp, wp,
                                                     relu, y, y_hi, y_lo, y_bs);
@@ -408,9 +417,9 @@ int groupnorm(const float* x, int64_t x_bs, const float* gamma, const float* bet
 // ------------------------------------------------------------------------------------------------
 // Patch embedding: normalise + zero pad + 4x4/4 conv + LayerNorm (maskformer_model.py:255-257, swin.py:479-495)
 // ------------------------------------------------------------------------------------------------
-// Persistent CTAs, one warp per PAIR of horizontally adjacent tokens: the conv weights are staged once per CTA in shared
+// Persistent CTAs, one warp per GROUP of 8 horizontally adjacent tokens: the conv weights are staged once per CTA in shared
 // memory transposed to [48][C]; lane l owns channels 4l..4l+3 (and 128+4l.. for C > 128), so each weight read is one
-// conflict-free 16-byte load reused for both tokens; the 48 (=3*4*4) normalised inputs per token are broadcast through
+// conflict-free 16-byte load reused for the 8 tokens; the 48 (=3*4*4) normalised inputs per token are broadcast through
 // shared memory; the LayerNorm is a warp reduction.
 template <typename T, int G>   // G = channel groups of 128 (C <= 128*G)
 __global__ void __launch_bounds__(256)
