@@ -428,6 +428,9 @@ def run_ours(args):
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
+            per = [torch.zeros_like(ms) for _ in range(world)]
+            dist.all_gather(per, ms)                              # every rank's own device time (diagnostic, see `per_rank`)
+            timed.last_per_rank = [float(t.item()) for t in per]
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
@@ -502,6 +505,26 @@ def run_ours(args):
     clocks.start()
     ms_total = timed(step_device, args.warmup, args.steps)
     clk = clocks.stop()
+    per_rank = None
+    if world > 1:
+        # diagnostic (not the metric): each rank's own device time per step with the exchange, and for the forward alone, plus
+        # its median SM clock -- tells board-power skew between the GPUs (the step is the MAX over ranks) from communication
+        with_x = [t / args.steps for t in timed.last_per_rank]
+
+        def step_local(i):
+            static_in.copy_(dev_imgs[i & 1], non_blocking=True)
+            if use_graph:
+                graph.replay()
+            else:
+                eng.forward_into(static_in, static_out)
+        og_saved, og = og, None
+        timed(step_local, 1, args.steps)
+        og = og_saved
+        alone = [t / args.steps for t in timed.last_per_rank]
+        mhz = torch.tensor([float(clk.get("sm_mhz") or 0)], device=dev)
+        mhzs = [torch.zeros_like(mhz) for _ in range(world)]
+        dist.all_gather(mhzs, mhz)
+        per_rank = {"ms_per_step": with_x, "ms_per_step_forward_only": alone, "sm_mhz": [float(t.item()) for t in mhzs]}
     ms_e2e = timed_e2e(max(2, args.warmup // 2), args.steps)
     value = world * B * args.steps / (ms_total * 1e-3)
     e2e = world * B * args.steps / (ms_e2e * 1e-3)
@@ -549,6 +572,8 @@ def run_ours(args):
         "gpu_launches_per_step": int(launches_per_step),
         "clocks": clk, "roofline": roofline,
     }
+    if per_rank:
+        line["per_rank"] = per_rank
     if cpu_baseline:
         line["cpu_baseline"] = cpu_baseline
     if gpu_baseline:
