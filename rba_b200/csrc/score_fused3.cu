@@ -22,11 +22,12 @@
 //   beyond it takes the exact path (four ex2 of individually clamped u_j) -- no clamp ever touches a tap.
 //   Image borders: out-of-range taps are replicated from the edge in the patch (= align_corners=False's clamped source index).
 //
-// Persistent kernel, one CTA per SM, 18 warps (96 registers: 5 warps share a sub-partition's 16 K registers).  Tile = 7 x 17 low-resolution pixels (119 of the M = 128 rows of the einsum; the
-// TMA box is 17 x 7 pixels) = 6 x 16 cells = 48 units: exactly three per compute warp, so no warp waits at the tile barrier
-// for a fourth round (an 8 x 16 tile has 105 cells = 52.5 units: 17 % of the warp cycles stalled on that barrier).
-// The queries beyond the last full k16 step (Q = 100: 4) take a k8 step with one (or two) queries per lane instead of a
-// seventh full step that would compute 12 padded queries.
+// Persistent kernel, one CTA per SM, 18 warps at 96 registers (with 18+ warps of equal size five warps share a sub-partition's
+// 16 K registers; `setmaxnreg` can only move registers that the CTA's own warps release).  Tile = 7 x 17 low-resolution pixels
+// (a 17 x 7 TMA box = 119 of the M = 128 rows of the einsum) = 6 x 16 cells = 48 units, a multiple of the 8 (or 16) warps that
+// share them: no warp waits at the tile barrier for a mostly empty last round (an 8 x 16 tile has 105 cells = 52.5 units; with 16
+// warps that cost 17 % of the warp cycles).  The queries beyond the last full k16 step (Q = 100: 4) take a k8 step with one (or
+// two) queries per lane instead of a seventh full step that would compute 12 padded queries.
 //   warp 0      TMA producer (feature planes NHWC + E' planes, K blocks of 32 channels, SWIZZLE_64B ring) and issuer of the einsum
 //               MMAs of the tiles to come (they run under the score phases)
 //   warp 1      tensor-memory allocation only
