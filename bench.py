@@ -469,9 +469,9 @@ def run_ours(args):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     # DRAM traffic of this kernel from the committed `ncu --set full` capture (dram__bytes_read.sum + dram__bytes_write.sum,
-    # per image; profiles/r2s_fused_score_traffic.json), scaled to this launch's batch
+    # per image; profiles/r2t_fused_score_traffic.json), scaled to this launch's batch
     traffic, issue = None, None
-    tp = os.path.join(ROOT, "profiles", "r2s_fused_score_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r2t_fused_score_traffic.json")
     other_bounds = None
     if os.path.exists(tp):
         cap = json.load(open(tp))
